@@ -1,0 +1,294 @@
+"""tests/golden/make_golden.py -- regenerates tests/golden/*.npz by running the REAL reference.
+
+Runs only in the build container (needs /root/reference and `make -C oracle ref`); the
+vectors it writes are committed and travel to the GPU box.  It imports the reference's
+own ``bluest.sap.SAP`` / ``bluest.mosap.MOSAP`` / ``bluest.misc`` through
+oracle/ref_shim.py (stubbed mpi4py/cvxpy/cvxopt) and records inputs and
+outputs of the sample-allocation hot path.
+
+    python tests/golden/make_golden.py
+
+Files written
+  synthetic.npz   Wishart covariances N=4,6,8: invcovs, psi, Phi, variance,
+                  gradient, Hessian, cleanup matrix, for dense / sparse / tiny / integer m and delta>0
+  tutorial.npz    the 5x5 covariance printed in tutorials/01_tutorial.ipynb:204-208 with the two
+                  stored MLBLUE allocations (:331-334, :459-461) and the printed errors / costs
+  hodgkin.npz     examples/paper_examples/hodgkin-huxley/model_graph_data.npz (M=12, 5 outputs,
+                  cond 1e9-5e10) with the stored K=7 allocation (samples.npz): per-output variances
+  matern.npz      restrictions_matern covariance (M=7, cond 1.5e9), K=7: reference inverses + outputs
+  enumeration.npz clique enumeration / union / mappings / ES from BLUEProblem.setup_solver code
+                  path (networkx) for complete and non-complete model graphs
+  pilot.npz       pilot-sample sums and C_hat computed with the reference's accumulation loop
+"""
+import os
+import sys
+from itertools import combinations
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_shim  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+REF = ref_shim.REF_DEFAULT
+
+
+def all_groups(N, K):
+    return [[list(c) for c in combinations(range(N), k)] for k in range(1, K + 1)]
+
+
+def wishart(N, seed):
+    rng = np.random.RandomState(seed)
+    A = rng.randn(N, 2 * N)
+    return A @ A.T / (2 * N)
+
+
+def record_case(ns, out, tag, C, K, groups, m_list, deltas, with_gh=True):
+    """Run the reference SAP on (C, groups) and store everything the hot path produces."""
+    groups_ref = [[list(g) for g in gk] for gk in groups]
+    L = sum(len(gk) for gk in groups)
+    sap = ns.sap.SAP(C.copy(), K, groups_ref, np.ones(L), verbose=False)
+    out[f"{tag}/C"] = C
+    out[f"{tag}/K"] = np.int64(K)
+    out[f"{tag}/sizes"] = np.array(sap.sizes, dtype=np.int64)
+    for k in range(K):
+        out[f"{tag}/groups{k+1}"] = np.asarray(sap.groups[k], dtype=np.int64).reshape(-1, k + 1)
+        out[f"{tag}/invcovs{k+1}"] = np.asarray(sap.invcovs[k], dtype=np.float64)
+    out[f"{tag}/psi"] = sap.psi
+    out[f"{tag}/e"] = np.asarray(sap.e, dtype=np.int64)
+    out[f"{tag}/n_m"] = np.int64(len(m_list))
+    for j, (m, delta) in enumerate(zip(m_list, deltas)):
+        out[f"{tag}/m{j}"] = m
+        out[f"{tag}/delta{j}"] = np.float64(delta)
+        out[f"{tag}/phi{j}"] = sap.get_phi(m, delta=delta)
+        try:
+            out[f"{tag}/variance{j}"] = np.float64(sap.variance(m, delta=delta))
+        except AssertionError:
+            out[f"{tag}/variance{j}"] = np.float64(np.nan)      # model 0 not in the support
+        if not with_gh:
+            continue
+        res = sap.variance_GH(m, delta=delta)
+        out[f"{tag}/gh_len{j}"] = np.int64(len(res))
+        out[f"{tag}/gh_var{j}"] = np.float64(res[0])
+        out[f"{tag}/gh_grad{j}"] = np.asarray(res[1], dtype=np.float64)
+        if len(res) == 3:
+            out[f"{tag}/gh_hess{j}"] = res[2]
+            out[f"{tag}/cleanup{j}"] = sap.get_cleanup_matrix(m, delta=delta)
+    return sap
+
+
+def make_synthetic(ns):
+    out = {}
+    for N, K, seed in [(4, 4, 0), (6, 6, 1), (8, 4, 2), (8, 8, 3)]:
+        C = wishart(N, seed)
+        groups = all_groups(N, K)
+        L = sum(len(g) for g in groups)
+        rng = np.random.RandomState(100 + seed)
+        m_dense = 1.0 + 10.0 * rng.rand(L)
+        m_sparse = np.zeros(L)
+        nz = rng.choice(L, size=min(2 * N, L), replace=False)
+        m_sparse[nz] = np.ceil(50 * rng.rand(len(nz)))
+        m_sparse[0] = 7.0
+        # only a few models supported: groups {0}, {1}, {0,1}
+        m_few = np.zeros(L); m_few[0] = 3.0; m_few[1] = 2.0; m_few[N] = 5.0
+        m_tiny = 0.01 * np.ones(L)                                     # early-out: max|m| < 0.05
+        m_int = np.round(m_dense).astype(np.int64)                     # integer m after rounding
+        m_thr = m_dense.copy(); m_thr[1] = 5e-7; m_thr[2] = 2e-6       # support threshold 1e-6
+        m_no0 = np.zeros(L); m_no0[1] = 4.0; m_no0[2] = 3.0            # model 0 not sampled
+        ms = [m_dense, m_sparse, m_few, m_tiny, m_int, m_thr, m_dense, m_no0]
+        ds = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1e-6, 0.0]
+        record_case(ns, out, f"N{N}K{K}", C, K, groups, ms, ds)
+    # a non-complete, user-style group list with an EMPTY size class (k=2 missing)
+    N = 6
+    C = wishart(N, 7)
+    groups = [[[0], [2], [5]], [], [[0, 1, 2], [0, 3, 5], [1, 2, 4]], [[0, 1, 2, 3], [0, 2, 4, 5]]]
+    L = sum(len(g) for g in groups)
+    rng = np.random.RandomState(5)
+    # NOTE: with an empty class the reference's variance_GH itself raises IndexError (pybind
+    # ``.data(0)`` on the empty invcovs array, misc.py:620), so only psi/Phi/variance are pinned.
+    record_case(ns, out, "ragged", C, 4, groups, [1.0 + 3.0 * rng.rand(L)], [0.0], with_gh=False)
+    np.savez_compressed(os.path.join(OUT, "synthetic.npz"), **out)
+    print("synthetic.npz:", len(out), "arrays")
+
+
+def make_tutorial(ns):
+    C = np.array([[2.53500581, 2.3583669, 2.36312599, 1.66331444, 0.72897923],
+                  [2.3583669, 2.27345322, 2.07702441, 1.67029559, 0.80520217],
+                  [2.36312599, 2.07702441, 2.40127866, 1.37242096, 0.47072499],
+                  [1.66331444, 1.67029559, 1.37242096, 1.29027193, 0.67275196],
+                  [0.72897923, 0.80520217, 0.47072499, 0.67275196, 1.56637342]])
+    N = 5
+    model_costs = np.array([2.0 ** (N - i) for i in range(N)])
+    groups = all_groups(N, N)
+    flat = [g for gk in groups for g in gk]
+    L = len(flat)
+    costs = np.array([model_costs[g].sum() for g in flat])
+    sap = ns.sap.SAP(C.copy(), N, [[list(g) for g in gk] for gk in groups], costs, verbose=False)
+    out = {"C": C, "model_costs": model_costs}
+    allocs = [([[2], [3], [0, 2, 3], [1, 2, 3], [0, 1, 2, 3]], [5938, 6797, 1, 493, 43], 0.01592249, 91120),
+              ([[1], [0, 3], [0, 1, 2, 3, 4]], [9882, 1794, 305], 0.01592225, 241606)]
+    for a, (gs, ns_, err, cost) in enumerate(allocs):
+        m = np.zeros(L, dtype=np.int64)
+        for g, n in zip(gs, ns_):
+            m[flat.index(g)] = n
+        out[f"m{a}"] = m
+        out[f"printed_error{a}"] = np.float64(err)
+        out[f"printed_cost{a}"] = np.float64(cost)
+        out[f"ref_variance{a}"] = np.float64(sap.variance(m))
+        out[f"ref_cost{a}"] = np.float64(m @ costs)
+        v, g_, _ = sap.variance_GH(m.astype(float), nohess=True)
+        out[f"ref_gh_var{a}"] = np.float64(v)
+        out[f"ref_grad{a}"] = g_
+        print("tutorial", a, np.sqrt(out[f"ref_variance{a}"]), out[f"ref_cost{a}"])
+    np.savez_compressed(os.path.join(OUT, "tutorial.npz"), **out)
+
+
+def make_hodgkin(ns):
+    d = np.load(os.path.join(REF, "examples/paper_examples/hodgkin-huxley/model_graph_data.npz"))
+    s = np.load(os.path.join(REF, "examples/paper_examples/hodgkin-huxley/samples.npz"))
+    M = int(d["M"]); No = int(d["n_outputs"]); K = 7
+    groups = all_groups(M, K)
+    L = sum(len(g) for g in groups)
+    samples = s["samples"]
+    assert len(samples) == L
+    out = {"M": np.int64(M), "K": np.int64(K), "n_outputs": np.int64(No), "costs": d["costs"], "samples": samples}
+    for n in range(No):
+        C = d[f"C{n}"]
+        sap = ns.sap.SAP(C.copy(), K, [[list(g) for g in gk] for gk in groups], np.ones(L), verbose=False)
+        out[f"C{n}"] = C
+        out[f"variance{n}"] = np.float64(sap.variance(samples))
+        v, g, _ = sap.variance_GH(samples.astype(float), nohess=True)
+        out[f"gh_var{n}"] = np.float64(v)
+        out[f"grad{n}"] = g
+        out[f"phi{n}"] = sap.get_phi(samples)
+        if n == 3:                                   # worst-conditioned output only (size)
+            for k in range(K):
+                out[f"invcovs{n}_{k+1}"] = np.asarray(sap.invcovs[k])
+        print("hodgkin", n, np.sqrt(out[f"variance{n}"] / C[0, 0]), np.linalg.cond(C))
+    flat_costs = np.array([d["costs"][g].sum() for gk in groups for g in gk])
+    out["total_cost"] = np.float64(samples @ flat_costs)
+    np.savez_compressed(os.path.join(OUT, "hodgkin.npz"), **out)
+
+
+def make_matern(ns):
+    d = np.load(os.path.join(REF, "examples/paper_examples/restrictions_matern/restrictions_matern_model_data.npz"))
+    C = d["C0"]
+    N = C.shape[0]
+    out = {}
+    groups = all_groups(N, N)
+    L = sum(len(g) for g in groups)
+    rng = np.random.RandomState(11)
+    record_case(ns, out, "matern", C, N, groups, [1.0 + 10.0 * rng.rand(L)], [0.0])
+    out["cond"] = np.float64(np.linalg.cond(C))
+    np.savez_compressed(os.path.join(OUT, "matern.npz"), **out)
+    print("matern cond", out["cond"])
+
+
+def make_enumeration(ns):
+    """Drive the clique enumeration exactly the way BLUEProblem.setup_solver does
+    (blue_models.py:458-501) on stand-alone networkx graphs."""
+    import networkx as nx
+    bm = ns.blue_models
+    out = {}
+
+    def enumerate_ref(graphs, K):
+        Ks, multi_groups = [], []
+        M = graphs[0].number_of_nodes()
+        K = min(K, M)
+        for G in graphs:
+            groups = [[] for _ in range(K)]
+            SG = G.subgraph(nx.node_connected_component(G, 0))      # model-0 component (check_graphs)
+            for clique in nx.enumerate_all_cliques(G):
+                kn = len(clique)
+                if kn > K:
+                    break
+                if all(node in SG for node in clique):
+                    groups[kn - 1].append(clique)
+            groups = [item for item in groups if len(item) > 0]
+            multi_groups.append(groups)
+            Ks.append(min(K, len(groups)))
+        K = max(Ks)
+        groups = [[] for _ in range(K)]
+        for n in range(len(graphs)):
+            for k in range(Ks[n]):
+                for group in multi_groups[n][k]:
+                    if group not in groups[k]:
+                        groups[k].append(group)
+        for k in range(K):
+            groups[k].sort()
+        return K, Ks, groups, multi_groups
+
+    def store(tag, K, Ks, groups, multi_groups, C_list):
+        out[f"{tag}/K"] = np.int64(K)
+        out[f"{tag}/Ks"] = np.array(Ks, dtype=np.int64)
+        out[f"{tag}/n_outputs"] = np.int64(len(multi_groups))
+        for k in range(K):
+            out[f"{tag}/groups{k+1}"] = np.array(groups[k], dtype=np.int64).reshape(-1, k + 1)
+        for n, mg in enumerate(multi_groups):
+            for k in range(Ks[n]):
+                out[f"{tag}/multi{n}_groups{k+1}"] = np.array(mg[k], dtype=np.int64).reshape(-1, k + 1)
+            out[f"{tag}/adj{n}"] = C_list[n]
+        # MOSAP mappings / ES through the reference constructor
+        L = sum(len(g) for g in groups)
+        N = C_list[0].shape[0]
+        Cs = [wishart(N, 40 + n) for n in range(len(multi_groups))]
+        mosap = ns.mosap.MOSAP([c.copy() for c in Cs], K, list(Ks), [[list(g) for g in gk] for gk in groups],
+                               [[[list(g) for g in gk] for gk in mg] for mg in multi_groups],
+                               np.ones(L), [np.ones(sum(len(g) for g in mg)) for mg in multi_groups], verbose=False)
+        for n in range(len(multi_groups)):
+            out[f"{tag}/mapping{n}"] = np.asarray(mosap.mappings[n], dtype=np.int64)
+            out[f"{tag}/Cwish{n}"] = Cs[n]
+        out[f"{tag}/ES"] = np.array(mosap.ES, dtype=np.int64)
+        rng = np.random.RandomState(3)
+        m = 1.0 + 5.0 * rng.rand(L)
+        out[f"{tag}/m"] = m
+        out[f"{tag}/variances"] = np.array(mosap.variances(m), dtype=np.float64)
+        vs, gs, _ = mosap.variance_GH(m, nohess=True)
+        for n in range(len(multi_groups)):
+            out[f"{tag}/grad{n}"] = gs[n]
+
+    # complete graphs: N=4 (K=4), N=6 (K=3)
+    for N, K in [(4, 4), (6, 3)]:
+        A = np.ones((N, N))
+        G = nx.from_numpy_array(A)
+        res = enumerate_ref([G], K)
+        store(f"complete_N{N}_K{K}", *res, [A])
+    # two outputs with different, non-complete coupling graphs on 6 models
+    A0 = np.ones((6, 6)); A0[0, 5] = A0[5, 0] = 0; A0[2, 4] = A0[4, 2] = 0
+    A1 = np.ones((6, 6)); A1[1, 3] = A1[3, 1] = 0
+    G0 = nx.from_numpy_array(A0); G1 = nx.from_numpy_array(A1)
+    res = enumerate_ref([G0, G1], 4)
+    store("two_outputs", *res, [A0, A1])
+    np.savez_compressed(os.path.join(OUT, "enumeration.npz"), **out)
+    print("enumeration.npz:", len(out), "arrays")
+
+
+def make_pilot():
+    """The reference accumulates the pilot sums one sample at a time (blue_fn.py:159-167, N1=1)
+    and then forms C_hat = sumsc/N - outer(sumse, sumse)/N^2 (blue_models.py:333)."""
+    rng = np.random.RandomState(21)
+    N, n = 5, 257
+    C = wishart(N, 9)
+    Y = rng.standard_normal((n, N)) @ np.linalg.cholesky(C).T + 0.3
+    sumse = [0.0 for _ in range(N)]
+    sumsc = np.zeros((N, N))
+    for s in range(n):
+        Ps = Y[s]
+        for i in range(N):
+            sumse[i] += Ps[i]
+        sumsc += np.array([[Ps[i] * Ps[j] for i in range(N)] for j in range(N)])
+    sumse = np.array(sumse)
+    C_hat = sumsc / n - np.outer(sumse, sumse) / n ** 2
+    np.savez_compressed(os.path.join(OUT, "pilot.npz"), Y=Y, sumse=sumse, sumsc=sumsc, C_hat=C_hat)
+
+
+if __name__ == "__main__":
+    ns = ref_shim.load(with_models=True)
+    make_synthetic(ns)
+    make_tutorial(ns)
+    make_hodgkin(ns)
+    make_matern(ns)
+    make_enumeration(ns)
+    make_pilot()
+    print("done")
