@@ -1,0 +1,17 @@
+"""bluest_b200 -- B200-native (sm_100a, FP64) sample-allocation hot path of BLUEST.
+
+Drop-in for the reference's ``SAP`` / ``MOSAP`` objective closures and its ``_cmisc_bluest``
+native routines; everything numerical runs in hand-written CUDA behind libbluest_b200.so
+(include/bluest_b200.h).  No CPU fallback: importing works anywhere, calling needs a GPU.
+"""
+from ._lib import BluError, device_count, lib          # noqa: F401
+from .groups import (balanced_slices, enumerate_cliques, enumerate_groups, group_costs,     # noqa: F401
+                     indicator_ES, mappings, union_groups)
+from .sap import SAP                                    # noqa: F401
+from .mosap import MOSAP, BLUESTError                   # noqa: F401
+from .pilot import pilot_covariance                     # noqa: F401
+from . import cmisc                                     # noqa: F401
+
+__all__ = ["SAP", "MOSAP", "BLUESTError", "BluError", "pilot_covariance", "cmisc", "enumerate_groups",
+           "enumerate_cliques", "union_groups", "group_costs", "indicator_ES", "mappings", "balanced_slices",
+           "device_count", "lib"]

@@ -1,0 +1,759 @@
+// blu_capi.cu -- C ABI of libbluest_b200.so (see include/bluest_b200.h).
+// Host-side orchestration only: argument checks, HBM allocation, kernel launches on the
+// context's stream, host<->device copies.  All arithmetic of the path runs in the kernels of
+// blu_invert.cuh / blu_phi.cuh / blu_grad.cuh / blu_hess.cuh / blu_gram.cuh / blu_level1.cuh.
+// There is no CPU fallback: without a CUDA device every entry point fails with BLU_ERR_NODEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "blu_common.cuh"
+#include "blu_jacobi.cuh"
+#include "blu_invert.cuh"
+#include "blu_phi.cuh"
+#include "blu_grad.cuh"
+#include "blu_hess.cuh"
+#include "blu_gram.cuh"
+#include "blu_level1.cuh"
+
+// --------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(e_ == cudaErrorMemoryAllocation ? BLU_ERR_NOMEM : BLU_ERR_CUDA,        \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define KERNEL_CHECK(ctx)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                   \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(BLU_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+        (ctx)->launches++;                                                                     \
+    } while (0)
+
+struct blu_ctx {
+    int device = 0, N = 0, K = 0, NP = 0, NCH = 0, nsm = 148;
+    long long L = 0, Lpad = 0, ldH = 0;
+    std::vector<long long> sizes;      // K entries
+    std::vector<BluClass> cls;         // non-empty classes only
+    std::vector<int> cls_of_k;         // k -> index in cls or -1
+    int Tmax = 1;
+    BluClass *d_cls = nullptr;
+    uint8_t *d_gidx = nullptr;
+    unsigned *d_gmask = nullptr;
+    uint16_t *d_lut = nullptr;
+    double *d_cinv = nullptr;
+    long long cinv_len = 0, gidx_len = 0;
+    double *d_C = nullptr, *d_m = nullptr, *d_part = nullptr, *d_phi = nullptr, *d_pinv = nullptr;
+    double *d_x = nullptr, *d_S = nullptr, *d_grad = nullptr, *d_U = nullptr, *d_V = nullptr, *d_H = nullptr;
+    long long H_rows = 0;              // rows allocated in d_H
+    BluEvalHeader *d_hdr = nullptr, *h_hdr = nullptr;
+    int grid_phi = 1, grid_grad = 1;
+    bool have_inv = false;
+    std::vector<char> inv_set;         // per class: inverses present
+    long long lo = 0, hi = 0;          // owned slice of the flat enumeration
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
+    int launches = 0;
+};
+
+static int use(blu_ctx *c)
+{
+    if (!c) return fail(BLU_ERR_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return BLU_OK;
+}
+
+extern "C" const char *blu_last_error(void) { return g_err.c_str(); }
+extern "C" const char *blu_version(void) { return "bluest_b200 0.1 (sm_100a, fp64)"; }
+
+extern "C" int blu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int need_device(int device)
+{
+    int n = blu_device_count();
+    if (n <= 0) return fail(BLU_ERR_NODEVICE, "no CUDA device visible: bluest_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(BLU_ERR_ARG, "device %d out of range (%d visible)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    return BLU_OK;
+}
+
+extern "C" int blu_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(BLU_ERR_ARG, "null out");
+    if (blu_device_count() <= 0) return fail(BLU_ERR_NODEVICE, "no CUDA device");
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return BLU_OK;
+}
+extern "C" int blu_host_free(void *p)
+{
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return BLU_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------------
+extern "C" int blu_ctx_destroy(blu_ctx *c)
+{
+    if (!c) return BLU_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_cls); cudaFree(c->d_gidx); cudaFree(c->d_gmask); cudaFree(c->d_lut); cudaFree(c->d_cinv);
+    cudaFree(c->d_C); cudaFree(c->d_m); cudaFree(c->d_part); cudaFree(c->d_phi); cudaFree(c->d_pinv);
+    cudaFree(c->d_x); cudaFree(c->d_S); cudaFree(c->d_grad); cudaFree(c->d_U); cudaFree(c->d_V); cudaFree(c->d_H);
+    cudaFree(c->d_hdr);
+    if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, const int64_t *groups_flat,
+                              blu_ctx **out)
+{
+    if (!out) return fail(BLU_ERR_ARG, "null out");
+    *out = nullptr;
+    if (N < 1 || N > BLU_MAX_MODELS) return fail(BLU_ERR_ARG, "N=%d outside [1,%d]", N, BLU_MAX_MODELS);
+    if (K < 1 || K > N) return fail(BLU_ERR_ARG, "K=%d outside [1,N=%d]", K, N);
+    if (!sizes) return fail(BLU_ERR_ARG, "null sizes");
+    int rc = need_device(device);
+    if (rc) return rc;
+
+    blu_ctx *c = new (std::nothrow) blu_ctx();
+    if (!c) return fail(BLU_ERR_NOMEM, "host allocation failed");
+    c->device = device; c->N = N; c->K = K;
+    c->NCH = (N + 3) / 4; c->NP = 4 * c->NCH;
+    c->sizes.assign(sizes, sizes + K);
+    c->cls_of_k.assign(K + 1, -1);
+    long long L = 0, ioff = 0, coff = 0; int lutoff = 0;
+    for (int k = 1; k <= K; ++k) {
+        long long Lk = sizes[k - 1];
+        if (Lk < 0) { delete c; return fail(BLU_ERR_ARG, "negative class size"); }
+        if (Lk > 0) {
+            BluClass ci{};
+            ci.k = k; ci.T = blu_tri(k); ci.Lk = Lk; ci.goff = L; ci.ioff = ioff; ci.coff = coff; ci.lutoff = lutoff;
+            c->cls_of_k[k] = (int)c->cls.size();
+            c->cls.push_back(ci);
+            ioff += Lk * k;
+            coff += ((Lk * ci.T + 15) / 16) * 16;           // class blocks start on 128-byte lines
+            lutoff += ci.T;
+            c->Tmax = std::max(c->Tmax, ci.T);
+        }
+        L += Lk;
+    }
+    if (L == 0) { delete c; return fail(BLU_ERR_ARG, "no groups"); }
+    if (L > 0 && !groups_flat) { delete c; return fail(BLU_ERR_ARG, "null groups"); }
+    c->L = L; c->gidx_len = ioff; c->cinv_len = coff; c->lo = 0; c->hi = L;
+    c->Lpad = ((L + BLU_HT - 1) / BLU_HT) * BLU_HT + BLU_HT;
+    c->ldH = ((L + 15) / 16) * 16;
+
+    // host-side tables: byte ids, masks, (j,l) look-up table
+    std::vector<uint8_t> gidx((size_t)ioff);
+    std::vector<unsigned> gmask((size_t)L);
+    std::vector<uint16_t> lut((size_t)std::max(lutoff, 1));
+    {
+        const int64_t *g = groups_flat;
+        for (const BluClass &ci : c->cls) {
+            for (long long i = 0; i < ci.Lk; ++i) {
+                unsigned mask = 0; long long prev = -1;
+                for (int j = 0; j < ci.k; ++j) {
+                    long long v = g[i * ci.k + j];
+                    if (v < 0 || v >= N || v <= prev) {
+                        delete c;
+                        return fail(BLU_ERR_ARG, "group %lld of class %d is not a strictly increasing subset of [0,%d)", i, ci.k, N);
+                    }
+                    prev = v; mask |= 1u << v;
+                    gidx[(size_t)(ci.ioff + i * ci.k + j)] = (uint8_t)v;
+                }
+                gmask[(size_t)(ci.goff + i)] = mask;
+            }
+            g += ci.Lk * ci.k;
+            int e = 0;
+            for (int j = 0; j < ci.k; ++j)
+                for (int l = j; l < ci.k; ++l) lut[(size_t)(ci.lutoff + e++)] = (uint16_t)((j << 8) | l);
+        }
+    }
+    c->inv_set.assign(c->cls.size(), 0);
+
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->nsm = prop.multiProcessorCount;
+#define CTX_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int code_ = fail(e_ == cudaErrorMemoryAllocation ? BLU_ERR_NOMEM : BLU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); blu_ctx_destroy(c); return code_; } } while (0)
+    CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CTX_TRY(cudaEventCreate(&e));
+    CTX_TRY(cudaMalloc(&c->d_cls, sizeof(BluClass) * c->cls.size()));
+    CTX_TRY(cudaMalloc(&c->d_gidx, std::max<long long>(ioff, 1)));
+    CTX_TRY(cudaMalloc(&c->d_gmask, sizeof(unsigned) * L));
+    CTX_TRY(cudaMalloc(&c->d_lut, sizeof(uint16_t) * lut.size()));
+    CTX_TRY(cudaMalloc(&c->d_cinv, sizeof(double) * std::max<long long>(coff, 1)));
+    CTX_TRY(cudaMemsetAsync(c->d_cinv, 0, sizeof(double) * std::max<long long>(coff, 1), c->stream));
+    CTX_TRY(cudaMemcpyAsync(c->d_cls, c->cls.data(), sizeof(BluClass) * c->cls.size(), cudaMemcpyHostToDevice, c->stream));
+    CTX_TRY(cudaMemcpyAsync(c->d_gidx, gidx.data(), gidx.size(), cudaMemcpyHostToDevice, c->stream));
+    CTX_TRY(cudaMemcpyAsync(c->d_gmask, gmask.data(), sizeof(unsigned) * L, cudaMemcpyHostToDevice, c->stream));
+    CTX_TRY(cudaMemcpyAsync(c->d_lut, lut.data(), sizeof(uint16_t) * lut.size(), cudaMemcpyHostToDevice, c->stream));
+
+    // launch geometry: enough warps to cover the groups, capped at a few CTAs per SM
+    const long long want = (L + BLU_PHI_WARPS * 4 - 1) / (BLU_PHI_WARPS * 4);
+    c->grid_phi = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->nsm * 4));
+    c->grid_grad = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->nsm * 8));
+
+    const size_t NN = (size_t)N * N;
+    CTX_TRY(cudaMalloc(&c->d_C, sizeof(double) * NN));
+    CTX_TRY(cudaMalloc(&c->d_m, sizeof(double) * L));
+    CTX_TRY(cudaMalloc(&c->d_part, sizeof(double) * NN * c->grid_phi));
+    CTX_TRY(cudaMalloc(&c->d_phi, sizeof(double) * (NN + 40)));   // + SUM-reducible support / non-tiny indicators
+    CTX_TRY(cudaMalloc(&c->d_pinv, sizeof(double) * NN));
+    CTX_TRY(cudaMalloc(&c->d_x, sizeof(double) * BLU_MAX_MODELS));
+    CTX_TRY(cudaMalloc(&c->d_S, sizeof(double) * NN));
+    CTX_TRY(cudaMalloc(&c->d_grad, sizeof(double) * L));
+    CTX_TRY(cudaMalloc(&c->d_hdr, sizeof(BluEvalHeader)));
+    CTX_TRY(cudaMemsetAsync(c->d_hdr, 0, sizeof(BluEvalHeader), c->stream));
+    CTX_TRY(cudaHostAlloc(&c->h_hdr, sizeof(BluEvalHeader), cudaHostAllocDefault));
+    memset(c->h_hdr, 0, sizeof(BluEvalHeader));
+    // opt in to large dynamic shared memory where needed
+    CTX_TRY(cudaFuncSetAttribute(blu_phi_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_FIN_SEG * 1024 * 8));
+    CTX_TRY(cudaFuncSetAttribute(blu_phi_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_PHI_WARPS * 1024 * 8));
+    CTX_TRY(cudaFuncSetAttribute(blu_gradu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1024 + BLU_GRAD_WARPS * 528) * 8));
+    CTX_TRY(cudaStreamSynchronize(c->stream));
+#undef CTX_TRY
+    *out = c;
+    return BLU_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel (1): inverses
+// --------------------------------------------------------------------------------------------
+template <int K>
+static void launch_invert(blu_ctx *c, const BluClass &ci, unsigned char *d_flag, double pivtol)
+{
+    constexpr int G = 32 / BluSub<K>::value;
+    const long long warps = (ci.Lk + G - 1) / G;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((warps + 3) / 4, (long long)c->nsm * 16));
+    blu_invert_groups_kernel<K><<<grid, 128, 0, c->stream>>>(c->d_C, c->N, c->d_gidx + ci.ioff, ci.Lk,
+                                                             c->d_cinv + ci.coff, d_flag + ci.goff, pivtol);
+}
+
+static void launch_invert_k(blu_ctx *c, const BluClass &ci, unsigned char *d_flag, double pivtol)
+{
+    switch (ci.k) {
+#define CASE(K) case K: launch_invert<K>(c, ci, d_flag, pivtol); break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+        CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+        CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24)
+        CASE(25) CASE(26) CASE(27) CASE(28) CASE(29) CASE(30) CASE(31) CASE(32)
+#undef CASE
+    }
+}
+
+extern "C" int blu_ctx_set_covariance(blu_ctx *c, const double *C, double pivot_rtol, int64_t *n_fallback)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!C) return fail(BLU_ERR_ARG, "null covariance");
+    if (!(pivot_rtol >= 0.0)) pivot_rtol = 1e-10;
+    const size_t NN = (size_t)c->N * c->N;
+    CUDA_TRY(cudaMemcpyAsync(c->d_C, C, sizeof(double) * NN, cudaMemcpyHostToDevice, c->stream));
+    unsigned char *d_flag = nullptr;
+    CUDA_TRY(cudaMalloc(&d_flag, (size_t)c->L));
+    CUDA_TRY(cudaMemsetAsync(d_flag, 0, (size_t)c->L, c->stream));
+    for (const BluClass &ci : c->cls) {
+        launch_invert_k(c, ci, d_flag, pivot_rtol);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { cudaFree(d_flag); return fail(BLU_ERR_CUDA, "invert kernel (k=%d): %s", ci.k, cudaGetErrorString(e)); }
+        c->launches++;
+    }
+    std::vector<unsigned char> flag((size_t)c->L);
+    cudaError_t e = cudaMemcpyAsync(flag.data(), d_flag, (size_t)c->L, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_flag);
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "group inversion failed: %s", cudaGetErrorString(e));
+    // slow path for flagged groups
+    long long nbad = 0;
+    for (const BluClass &ci : c->cls) {
+        std::vector<long long> todo;
+        for (long long i = 0; i < ci.Lk; ++i) if (flag[(size_t)(ci.goff + i)]) todo.push_back(i);
+        if (todo.empty()) continue;
+        nbad += (long long)todo.size();
+        long long *d_todo = nullptr;
+        CUDA_TRY(cudaMalloc(&d_todo, sizeof(long long) * todo.size()));
+        CUDA_TRY(cudaMemcpyAsync(d_todo, todo.data(), sizeof(long long) * todo.size(), cudaMemcpyHostToDevice, c->stream));
+        blu_pinv_groups_kernel<<<(unsigned)todo.size(), 256, 0, c->stream>>>(c->d_C, c->N, ci.k, c->d_gidx + ci.ioff, d_todo,
+                                                                              c->d_cinv + ci.coff, 1.0e-15);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_todo);
+        if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "pinv kernel (k=%d): %s", ci.k, cudaGetErrorString(e));
+        c->launches++;
+    }
+    if (n_fallback) *n_fallback = nbad;
+    std::fill(c->inv_set.begin(), c->inv_set.end(), 1);
+    c->have_inv = true;
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_set_invcovs(blu_ctx *c, int k, const double *invcovs_k)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (k < 1 || k > c->K) return fail(BLU_ERR_ARG, "class k=%d outside [1,%d]", k, c->K);
+    const int idx = c->cls_of_k[k];
+    if (idx < 0) return BLU_OK;                       // empty class: nothing to ingest (sap.py:79)
+    if (!invcovs_k) return fail(BLU_ERR_ARG, "null invcovs");
+    const BluClass &ci = c->cls[idx];
+    const size_t n = (size_t)ci.Lk * k * k;
+    double *d_full = nullptr;
+    CUDA_TRY(cudaMalloc(&d_full, sizeof(double) * n));
+    cudaError_t e = cudaMemcpyAsync(d_full, invcovs_k, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        const long long total = ci.Lk * ci.T;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->nsm * 8));
+        blu_pack_invcovs_kernel<<<grid, 256, 0, c->stream>>>(d_full, k, ci.Lk, c->d_cinv + ci.coff);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_full);
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "set_invcovs: %s", cudaGetErrorString(e));
+    c->inv_set[idx] = 1;
+    c->have_inv = std::all_of(c->inv_set.begin(), c->inv_set.end(), [](char v) { return v != 0; });
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_get_invcovs(blu_ctx *c, int k, double *invcovs_k)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (k < 1 || k > c->K) return fail(BLU_ERR_ARG, "class k=%d outside [1,%d]", k, c->K);
+    const int idx = c->cls_of_k[k];
+    if (idx < 0) return BLU_OK;
+    if (!c->inv_set[idx]) return fail(BLU_ERR_STATE, "inverses of class %d not set", k);
+    if (!invcovs_k) return fail(BLU_ERR_ARG, "null invcovs");
+    const BluClass &ci = c->cls[idx];
+    const size_t n = (size_t)ci.Lk * k * k;
+    double *d_full = nullptr;
+    CUDA_TRY(cudaMalloc(&d_full, sizeof(double) * n));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(((long long)n + 255) / 256, (long long)c->nsm * 8));
+    blu_unpack_invcovs_kernel<<<grid, 256, 0, c->stream>>>(c->d_cinv + ci.coff, k, ci.Lk, d_full);
+    cudaError_t e = cudaGetLastError();
+    c->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(invcovs_k, d_full, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_full);
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "get_invcovs: %s", cudaGetErrorString(e));
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_assemble_psi(blu_ctx *c, double *psi)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->have_inv) return fail(BLU_ERR_STATE, "inverses not set");
+    if (!psi) return fail(BLU_ERR_ARG, "null psi");
+    const long long NN = (long long)c->N * c->N;
+    // column panels of at most ~256 MB so the device footprint stays bounded at large L
+    const long long panel = std::max<long long>(1, std::min<long long>(c->L, (256ll << 20) / (8 * NN)));
+    double *d_psi = nullptr;
+    CUDA_TRY(cudaMalloc(&d_psi, sizeof(double) * NN * panel));
+    cudaError_t e = cudaSuccess;
+    for (long long col0 = 0; col0 < c->L && e == cudaSuccess; col0 += panel) {
+        const long long nc = std::min(panel, c->L - col0);
+        e = cudaMemsetAsync(d_psi, 0, sizeof(double) * NN * nc, c->stream);
+        if (e != cudaSuccess) break;
+        blu_psi_kernel<<<c->nsm * 4, 256, 0, c->stream>>>(c->d_cls, (int)c->cls.size(), c->N, col0, nc, c->d_gidx, c->d_cinv, d_psi);
+        e = cudaGetLastError();
+        c->launches++;
+        if (e != cudaSuccess) break;
+        // (NN, nc) panel -> columns [col0, col0+nc) of the (NN, L) host matrix
+        e = cudaMemcpy2DAsync(psi + col0, sizeof(double) * c->L, d_psi, sizeof(double) * nc, sizeof(double) * nc, NN,
+                              cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(d_psi);
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "assemble_psi: %s", cudaGetErrorString(e));
+    return BLU_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// evaluation pipeline
+// --------------------------------------------------------------------------------------------
+static int launch_phi(blu_ctx *c, const double *d_m, double delta, int mode)
+{
+    const int NN = c->N * c->N;
+    blu_phi_partial_kernel<<<c->grid_phi, BLU_PHI_WARPS * 32, sizeof(double) * NN * BLU_PHI_WARPS, c->stream>>>(
+        c->d_cls, (int)c->cls.size(), c->N, c->d_gidx, c->d_cinv, c->d_lut, d_m, c->lo, c->hi, c->d_part, c->d_hdr);
+    KERNEL_CHECK(c);
+    blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
+        c->N, c->grid_phi, c->d_part, delta, mode, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr);
+    KERNEL_CHECK(c);
+    return BLU_OK;
+}
+
+static int ensure_uv(blu_ctx *c)
+{
+    if (c->d_U) return BLU_OK;
+    const size_t n = (size_t)c->Lpad * c->NP;
+    CUDA_TRY(cudaMalloc(&c->d_U, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc(&c->d_V, sizeof(double) * n));
+    CUDA_TRY(cudaMemsetAsync(c->d_U, 0, sizeof(double) * n, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_V, 0, sizeof(double) * n, c->stream));
+    return BLU_OK;
+}
+
+static int launch_grad(blu_ctx *c, int want_uv)
+{
+    if (!want_uv) {
+        blu_grad_kernel<<<c->grid_grad, BLU_GRAD_WARPS * 32, 0, c->stream>>>(
+            c->d_cls, (int)c->cls.size(), c->N, c->d_gidx, c->d_cinv, c->d_lut, c->d_x, c->lo, c->hi, c->d_grad);
+        KERNEL_CHECK(c);
+        return BLU_OK;
+    }
+    int rc = ensure_uv(c);
+    if (rc) return rc;
+    const size_t smem = sizeof(double) * ((size_t)c->N * c->N + (size_t)BLU_GRAD_WARPS * c->Tmax);
+    blu_gradu_kernel<<<c->grid_grad, BLU_GRAD_WARPS * 32, smem, c->stream>>>(
+        c->d_cls, (int)c->cls.size(), c->N, c->NP, c->Tmax, c->d_gidx, c->d_gmask, c->d_cinv, c->d_x, c->d_S,
+        c->lo, c->hi, c->d_grad, c->d_U, c->d_V);
+    KERNEL_CHECK(c);
+    return BLU_OK;
+}
+
+template <int NCH>
+static void launch_hess_t(blu_ctx *c, bool sym, const double *Ua, long long Lrows, double *H)
+{
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[sym]) {
+        if (sym) cudaFuncSetAttribute(blu_hess_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM);
+        else cudaFuncSetAttribute(blu_hess_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM);
+        attr_done[sym] = true;
+    }
+    const int nTc = (int)((c->L + BLU_HT - 1) / BLU_HT);
+    if (sym) {
+        const long long pairs = (long long)nTc * (nTc + 1) / 2;
+        blu_hess_kernel<NCH, true><<<(unsigned)pairs, 128, BLU_HESS_SMEM, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
+    } else {
+        const int nTr = (int)((Lrows + BLU_HT - 1) / BLU_HT);
+        dim3 grid((unsigned)nTc, (unsigned)nTr);
+        blu_hess_kernel<NCH, false><<<grid, 128, BLU_HESS_SMEM, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
+    }
+}
+
+static int launch_hess(blu_ctx *c, bool sym)
+{
+    const long long rows = sym ? c->L : (c->hi - c->lo);
+    if (!c->d_H || c->H_rows < rows) {
+        if (c->d_H) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->d_H)); c->d_H = nullptr; }
+        CUDA_TRY(cudaMalloc(&c->d_H, sizeof(double) * (size_t)rows * (size_t)c->ldH));
+        c->H_rows = rows;
+    }
+    const double *Ua = c->d_U + (sym ? 0 : c->lo * c->NP);
+    switch (c->NCH) {
+        case 1: launch_hess_t<1>(c, sym, Ua, rows, c->d_H); break;
+        case 2: launch_hess_t<2>(c, sym, Ua, rows, c->d_H); break;
+        case 3: launch_hess_t<3>(c, sym, Ua, rows, c->d_H); break;
+        case 4: launch_hess_t<4>(c, sym, Ua, rows, c->d_H); break;
+        case 5: launch_hess_t<5>(c, sym, Ua, rows, c->d_H); break;
+        case 6: launch_hess_t<6>(c, sym, Ua, rows, c->d_H); break;
+        case 7: launch_hess_t<7>(c, sym, Ua, rows, c->d_H); break;
+        default: launch_hess_t<8>(c, sym, Ua, rows, c->d_H); break;
+    }
+    KERNEL_CHECK(c);
+    return BLU_OK;
+}
+
+extern "C" int blu_eval_device(blu_ctx *c, const double *d_m, double delta, int want_grad, int want_hess)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->have_inv) return fail(BLU_ERR_STATE, "inverses not set: call blu_ctx_set_covariance / blu_ctx_set_invcovs first");
+    if (c->lo != 0 || c->hi != c->L) return fail(BLU_ERR_STATE, "context owns a slice: use the blu_shard_* calls");
+    if (!d_m) d_m = c->d_m;
+    c->launches = 0;
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    rc = launch_phi(c, d_m, delta, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if (want_grad || want_hess) { rc = launch_grad(c, want_hess); if (rc) return rc; }
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (want_hess) { rc = launch_hess(c, true); if (rc) return rc; }
+    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    c->timed = true;
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_sync(blu_ctx *c)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_stream(blu_ctx *c, void **s)
+{
+    if (!c || !s) return fail(BLU_ERR_ARG, "null argument");
+    *s = (void *)c->stream;
+    return BLU_OK;
+}
+
+static int fetch_header(blu_ctx *c)
+{
+    CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, sizeof(BluEvalHeader), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_last_result(blu_ctx *c, double *var, unsigned *flags)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    rc = fetch_header(c);
+    if (rc) return rc;
+    if (var) *var = c->h_hdr->scal[0];
+    if (flags) *flags = c->h_hdr->flags;
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_last_timing(blu_ctx *c, float *ms)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!ms) return fail(BLU_ERR_ARG, "null ms");
+    if (!c->timed) return fail(BLU_ERR_STATE, "no timed evaluation yet");
+    CUDA_TRY(cudaEventSynchronize(c->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[1], c->ev[1], c->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[2], c->ev[2], c->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[3], c->ev[0], c->ev[3]));
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_last_launches(blu_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int blu_ctx_device_ptr(blu_ctx *c, int which, void **ptr, int64_t *nbytes)
+{
+    if (!c || !ptr) return fail(BLU_ERR_ARG, "null argument");
+    const int64_t NN = (int64_t)c->N * c->N;
+    void *p = nullptr; int64_t n = 0;
+    switch (which) {
+        case BLU_BUF_M: p = c->d_m; n = 8 * c->L; break;
+        case BLU_BUF_PHI: p = c->d_phi; n = 8 * NN; break;
+        case BLU_BUF_PINV: p = c->d_pinv; n = 8 * NN; break;
+        case BLU_BUF_GRAD: p = c->d_grad; n = 8 * c->L; break;
+        case BLU_BUF_U: { int rc = use(c); if (rc) return rc; rc = ensure_uv(c); if (rc) return rc; p = c->d_U; n = 8 * c->Lpad * c->NP; break; }
+        case BLU_BUF_V: { int rc = use(c); if (rc) return rc; rc = ensure_uv(c); if (rc) return rc; p = c->d_V; n = 8 * c->Lpad * c->NP; break; }
+        case BLU_BUF_HESS: p = c->d_H; n = 8 * c->H_rows * c->ldH; break;
+        case BLU_BUF_CINV: p = c->d_cinv; n = 8 * c->cinv_len; break;
+        case BLU_BUF_SCAL: p = c->d_hdr->scal; n = 64; break;
+        default: return fail(BLU_ERR_ARG, "unknown buffer id %d", which);
+    }
+    *ptr = p;
+    if (nbytes) *nbytes = n;
+    return BLU_OK;
+}
+
+// ---- host-pointer closures ----------------------------------------------------------------
+static int upload_m(blu_ctx *c, const double *m)
+{
+    if (!m) return fail(BLU_ERR_ARG, "null m");
+    CUDA_TRY(cudaMemcpyAsync(c->d_m, m, sizeof(double) * c->L, cudaMemcpyHostToDevice, c->stream));
+    return BLU_OK;
+}
+
+extern "C" int blu_get_phi(blu_ctx *c, const double *m, double delta, double *phi)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->have_inv) return fail(BLU_ERR_STATE, "inverses not set");
+    if (!phi) return fail(BLU_ERR_ARG, "null phi");
+    if ((rc = upload_m(c, m))) return rc;
+    c->launches = 0;
+    if ((rc = launch_phi(c, c->d_m, delta, 0))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(phi, c->d_phi, sizeof(double) * c->N * c->N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return BLU_OK;
+}
+
+extern "C" int blu_variance(blu_ctx *c, const double *m, double delta, double *var, unsigned *flags)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if ((rc = upload_m(c, m))) return rc;
+    if ((rc = blu_eval_device(c, c->d_m, delta, 0, 0))) return rc;
+    return blu_ctx_last_result(c, var, flags);
+}
+
+extern "C" int blu_variance_GH(blu_ctx *c, const double *m, double delta, double *var, double *grad,
+                               double *hess, unsigned *flags)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!grad) return fail(BLU_ERR_ARG, "null grad");
+    if ((rc = upload_m(c, m))) return rc;
+    if ((rc = blu_eval_device(c, c->d_m, delta, 1, hess != nullptr))) return rc;
+    // small results first; the Hessian D2H (the long pole) is queued behind them on the same stream
+    CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, sizeof(BluEvalHeader), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(grad, c->d_grad, sizeof(double) * c->L, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const unsigned fl = c->h_hdr->flags;
+    if (var) *var = c->h_hdr->scal[0];
+    if (flags) *flags = fl;
+    if (fl & BLU_FLAG_TINY) {
+        for (long long i = 0; i < c->L; ++i) grad[i] = std::numeric_limits<double>::infinity();
+        return BLU_OK;
+    }
+    if (hess) {
+        CUDA_TRY(cudaMemcpy2DAsync(hess, sizeof(double) * c->L, c->d_H, sizeof(double) * c->ldH, sizeof(double) * c->L,
+                                   (size_t)c->L, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return BLU_OK;
+}
+
+extern "C" int blu_cleanup_matrix(blu_ctx *c, const double *m, double delta, int mode, double *X, unsigned *flags)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!X) return fail(BLU_ERR_ARG, "null X");
+    if (mode != 0 && mode != 1) return fail(BLU_ERR_ARG, "mode must be 0 (reference) or 1 (corrected)");
+    if ((rc = upload_m(c, m))) return rc;
+    if ((rc = blu_eval_device(c, c->d_m, delta, 0, 0))) return rc;
+    unsigned fl = 0;
+    if ((rc = blu_ctx_last_result(c, nullptr, &fl))) return rc;
+    if (flags) *flags = fl;
+    if (fl & BLU_FLAG_TINY) return BLU_OK;
+    double *d_X = nullptr;
+    const size_t n = (size_t)c->N * c->L;
+    CUDA_TRY(cudaMalloc(&d_X, sizeof(double) * n));
+    cudaError_t e = cudaMemsetAsync(d_X, 0, sizeof(double) * n, c->stream);
+    if (e == cudaSuccess) {
+        blu_cleanup_kernel<<<c->nsm * 4, 256, 0, c->stream>>>(c->d_cls, (int)c->cls.size(), c->N, c->L, c->d_gidx, c->d_cinv,
+                                                              c->d_x, mode, d_X);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(X, d_X, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_X);
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "cleanup_matrix: %s", cudaGetErrorString(e));
+    return BLU_OK;
+}
+
+// ---- group-sharded phases -----------------------------------------------------------------
+extern "C" int blu_ctx_set_slice(blu_ctx *c, int64_t lo, int64_t hi)
+{
+    if (!c) return fail(BLU_ERR_ARG, "null context");
+    if (lo < 0 || hi > c->L || lo > hi) return fail(BLU_ERR_ARG, "slice [%lld,%lld) outside [0,%lld]", (long long)lo, (long long)hi, c->L);
+    c->lo = lo; c->hi = hi;
+    return BLU_OK;
+}
+
+extern "C" int blu_shard_phi(blu_ctx *c, const double *d_m)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->have_inv) return fail(BLU_ERR_STATE, "inverses not set");
+    if (!d_m) d_m = c->d_m;
+    c->launches = 0;
+    return launch_phi(c, d_m, 0.0, 2);
+}
+
+extern "C" int blu_shard_finish(blu_ctx *c, double delta, int want_grad, int want_uv)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    const int NN = c->N * c->N;
+    // BLU_BUF_PHI now holds the all-reduced upper-triangle sum; supp / max|m| were reduced by the host
+    blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
+        c->N, 0, c->d_part, delta, 1, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr);
+    KERNEL_CHECK(c);
+    if (want_grad || want_uv) return launch_grad(c, want_uv);
+    return BLU_OK;
+}
+
+extern "C" int blu_shard_hess(blu_ctx *c)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->d_U) return fail(BLU_ERR_STATE, "U/V not computed");
+    return launch_hess(c, false);
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel (4): pilot covariance
+// --------------------------------------------------------------------------------------------
+extern "C" int blu_pilot_covariance(int device, const double *Y, int64_t n, int N, int y_on_device,
+                                    double *s1, double *S2, double *C_hat, float *kernel_ms)
+{
+    int rc = need_device(device);
+    if (rc) return rc;
+    if (!Y || n < 1 || N < 1 || N > BLU_MAX_MODELS) return fail(BLU_ERR_ARG, "bad pilot-sample arguments");
+    return blu_gram_run(Y, n, N, y_on_device, s1, S2, C_hat, kernel_ms, g_err);
+}
+
+// --------------------------------------------------------------------------------------------
+// Level 1
+// --------------------------------------------------------------------------------------------
+extern "C" int blu_assemble_psi_c(double *psi, int N, int k, int Lk, const int64_t *groupsk, const double *invcovsk)
+{
+    int rc = need_device(0);
+    if (rc) return rc;
+    return blu_l1_psi(psi, N, k, Lk, groupsk, invcovsk, g_err);
+}
+extern "C" int blu_objectiveK_c(double *PHI, int N, int k, int Lk, const double *mk, const int64_t *groupsk, const double *invcovsk)
+{
+    int rc = need_device(0);
+    if (rc) return rc;
+    return blu_l1_phi(PHI, N, k, Lk, mk, nullptr, groupsk, invcovsk, g_err);
+}
+extern "C" int blu_objectiveK_c_i64(double *PHI, int N, int k, int Lk, const int64_t *mk, const int64_t *groupsk, const double *invcovsk)
+{
+    int rc = need_device(0);
+    if (rc) return rc;
+    return blu_l1_phi(PHI, N, k, Lk, nullptr, mk, groupsk, invcovsk, g_err);
+}
+extern "C" int blu_cleanupK_c(double *X, int N, int k, int Lk, const int64_t *groupsk, const double *invcovsk, const double *invPHI_0)
+{
+    int rc = need_device(0);
+    if (rc) return rc;
+    return blu_l1_cleanup(X, N, k, Lk, groupsk, invcovsk, invPHI_0, g_err);
+}
+extern "C" int blu_gradK_c(double *grad, int N, int k, int Lk, const int64_t *groupsk, const double *invcovsk, const double *invPHI_0)
+{
+    int rc = need_device(0);
+    if (rc) return rc;
+    return blu_l1_grad(grad, N, k, Lk, groupsk, invcovsk, invPHI_0, g_err);
+}
+extern "C" int blu_hessKQ_c(double *hess, int N, int k, int q, int Lk, int Lq, const int64_t *groupsk, const int64_t *groupsq,
+                            const double *invcovsk, const double *invcovsq, const double *invPHI)
+{
+    int rc = need_device(0);
+    if (rc) return rc;
+    return blu_l1_hess(hess, N, k, q, Lk, Lq, groupsk, groupsq, invcovsk, invcovsq, invPHI, g_err);
+}

@@ -1,0 +1,175 @@
+// blu_gram.cuh -- kernel (4): pilot-sample covariance as an FP64 tensor-core Gram contraction.
+//
+// Replaces the per-sample Python accumulation of blue_fn.py:159-167 (sumse[i] += P_i,
+// sumsc[j,i] += P_i P_j) and the formula of blue_models.py:333,
+//     C_hat = sumsc / n - outer(sumse, sumse) / n^2      (biased, one pass).
+// Y is the (n, N) row-major sample matrix.  The model axis is padded to NT tiles of 8 columns with
+// one extra column of ones at index N, so the column sums come out of the same contraction:
+// G = [Y 1]^T [Y 1]  =>  S2 = G[:N,:N], s1 = G[:N, N].
+// A warp walks its contiguous slab of samples 4 at a time: the fragment of tile t held by a lane
+// (sample lane&3, column 8t + lane>>2) is at once the A operand (row = column index, k = sample)
+// and the B operand (k = sample, col = column index) of mma.m8n8k4.f64, so every loaded double is
+// used NT times.  Only tile pairs ti <= tj are accumulated.  Reduction: warps -> CTA in shared
+// memory in warp order, CTAs -> result in block order by a second kernel: no atomics,
+// bit-reproducible.  The kernel is an HBM stream of 8 n N bytes.
+#pragma once
+#include <string>
+#include "blu_common.cuh"
+#include "blu_hess.cuh"
+
+#define BLU_GRAM_WARPS 8
+
+template <int NT>
+__global__ void __launch_bounds__(BLU_GRAM_WARPS * 32)
+blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab, double *__restrict__ part)
+{
+    constexpr int NPG = 8 * NT;
+    constexpr int NPAIR = NT * (NT + 1) / 2;
+    extern __shared__ double sred_raw[];                  // BLU_GRAM_WARPS x NPG*NPG
+    double (*sred)[NPG * NPG] = reinterpret_cast<double (*)[NPG * NPG]>(sred_raw);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ks = lane & 3, cq = lane >> 2;
+    const long long gw = (long long)blockIdx.x * BLU_GRAM_WARPS + w;
+    long long s0 = gw * slab, s1 = s0 + slab;
+    if (s1 > n) s1 = n;
+    double acc[NPAIR][2];
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) { acc[p][0] = 0.0; acc[p][1] = 0.0; }
+    for (long long s = s0; s < s1; s += 8) {
+        double f[2][NT];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long row = s + 4 * h + ks;
+            const bool rok = row < s1;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int col = 8 * t + cq;
+                double v = 0.0;
+                if (rok) v = (col < N) ? Y[row * N + col] : (col == N ? 1.0 : 0.0);
+                f[h][t] = v;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int p = 0;
+#pragma unroll
+            for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+                for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[p][0], acc[p][1], f[h][ti], f[h][tj]); ++p; }
+        }
+    }
+    // warp tile -> shared (C fragment: row lane>>2, cols 2*(lane&3)+{0,1})
+    {
+        int p = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < NT; ++tj) {
+                const int r = 8 * ti + cq, c = 8 * tj + 2 * ks;
+                sred[w][r * NPG + c] = acc[p][0];
+                sred[w][r * NPG + c + 1] = acc[p][1];
+                ++p;
+            }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NPG * NPG; t += blockDim.x) {
+        const int r = t / NPG, c = t - r * NPG;
+        if ((r >> 3) > (c >> 3)) continue;                  // lower tiles are never produced
+        double sum = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < BLU_GRAM_WARPS; ++ww) sum += sred[ww][t];
+        part[(long long)blockIdx.x * NPG * NPG + t] = sum;
+    }
+}
+
+// Fixed-order reduction over CTAs + covariance formula.  One CTA.
+__global__ void blu_gram_finish_kernel(const double *__restrict__ part, int nparts, int NPG, int N, long long n,
+                                       double *__restrict__ s1, double *__restrict__ S2, double *__restrict__ Chat)
+{
+    extern __shared__ double G[];        // NPG*NPG
+    for (int t = threadIdx.x; t < NPG * NPG; t += blockDim.x) {
+        const int r = t / NPG, c = t - r * NPG;
+        double sum = 0.0;
+        if ((r >> 3) <= (c >> 3))
+            for (int p = 0; p < nparts; ++p) sum += part[(long long)p * NPG * NPG + t];
+        G[t] = sum;
+    }
+    __syncthreads();
+    const double dn = (double)n;
+    for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
+        const int r = t / N, c = t - r * N;
+        const int lo = r < c ? r : c, hi = r < c ? c : r;
+        const double g = G[lo * NPG + hi];                 // upper triangle holds the sums
+        const double a = G[r * NPG + N], b = G[c * NPG + N];
+        S2[t] = g;
+        Chat[t] = g / dn - (a * b) / (dn * dn);
+    }
+    for (int t = threadIdx.x; t < N; t += blockDim.x) s1[t] = G[t * NPG + N];
+}
+
+template <int NT>
+static cudaError_t blu_gram_launch(const double *dY, long long n, int N, int grid, long long slab, double *d_part, cudaStream_t st)
+{
+    const size_t smem = sizeof(double) * BLU_GRAM_WARPS * (8 * NT) * (8 * NT);
+    cudaError_t e = cudaFuncSetAttribute(blu_gram_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    blu_gram_kernel<NT><<<grid, BLU_GRAM_WARPS * 32, smem, st>>>(dY, n, N, slab, d_part);
+    return cudaGetLastError();
+}
+
+static int blu_gram_run(const double *Y, long long n, int N, int y_on_device, double *s1, double *S2, double *C_hat,
+                        float *kernel_ms, std::string &err)
+{
+    const int NT = (N + 1 + 7) / 8, NPG = 8 * NT;
+    cudaDeviceProp prop; int dev = 0;
+    cudaGetDevice(&dev);
+    cudaGetDeviceProperties(&prop, dev);
+    const long long warps_wanted = (n + 255) / 256;                       // >= 256 samples per warp
+    int grid = (int)std::max<long long>(1, std::min<long long>((warps_wanted + BLU_GRAM_WARPS - 1) / BLU_GRAM_WARPS,
+                                                                  (long long)prop.multiProcessorCount * 4));
+    const long long nwarps = (long long)grid * BLU_GRAM_WARPS;
+    long long slab = (n + nwarps - 1) / nwarps;
+    slab = ((slab + 7) / 8) * 8;
+    double *dY = nullptr, *d_part = nullptr, *d_out = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto done = [&](int code) {
+        if (!y_on_device) cudaFree(dY);
+        cudaFree(d_part); cudaFree(d_out);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (st) cudaStreamDestroy(st);
+        if (code) err = std::string("pilot covariance: ") + cudaGetErrorString(e);
+        return code;
+    };
+    if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return done(BLU_ERR_CUDA);
+    if (y_on_device) dY = const_cast<double *>(Y);
+    else {
+        if ((e = cudaMalloc(&dY, sizeof(double) * n * N)) != cudaSuccess) return done(BLU_ERR_NOMEM);
+        if ((e = cudaMemcpyAsync(dY, Y, sizeof(double) * n * N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return done(BLU_ERR_CUDA);
+    }
+    if ((e = cudaMalloc(&d_part, sizeof(double) * NPG * NPG * grid)) != cudaSuccess) return done(BLU_ERR_NOMEM);
+    if ((e = cudaMalloc(&d_out, sizeof(double) * (2 * N * N + N))) != cudaSuccess) return done(BLU_ERR_NOMEM);
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    switch (NT) {
+        case 1: e = blu_gram_launch<1>(dY, n, N, grid, slab, d_part, st); break;
+        case 2: e = blu_gram_launch<2>(dY, n, N, grid, slab, d_part, st); break;
+        case 3: e = blu_gram_launch<3>(dY, n, N, grid, slab, d_part, st); break;
+        case 4: e = blu_gram_launch<4>(dY, n, N, grid, slab, d_part, st); break;
+        default: e = blu_gram_launch<5>(dY, n, N, grid, slab, d_part, st); break;
+    }
+    if (e != cudaSuccess) return done(BLU_ERR_CUDA);
+    blu_gram_finish_kernel<<<1, 256, sizeof(double) * NPG * NPG, st>>>(d_part, grid, NPG, N, n, d_out, d_out + N, d_out + N + N * N);
+    if ((e = cudaGetLastError()) != cudaSuccess) return done(BLU_ERR_CUDA);
+    cudaEventRecord(e1, st);
+    std::vector<double> h((size_t)(2 * N * N + N));
+    if ((e = cudaMemcpyAsync(h.data(), d_out, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(BLU_ERR_CUDA);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(BLU_ERR_CUDA);
+    if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
+    if (s1) memcpy(s1, h.data(), sizeof(double) * N);
+    if (S2) memcpy(S2, h.data() + N, sizeof(double) * N * N);
+    if (C_hat) memcpy(C_hat, h.data() + N + N * N, sizeof(double) * N * N);
+    return done(BLU_OK);
+}

@@ -1,0 +1,135 @@
+// blu_hess.cuh -- kernel (3b): dense Hessian  H = U S U^T = U V^T   (L x L, FP64).
+//
+// Replaces the K^2 calls of hessKQ_c (cmisc.cpp:74-97, a six-deep scalar loop with
+// (sum_k C(N,k) k^2)^2 inner iterations) plus ``hess += hess.T`` (misc.py:497-503) by a rank-N
+// product: 2 N L^2 flops, bounded by WRITING the 8 L^2 bytes of H (8.59 GB at N = 15).
+//
+// One CTA (4 warps) computes a 64 x 64 tile with FP64 tensor-core MMAs
+// (mma.sync.m8n8k4.f64 -- there is no FP64 in tcgen05), operands read straight from the
+// L2-resident U / V rows (the K dimension is only NP = 4*NCH <= 32, so there is no K loop to
+// pipeline), accumulators staged through shared memory so that every global store instruction
+// writes whole 128-byte lines (32 lanes x 16 B = one 512 B row segment), streaming (.cs).
+// SYM = true: only tiles I <= J are computed; the tile is staged a second time transposed and
+// written to (J, I) as well, so the tensor pipe does half the work and H is exactly symmetric
+// bit for bit, as the reference's ``hess += hess.T`` makes it.  Diagonal tiles are symmetrised.
+// SYM = false: rectangular row panel (U = the rank's own Lrows rows, V = all Lcols rows, H = the
+// rank's (Lrows, ldH) panel), for the group-sharded multi-GPU path where a rank owns a row block.
+//
+// K-slot permutation: within a k-chunk the MMA's k index of lane (lane&3) is mapped to model
+// column (lane&3)*NCH + kc, so a lane's NCH operands are contiguous in memory (32 B at N <= 16).
+// A and B use the same map, so the contraction is unchanged.
+#pragma once
+#include "blu_common.cuh"
+
+#define BLU_HT 64              // tile edge
+#define BLU_HLDN 72            // staging pitch, normal tile   (72*8 B: rows 2 apart never share a bank phase)
+#define BLU_HLDT 66            // staging pitch, transposed tile
+#define BLU_HESS_SMEM ((BLU_HT * BLU_HLDN + BLU_HT * BLU_HLDT) * 8)
+
+__device__ __forceinline__ void blu_dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NCH, bool SYM>
+__global__ void __launch_bounds__(128, 3)
+blu_hess_kernel(const double *__restrict__ U, const double *__restrict__ V, long long Lrows,
+                long long Lcols, long long ldH, double *__restrict__ H, int nT, int tI0)
+{
+    constexpr int NP = 4 * NCH;
+    extern __shared__ double hsm[];
+    double *sN = hsm;
+    double *sT = hsm + BLU_HT * BLU_HLDN;
+
+    int I, J;
+    if (SYM) {
+        // linear id over the upper triangle, row-major: row I holds nT - I tiles
+        const long long pid = blockIdx.x;
+        const double nt = (double)nT;
+        int i = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)pid)) * 0.5);
+        if (i < 0) i = 0;
+        if (i > nT - 1) i = nT - 1;
+        // first(i) = i*nT - i(i-1)/2
+        while ((long long)i * nT - (long long)i * (i - 1) / 2 > pid) --i;
+        while ((long long)(i + 1) * nT - (long long)(i + 1) * i / 2 <= pid) ++i;
+        I = i;
+        J = i + (int)(pid - ((long long)i * nT - (long long)i * (i - 1) / 2));
+    } else {
+        J = blockIdx.x;
+        I = tI0 + blockIdx.y;
+    }
+
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy = w >> 1, wx = w & 1;
+    const int gq = lane >> 2, s = lane & 3;
+
+    double a[4][NCH], b[4][NCH];
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb) {
+        const double *up = U + ((long long)I * BLU_HT + wy * 32 + rb * 8 + gq) * NP + s * NCH;
+        const double *vp = V + ((long long)J * BLU_HT + wx * 32 + rb * 8 + gq) * NP + s * NCH;
+        if (NCH % 2 == 0) {
+#pragma unroll
+            for (int kc = 0; kc < NCH; kc += 2) {
+                const double2 t = *reinterpret_cast<const double2 *>(up + kc);
+                const double2 r = *reinterpret_cast<const double2 *>(vp + kc);
+                a[rb][kc] = t.x; a[rb][kc + 1] = t.y;
+                b[rb][kc] = r.x; b[rb][kc + 1] = r.y;
+            }
+        } else {
+#pragma unroll
+            for (int kc = 0; kc < NCH; ++kc) { a[rb][kc] = up[kc]; b[rb][kc] = vp[kc]; }
+        }
+    }
+    double c[4][4][2];
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) { c[rb][cb][0] = 0.0; c[rb][cb][1] = 0.0; }
+#pragma unroll
+    for (int kc = 0; kc < NCH; ++kc)
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) blu_dmma(c[rb][cb][0], c[rb][cb][1], a[rb][kc], b[cb][kc]);
+
+    const bool offdiag = SYM && (I != J);
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const int row = wy * 32 + rb * 8 + gq;
+            const int col = wx * 32 + cb * 8 + 2 * s;
+            *reinterpret_cast<double2 *>(sN + row * BLU_HLDN + col) = make_double2(c[rb][cb][0], c[rb][cb][1]);
+            if (offdiag) {
+                sT[col * BLU_HLDT + row] = c[rb][cb][0];
+                sT[(col + 1) * BLU_HLDT + row] = c[rb][cb][1];
+            }
+        }
+    __syncthreads();
+
+    const long long gcolN = (long long)J * BLU_HT + 2 * lane;
+    const long long gcolT = (long long)I * BLU_HT + 2 * lane;
+    const bool diag = SYM && (I == J);
+    for (int r = w; r < BLU_HT; r += 4) {
+        const long long grow = (long long)I * BLU_HT + r;
+        if (grow < Lrows && gcolN < ldH) {
+            double2 v = *reinterpret_cast<const double2 *>(sN + r * BLU_HLDN + 2 * lane);
+            if (diag) {
+                v.x = 0.5 * (v.x + sN[(2 * lane) * BLU_HLDN + r]);
+                v.y = 0.5 * (v.y + sN[(2 * lane + 1) * BLU_HLDN + r]);
+            }
+            __stcs(reinterpret_cast<double2 *>(H + grow * ldH + gcolN), v);
+        }
+    }
+    if (offdiag) {
+        for (int r = w; r < BLU_HT; r += 4) {
+            const long long grow = (long long)J * BLU_HT + r;
+            if (grow < Lcols && gcolT < ldH) {
+                const double2 v = *reinterpret_cast<const double2 *>(sT + r * BLU_HLDT + 2 * lane);
+                __stcs(reinterpret_cast<double2 *>(H + grow * ldH + gcolT), v);
+            }
+        }
+    }
+}

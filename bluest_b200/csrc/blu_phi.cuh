@@ -1,0 +1,211 @@
+// blu_phi.cuh -- kernel (2): Phi(m) = delta I + sum_i m_i R_i^T Cinv_i R_i   (replaces the dense
+// GEMV psi@m of misc.py:459-461 / the sparse loop objectiveK_c, cmisc.cpp:25-40), followed by the
+// N x N pseudo-inverse and the variance (misc.py:463-477, 487-490).
+//
+// blu_phi_partial_kernel: each warp streams whole groups of the packed inverse array; lane e of a
+// 32-entry step owns packed entry (j,l) of the group and adds m_i * Cinv_i[j,l] into the warp's
+// PRIVATE N x N accumulator tile in shared memory at (g[j], g[l]).  Inside one group all targets
+// are distinct, so the read-modify-write needs no atomics; groups are separated by __syncwarp().
+// Only the upper triangle is ever touched (groups are sorted, j <= l).  Warps are combined in a
+// fixed order into one partial tile per CTA -- atomic-free and run-to-run deterministic.
+// Groups with m_i == 0 are skipped (they contribute exact zeros): an optimiser iterate with 2N
+// non-zeros reads 2N groups, not 2^N.
+// Also reduced here: the support mask (models touched by groups with |m_i| > 1e-6,
+// misc.py:453-457) and max|m| (early-out of misc.py:464,484) -- both by order-independent
+// integer atomics (OR, MAX on the IEEE bit pattern), hence deterministic.
+//
+// blu_phi_finish_kernel (one CTA): fixed-order sum of the CTA partials, mirror, + delta I, then
+// pinv(Phi) by parallel Jacobi, x = first row, S = 2 pinv(Phi), and the variance from the support
+// sub-block exactly as misc.py:489-490 does.
+#pragma once
+#include "blu_common.cuh"
+#include "blu_jacobi.cuh"
+
+#define BLU_PHI_WARPS 8
+
+struct BluEvalHeader {          // small device-side status block of a context
+    unsigned supp;              // support mask (OR)
+    unsigned flags;             // BLU_FLAG_* of the last evaluation
+    unsigned long long maxbits; // bit pattern of max|m|
+    double scal[8];             // [0] variance [1] max|m| [2] sweeps [3] lambda_max [4] var (full pinv)
+};
+
+__global__ void __launch_bounds__(BLU_PHI_WARPS * 32)
+blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N,
+                       const uint8_t *__restrict__ gidx, const double *__restrict__ cinv,
+                       const uint16_t *__restrict__ lut, const double *__restrict__ m,
+                       long long lo, long long hi,          // owned slice of the flat enumeration
+                       double *__restrict__ part, BluEvalHeader *hdr)
+{
+    extern __shared__ double sacc[];                 // BLU_PHI_WARPS tiles of N*N
+    const int NN = N * N;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *acc = sacc + w * NN;
+    for (int t = lane; t < NN; t += 32) acc[t] = 0.0;
+    __syncwarp();
+
+    unsigned supp = 0u;
+    double mymax = 0.0;
+    const long long gw = (long long)blockIdx.x * BLU_PHI_WARPS + w;
+    const long long nw = (long long)gridDim.x * BLU_PHI_WARPS;
+
+    for (int c = 0; c < ncls; ++c) {
+        const BluClass ci = cls[c];
+        const int k = ci.k, T = ci.T;
+        const uint16_t *lt = lut + ci.lutoff;
+        long long i0 = lo > ci.goff ? lo - ci.goff : 0;
+        long long i1 = hi < ci.goff + ci.Lk ? hi - ci.goff : ci.Lk;
+        for (long long i = i0 + gw; i < i1; i += nw) {
+            const double mi = m[ci.goff + i];
+            const double am = fabs(mi);
+            mymax = fmax(mymax, am);
+            if (mi == 0.0) continue;                  // warp-uniform
+            const int gv = lane < k ? (int)gidx[ci.ioff + i * k + lane] : 0;
+            if (am > 1.0e-6 && lane < k) supp |= 1u << gv;
+            const double *cp = cinv + ci.coff + i * T;
+            for (int e0 = 0; e0 < T; e0 += 32) {
+                const int e = e0 + lane;
+                const bool ok = e < T;
+                const unsigned jl = ok ? lt[e] : 0u;
+                const double v = ok ? cp[e] : 0.0;
+                const int a = __shfl_sync(BLU_FULL, gv, jl >> 8);
+                const int b = __shfl_sync(BLU_FULL, gv, jl & 255u);
+                if (ok) acc[a * N + b] += mi * v;
+            }
+            __syncwarp();
+        }
+    }
+    supp = __reduce_or_sync(BLU_FULL, supp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mymax = fmax(mymax, __shfl_xor_sync(BLU_FULL, mymax, o));
+    if (lane == 0) {
+        if (supp) atomicOr(&hdr->supp, supp);
+        atomicMax(&hdr->maxbits, (unsigned long long)__double_as_longlong(mymax));
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NN; t += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < BLU_PHI_WARPS; ++ww) s += sacc[ww * NN + t];
+        part[(long long)blockIdx.x * NN + t] = s;
+    }
+}
+
+#define BLU_FIN_THREADS 512
+#define BLU_FIN_SEG 8
+
+// mode 0: reduce + mirror + delta only (get_phi).  mode 1: + pinv, x, S, variance.
+// mode 2: reduce only, no mirror/delta (partial Phi of a group slice, before the all-reduce).
+// nparts == 0: Phi already sits in `phi` as an un-mirrored upper-triangle sum (after all-reduce).
+__global__ void __launch_bounds__(BLU_FIN_THREADS)
+blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double delta, int mode,
+                      double *__restrict__ phi, double *__restrict__ pinv, double *__restrict__ xrow,
+                      double *__restrict__ S, BluEvalHeader *hdr)
+{
+    __shared__ double A[BLU_JMAX * BLU_JLD], V[BLU_JMAX * BLU_JLD], Ph[BLU_JMAX * BLU_JLD];
+    extern __shared__ double red[];              // BLU_FIN_SEG x N*N staging for the partial sums
+    __shared__ BluJacobiScratch js;
+    __shared__ int sidx[BLU_JMAX];
+    __shared__ int ns;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int NN = N * N;
+
+    if (nparts > 0) {
+        for (int t = tid; t < NN * BLU_FIN_SEG; t += nthr) {
+            const int seg = t / NN, e = t - seg * NN;
+            double s = 0.0;
+            for (int p = seg; p < nparts; p += BLU_FIN_SEG) s += part[(long long)p * NN + e];
+            red[seg * NN + e] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < NN; e += nthr) {
+            double s = 0.0;
+#pragma unroll
+            for (int seg = 0; seg < BLU_FIN_SEG; ++seg) s += red[seg * NN + e];
+            Ph[(e / N) * BLU_JLD + (e % N)] = s;
+        }
+    } else {
+        for (int e = tid; e < NN; e += nthr) Ph[(e / N) * BLU_JLD + (e % N)] = phi[e];
+    }
+    __syncthreads();
+    if (mode == 2) {
+        // partial of a group slice: raw upper-triangle sums, followed by SUM-reducible encodings
+        // of the support mask (32 indicators) and of "max|m| >= 0.05" (1 indicator)
+        for (int e = tid; e < NN; e += nthr) phi[e] = Ph[(e / N) * BLU_JLD + (e % N)];
+        const unsigned sp = hdr->supp;
+        const double mx = __longlong_as_double((long long)hdr->maxbits);
+        __syncthreads();
+        if (tid < 32) phi[NN + tid] = (sp >> tid) & 1u ? 1.0 : 0.0;
+        if (tid == 32) phi[NN + 32] = mx >= 0.05 ? 1.0 : 0.0;
+        if (tid == 0) { hdr->supp = 0u; hdr->maxbits = 0ull; }
+        return;
+    }
+    // mirror the upper triangle, add delta on the diagonal
+    for (int e = tid; e < NN; e += nthr) {
+        const int r = e / N, c = e - r * N;
+        const int lo = r < c ? r : c, hi = r < c ? c : r;
+        double v = Ph[lo * BLU_JLD + hi];
+        if (r == c) v += delta;
+        phi[e] = v;
+    }
+    __syncthreads();
+    unsigned supp;
+    double maxabs;
+    if (nparts > 0) {
+        supp = hdr->supp;
+        maxabs = __longlong_as_double((long long)hdr->maxbits);
+    } else {                              // all-reduced encodings written by mode 2
+        supp = 0u;
+        for (int a = 0; a < 32; ++a) if (phi[NN + a] > 0.0) supp |= 1u << a;
+        maxabs = phi[NN + 32] > 0.0 ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {                      // reset the reduction cells for the next evaluation
+        hdr->supp = 0u; hdr->maxbits = 0ull;
+        hdr->scal[1] = maxabs;
+    }
+    if (mode == 0) return;
+
+    unsigned flags = 0u;
+    if (maxabs < 0.05) {                 // misc.py:464,484
+        if (tid == 0) { hdr->flags = BLU_FLAG_TINY; hdr->scal[0] = INFINITY; }
+        return;
+    }
+    const unsigned all = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
+    if (!(supp & 1u)) flags |= BLU_FLAG_NO_MODEL0;
+    if ((supp & all) != all) flags |= BLU_FLAG_PARTIAL;
+
+    // ---- full pseudo-inverse (misc.py:487) ----
+    const int n = N + (N & 1);
+    for (int t = tid; t < n * n; t += nthr) {
+        const int r = t / n, c = t - r * n;
+        A[r * BLU_JLD + c] = (r < N && c < N) ? phi[r * N + c] : 0.0;
+    }
+    __syncthreads();
+    blu_sym_pinv(A, V, n, &js, pinv, N, N, 1.0e-15, tid, nthr);
+    for (int e = tid; e < NN; e += nthr) S[e] = 2.0 * pinv[e];
+    if (tid < N) xrow[tid] = pinv[tid];
+    if (tid == 0) { hdr->scal[2] = (double)js.sweeps; hdr->scal[3] = js.lmax; hdr->scal[4] = pinv[0]; }
+    __syncthreads();
+
+    // ---- variance on the support sub-block (misc.py:489-490) ----
+    if (!(flags & BLU_FLAG_PARTIAL)) {
+        if (tid == 0) { hdr->scal[0] = pinv[0]; hdr->flags = flags; }
+        return;
+    }
+    if (tid == 0) {
+        int cnt = 0;
+        for (int a = 0; a < N; ++a) if (supp >> a & 1u) sidx[cnt++] = a;
+        ns = cnt;
+    }
+    __syncthreads();
+    const int nsub = ns;
+    const int n2 = nsub + (nsub & 1);
+    for (int t = tid; t < n2 * n2; t += nthr) {
+        const int r = t / n2, c = t - r * n2;
+        A[r * BLU_JLD + c] = (r < nsub && c < nsub) ? phi[sidx[r] * N + sidx[c]] : 0.0;
+    }
+    __syncthreads();
+    blu_sym_pinv(A, V, n2, &js, Ph, BLU_JLD, nsub > 0 ? 1 : 0, 1.0e-15, tid, nthr);
+    if (tid == 0) { hdr->scal[0] = nsub > 0 ? Ph[0] : INFINITY; hdr->flags = flags; }
+}

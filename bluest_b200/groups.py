@@ -1,0 +1,118 @@
+"""Group enumeration and integer index maps -- host-side, exact.
+
+Mirrors the integer logic of ``BLUEProblem.setup_solver`` (blue_models.py:458-501) and
+``MOSAP.__init__`` (mosap.py:41-67): groups are size-major, lexicographic inside a size class;
+the flat index of a group is ``cumsizes[k-1] + rank``.
+"""
+from itertools import combinations
+
+import numpy as np
+
+
+def enumerate_groups(N, K=None):
+    """All subsets of {0..N-1} of size <= K: what nx.enumerate_all_cliques yields on a complete
+    model graph after ``groups[k].sort()`` (blue_models.py:462-474, :500-501)."""
+    K = N if K is None else min(K, N)
+    return [[list(c) for c in combinations(range(N), k)] for k in range(1, K + 1)]
+
+
+def enumerate_cliques(adj, K, component_of=0):
+    """Cliques of size <= K of the coupling graph ``adj`` (non-zero = edge), restricted to the
+    connected component of model ``component_of`` (blue_models.py:462-474, :468).  Plain
+    breadth-first extension with increasing vertex ids, which reproduces networkx's
+    size-major, lexicographic order."""
+    adj = np.asarray(adj) != 0
+    N = adj.shape[0]
+    comp = {component_of}
+    frontier = [component_of]
+    while frontier:
+        nxt = []
+        for u in frontier:
+            for v in range(N):
+                if v != u and adj[u, v] and v not in comp:
+                    comp.add(v); nxt.append(v)
+        frontier = nxt
+    level = [[v] for v in range(N) if v in comp]
+    out = []
+    for k in range(1, min(K, N) + 1):
+        if not level:
+            break
+        out.append(level)
+        nxt = []
+        for c in level:
+            for v in range(c[-1] + 1, N):
+                if v in comp and all(adj[u, v] for u in c):
+                    nxt.append(c + [v])
+        level = nxt
+    return out
+
+
+def union_groups(multi_groups):
+    """Union over outputs + per-size lexicographic sort (blue_models.py:493-501), O(L log L)."""
+    K = max(len(mg) for mg in multi_groups)
+    out = []
+    for k in range(K):
+        seen = set()
+        for mg in multi_groups:
+            if k < len(mg):
+                seen.update(tuple(int(v) for v in g) for g in mg[k])
+        out.append([list(g) for g in sorted(seen)])
+    return out
+
+
+def group_costs(groups, model_costs):
+    """blue_models.py:137-140."""
+    mc = np.asarray(model_costs)
+    return np.array([sum(mc[list(g)]) for gk in groups for g in gk])
+
+
+def indicator_ES(group_arrays, N):
+    """ES[i][g] = int(model i in group g)  (sap.py:89-95, mosap.py:46-52), vectorised."""
+    L = sum(len(g) for g in group_arrays)
+    ES = np.zeros((N, L), dtype=np.int64)
+    off = 0
+    for g in group_arrays:
+        g = np.asarray(g, dtype=np.int64)
+        if g.size:
+            cols = off + np.repeat(np.arange(g.shape[0]), g.shape[1])
+            ES[g.ravel(), cols] = 1
+        off += len(g)
+    return [ES[i].copy() for i in range(N)]
+
+
+def mappings(groups, multi_groups):
+    """mappings[n][j] = flat position in ``groups`` of the j-th group of output n
+    (mosap.py:54-67); dictionary look-up instead of the reference's O(L^2) scan."""
+    sizes = [0] + [len(gk) for gk in groups]
+    cum = np.cumsum(sizes)
+    where = {}
+    for k, gk in enumerate(groups):
+        for j, g in enumerate(gk):
+            where[tuple(int(v) for v in g)] = int(cum[k] + j)
+    out = []
+    for mg in multi_groups:
+        pos = []
+        for gk in mg:
+            for g in gk:
+                key = tuple(int(v) for v in g)
+                if key not in where:
+                    raise AssertionError("group %s of an output is missing from the union" % (key,))
+                pos.append(where[key])
+        out.append(np.array(pos, dtype=np.int64))
+    return out
+
+
+def balanced_slices(sizes, world):
+    """Contiguous slices of the flat enumeration with equal work sum(k^2).
+    ``sizes`` = [L1..LK].  Returns ``world`` (lo, hi) pairs."""
+    work = np.concatenate([np.full(int(Lk), (k + 1) ** 2, dtype=np.float64) for k, Lk in enumerate(sizes)]) if sum(sizes) else np.zeros(0)
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(cum, total * r / world)))
+    bounds.append(len(work))
+    bounds = [min(max(b, 0), len(work)) for b in bounds]
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]

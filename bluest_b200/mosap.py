@@ -1,0 +1,81 @@
+"""MOSAP -- multi-output wrapper (mirror of bluest/mosap.py:18-123 for the hot path).
+
+One ``SAP`` (device context) per output, evaluated on ``m[mappings[n]]``; same constructor
+signature, attributes (``SAPS``, ``mappings``, ``ES``, ``e``, ``sizes``, ``cumsizes``, ``L``) and
+methods ``variances`` / ``variance_GH`` / ``get_cleanup_matrices`` as the reference.
+"""
+import numpy as np
+
+from .groups import indicator_ES, mappings as build_mappings
+from .sap import SAP
+
+
+class BLUESTError(RuntimeError):
+    pass
+
+
+class MOSAP(object):
+    ''' MOSAP, MultiObjectiveSampleAllocationProblem '''
+
+    def __init__(self, C, K, Ks, groups, multi_groups, costs, multi_costs, verbose=True, device=0):
+        self.verbose = verbose
+        self.n_outputs = len(C)
+        self.C = C
+        self.N = C[0].shape[0]
+        self.K = K
+        self.Ks = Ks
+        self.costs = costs
+        self.multi_groups = multi_groups
+        self.multi_costs = multi_costs
+        flattened_groups = []
+        for k in range(K):
+            flattened_groups += [list(g) for g in groups[k]]
+            groups[k] = np.array(groups[k], dtype=np.int64)       # mosap.py:34
+        self.flattened_groups = flattened_groups
+        self.groups = groups
+
+        self.SAPS = [SAP(C[n], Ks[n], multi_groups[n], multi_costs[n], verbose=self.verbose, device=device)
+                     for n in range(self.n_outputs)]
+
+        self.sizes = [0] + [len(groupsk) for groupsk in groups]
+        self.cumsizes = np.cumsum(self.sizes)
+        self.L = self.cumsizes[-1]
+        self.ES = indicator_ES(groups, self.N)
+        self.e = self.ES[0]
+        # m <-> groups, and m[mappings[n]] = m_n <-> multi_groups[n]   (mosap.py:54-67)
+        self.mappings = build_mappings(groups, multi_groups)
+
+        self.samples = None
+        self.budget = None
+        self.eps = None
+        self.tot_cost = None
+
+    def check_input(self, budget, eps):
+        if budget is None and eps is None:
+            raise ValueError("Need to specify either budget or RMSE tolerance")
+        if eps is not None:
+            try:
+                if len(eps) != self.n_outputs:
+                    raise ValueError("eps must be a scalar or an array of tolerances")
+                eps = np.array(eps)
+            except TypeError:
+                eps = np.array([eps for n in range(self.n_outputs)])
+        return budget, eps
+
+    def variances(self, m, delta=0):
+        return [self.SAPS[n].variance(m[self.mappings[n]], delta=delta) for n in range(self.n_outputs)]
+
+    def variance_GH(self, m, nohess=False, delta=0):
+        out = [self.SAPS[n].variance_GH(m[self.mappings[n]], nohess=nohess, delta=delta) for n in range(self.n_outputs)]
+        variances = [item[0] for item in out]
+        gradients = [item[1] for item in out]
+        hessians = [item[2] for item in out]
+        return variances, gradients, hessians
+
+    def get_cleanup_matrices(self, m, delta=0):
+        Xs = []
+        for n in range(self.n_outputs):
+            X = np.zeros((self.N, self.L))
+            X[:, self.mappings[n]] = self.SAPS[n].get_cleanup_matrix(m[self.mappings[n]], delta=delta)
+            Xs.append(X)
+        return np.vstack(Xs)

@@ -1,0 +1,280 @@
+"""SAP -- the sample-allocation problem of one output, on the B200.
+
+Host-side mirror of the reference's ``bluest.sap.SAP`` (sap.py:52-143) for the hot path:
+same constructor, same attributes, same closures with the same return conventions
+(``get_phi``, ``variance``, ``variance_GH``, ``get_cleanup_matrix``), but the per-group
+inverses live packed in HBM inside a ``blu_ctx`` and every closure is one call into
+libbluest_b200.so.  ``psi`` and ``invcovs`` are materialised lazily for the host-side SDP
+builders that read them (sap.py:250,328).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import BluError, check, dptr, f64, iptr, lib
+from .groups import indicator_ES
+
+
+class SAP(object):
+    def __init__(self, C, K, groups, costs, verbose=True, device=0, invcovs=None, pivot_rtol=1e-10):
+        """C (N,N) covariance; ``groups[k-1]`` = list of sorted model-index lists of size k
+        (converted in place to int64 arrays, like sap.py:77); ``costs`` (L,).
+
+        ``invcovs`` (optional): the reference's per-class flat inverse arrays to ingest instead of
+        inverting on the device (parity testing of the later stages)."""
+        _lib.require_device()
+        self.verbose = verbose
+        self.C = C
+        self.N = C.shape[0]
+        self.K = K
+        self.costs = costs
+        self.samples = None
+        self.budget = None
+        self.eps = None
+        self.tot_cost = None
+        self.device = device
+
+        flattened_groups = []
+        sizes = [0] + [len(groupsk) for groupsk in groups]
+        flat = []
+        for k in range(1, K + 1):
+            gk = groups[k - 1]
+            flattened_groups.extend(list(g) for g in gk)
+            arr = np.array(gk, dtype=np.int64).reshape(len(gk), k) if len(gk) else np.array(gk, dtype=np.int64)
+            groups[k - 1] = arr                                  # sap.py:77 mutates the caller's list too
+            if len(gk):
+                flat.append(arr.ravel())
+        self.sizes = sizes
+        self.groups = groups
+        self.flattened_groups = flattened_groups
+        self.cumsizes = np.cumsum(sizes)
+        self.L = self.cumsizes[-1]
+
+        sz = np.array(sizes[1:], dtype=np.int64)
+        gflat = np.ascontiguousarray(np.concatenate(flat)) if flat else np.zeros(0, dtype=np.int64)
+        self._ctx = ctypes.c_void_p()
+        check(lib().blu_ctx_create(device, self.N, K, iptr(sz), iptr(gflat), ctypes.byref(self._ctx)))
+        self.n_fallback = 0
+        if invcovs is None:
+            nf = ctypes.c_int64(0)
+            Cd = np.ascontiguousarray(np.asarray(C, dtype=np.float64))
+            check(lib().blu_ctx_set_covariance(self._ctx, dptr(Cd), float(pivot_rtol), ctypes.byref(nf)))
+            self.n_fallback = int(nf.value)
+        else:
+            for k in range(1, K + 1):
+                if sizes[k]:
+                    a = f64(invcovs[k - 1], sizes[k] * k * k, "invcovs[%d]" % (k - 1))
+                    check(lib().blu_ctx_set_invcovs(self._ctx, k, dptr(a)))
+        self._invcovs = None
+        self._psi = None
+
+        self.ES = indicator_ES([g for g in groups], self.N)
+        self.e = self.ES[0]
+        self.get_variance_functions()
+
+    # ---- lazily materialised host views ------------------------------------------------------
+    @property
+    def invcovs(self):
+        """``invcovs[k-1]``: flat (Lk*k*k) float64, row-major [i][j][l] (sap.py:78-79)."""
+        if self._invcovs is None:
+            out = []
+            for k in range(1, self.K + 1):
+                Lk = self.sizes[k]
+                if Lk == 0:
+                    out.append(np.array([]))
+                    continue
+                a = np.empty(Lk * k * k)
+                check(lib().blu_ctx_get_invcovs(self._ctx, k, dptr(a)))
+                out.append(a)
+            self._invcovs = out
+        return self._invcovs
+
+    @property
+    def psi(self):
+        """Dense (N^2, L) matrix of sap.py:129, assembled on the device on first use."""
+        if self._psi is None:
+            psi = np.empty((self.N * self.N, int(self.L)))
+            check(lib().blu_ctx_assemble_psi(self._ctx, dptr(psi)))
+            self._psi = psi
+        return self._psi
+
+    def _m(self, m):
+        return f64(m, int(self.L), "m")
+
+    def get_variance_functions(self):
+        ctx, L, N = self._ctx, int(self.L), self.N
+
+        def get_phi(m, delta=0):
+            phi = np.empty((N, N))
+            check(lib().blu_get_phi(ctx, dptr(self._m(m)), float(delta), dptr(phi)))
+            return phi
+
+        def variance(m, delta=0):
+            var = ctypes.c_double(0.0); fl = ctypes.c_uint(0)
+            check(lib().blu_variance(ctx, dptr(self._m(m)), float(delta), ctypes.byref(var), ctypes.byref(fl)))
+            if fl.value & _lib.FLAG_TINY:
+                return np.inf                                   # misc.py:464
+            # misc.py:470 -- the model 0 must always be sampled
+            assert not (fl.value & _lib.FLAG_NO_MODEL0)
+            return var.value
+
+        def variance_GH(m, delta=0, nohess=False):
+            var = ctypes.c_double(0.0); fl = ctypes.c_uint(0)
+            grad = np.empty(L)
+            hess = None if nohess else _lib.pinned_pool.empty((L, L))
+            hp = None if nohess else ctypes.c_void_p(hess.ctypes.data)
+            check(lib().blu_variance_GH(ctx, dptr(self._m(m)), float(delta), ctypes.byref(var), dptr(grad), hp, ctypes.byref(fl)))
+            if fl.value & _lib.FLAG_TINY:
+                return np.inf, grad                             # 2-tuple, misc.py:484 (grad is inf*ones)
+            return var.value, grad, hess
+
+        def get_cleanup_matrix(m, delta=0, corrected=False):
+            X = np.empty((N, L)); fl = ctypes.c_uint(0)
+            check(lib().blu_cleanup_matrix(ctx, dptr(self._m(m)), float(delta), 1 if corrected else 0, dptr(X), ctypes.byref(fl)))
+            if fl.value & _lib.FLAG_TINY:
+                raise ValueError("No entry greater or equal than 1 found in m.")     # misc.py:510
+            return X
+
+        self.get_phi = get_phi
+        self.variance = variance
+        self.variance_GH = variance_GH
+        self.get_cleanup_matrix = get_cleanup_matrix
+
+    # ---- device-resident interface (no host round trip of the big arrays) ---------------------
+    def eval_device(self, d_m=None, delta=0.0, grad=True, hess=False):
+        """Asynchronous evaluation with m already in HBM (``d_m``: device pointer / torch tensor /
+        None to reuse the last uploaded m).  Results stay on the device (``device_buffer``)."""
+        ptr = None
+        if d_m is not None:
+            ptr = ctypes.c_void_p(int(d_m.data_ptr()) if hasattr(d_m, "data_ptr") else int(d_m))
+        check(lib().blu_eval_device(self._ctx, ptr, float(delta), int(bool(grad)), int(bool(hess))))
+
+    def upload_m(self, m):
+        """Copy a host m into the context's device buffer (BLU_BUF_M)."""
+        import torch
+        t = self.device_buffer(_lib.BUF_M)
+        t.copy_(torch.from_numpy(self._m(m)))
+        return t
+
+    def sync(self):
+        check(lib().blu_ctx_sync(self._ctx))
+
+    def last_result(self):
+        var = ctypes.c_double(0.0); fl = ctypes.c_uint(0)
+        check(lib().blu_ctx_last_result(self._ctx, ctypes.byref(var), ctypes.byref(fl)))
+        return var.value, fl.value
+
+    def last_timing(self):
+        ms = (ctypes.c_float * 4)()
+        check(lib().blu_ctx_last_timing(self._ctx, ms))
+        return {"phi_pinv_ms": ms[0], "grad_ms": ms[1], "hess_ms": ms[2], "total_ms": ms[3]}
+
+    def last_launches(self):
+        return int(lib().blu_ctx_last_launches(self._ctx))
+
+    def device_ptr(self, which):
+        p = ctypes.c_void_p(); n = ctypes.c_int64(0)
+        check(lib().blu_ctx_device_ptr(self._ctx, which, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def device_buffer(self, which):
+        """A torch float64 tensor aliasing one of the context's HBM buffers (no copy)."""
+        import torch
+        ptr, nbytes = self.device_ptr(which)
+        if not ptr:
+            raise BluError(_lib.BLU_ERR_STATE, "buffer %d not allocated yet" % which)
+
+        class _Holder:       # __cuda_array_interface__ exporter keeping the SAP (hence the ctx) alive
+            pass
+        h = _Holder()
+        h.owner = self
+        h.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+        return torch.as_tensor(h, device="cuda:%d" % self.device)
+
+    def stream(self):
+        p = ctypes.c_void_p()
+        check(lib().blu_ctx_stream(self._ctx, ctypes.byref(p)))
+        return p.value
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            lib().blu_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host orchestration kept from the reference -------------------------------------------
+    def get_max_sample_constraints(self, max_model_samples):
+        """sap.py:222-240."""
+        if max_model_samples is None:
+            return [], []
+        if not isinstance(max_model_samples, np.ndarray) or len(max_model_samples) != self.N:
+            raise ValueError("The maximum number of model samples must be prescribed as a numpy array of the same length as the number of models.")
+        if max_model_samples[0] < 1:
+            raise ValueError("The high-fidelity model must be sampled at least once.")
+        es, rhs = [], []
+        for i in range(self.N):
+            if np.isfinite(max_model_samples[i]):
+                es.append(self.ES[i])
+                rhs.append(int(np.round(max_model_samples[i])))
+        return es, rhs
+
+    def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=True, max_model_samples=None, solver_params=None):
+        """Host-side driver kept from sap.py:189-220.  Only ``solver="scipy"`` (trust-constr
+        iterating on the GPU closures) is provided here; the SDP solvers (cvxopt / cvxpy) and
+        ipopt are third-party host code that consume ``self.psi`` and are not part of this package."""
+        if budget is None and eps is None:
+            raise ValueError("Need to specify either budget or RMSE tolerance")
+        if solver != "scipy":
+            raise ValueError("bluest_b200.SAP.solve provides solver='scipy'; for 'cvxopt'/'cvxpy'/'ipopt' hand "
+                             "`sap.psi`, `sap.variance`, `sap.variance_GH` to the reference's own drivers (INTEGRATION.md)")
+        samples = self.scipy_solve(budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples)
+        if samples is None:
+            self.samples = None
+            return None
+        if not continuous_relaxation:
+            raise NotImplementedError("integer projection (misc.py:313-413) stays with the reference host code")
+        self.samples = samples
+        self.budget = budget
+        self.eps = eps
+        self.tot_cost = samples @ self.costs
+        return samples
+
+    def scipy_solve(self, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000):
+        """sap.py:378-418 -- same constraints, tolerances and callbacks; the callbacks are the GPU closures."""
+        from scipy.optimize import Bounds, LinearConstraint, NonlinearConstraint, minimize
+        if budget is None and eps is None:
+            raise ValueError("Need to specify either budget or RMSE tolerance")
+        delta = 0
+        L = int(self.L)
+        w = self.costs
+        e = self.e
+        es, rhs = self.get_max_sample_constraints(max_model_samples)
+        constraint1 = Bounds(0.0 * np.ones((L,)), np.inf * np.ones((L,)), keep_feasible=True)
+        constraint3 = LinearConstraint(e, 1, np.inf, keep_feasible=True)
+        constraint4 = [LinearConstraint(ee, -np.inf, rr) for ee, rr in zip(es, rhs)]
+        opts = {"factorization_method": None, "disp": False, "maxiter": maxiter, "verbose": 3 * int(self.verbose)}
+        if budget is not None:
+            constraint2 = LinearConstraint(w, -np.inf, budget)
+            if x0 is None:
+                x0 = np.ceil(10 * abs(np.random.randn(L)))
+            res = minimize(lambda x: self.variance_GH(x, nohess=True, delta=delta)[:-1], x0, jac=True,
+                           hess=lambda x: self.variance_GH(x, delta=delta)[-1], bounds=constraint1,
+                           constraints=[constraint2, constraint3] + constraint4, method="trust-constr", options=opts, tol=1.0e-8)
+        else:
+            epsq = eps ** 2
+            constraint2 = NonlinearConstraint(lambda x: self.variance(x, delta=delta), epsq, epsq,
+                                              jac=lambda x: self.variance_GH(x, nohess=True, delta=delta)[1],
+                                              hess=lambda x, p: self.variance_GH(x, delta=delta)[2] * p)
+            if x0 is None:
+                x0 = np.ceil(eps ** -2 * np.random.rand(L))
+            wn = w / np.linalg.norm(w)
+            res = minimize(lambda x: [wn @ x, wn], x0, jac=True, hessp=lambda x, p: np.zeros((len(x),)), bounds=constraint1,
+                           constraints=[constraint2, constraint3] + constraint4, method="trust-constr", options=opts, tol=1.0e-10)
+        self.scipy_result = res
+        return res.x

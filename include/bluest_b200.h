@@ -1,0 +1,173 @@
+/*
+ * bluest_b200.h -- C ABI of libbluest_b200.so: the B200 (sm_100a, FP64) replacement for the
+ * sample-allocation hot path of BLUEST (reference: croci/bluest).
+ *
+ * Two levels, mirroring SURVEY.md section 8(b):
+ *
+ *   Level 1  stateless drop-ins for the five routines of the reference's pybind11 module
+ *            `_cmisc_bluest` (bluest/cmisc.cpp:99-110).  Same argument order, same
+ *            "caller-allocated, pre-zeroed, accumulated in place" convention, HOST pointers.
+ *   Level 2  a device-resident problem context that replaces `SAP.__init__` +
+ *            `SAP.get_variance_functions` (bluest/sap.py:53-143) and the numpy orchestration in
+ *            bluest/misc.py:453-516.  This is the boundary that matters for speed: the packed
+ *            per-group inverses stay in HBM, one call evaluates Phi / variance / gradient / Hessian.
+ *
+ * All entry points are extern "C", take plain pointers and sizes, return an int status
+ * (BLU_OK == 0) and never throw.  blu_last_error() returns a thread-local message for the last
+ * non-zero status.  Pointers named h_* / without prefix are host memory; d_* are device
+ * memory of the context's device.  Floating point is FP64, group indices are int64 (the reference's
+ * `long int`, cmisc.cpp:10).  A context is used from one host thread at a time.
+ *
+ * Naming (reference convention): N = number of models, K = largest group
+ * size, "size class k" = the Lk groups with exactly k models, L = sum_k Lk = number of groups.
+ */
+#ifndef BLUEST_B200_H
+#define BLUEST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLU_OK            0
+#define BLU_ERR_ARG       1   /* bad argument (NULL, size out of range, unsorted group, ...) */
+#define BLU_ERR_CUDA      2   /* a CUDA runtime call or kernel failed */
+#define BLU_ERR_STATE     3   /* call order violated (e.g. evaluate before inverses are set) */
+#define BLU_ERR_NOMEM     4
+#define BLU_ERR_NODEVICE  5   /* no CUDA device: the product path has no CPU fallback */
+
+#define BLU_MAX_MODELS    32  /* group membership is a 32-bit mask */
+
+/* status bits reported by the evaluation calls (out-parameter `flags`) */
+#define BLU_FLAG_TINY      1u /* max|m| < 0.05: reference returns inf (misc.py:464,484,510) */
+#define BLU_FLAG_NO_MODEL0 2u /* model 0 not in the support of m (misc.py:470 asserts) */
+#define BLU_FLAG_PARTIAL   4u /* support is a strict subset of the models (singular Phi) */
+
+/* `which` for blu_ctx_device_ptr */
+#define BLU_BUF_M      0   /* (L)        sample vector of the last evaluation */
+#define BLU_BUF_PHI    1   /* (N,N)      Phi(m) = delta I + sum m_i Psi_i */
+#define BLU_BUF_PINV   2   /* (N,N)      pinv(Phi), symmetric */
+#define BLU_BUF_GRAD   3   /* (L)        gradient of the variance */
+#define BLU_BUF_U      4   /* (Lpad,NP)  row i = u_i = R_i^T Cinv_i R_i x, NP = 4*ceil(N/4) */
+#define BLU_BUF_V      5   /* (Lpad,NP)  row i = 2 pinv(Phi) u_i */
+#define BLU_BUF_HESS   6   /* (L,ldH)    dense Hessian, row pitch ldH = 16*ceil(L/16) doubles */
+#define BLU_BUF_CINV   7   /* packed upper-triangular per-group inverses */
+#define BLU_BUF_SCAL   8   /* (8) doubles: [0]=variance, [1]=max|m|, [2]=sweeps, [3]=lambda_max */
+
+typedef struct blu_ctx blu_ctx;
+
+const char *blu_last_error(void);
+int  blu_device_count(void);               /* 0 when no usable CUDA device */
+const char *blu_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Level 2: device-resident context
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces the bookkeeping half of SAP.__init__ (sap.py:57-87): uploads the group tables.
+ *   sizes[k-1]   = Lk for k = 1..K (empty classes allowed, sap.py:78-79)
+ *   groups_flat  = concatenation over k of the (Lk,k) row-major int64 tables (sap.py:77);
+ *                  every group strictly increasing, entries in [0,N).
+ * No covariance yet: call blu_ctx_set_covariance or blu_ctx_set_invcovs next. */
+int blu_ctx_create(int device, int N, int K, const int64_t *sizes, const int64_t *groups_flat,
+                   blu_ctx **out);
+int blu_ctx_destroy(blu_ctx *ctx);
+
+/* Kernel (1): batched inversion of C[g_i,g_i] for every group (replaces the L calls of
+ * np.linalg.pinv at sap.py:72-74).  One warp-slice per group, shuffle-based Gauss-Jordan; groups
+ * whose pivots drop below `pivot_rtol` x diagonal are redone with a Jacobi-eigenvalue pseudo-inverse
+ * using numpy's cutoff (1e-15 x sigma_max).  C is (N,N) row-major and may hold NaN where models are
+ * never coupled.  n_fallback (optional) receives the number of groups that took the Jacobi route. */
+int blu_ctx_set_covariance(blu_ctx *ctx, const double *C, double pivot_rtol, int64_t *n_fallback);
+
+/* Ingest / read back inverses in the reference's layout: invcovs_k is the flat (Lk,k,k) array
+ * `SAP.invcovs[k-1]` (sap.py:78).  Ingest symmetrises ((A+A^T)/2) and packs the upper triangle. */
+int blu_ctx_set_invcovs(blu_ctx *ctx, int k, const double *invcovs_k);
+int blu_ctx_get_invcovs(blu_ctx *ctx, int k, double *invcovs_k);
+
+/* Dense psi (N*N, L) row-major, the matrix the host SDP builders read (sap.py:129,250,328). */
+int blu_ctx_assemble_psi(blu_ctx *ctx, double *psi);
+
+/* get_phi (misc.py:459-461): phi is (N,N) row-major. */
+int blu_get_phi(blu_ctx *ctx, const double *m, double delta, double *phi);
+
+/* variance (misc.py:463-477).  *var = inf with BLU_FLAG_TINY when max|m| < 0.05.
+ * BLU_FLAG_NO_MODEL0 is where the reference asserts. */
+int blu_variance(blu_ctx *ctx, const double *m, double delta, double *var, unsigned *flags);
+
+/* variance_GH (misc.py:479-505).  grad: (L).  hess: (L,L) row-major host array or NULL
+ * (nohess).  With BLU_FLAG_TINY set, *var = inf and grad is filled with inf (the reference's
+ * 2-tuple early-out); hess is left untouched. */
+int blu_variance_GH(blu_ctx *ctx, const double *m, double delta, double *var, double *grad,
+                    double *hess, unsigned *flags);
+
+/* get_cleanup_matrix (misc.py:507-516): X is (N,L) row-major.  mode 0 reproduces the reference's
+ * assignment semantics (cmisc.cpp:51, only l = k-1 survives); mode 1 returns the intended
+ * X[:,i] = u_i.  Returns BLU_ERR_ARG-free status with BLU_FLAG_TINY when the reference would
+ * raise ValueError. */
+int blu_cleanup_matrix(blu_ctx *ctx, const double *m, double delta, int mode, double *X,
+                       unsigned *flags);
+
+/* Device-resident evaluation: d_m lives on the context's device (or NULL to reuse BLU_BUF_M).
+ * want_grad / want_hess select the work; results stay in the context's buffers
+ * (blu_ctx_device_ptr).  The call is asynchronous on the context's stream. */
+int blu_eval_device(blu_ctx *ctx, const double *d_m, double delta, int want_grad, int want_hess);
+int blu_ctx_sync(blu_ctx *ctx);
+int blu_ctx_device_ptr(blu_ctx *ctx, int which, void **ptr, int64_t *nbytes);
+int blu_ctx_stream(blu_ctx *ctx, void **cuda_stream);
+/* Read back the status flags / variance of the last evaluation (synchronises). */
+int blu_ctx_last_result(blu_ctx *ctx, double *var, unsigned *flags);
+/* Time the device part of the last blu_eval_device call (CUDA events on the context's stream):
+ * ms[0]=Phi+pinv, ms[1]=grad/U, ms[2]=Hessian, ms[3]=total. */
+int blu_ctx_last_timing(blu_ctx *ctx, float *ms);
+/* Number of kernels the last evaluation launched. */
+int blu_ctx_last_launches(blu_ctx *ctx);
+
+/* Group-sharded evaluation: a context may own a contiguous slice
+ * [lo,hi) of the flat group enumeration.  The three phases are exposed separately so the host
+ * can put the NCCL exchange between them:
+ *   blu_shard_phi      partial Phi of the slice -> BLU_BUF_PHI (N*N doubles, no delta, no pinv)
+ *   (all-reduce BLU_BUF_PHI across ranks)
+ *   blu_shard_finish   delta*I, pinv, variance on the reduced Phi; grad and U,V rows of the slice
+ *   (all-gather U,V rows)
+ *   blu_shard_hess     rows [lo,hi) of the Hessian against all L columns. */
+int blu_ctx_set_slice(blu_ctx *ctx, int64_t lo, int64_t hi);
+int blu_shard_phi(blu_ctx *ctx, const double *d_m);
+int blu_shard_finish(blu_ctx *ctx, double delta, int want_grad, int want_uv);
+int blu_shard_hess(blu_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel (4): pilot-sample covariance (blue_fn.py:159-167, blue_models.py:333).
+ * Y is (n,N) row-major.  Outputs (host): s1 (N) column sums, S2 (N,N) Gram matrix Y^T Y,
+ * C_hat (N,N) = S2/n - s1 s1^T/n^2.  FP64 DMMA contraction, deterministic two-stage reduce.
+ * y_on_device != 0: Y is a device pointer. */
+int blu_pilot_covariance(int device, const double *Y, int64_t n, int N, int y_on_device,
+                         double *s1, double *S2, double *C_hat, float *kernel_ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Level 1: drop-ins for `_cmisc_bluest` (bluest/cmisc.cpp).  Host pointers, in-place "+=".
+ * ------------------------------------------------------------------------------------------ */
+/* assemble_psi_c, cmisc.cpp:10-23 */
+int blu_assemble_psi_c(double *psi, int N, int k, int Lk, const int64_t *groupsk,
+                       const double *invcovsk);
+/* objectiveK_c<double>, cmisc.cpp:25-40,104 ; objectiveK_c<long int>, cmisc.cpp:105 */
+int blu_objectiveK_c(double *PHI, int N, int k, int Lk, const double *mk, const int64_t *groupsk,
+                     const double *invcovsk);
+int blu_objectiveK_c_i64(double *PHI, int N, int k, int Lk, const int64_t *mk,
+                         const int64_t *groupsk, const double *invcovsk);
+/* cleanupK_c, cmisc.cpp:42-56 (assignment semantics); N = leading dimension of X = number of models */
+int blu_cleanupK_c(double *X, int N, int k, int Lk, const int64_t *groupsk, const double *invcovsk,
+                   const double *invPHI_0);
+/* gradK_c, cmisc.cpp:58-72; N = length of invPHI_0 */
+int blu_gradK_c(double *grad, int N, int k, int Lk, const int64_t *groupsk, const double *invcovsk,
+                const double *invPHI_0);
+/* hessKQ_c, cmisc.cpp:74-97 */
+int blu_hessKQ_c(double *hess, int N, int k, int q, int Lk, int Lq, const int64_t *groupsk,
+                 const int64_t *groupsq, const double *invcovsk, const double *invcovsq,
+                 const double *invPHI);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLUEST_B200_H */

@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / the SAP mirror) against the oracle and
+the committed golden vectors of the reference.  Integer work bit-exact, FP64 outputs to
+max-norm relative error <= 1e-12 (north_star), looser only where the test says why."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from conftest import GOLDEN, maxrel
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def blu():
+    import bluest_b200
+    if bluest_b200.device_count() <= 0:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    return bluest_b200
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def _case(d, tag):
+    K = int(d[f"{tag}/K"])
+    groups = [d[f"{tag}/groups{k+1}"].tolist() for k in range(K)]
+    invcovs = [d[f"{tag}/invcovs{k+1}"] for k in range(K)]
+    return d[f"{tag}/C"], K, groups, invcovs
+
+
+def _copy(groups):
+    return [[list(g) for g in gk] for gk in groups]
+
+
+SYN_TAGS = ["N4K4", "N6K6", "N8K4", "N8K8"]
+
+
+@pytest.mark.parametrize("tag", SYN_TAGS + ["ragged"])
+def test_group_inversion_and_psi_vs_reference(blu, tag):
+    """kernel (1) + psi assembly against the reference's pinv inverses / psi (golden)."""
+    d = _load("synthetic.npz")
+    C, K, groups, invcovs = _case(d, tag)
+    L = sum(len(g) for g in groups)
+    sap = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False)
+    assert sap.n_fallback == 0
+    assert sap.sizes == d[f"{tag}/sizes"].tolist()
+    for k in range(K):
+        assert sap.invcovs[k].shape == invcovs[k].shape
+        if invcovs[k].size:
+            assert maxrel(sap.invcovs[k], invcovs[k]) < TOL
+    assert sap.psi.shape == d[f"{tag}/psi"].shape
+    assert maxrel(sap.psi, d[f"{tag}/psi"]) < TOL
+    assert np.array_equal(sap.e, d[f"{tag}/e"])
+    # structure of psi is integer work: the zero pattern must be identical
+    assert np.array_equal(sap.psi != 0, d[f"{tag}/psi"] != 0)
+
+
+@pytest.mark.parametrize("tag", SYN_TAGS)
+@pytest.mark.parametrize("ingest", [False, True])
+def test_closures_vs_reference_golden(blu, tag, ingest):
+    """Phi / variance / gradient / Hessian / cleanup matrix on all the m vectors of the golden
+    file, with device-side inversion and with the reference's inverses ingested."""
+    d = _load("synthetic.npz")
+    C, K, groups, invcovs = _case(d, tag)
+    L = sum(len(g) for g in groups)
+    N = C.shape[0]
+    sap = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False, invcovs=invcovs if ingest else None)
+    o = orc.SapOracle(C, K, groups, invcovs=invcovs)
+    for j in range(int(d[f"{tag}/n_m"])):
+        m = d[f"{tag}/m{j}"]; delta = float(d[f"{tag}/delta{j}"])
+        assert maxrel(sap.get_phi(m, delta), d[f"{tag}/phi{j}"]) < TOL
+        vref = float(d[f"{tag}/variance{j}"])
+        if np.isnan(vref):
+            with pytest.raises(AssertionError):
+                sap.variance(m, delta)
+        elif np.isinf(vref):
+            assert np.isinf(sap.variance(m, delta))
+        else:
+            assert abs(sap.variance(m, delta) - vref) <= TOL * abs(vref)
+        res = sap.variance_GH(m, delta)
+        assert len(res) == int(d[f"{tag}/gh_len{j}"])
+        if len(res) == 2:
+            assert np.isinf(res[0]) and res[1].shape == (L,) and np.all(np.isinf(res[1]))
+            with pytest.raises(ValueError):
+                sap.get_cleanup_matrix(m, delta)
+            continue
+        mf = m.astype(float)
+        full_rank = len(o.support(m)) == N and np.min(np.abs(mf[np.abs(mf) > 0])) > 1e-5
+        # singular / nearly singular Phi (SURVEY.md 8a'): pinv noise at the 1e-19 level is amplified
+        tol = TOL if full_rank else 1e-9
+        gv = float(d[f"{tag}/gh_var{j}"])
+        assert abs(res[0] - gv) <= TOL * abs(gv)
+        assert maxrel(res[1], d[f"{tag}/gh_grad{j}"]) < tol
+        H = res[2]
+        assert H.shape == (L, L)
+        assert maxrel(H, d[f"{tag}/gh_hess{j}"]) < tol
+        assert np.array_equal(H, H.T)                      # bit-exact symmetry, like ``hess += hess.T``
+        vn, gn, hn = sap.variance_GH(m, delta, nohess=True)
+        assert hn is None and maxrel(gn, d[f"{tag}/gh_grad{j}"]) < tol and abs(vn - gv) <= TOL * abs(gv)
+        assert maxrel(sap.get_cleanup_matrix(m, delta), d[f"{tag}/cleanup{j}"]) < tol
+        U = sap.get_cleanup_matrix(m, delta, corrected=True)
+        x = np.linalg.pinv(d[f"{tag}/phi{j}"])[0]
+        assert maxrel(U, o.ufactor(x)) < tol
+
+
+def test_ragged_groups_with_empty_class(blu):
+    d = _load("synthetic.npz")
+    C, K, groups, invcovs = _case(d, "ragged")
+    L = sum(len(g) for g in groups)
+    sap = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False)
+    m = d["ragged/m0"]
+    assert maxrel(sap.get_phi(m), d["ragged/phi0"]) < TOL
+    assert abs(sap.variance(m) - float(d["ragged/variance0"])) <= TOL * float(d["ragged/variance0"])
+    o = orc.SapOracle(C, K, groups, invcovs=invcovs)
+    v, g, h = sap.variance_GH(m)
+    vo, go, ho = o.variance_GH(m)
+    assert abs(v - vo) <= TOL * vo and maxrel(g, go) < TOL and maxrel(h, ho) < TOL
+    assert sap.invcovs[1].size == 0
+
+
+def test_tutorial_known_answers(blu):
+    d = _load("tutorial.npz")
+    N = 5
+    groups = blu.enumerate_groups(N)
+    costs = blu.group_costs(groups, d["model_costs"])
+    sap = blu.SAP(d["C"], N, groups, costs, verbose=False)
+    for a in range(2):
+        m = d[f"m{a}"]
+        v = sap.variance(m)
+        assert abs(v - float(d[f"ref_variance{a}"])) <= 1e-11 * v
+        assert abs(np.sqrt(v) - float(d[f"printed_error{a}"])) < 5e-9
+        assert m @ costs == float(d[f"printed_cost{a}"])
+        vg, g, _ = sap.variance_GH(m.astype(float), nohess=True)
+        assert abs(vg - float(d[f"ref_gh_var{a}"])) <= 1e-10 * vg
+        sup = np.abs(d[f"ref_grad{a}"]) > 1e-12 * np.abs(d[f"ref_grad{a}"]).max()
+        assert maxrel(g[sup], d[f"ref_grad{a}"][sup]) < 1e-9
+
+
+def test_hodgkin_huxley_fixture(blu):
+    """M=12, K=7, 5 outputs, cond(C) 1e9..5e10 (MOSAP batch of outputs, shared groups)."""
+    d = _load("hodgkin.npz")
+    M, K, No = int(d["M"]), int(d["K"]), int(d["n_outputs"])
+    groups = blu.enumerate_groups(M, K)
+    L = sum(len(g) for g in groups)
+    samples = d["samples"]
+    Cs = [d[f"C{n}"] for n in range(No)]
+    mos = blu.MOSAP(Cs, K, [K] * No, _copy(groups), [_copy(groups) for _ in range(No)], np.ones(L), [np.ones(L)] * No, verbose=False)
+    assert all(np.array_equal(mp, np.arange(L)) for mp in mos.mappings)
+    Vs = mos.variances(samples)
+    expect = [8.9059e-4, 1.00004e-3, 9.4788e-4, 5.4767e-4, 5.5831e-4]
+    for n in range(No):
+        # elimination-based inverses differ from SVD pinv by cond*eps (SURVEY.md section 7 hard part 1)
+        assert abs(Vs[n] - float(d[f"variance{n}"])) <= 1e-5 * Vs[n]
+        assert abs(np.sqrt(Vs[n] / Cs[n][0, 0]) - expect[n]) < 5e-8
+    # later stages alone, with the reference's inverses: exact to cond(Phi)*eps
+    inv3 = [d[f"invcovs3_{k+1}"] for k in range(K)]
+    sap = blu.SAP(Cs[3], K, _copy(groups), np.ones(L), verbose=False, invcovs=inv3)
+    assert maxrel(sap.get_phi(samples), d["phi3"]) < TOL
+    o = orc.SapOracle(Cs[3], K, groups, invcovs=inv3)
+    idx = o.support(samples)
+    cond = np.linalg.cond(d["phi3"][np.ix_(idx, idx)])
+    tol = max(TOL, 10 * cond * np.finfo(float).eps)
+    assert abs(sap.variance(samples) - float(d["variance3"])) <= tol * float(d["variance3"])
+
+
+def test_matern_ill_conditioned_fallback(blu):
+    d = _load("matern.npz")
+    C, K, groups, invcovs = _case(d, "matern")
+    L = sum(len(g) for g in groups)
+    sap = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False, invcovs=invcovs)
+    m = d["matern/m0"]
+    # cond(C_k) up to 1.5e9: the reference's SVD pinv blocks are themselves asymmetric at the
+    # 1e-10 level, so its Phi is not symmetric.  The packed layout stores (A + A^T)/2, i.e. the
+    # symmetric part -- compare with that, and check the gap to the raw Phi IS that asymmetry.
+    phi_ref = d["matern/phi0"]
+    phi = sap.get_phi(m)
+    assert maxrel(phi, 0.5 * (phi_ref + phi_ref.T)) < TOL
+    assert maxrel(phi, phi_ref) <= 1.01 * maxrel(phi_ref, phi_ref.T)
+    cond_phi = np.linalg.cond(d["matern/phi0"])
+    tol = max(TOL, 50 * cond_phi * np.finfo(float).eps)
+    v, g, h = sap.variance_GH(m)
+    assert abs(v - float(d["matern/gh_var0"])) <= tol * abs(v)
+    assert maxrel(g, d["matern/gh_grad0"]) < tol
+    # device inversion with a strict pivot threshold sends the bad groups through the Jacobi pinv
+    sap2 = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False, pivot_rtol=1e-6)
+    assert sap2.n_fallback > 0
+    for k in range(K):
+        # both are backward stable; agreement is limited by cond(C_k)*eps ~ 1e9*1e-16
+        assert maxrel(sap2.invcovs[k], invcovs[k]) < 1e-5
+    # rank-deficient covariance: pinv semantics (cutoff 1e-15 sigma_max) must hold
+    B = np.random.RandomState(0).randn(5, 3)
+    Cs = B @ B.T
+    g5 = blu.enumerate_groups(5)
+    sap3 = blu.SAP(Cs, 5, g5, np.ones(31), verbose=False)
+    assert sap3.n_fallback > 0
+    ref = np.linalg.pinv(Cs)
+    got = sap3.invcovs[4].reshape(5, 5)
+    assert maxrel(got, ref) < 1e-9
+
+
+@pytest.mark.parametrize("N,K,seed", [(10, 10, 0), (12, 5, 1), (13, 13, 2)])
+def test_random_vs_oracle(blu, N, K, seed):
+    """Fresh seeded inputs at sizes the oracle finishes in seconds (factored Hessian in the oracle)."""
+    C = orc.wishart_cov(N, seed)
+    groups = orc.enumerate_groups(N, K)
+    L = sum(len(g) for g in groups)
+    o = orc.SapOracle(C, K, groups)
+    sap = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False)
+    for k in range(K):
+        assert maxrel(sap.invcovs[k], o.invcovs[k]) < TOL
+    for m in (orc.dense_m(L, seed), orc.sparse_m(L, N, seed)):
+        full = len(o.support(m)) == N
+        tol = TOL if full else 1e-9
+        assert maxrel(sap.get_phi(m), o.get_phi(m)) < TOL
+        vo = o.variance(m)
+        assert abs(sap.variance(m) - vo) <= TOL * vo
+        v, g, h = sap.variance_GH(m)
+        vo, go, ho = o.variance_GH(m, hess_mode="factored")
+        assert abs(v - vo) <= TOL * vo
+        assert maxrel(g, go) < tol
+        assert maxrel(h, ho) < tol
+        assert np.array_equal(h, h.T)
+
+
+def test_level1_cmisc_dropins(blu):
+    """The five `_cmisc_bluest` routines, reference calling convention (in-place +=)."""
+    cm = blu.cmisc
+    N, k, q = 7, 3, 4
+    C = orc.wishart_cov(N, 5)
+    groups = orc.enumerate_groups(N, 4)
+    o = orc.SapOracle(C, 4, groups)
+    gk, gq = o.groups[k - 1], o.groups[q - 1]
+    ck, cq = o.invcovs[k - 1], o.invcovs[q - 1]
+    Lk, Lq = len(gk), len(gq)
+    P = np.linalg.pinv(o.get_phi(orc.dense_m(o.L)))
+    x = np.ascontiguousarray(P[0])
+    Lb = orc.lib()
+    rng = np.random.RandomState(3)
+    # psi
+    a = np.zeros(N * N * Lk); b = np.zeros((N * N, Lk))
+    cm.assemble_psi_c(a, N, k, Lk, gk.ravel(), ck)
+    Lb.orc_psi_class(orc._d(b), N, k, Lk, orc._l(gk), orc._d(ck))
+    assert np.array_equal(a.reshape(N * N, Lk), b)
+    assert np.array_equal(cm.assemble_psi(N, k, Lk, gk, ck), b)
+    # Phi accumulate (float and integer m), onto a non-zero start to check "+="
+    for mk in (1 + rng.rand(Lk), rng.randint(0, 9, Lk).astype(np.int64)):
+        start = rng.rand(N * N)
+        a = start.copy(); b = start.copy()
+        cm.objectiveK_c(a, N, k, Lk, mk, gk.ravel(), ck)
+        if mk.dtype == np.int64:
+            Lb.orc_phi_class_i64(orc._d(b), N, k, Lk, orc._l(mk), orc._l(gk), orc._d(ck))
+        else:
+            Lb.orc_phi_class(orc._d(b), N, k, Lk, orc._d(mk), orc._l(gk), orc._d(ck))
+        assert maxrel(a, b) < 1e-14
+    # gradient
+    a = np.zeros(Lk); b = np.zeros(Lk)
+    cm.gradK_c(a, k, Lk, gk.ravel(), ck, x)
+    Lb.orc_grad_class(orc._d(b), k, Lk, orc._l(gk), orc._d(ck), orc._d(x))
+    assert maxrel(a, b) < 1e-13
+    assert maxrel(cm.gradK(k, Lk, gk, ck, P), b) < 1e-13
+    # Hessian block
+    a = np.zeros(Lk * Lq); b = np.zeros((Lk, Lq))
+    Pf = np.ascontiguousarray(P).ravel()
+    cm.hessKQ_c(a, N, k, q, Lk, Lq, gk.ravel(), gq.ravel(), ck, cq, Pf)
+    Lb.orc_hess_block(orc._d(b), N, k, q, Lk, Lq, orc._l(gk), orc._l(gq), orc._d(ck), orc._d(cq), orc._d(Pf))
+    assert maxrel(a, b.ravel()) < 1e-12
+    assert maxrel(cm.hessKQ(k, q, Lk, Lq, gk, gq, ck, cq, P), b) < 1e-12
+    # cleanup (assignment semantics)
+    a = np.zeros(N * Lk); b = np.zeros((N, Lk))
+    cm.cleanupK_c(a, k, Lk, gk.ravel(), ck, x)
+    Lb.orc_cleanup_class(orc._d(b), k, Lk, orc._l(gk), orc._d(ck), orc._d(x))
+    assert np.array_equal(a.reshape(N, Lk), b)
+    # dtype strictness
+    with pytest.raises(TypeError):
+        cm.gradK_c(np.zeros(Lk, dtype=np.float32), k, Lk, gk.ravel(), ck, x)
+
+
+def test_pilot_covariance(blu):
+    d = _load("pilot.npz")
+    s1, S2, C = blu.pilot_covariance(d["Y"])
+    assert maxrel(s1, d["sumse"]) < TOL
+    assert maxrel(S2, d["sumsc"]) < TOL
+    assert maxrel(C, d["C_hat"]) < 1e-11
+    rng = np.random.RandomState(2)
+    for n, N in [(1, 3), (7, 8), (1000, 20), (4099, 31), (20000, 32)]:
+        Y = rng.standard_normal((n, N)) @ np.linalg.cholesky(orc.wishart_cov(N, 1)).T
+        s1, S2, C = blu.pilot_covariance(Y)
+        o1, o2, oc = orc.pilot_covariance(Y)
+        assert maxrel(s1, o1) < 1e-12 and maxrel(S2, o2) < TOL and maxrel(C, oc) < 1e-11
+        assert np.array_equal(S2, S2.T)
+
+
+def test_multi_output_mappings_and_variances(blu):
+    d = _load("enumeration.npz")
+    tag = "two_outputs"
+    K = int(d[f"{tag}/K"]); Ks = d[f"{tag}/Ks"].tolist()
+    multi = [[d[f"{tag}/multi{n}_groups{k+1}"].tolist() for k in range(Ks[n])] for n in range(2)]
+    # a1: our clique enumeration reproduces networkx's, bit-exact
+    for n in range(2):
+        mine = blu.enumerate_cliques(d[f"{tag}/adj{n}"], 4)
+        assert len(mine) == Ks[n]
+        for k in range(Ks[n]):
+            assert np.array_equal(np.array(mine[k], dtype=np.int64), d[f"{tag}/multi{n}_groups{k+1}"])
+    groups = blu.union_groups(multi)
+    for k in range(K):
+        assert np.array_equal(np.array(groups[k], dtype=np.int64).reshape(-1, k + 1), d[f"{tag}/groups{k+1}"])
+    L = sum(len(g) for g in groups)
+    Cs = [d[f"{tag}/Cwish{n}"] for n in range(2)]
+    mos = blu.MOSAP(Cs, K, Ks, _copy(groups), [_copy(mg) for mg in multi], np.ones(L),
+                    [np.ones(sum(len(g) for g in mg)) for mg in multi], verbose=False)
+    for n in range(2):
+        assert np.array_equal(mos.mappings[n], d[f"{tag}/mapping{n}"])
+    assert np.array_equal(np.array(mos.ES), d[f"{tag}/ES"])
+    m = d[f"{tag}/m"]
+    Vs = mos.variances(m)
+    assert maxrel(Vs, d[f"{tag}/variances"]) < TOL
+    vs, gs, hs = mos.variance_GH(m, nohess=True)
+    for n in range(2):
+        assert maxrel(gs[n], d[f"{tag}/grad{n}"]) < TOL and hs[n] is None
+
+
+def test_determinism(blu):
+    """Atomic-free fixed-order reductions: repeated evaluations are bit-identical."""
+    N = 12
+    C = orc.wishart_cov(N, 3)
+    groups = orc.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    sap = blu.SAP(C, N, _copy(groups), np.ones(L), verbose=False)
+    m = orc.dense_m(L, 1)
+    a = sap.variance_GH(m)
+    for _ in range(3):
+        b = sap.variance_GH(m)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(sap.get_phi(m), sap.get_phi(m))
