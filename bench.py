@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the BLUEST sample-allocation hot path on B200.
+
+Metric (BASELINE.json): Psi+grad+Hessian evaluations/s at 15 models (all 32767 groups).
+One "step" = one full evaluation for one sample vector m: Phi(m) assembly over all groups,
+N x N pseudo-inverse + variance, gradient, U/V factors and the dense (L,L) FP64 Hessian.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--models 15] [--impl ours|reference]
+
+* value        device-resident throughput: m already in HBM, results left in HBM, K steps
+               back to back on the context's stream, timed with CUDA events on that stream.
+* e2e          the same evaluation through the reference-facing API ``SAP.variance_GH(m)``
+               with HOST buffers: H2D of m from pinned memory, D2H of variance, gradient and the
+               dense Hessian into pinned memory, all inside the timed region.
+* roofline     the dominant kernel (blu_hess_kernel): algorithmic bytes 8 L^2 per launch
+                / its average launch duration from per-launch CUDA events recorded
+               inside the timed loop, against the measured HBM copy peak (MEASURED_PEAKS.json).
+* cpu_baseline the reference's own native loops (oracle/_ref, compiled from the reference's
+               cmisc.cpp) timed on the host cores on a bounded sample of the same workload.
+* N > 1        budget sweep of independent SAP instances split across ranks (BASELINE config 3):
+               one context per GPU, different m per rank, no data-path collective ("weak").
+
+--impl reference times only the CPU reference arm and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "Psi+grad+Hessian evals/s at L=15 (32767 groups)"
+UNIT = "evals/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p_ in zip(sm, pw) if p_ > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm
+# ---------------------------------------------------------------------------------------------
+def _load_ref_cmisc():
+    import importlib
+    d = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isdir(d) and any(f.startswith("_cmisc_bluest") and f.endswith(".so") for f in os.listdir(d)):
+        if d not in sys.path:
+            sys.path.insert(0, d)
+        try:
+            return importlib.import_module("_cmisc_bluest"), "reference"
+        except Exception:
+            pass
+    return None, "port"
+
+
+def _hess_block_job(args):
+    """Time one (k,q) sub-block of the reference Hessian loop in a worker process."""
+    kind, N, k, q, gk, gq, ck, cq, P = args
+    Lk, Lq = len(gk), len(gq)
+    out = np.zeros(Lk * Lq)
+    if kind == "reference":
+        cm, _ = _load_ref_cmisc()
+        t0 = time.perf_counter()
+        cm.hessKQ_c(out, N, k, q, Lk, Lq, gk.ravel(), gq.ravel(), ck, cq, P)
+        dt = time.perf_counter() - t0
+    else:
+        import oracle as orc
+        L = orc.lib()
+        o2 = out.reshape(Lk, Lq)
+        t0 = time.perf_counter()
+        L.orc_hess_block(orc._d(o2), N, k, q, Lk, Lq, orc._l(gk), orc._l(gq), orc._d(ck), orc._d(cq), orc._d(P))
+        dt = time.perf_counter() - t0
+    return (k, q, Lk * Lq * k * k * q * q, dt)
+
+
+class CpuReference:
+    """The reference's CPU path for one evaluation: psi@m (BLAS), two N x N pinv,
+    the gradK_c loops over all classes, and the K^2 hessKQ_c blocks.  The Hessian loop is ~2 h on
+    one core at N=15, so it is timed on sampled (k,q) sub-blocks and extrapolated by inner-iteration
+    count; the blocks are farmed over all host cores (one process each), which the single-threaded
+    reference itself does not do -- the baseline is generous."""
+
+    def __init__(self, N, seed=0, work=5.0e8):
+        import oracle as orc
+        self.orc = orc
+        self.N = N
+        self.C = orc.wishart_cov(N, seed)
+        self.groups = orc.enumerate_groups(N)
+        t0 = time.perf_counter()
+        self.o = orc.SapOracle(self.C, N, self.groups)
+        self.setup_s = time.perf_counter() - t0
+        self.L = self.o.L
+        self.m = orc.dense_m(self.L, seed)
+        self.cm, self.kind = _load_ref_cmisc()
+        self.work = work
+        self.cores = os.cpu_count() or 1
+        self.psi = self.o.psi
+
+    def _small_parts(self):
+        o, N, m = self.o, self.N, self.m
+        t0 = time.perf_counter()
+        phi = (self.psi @ m).reshape(N, N)
+        t_phi = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        P = np.linalg.pinv(phi)
+        idx = o.support(m)
+        np.linalg.pinv(phi[np.ix_(idx, idx)])
+        t_pinv = time.perf_counter() - t0
+        x = np.ascontiguousarray(P[0])
+        t0 = time.perf_counter()
+        for k in range(1, N + 1):
+            Lk = o.sizes[k]
+            g = np.zeros(Lk)
+            if self.kind == "reference":
+                self.cm.gradK_c(g, k, Lk, o.groups[k - 1].ravel(), o.invcovs[k - 1], x)
+            else:
+                self.orc.lib().orc_grad_class(self.orc._d(g), k, Lk, self.orc._l(o.groups[k - 1]), self.orc._d(o.invcovs[k - 1]), self.orc._d(x))
+        t_grad = time.perf_counter() - t0
+        return t_phi, t_pinv, t_grad, np.ascontiguousarray(P).ravel()
+
+    def sample(self):
+        """One bounded sample -> estimated seconds per full evaluation and a description."""
+        import multiprocessing as mp
+        o, N = self.o, self.N
+        t_phi, t_pinv, t_grad, Pf = self._small_parts()
+        # sampled (k,q) pairs around the bulk of the work (k,q ~ N/2 .. 2N/3) plus the extremes
+        ks = sorted(set(max(1, min(N, v)) for v in (N // 5, N // 3, N // 2, N // 2 + 1, (2 * N) // 3, (4 * N) // 5)))
+        pairs = [(k, q) for k in ks for q in ks if k <= q]
+        jobs = []
+        for (k, q) in pairs:
+            # ~self.work inner iterations per sampled block (about half a second of one core)
+            b = int(max(8, np.sqrt(self.work / float(k * k * q * q))))
+            gk = o.groups[k - 1][:b]; gq = o.groups[q - 1][:b]
+            ck = o.invcovs[k - 1][:len(gk) * k * k]; cq = o.invcovs[q - 1][:len(gq) * q * q]
+            jobs.append((self.kind, N, k, q, np.ascontiguousarray(gk), np.ascontiguousarray(gq), ck, cq, Pf))
+        nproc = min(self.cores, len(jobs))
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(nproc) as pool:
+            res = pool.map(_hess_block_job, jobs)
+        wall = time.perf_counter() - t0
+        rate = {(k, q): it / dt for (k, q, it, dt) in res}           # inner iterations / s / core
+        for (k, q) in list(rate):
+            rate[(q, k)] = rate[(k, q)]
+        # extrapolate every (k,q) block with the rate of the nearest sampled pair
+        total_it, t_hess_1core = 0.0, 0.0
+        for k in range(1, N + 1):
+            for q in range(1, N + 1):
+                it = float(o.sizes[k]) * o.sizes[q] * k * k * q * q
+                kk = min(ks, key=lambda v: abs(v - k)); qq = min(ks, key=lambda v: abs(v - q))
+                total_it += it
+                t_hess_1core += it / rate[(kk, qq)]
+        t_hess = t_hess_1core / self.cores          # blocks are independent: ideal spread over the cores
+        t_eval = t_phi + t_pinv + t_grad + t_hess
+        desc = ("N=%d: psi@m %.1f ms, 2x pinv %.2f ms, gradK_c all classes %.1f ms measured in full; hessKQ_c timed on %d "
+                "sampled (k,q) sub-blocks of ~%.0e inner iterations each (%.1f s wall on %d processes, %.2e inner it/s/core) and extrapolated "
+                "to %.3e inner iterations = %.0f s on 1 core, %.0f s spread over %d cores"
+                % (N, 1e3 * t_phi, 1e3 * t_pinv, 1e3 * t_grad, len(jobs), self.work, wall, nproc,
+                   total_it / t_hess_1core, total_it, t_hess_1core, t_hess, self.cores))
+        return t_eval, desc, {"t_phi": t_phi, "t_pinv": t_pinv, "t_grad": t_grad, "t_hess_1core": t_hess_1core}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref = CpuReference(args.models, seed=0)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        ref.sample()
+    ts, desc = [], ""
+    for _ in range(args.steps):
+        t, desc, _ = ref.sample()
+        ts.append(t)
+    t_eval = float(np.median(ts))
+    val = 1.0 / t_eval
+    out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * t_eval, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "impl": "reference",
+           "config": workload_config(args.models, ref.L),
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": desc},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def workload_config(N, L):
+    return {"workload": "single-output MLBLUE, %d models, all %d groups (K=N), Wishart covariance seed 0, m=1+10*rand: "
+                        "Phi + pinv + variance + gradient + dense (L,L) Hessian per evaluation" % (N, L),
+            "models": N, "groups": int(L), "hessian": "dense", "instances": "one sample vector per step per GPU (budget sweep across GPUs)",
+            "l2_policy": "every step streams the %.2f GB Hessian (>> 126 MB L2) through HBM, evicting all inputs" % (8.0 * L * L / 1e9)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import bluest_b200 as blu
+    import oracle as orc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if blu.device_count() <= 0:
+        raise RuntimeError("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    N = args.models
+    C = orc.wishart_cov(N, 0)
+    groups = blu.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    model_costs = 2.0 ** (N - np.arange(N))
+    costs = blu.group_costs(groups, model_costs)
+    t0 = time.perf_counter()
+    sap = blu.SAP(C, N, groups, costs, verbose=False, device=local)
+    setup_s = time.perf_counter() - t0
+
+    # a small pool of sample vectors per rank (sweep instances), resident in HBM
+    npool = 4
+    ms_host = [orc.dense_m(L, 100 * rank + j) for j in range(npool)]
+    ms_dev = [torch.from_numpy(m).to("cuda:%d" % local) for m in ms_host]
+    ext = torch.cuda.ExternalStream(sap.stream(), device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for i in range(args.warmup):
+        sap.eval_device(ms_dev[i % npool], 0.0, grad=True, hess=True)
+    sap.sync()
+    var0, flags0 = sap.last_result()
+    launches_per_eval = sap.last_launches()
+    sap.timing_log(args.steps)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for i in range(args.steps):
+        sap.eval_device(ms_dev[i % npool], 0.0, grad=True, hess=True)
+    e1.record(ext)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    phases = sap.timing_read()                     # (steps, 4) ms
+    sap.timing_log(0)
+
+    # ---- end to end through the reference-facing closure ----------------------------------------
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    pinned_m = [torch.from_numpy(m).pin_memory() for m in ms_host]
+    for i in range(2):
+        res = sap.variance_GH(pinned_m[i % npool].numpy())
+    del res
+    barrier()
+    t0 = time.perf_counter()
+    chk = 0.0
+    for i in range(e2e_steps):
+        v, g, H = sap.variance_GH(pinned_m[i % npool].numpy())
+        chk += v
+        del H
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        hess_ms = float(np.mean(phases[:, 2]))
+        algo_bytes = 8.0 * L * L
+        achieved = algo_bytes / (hess_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "hess_kernel_traffic.json")
+        if os.path.isfile(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        value = world * args.steps / (dev_ms_max * 1e-3)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "impl": "ours",
+               "config": workload_config(N, L),
+               "roofline": {"bound": "hbm", "kernel": "blu_hess_kernel<4,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                            "avg_launch_ms": hess_ms, "peak_source": peak_src,
+                            "whole_eval_frac": (8.0 * L * L + 16.0 * N * L + 16.0 * 8 * N * (N + 1) * 2 ** (N - 2) + 24.0 * L)
+                                               / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak},
+               "phases_ms": {"phi_pinv": float(np.mean(phases[:, 0])), "grad_uv": float(np.mean(phases[:, 1])),
+                             "hessian": hess_ms, "eval_total": float(np.mean(phases[:, 3]))},
+               "e2e": {"value": world * e2e_steps / e2e_s_max, "unit": UNIT, "steps": e2e_steps,
+                       "h2d_bytes_per_step": 8 * L, "d2h_bytes_per_step": 8 * L * L + 8 * L + 8,
+                       "api": "SAP.variance_GH(m) -> (var, grad (L,), hess (L,L)) numpy, pinned host buffers"},
+               "gpu_launches": launches_per_eval * args.steps,
+               "launches_per_eval": launches_per_eval,
+               "clocks": clocks, "setup_s": setup_s, "variance_check": var0}
+        if world == 1 and not args.no_cpu:
+            try:
+                ref = CpuReference(N, seed=0)
+                t_eval, desc, _ = ref.sample()
+                out["cpu_baseline"] = {"value": 1.0 / t_eval, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": desc}
+            except Exception as ex:       # the baseline must never take the GPU number down with it
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+        print(json.dumps(out))
+    sap.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--models", type=int, default=15, help="number of models N (BASELINE.json calls it L)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = min(args.steps, 5)
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

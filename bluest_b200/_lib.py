@@ -41,6 +41,8 @@ SIGNATURES = {
     "blu_ctx_last_result": (c_int, [p_void, p_dbl, ctypes.POINTER(c_uint)]),
     "blu_ctx_last_timing": (c_int, [p_void, ctypes.POINTER(ctypes.c_float)]),
     "blu_ctx_last_launches": (c_int, [p_void]),
+    "blu_ctx_timing_log": (c_int, [p_void, c_int]),
+    "blu_ctx_timing_read": (c_int, [p_void, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(c_int)]),
     "blu_ctx_set_slice": (c_int, [p_void, c_i64, c_i64]),
     "blu_shard_phi": (c_int, [p_void, p_void]),
     "blu_shard_finish": (c_int, [p_void, c_dbl, c_int, c_int]),
@@ -52,7 +54,6 @@ SIGNATURES = {
     "blu_cleanupK_c": (c_int, [p_dbl, c_int, c_int, c_int, p_i64, p_dbl, p_dbl]),
     "blu_gradK_c": (c_int, [p_dbl, c_int, c_int, c_int, p_i64, p_dbl, p_dbl]),
     "blu_hessKQ_c": (c_int, [p_dbl, c_int, c_int, c_int, c_int, c_int, p_i64, p_i64, p_dbl, p_dbl, p_dbl]),
-    # helpers outside the header's reference-facing surface
     "blu_host_alloc": (c_int, [ctypes.c_size_t, ctypes.POINTER(p_void)]),
     "blu_host_free": (c_int, [p_void]),
 }

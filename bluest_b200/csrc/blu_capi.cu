@@ -76,6 +76,8 @@ struct blu_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
     int launches = 0;
+    std::vector<cudaEvent_t> evlog;    // optional per-evaluation event log (4 events per evaluation)
+    int evlog_n = 0;
 };
 
 static int use(blu_ctx *c)
@@ -131,6 +133,7 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     cudaFree(c->d_hdr);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->evlog) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return BLU_OK;
@@ -455,8 +458,9 @@ static void launch_hess_t(blu_ctx *c, bool sym, const double *Ua, long long Lrow
     }
     const int nTc = (int)((c->L + BLU_HT - 1) / BLU_HT);
     if (sym) {
-        const long long pairs = (long long)nTc * (nTc + 1) / 2;
-        blu_hess_kernel<NCH, true><<<(unsigned)pairs, 128, BLU_HESS_SMEM, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
+        const int nB = (nTc + BLU_HSB - 1) / BLU_HSB;
+        dim3 grid(BLU_HSB * BLU_HSB, (unsigned)((long long)nB * (nB + 1) / 2));
+        blu_hess_kernel<NCH, true><<<grid, 128, BLU_HESS_SMEM, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
     } else {
         const int nTr = (int)((Lrows + BLU_HT - 1) / BLU_HT);
         dim3 grid((unsigned)nTc, (unsigned)nTr);
@@ -495,15 +499,50 @@ extern "C" int blu_eval_device(blu_ctx *c, const double *d_m, double delta, int 
     if (c->lo != 0 || c->hi != c->L) return fail(BLU_ERR_STATE, "context owns a slice: use the blu_shard_* calls");
     if (!d_m) d_m = c->d_m;
     c->launches = 0;
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    cudaEvent_t *ev = c->ev;
+    if ((size_t)(c->evlog_n + 1) * 4 <= c->evlog.size()) { ev = c->evlog.data() + (size_t)c->evlog_n * 4; c->evlog_n++; }
+    CUDA_TRY(cudaEventRecord(ev[0], c->stream));
     rc = launch_phi(c, d_m, delta, 1);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    CUDA_TRY(cudaEventRecord(ev[1], c->stream));
     if (want_grad || want_hess) { rc = launch_grad(c, want_hess); if (rc) return rc; }
-    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    CUDA_TRY(cudaEventRecord(ev[2], c->stream));
     if (want_hess) { rc = launch_hess(c, true); if (rc) return rc; }
-    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    c->timed = true;
+    CUDA_TRY(cudaEventRecord(ev[3], c->stream));
+    c->timed = (ev == c->ev);
+    return BLU_OK;
+}
+
+// Per-evaluation event log: after blu_ctx_timing_log(ctx, cap) the next `cap` calls of
+// blu_eval_device record their four phase events into a log instead of the single "last" slot, so
+// a benchmark can time every kernel of a long run without a host sync inside the timed region.
+extern "C" int blu_ctx_timing_log(blu_ctx *c, int capacity)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (capacity < 0) return fail(BLU_ERR_ARG, "negative capacity");
+    for (auto &e : c->evlog) if (e) cudaEventDestroy(e);
+    c->evlog.assign((size_t)capacity * 4, nullptr);
+    for (auto &e : c->evlog) CUDA_TRY(cudaEventCreate(&e));
+    c->evlog_n = 0;
+    return BLU_OK;
+}
+
+// ms: (n,4) floats  [phi+pinv, grad/U, Hessian, total] per logged evaluation; *n = evaluations logged.
+extern "C" int blu_ctx_timing_read(blu_ctx *c, float *ms, int *n)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!ms || !n) return fail(BLU_ERR_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < c->evlog_n; ++i) {
+        cudaEvent_t *ev = c->evlog.data() + (size_t)i * 4;
+        CUDA_TRY(cudaEventElapsedTime(&ms[4 * i + 0], ev[0], ev[1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[4 * i + 1], ev[1], ev[2]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[4 * i + 2], ev[2], ev[3]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[4 * i + 3], ev[0], ev[3]));
+    }
+    *n = c->evlog_n;
     return BLU_OK;
 }
 

@@ -9,7 +9,7 @@
 // L2-resident U / V rows (the K dimension is only NP = 4*NCH <= 32, so there is no K loop to
 // pipeline), accumulators staged through shared memory so that every global store instruction
 // writes whole 128-byte lines (32 lanes x 16 B = one 512 B row segment), streaming (.cs).
-// SYM = true: only tiles I <= J are computed; the tile is staged a second time transposed and
+// SYM = true: only tiles I <= J are computed; the tile is staged a second time, transposed, and
 // written to (J, I) as well, so the tensor pipe does half the work and H is exactly symmetric
 // bit for bit, as the reference's ``hess += hess.T`` makes it.  Diagonal tiles are symmetrised.
 // SYM = false: rectangular row panel (U = the rank's own Lrows rows, V = all Lcols rows, H = the
@@ -22,6 +22,7 @@
 #include "blu_common.cuh"
 
 #define BLU_HT 64              // tile edge
+#define BLU_HSB 16             // super-block edge in tiles (rasterisation)
 #define BLU_HLDN 72            // staging pitch, normal tile   (72*8 B: rows 2 apart never share a bank phase)
 #define BLU_HLDT 66            // staging pitch, transposed tile
 #define BLU_HESS_SMEM ((BLU_HT * BLU_HLDN + BLU_HT * BLU_HLDT) * 8)
@@ -44,17 +45,24 @@ blu_hess_kernel(const double *__restrict__ U, const double *__restrict__ V, long
 
     int I, J;
     if (SYM) {
-        // linear id over the upper triangle, row-major: row I holds nT - I tiles
-        const long long pid = blockIdx.x;
-        const double nt = (double)nT;
-        int i = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)pid)) * 0.5);
-        if (i < 0) i = 0;
-        if (i > nT - 1) i = nT - 1;
-        // first(i) = i*nT - i(i-1)/2
-        while ((long long)i * nT - (long long)i * (i - 1) / 2 > pid) --i;
-        while ((long long)(i + 1) * nT - (long long)(i + 1) * i / 2 <= pid) ++i;
-        I = i;
-        J = i + (int)(pid - ((long long)i * nT - (long long)i * (i - 1) / 2));
+        // Rasterisation: tiles are visited super-block by super-block (BLU_HSB x BLU_HSB tiles =
+        // 1024 x 1024 entries), so that BOTH the (I,J) tile and its transposed image (J,I) land in a
+        // compact 2-D region that is completely written within a short time window: the L2 then
+        // evicts whole multi-KB row runs instead of isolated 512-byte chunks (DRAM page locality).
+        // blockIdx.y = super-block pair (bi <= bj, row-major over the triangle), blockIdx.x = tile
+        // inside the super-block.
+        const int nB = (nT + BLU_HSB - 1) / BLU_HSB;
+        const long long pid = blockIdx.y;
+        const double nb = (double)nB;
+        int bi = (int)floor(((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)pid)) * 0.5);
+        if (bi < 0) bi = 0;
+        if (bi > nB - 1) bi = nB - 1;
+        while ((long long)bi * nB - (long long)bi * (bi - 1) / 2 > pid) --bi;
+        while ((long long)(bi + 1) * nB - (long long)(bi + 1) * bi / 2 <= pid) ++bi;
+        const int bj = bi + (int)(pid - ((long long)bi * nB - (long long)bi * (bi - 1) / 2));
+        I = bi * BLU_HSB + (int)(blockIdx.x / BLU_HSB);
+        J = bj * BLU_HSB + (int)(blockIdx.x % BLU_HSB);
+        if (I >= nT || J >= nT || I > J) return;
     } else {
         J = blockIdx.x;
         I = tI0 + blockIdx.y;
@@ -94,7 +102,9 @@ blu_hess_kernel(const double *__restrict__ U, const double *__restrict__ V, long
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) blu_dmma(c[rb][cb][0], c[rb][cb][1], a[rb][kc], b[cb][kc]);
 
+    // ---- epilogue: registers -> shared staging -> whole-line streaming stores -------------------
     const bool offdiag = SYM && (I != J);
+    const bool diag = SYM && (I == J);
 #pragma unroll
     for (int rb = 0; rb < 4; ++rb)
 #pragma unroll
@@ -108,28 +118,35 @@ blu_hess_kernel(const double *__restrict__ U, const double *__restrict__ V, long
             }
         }
     __syncthreads();
-
     const long long gcolN = (long long)J * BLU_HT + 2 * lane;
     const long long gcolT = (long long)I * BLU_HT + 2 * lane;
-    const bool diag = SYM && (I == J);
-    for (int r = w; r < BLU_HT; r += 4) {
-        const long long grow = (long long)I * BLU_HT + r;
-        if (grow < Lrows && gcolN < ldH) {
-            double2 v = *reinterpret_cast<const double2 *>(sN + r * BLU_HLDN + 2 * lane);
-            if (diag) {
+    if (!diag) {
+#pragma unroll 4
+        for (int r = w; r < BLU_HT; r += 4) {
+            const long long grow = (long long)I * BLU_HT + r;
+            if (grow < Lrows && gcolN < ldH)
+                __stcs(reinterpret_cast<double2 *>(H + grow * ldH + gcolN),
+                       *reinterpret_cast<const double2 *>(sN + r * BLU_HLDN + 2 * lane));
+        }
+    } else {
+        // diagonal tile: symmetrise so that H == H^T bit for bit (``hess += hess.T``, misc.py:503)
+        for (int r = w; r < BLU_HT; r += 4) {
+            const long long grow = (long long)I * BLU_HT + r;
+            if (grow < Lrows && gcolN < ldH) {
+                double2 v = *reinterpret_cast<const double2 *>(sN + r * BLU_HLDN + 2 * lane);
                 v.x = 0.5 * (v.x + sN[(2 * lane) * BLU_HLDN + r]);
                 v.y = 0.5 * (v.y + sN[(2 * lane + 1) * BLU_HLDN + r]);
+                __stcs(reinterpret_cast<double2 *>(H + grow * ldH + gcolN), v);
             }
-            __stcs(reinterpret_cast<double2 *>(H + grow * ldH + gcolN), v);
         }
     }
     if (offdiag) {
+#pragma unroll 4
         for (int r = w; r < BLU_HT; r += 4) {
             const long long grow = (long long)J * BLU_HT + r;
-            if (grow < Lcols && gcolT < ldH) {
-                const double2 v = *reinterpret_cast<const double2 *>(sT + r * BLU_HLDT + 2 * lane);
-                __stcs(reinterpret_cast<double2 *>(H + grow * ldH + gcolT), v);
-            }
+            if (grow < Lcols && gcolT < ldH)
+                __stcs(reinterpret_cast<double2 *>(H + grow * ldH + gcolT),
+                       *reinterpret_cast<const double2 *>(sT + r * BLU_HLDT + 2 * lane));
         }
     }
 }

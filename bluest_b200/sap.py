@@ -170,6 +170,17 @@ class SAP(object):
         check(lib().blu_ctx_last_timing(self._ctx, ms))
         return {"phi_pinv_ms": ms[0], "grad_ms": ms[1], "hess_ms": ms[2], "total_ms": ms[3]}
 
+    def timing_log(self, capacity):
+        """Log the phase events of the next ``capacity`` device evaluations (no sync in between)."""
+        check(lib().blu_ctx_timing_log(self._ctx, int(capacity)))
+
+    def timing_read(self):
+        """(n,4) array of ms: [phi+pinv, grad/U, Hessian, total] per logged evaluation."""
+        cap = 4096
+        buf = (ctypes.c_float * (4 * cap))(); n = ctypes.c_int(0)
+        check(lib().blu_ctx_timing_read(self._ctx, buf, ctypes.byref(n)))
+        return np.array(buf[:4 * n.value], dtype=np.float64).reshape(n.value, 4)
+
     def last_launches(self):
         return int(lib().blu_ctx_last_launches(self._ctx))
 

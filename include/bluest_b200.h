@@ -24,6 +24,7 @@
 #ifndef BLUEST_B200_H
 #define BLUEST_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -121,6 +122,11 @@ int blu_ctx_last_result(blu_ctx *ctx, double *var, unsigned *flags);
 /* Time the device part of the last blu_eval_device call (CUDA events on the context's stream):
  * ms[0]=Phi+pinv, ms[1]=grad/U, ms[2]=Hessian, ms[3]=total. */
 int blu_ctx_last_timing(blu_ctx *ctx, float *ms);
+/* Per-evaluation event log: the next `capacity` blu_eval_device calls record their phase events into
+ * a log (no host sync inside a timed loop); blu_ctx_timing_read synchronises and returns (n,4)
+ * floats [phi+pinv, grad/U, Hessian, total] in ms. */
+int blu_ctx_timing_log(blu_ctx *ctx, int capacity);
+int blu_ctx_timing_read(blu_ctx *ctx, float *ms, int *n);
 /* Number of kernels the last evaluation launched. */
 int blu_ctx_last_launches(blu_ctx *ctx);
 
@@ -136,6 +142,11 @@ int blu_ctx_set_slice(blu_ctx *ctx, int64_t lo, int64_t hi);
 int blu_shard_phi(blu_ctx *ctx, const double *d_m);
 int blu_shard_finish(blu_ctx *ctx, double delta, int want_grad, int want_uv);
 int blu_shard_hess(blu_ctx *ctx);
+
+/* Page-locked host memory for large results (the dense Hessian): pageable destinations make
+ * the D2H copy several times slower. */
+int blu_host_alloc(size_t bytes, void **out);
+int blu_host_free(void *p);
 
 /* ------------------------------------------------------------------------------------------
  * Kernel (4): pilot-sample covariance (blue_fn.py:159-167, blue_models.py:333).
