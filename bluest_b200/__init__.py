@@ -11,7 +11,8 @@ from .sap import SAP                                    # noqa: F401
 from .mosap import MOSAP, BLUESTError                   # noqa: F401
 from .pilot import pilot_covariance                     # noqa: F401
 from . import cmisc                                     # noqa: F401
+from .dist import ShardedEvaluator, GpuEngine          # noqa: F401
 
 __all__ = ["SAP", "MOSAP", "BLUESTError", "BluError", "pilot_covariance", "cmisc", "enumerate_groups",
            "enumerate_cliques", "union_groups", "group_costs", "indicator_ES", "mappings", "balanced_slices",
-           "device_count", "lib"]
+           "device_count", "lib", "ShardedEvaluator", "GpuEngine"]

@@ -224,7 +224,7 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
 
     // launch geometry: enough warps to cover the groups, capped at a few CTAs per SM
     const long long want = (L + BLU_PHI_WARPS * 4 - 1) / (BLU_PHI_WARPS * 4);
-    c->grid_phi = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->nsm * 4));
+    c->grid_phi = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->nsm * 2));
     c->grid_grad = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->nsm * 8));
 
     const size_t NN = (size_t)N * N;

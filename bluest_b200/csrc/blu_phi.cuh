@@ -21,7 +21,7 @@
 #include "blu_common.cuh"
 #include "blu_jacobi.cuh"
 
-#define BLU_PHI_WARPS 8
+#define BLU_PHI_WARPS 16
 
 struct BluEvalHeader {          // small device-side status block of a context
     unsigned supp;              // support mask (OR)
@@ -91,6 +91,67 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N,
     }
 }
 
+// Block-parallel in-place Gauss-Jordan inverse of the SPD n x n matrix in A (ld BLU_JLD), ping-pong
+// with B; one __syncthreads per pivot.  Returns (uniformly) false as soon as a pivot falls below
+// tol x its original diagonal entry (rank-deficient / indefinite): the caller then takes the
+// Jacobi pseudo-inverse.  On success the inverse is in the buffer returned through *out.
+__device__ __forceinline__ bool blu_block_gj(double *A, double *B, const double *diag0, int n, double tol,
+                                             double **out, int tid, int nthr)
+{
+    double *src = A, *dst = B;
+    for (int p = 0; p < n; ++p) {
+        const double piv = src[p * BLU_JLD + p];
+        if (!(piv > tol * diag0[p])) return false;            // same value in every thread
+        const double d = 1.0 / piv;
+        for (int t = tid; t < n * n; t += nthr) {
+            const int r = t / n, c = t - r * n;
+            const double arp = src[r * BLU_JLD + p], apc = src[p * BLU_JLD + c];
+            double v;
+            if (r == p) v = (c == p) ? d : apc * d;
+            else if (c == p) v = -(arp * d);
+            else v = fma(-(arp * d), apc, src[r * BLU_JLD + c]);
+            dst[r * BLU_JLD + c] = v;
+        }
+        __syncthreads();
+        double *tmp = src; src = dst; dst = tmp;
+    }
+    *out = src;
+    return true;
+}
+
+// pinv of the sub-block Phi[idx, idx] (idx: ns model ids) into P (ld BLU_JLD, ns x ns).
+// Fast path: Gauss-Jordan (the block is SPD and well conditioned in every regular evaluation);
+// fallback: Jacobi eigen pseudo-inverse with numpy's cutoff.  Returns the sweeps used (0 = fast path).
+__device__ __forceinline__ int blu_block_pinv(const double *phi, int N, const int *idx, int ns, double *A, double *V,
+                                              double *P, double *diag0, BluJacobiScratch *js, int tid, int nthr)
+{
+    for (int t = tid; t < ns * ns; t += nthr) {
+        const int r = t / ns, c = t - r * ns;
+        A[r * BLU_JLD + c] = phi[idx[r] * N + idx[c]];
+    }
+    if (tid < ns) diag0[tid] = phi[idx[tid] * N + idx[tid]];
+    __syncthreads();
+    double *res = nullptr;
+    if (blu_block_gj(A, V, diag0, ns, 1.0e-12, &res, tid, nthr)) {
+        for (int t = tid; t < ns * ns; t += nthr) {
+            const int r = t / ns, c = t - r * ns;
+            const int lo = r < c ? r : c, hi = r < c ? c : r;
+            P[r * BLU_JLD + c] = res[lo * BLU_JLD + hi];       // exactly symmetric
+        }
+        __syncthreads();
+        return 0;
+    }
+    __syncthreads();
+    const int n2 = ns + (ns & 1);
+    for (int t = tid; t < n2 * n2; t += nthr) {
+        const int r = t / n2, c = t - r * n2;
+        A[r * BLU_JLD + c] = (r < ns && c < ns) ? phi[idx[r] * N + idx[c]] : 0.0;
+    }
+    __syncthreads();
+    blu_sym_pinv(A, V, n2, js, P, BLU_JLD, ns, 1.0e-15, tid, nthr);
+    return js->sweeps;
+}
+
 #define BLU_FIN_THREADS 512
 #define BLU_FIN_SEG 8
 
@@ -106,7 +167,9 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
     extern __shared__ double red[];              // BLU_FIN_SEG x N*N staging for the partial sums
     __shared__ BluJacobiScratch js;
     __shared__ int sidx[BLU_JMAX];
+    __shared__ double diag0[BLU_JMAX];
     __shared__ int ns;
+    __shared__ unsigned amask;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int NN = N * N;
 
@@ -176,36 +239,53 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
     if ((supp & all) != all) flags |= BLU_FLAG_PARTIAL;
 
     // ---- full pseudo-inverse (misc.py:487) ----
-    const int n = N + (N & 1);
-    for (int t = tid; t < n * n; t += nthr) {
-        const int r = t / n, c = t - r * n;
-        A[r * BLU_JLD + c] = (r < N && c < N) ? phi[r * N + c] : 0.0;
+    // Rows/columns of Phi that are entirely zero (models in no group with m_i != 0) split off as a
+    // zero block: pinv([[A,0],[0,0]]) = [[pinv(A),0],[0,0]].  The remaining "active" block is SPD
+    // in every regular evaluation and is inverted by Gauss-Jordan; Jacobi only if that fails.
+    if (tid < 32) {
+        bool nz = false;
+        if (tid < N) for (int c = 0; c < N; ++c) nz = nz || (phi[tid * N + c] != 0.0);
+        const unsigned am = __ballot_sync(BLU_FULL, nz);
+        if (tid == 0) {
+            int cnt = 0;
+            for (int a = 0; a < N; ++a) if (am >> a & 1u) sidx[cnt++] = a;
+            ns = cnt;
+            amask = am;
+        }
     }
     __syncthreads();
-    blu_sym_pinv(A, V, n, &js, pinv, N, N, 1.0e-15, tid, nthr);
-    for (int e = tid; e < NN; e += nthr) S[e] = 2.0 * pinv[e];
-    if (tid < N) xrow[tid] = pinv[tid];
-    if (tid == 0) { hdr->scal[2] = (double)js.sweeps; hdr->scal[3] = js.lmax; hdr->scal[4] = pinv[0]; }
+    const int na = ns;
+    const unsigned active = amask;
+    if (tid == 0) js.lmax = 0.0;
+    int sweeps = blu_block_pinv(phi, N, sidx, na, A, V, Ph, diag0, &js, tid, nthr);
+    for (int e = tid; e < NN; e += nthr) {
+        const int r = e / N, c = e - r * N;
+        double v = 0.0;
+        if ((active >> r & 1u) && (active >> c & 1u))
+            v = Ph[__popc(active & ((1u << r) - 1u)) * BLU_JLD + __popc(active & ((1u << c) - 1u))];
+        pinv[e] = v;
+        S[e] = 2.0 * v;
+        if (r == 0) xrow[c] = v;
+    }
     __syncthreads();
+    if (tid == 0) { hdr->scal[2] = (double)sweeps; hdr->scal[3] = js.lmax; hdr->scal[4] = pinv[0]; }
 
     // ---- variance on the support sub-block (misc.py:489-490) ----
-    if (!(flags & BLU_FLAG_PARTIAL)) {
-        if (tid == 0) { hdr->scal[0] = pinv[0]; hdr->flags = flags; }
+    const unsigned sup = supp & all;
+    if (sup == (active & all)) {
+        // pinv(Phi[idx,idx])[0,0] is the (first supported model) diagonal entry of the block above
+        const int s0 = sup ? __ffs(sup) - 1 : 0;
+        if (tid == 0) { hdr->scal[0] = sup ? pinv[s0 * N + s0] : INFINITY; hdr->flags = flags; }
         return;
     }
+    __syncthreads();
     if (tid == 0) {
         int cnt = 0;
-        for (int a = 0; a < N; ++a) if (supp >> a & 1u) sidx[cnt++] = a;
+        for (int a = 0; a < N; ++a) if (sup >> a & 1u) sidx[cnt++] = a;
         ns = cnt;
     }
     __syncthreads();
     const int nsub = ns;
-    const int n2 = nsub + (nsub & 1);
-    for (int t = tid; t < n2 * n2; t += nthr) {
-        const int r = t / n2, c = t - r * n2;
-        A[r * BLU_JLD + c] = (r < nsub && c < nsub) ? phi[sidx[r] * N + sidx[c]] : 0.0;
-    }
-    __syncthreads();
-    blu_sym_pinv(A, V, n2, &js, Ph, BLU_JLD, nsub > 0 ? 1 : 0, 1.0e-15, tid, nthr);
+    if (nsub > 0) blu_block_pinv(phi, N, sidx, nsub, A, V, Ph, diag0, &js, tid, nthr);
     if (tid == 0) { hdr->scal[0] = nsub > 0 ? Ph[0] : INFINITY; hdr->flags = flags; }
 }

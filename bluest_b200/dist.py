@@ -1,0 +1,128 @@
+"""Group-sharded evaluation across the GPUs of one box.
+
+Each rank owns a contiguous, work-balanced slice of the flat group enumeration and the packed
+inverses of that slice only.  One evaluation is three local phases with two small exchanges:
+
+    shard_phi      partial Phi of the slice                     (kernel 2, local)
+    ALL-REDUCE     N*N (+33 indicator) doubles                  <- the one real exchange of the path
+    shard_finish   delta*I, pinv, variance (redundant on every rank); gradient, U, V of the slice
+    ALL-GATHER     U, V rows (N*L doubles each) -- only when the dense Hessian is wanted
+    shard_hess     rows [lo,hi) of H against all columns        (kernel 3b, local; H stays sharded)
+
+The choreography is engine-agnostic: ``GpuEngine`` drives a ``blu_ctx`` through the C ABI and
+``torch.distributed`` (NCCL over NVLink); the CPU tests plug a numpy engine into the same class and
+run it under gloo with world_size 2.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .groups import balanced_slices
+
+
+class ShardedEvaluator:
+    def __init__(self, engine, sizes, rank, world, dist=None, group=None):
+        """engine: object with shard_phi / shard_finish / shard_hess / buffers (see GpuEngine).
+        sizes = [L1..LK]."""
+        self.engine = engine
+        self.rank, self.world = rank, world
+        self.dist, self.group = dist, group
+        self.L = int(sum(sizes))
+        self.slices = balanced_slices(list(sizes), world)
+        self.lo, self.hi = self.slices[rank]
+        self.max_rows = max(hi - lo for lo, hi in self.slices)
+        engine.set_slice(self.lo, self.hi)
+
+    # -- collectives (no-ops at world == 1) --------------------------------------------------
+    def _all_reduce(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def _all_gather_rows(self, full, width):
+        """Every rank has filled rows [lo,hi) of ``full`` (rows x width, row-major, flat tensor);
+        gather the other ranks' rows.  Slices are uneven, so a padded all_gather_into_tensor."""
+        if self.world == 1:
+            return
+        import torch
+        full2 = full[: (full.numel() // width) * width].view(-1, width)
+        send = torch.zeros((self.max_rows, width), dtype=full.dtype, device=full.device)
+        send[: self.hi - self.lo] = full2[self.lo:self.hi]
+        recv = torch.empty((self.world * self.max_rows, width), dtype=full.dtype, device=full.device)
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        for r, (lo, hi) in enumerate(self.slices):
+            if r != self.rank and hi > lo:
+                full2[lo:hi] = recv[r * self.max_rows: r * self.max_rows + (hi - lo)]
+
+    # -- one evaluation ----------------------------------------------------------------------
+    def evaluate(self, m, delta=0.0, grad=True, hess=False, gather_grad=True):
+        """m: full-length sample vector (every rank passes the same values).  Returns a dict with
+        var, flags, and -- as the engine's buffers -- grad (full length if gather_grad, else only the
+        own slice is valid) and the own Hessian row panel when hess=True."""
+        e = self.engine
+        with e.stream_context():
+            buf = e.shard_phi(m)                    # (N*N + 40) partial sums + indicators
+            self._all_reduce(buf)
+            e.shard_finish(delta, grad or hess, hess)
+            out = {}
+            if grad and gather_grad:
+                self._all_gather_rows(e.grad_buffer(), 1)
+            if hess:
+                self._all_gather_rows(e.u_buffer(), e.NP)
+                self._all_gather_rows(e.v_buffer(), e.NP)
+                e.shard_hess()
+        var, flags = e.result()
+        out.update(var=var, flags=flags, lo=self.lo, hi=self.hi)
+        return out
+
+
+class GpuEngine:
+    """blu_ctx-backed engine: every rank builds the context for ALL groups' tables (a few MB of
+    ids/masks) but evaluates only its slice; buffers are torch tensors aliasing HBM."""
+
+    def __init__(self, sap):
+        import torch
+        self.torch = torch
+        self.sap = sap
+        self.N = sap.N
+        self.NP = 4 * ((sap.N + 3) // 4)
+        self._ext = torch.cuda.ExternalStream(sap.stream(), device=sap.device)
+
+    def stream_context(self):
+        return self.torch.cuda.stream(self._ext)
+
+    def set_slice(self, lo, hi):
+        _lib.check(_lib.lib().blu_ctx_set_slice(self.sap._ctx, int(lo), int(hi)))
+
+    def shard_phi(self, m):
+        if m is not None:
+            if hasattr(m, "data_ptr"):
+                ptr = ctypes.c_void_p(int(m.data_ptr()))
+            else:
+                self.sap.device_buffer(_lib.BUF_M).copy_(self.torch.from_numpy(np.ascontiguousarray(m, dtype=np.float64)), non_blocking=True)
+                ptr = None
+        else:
+            ptr = None
+        _lib.check(_lib.lib().blu_shard_phi(self.sap._ctx, ptr))
+        return self.sap.device_buffer(_lib.BUF_PHI)
+
+    def shard_finish(self, delta, want_grad, want_uv):
+        _lib.check(_lib.lib().blu_shard_finish(self.sap._ctx, float(delta), int(bool(want_grad)), int(bool(want_uv))))
+
+    def shard_hess(self):
+        _lib.check(_lib.lib().blu_shard_hess(self.sap._ctx))
+
+    def grad_buffer(self):
+        return self.sap.device_buffer(_lib.BUF_GRAD)
+
+    def u_buffer(self):
+        return self.sap.device_buffer(_lib.BUF_U)
+
+    def v_buffer(self):
+        return self.sap.device_buffer(_lib.BUF_V)
+
+    def hess_panel(self):
+        return self.sap.device_buffer(_lib.BUF_HESS)
+
+    def result(self):
+        return self.sap.last_result()

@@ -1,0 +1,138 @@
+"""The N>1 choreography (bluest_b200/dist.py) under gloo with world_size 2 on CPU.
+
+The ShardedEvaluator is engine-agnostic; here a numpy engine built on the ORACLE (test
+infrastructure) plays the role of the per-rank blu_ctx, so what is exercised is exactly the
+host-side logic that runs on the GPU box: slice balancing, the all-reduce of the partial Phi with
+its SUM-reducible support / early-out indicators, the padded all-gather of uneven row slices,
+and the row-panel Hessian."""
+import contextlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class NumpyEngine:
+    """Same interface as bluest_b200.dist.GpuEngine, arithmetic from the oracle restatement."""
+
+    def __init__(self, o):
+        self.o = o
+        self.N = o.N
+        self.NP = 4 * ((o.N + 3) // 4)
+        L = o.L
+        self.phi = torch.zeros(o.N * o.N + 40, dtype=torch.float64)
+        self.grad = torch.zeros(L, dtype=torch.float64)
+        self.U = torch.zeros(L * self.NP, dtype=torch.float64)
+        self.V = torch.zeros(L * self.NP, dtype=torch.float64)
+        self.var, self.flags = None, 0
+
+    def stream_context(self):
+        return contextlib.nullcontext()
+
+    def set_slice(self, lo, hi):
+        self.lo, self.hi = lo, hi
+
+    def shard_phi(self, m):
+        o, N = self.o, self.N
+        self.m = np.asarray(m, dtype=float)
+        ms = np.zeros_like(self.m); ms[self.lo:self.hi] = self.m[self.lo:self.hi]
+        phi = o.get_phi(ms)                       # groups outside the slice contribute exact zeros
+        buf = np.zeros(N * N + 40)
+        buf[:N * N] = np.triu(phi).ravel()        # un-mirrored upper-triangle sums, like the kernel
+        flat_groups = [g for gk in o.groups for g in gk]
+        for i in range(self.lo, self.hi):
+            if abs(self.m[i]) > 1e-6:
+                buf[N * N + np.asarray(flat_groups[i])] = 1.0
+        buf[N * N + 32] = 1.0 if np.abs(self.m[self.lo:self.hi]).max(initial=0.0) >= 0.05 else 0.0
+        self.phi.copy_(torch.from_numpy(buf))
+        return self.phi
+
+    def shard_finish(self, delta, want_grad, want_uv):
+        o, N = self.o, self.N
+        buf = self.phi.numpy()
+        up = buf[:N * N].reshape(N, N)
+        phi = up + np.triu(up, 1).T + delta * np.eye(N)
+        self.flags = 0
+        if buf[N * N + 32] <= 0:
+            self.flags = 1; self.var = np.inf
+            return
+        supp = np.where(buf[N * N:N * N + N] > 0)[0]
+        P = np.linalg.pinv(phi)
+        self.var = np.linalg.pinv(phi[np.ix_(supp, supp)])[0, 0]
+        self.P = P
+        x = np.ascontiguousarray(P[0])
+        Uall = o.ufactor(x).T                      # (L, N)
+        g = -(Uall @ x)
+        self.grad.zero_(); self.grad[self.lo:self.hi] = torch.from_numpy(g[self.lo:self.hi])
+        if want_uv:
+            U = np.zeros((o.L, self.NP)); V = np.zeros((o.L, self.NP))
+            U[self.lo:self.hi, :N] = Uall[self.lo:self.hi]
+            V[self.lo:self.hi, :N] = Uall[self.lo:self.hi] @ (2 * P)
+            self.U.copy_(torch.from_numpy(U.ravel())); self.V.copy_(torch.from_numpy(V.ravel()))
+
+    def shard_hess(self):
+        U = self.U.numpy().reshape(-1, self.NP); V = self.V.numpy().reshape(-1, self.NP)
+        self.H = U[self.lo:self.hi] @ V.T
+
+    def grad_buffer(self): return self.grad
+    def u_buffer(self): return self.U
+    def v_buffer(self): return self.V
+    def result(self): return self.var, self.flags
+
+
+def _worker(rank, world, port, N, K, ret):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle as orc
+    from bluest_b200.dist import ShardedEvaluator
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        C = orc.wishart_cov(N, 4)
+        groups = orc.enumerate_groups(N, K)
+        o = orc.SapOracle(C, K, groups)
+        ev = ShardedEvaluator(NumpyEngine(o), o.sizes[1:], rank, world, dist=dist)
+        out = {}
+        for name, m in (("dense", orc.dense_m(o.L, 2)), ("sparse", orc.sparse_m(o.L, N, 2)), ("tiny", 0.01 * np.ones(o.L))):
+            r = ev.evaluate(m, delta=0.0, grad=True, hess=(name != "tiny"))
+            e = ev.engine
+            out[name] = dict(var=r["var"], flags=r["flags"], lo=r["lo"], hi=r["hi"],
+                             grad=e.grad.numpy().copy(), H=getattr(e, "H", None) if name != "tiny" else None)
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,K", [(7, 7), (8, 4)])
+def test_sharded_evaluation_world2(N, K):
+    import oracle as orc
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, N, K, ret), nprocs=world, join=True)
+    C = orc.wishart_cov(N, 4)
+    groups = orc.enumerate_groups(N, K)
+    o = orc.SapOracle(C, K, groups)
+    for name, m in (("dense", orc.dense_m(o.L, 2)), ("sparse", orc.sparse_m(o.L, N, 2))):
+        v, g, H = o.variance_GH(m, hess_mode="factored")
+        rows = []
+        for r in range(world):
+            res = ret[r][name]
+            assert abs(res["var"] - v) <= 1e-12 * abs(v)
+            tol = 1e-12 if name == "dense" else 1e-9
+            assert np.max(np.abs(res["grad"] - g)) <= tol * np.max(np.abs(g))       # gathered: full length on every rank
+            rows.append(res["H"])
+            assert res["H"].shape == (res["hi"] - res["lo"], o.L)
+        Hcat = np.vstack(rows)
+        assert np.max(np.abs(Hcat - H)) <= (1e-12 if name == "dense" else 1e-9) * np.max(np.abs(H))
+    for r in range(world):
+        assert ret[r]["tiny"]["flags"] & 1 and np.isinf(ret[r]["tiny"]["var"])
+    assert ret[0]["dense"]["hi"] == ret[1]["dense"]["lo"]

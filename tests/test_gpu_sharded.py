@@ -1,0 +1,70 @@
+"""Group-sharded kernels on ONE GPU: two contexts own the two halves of the group enumeration and
+the exchange steps are emulated with torch copies (no spin-waits between kernels; the real NCCL
+choreography is covered by tests/test_dist_gloo.py on CPU and by bench.py --mode shard)."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from conftest import maxrel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,K", [(9, 9), (12, 6)])
+def test_two_slices_reproduce_the_full_evaluation(N, K):
+    import torch
+    import bluest_b200 as blu
+    from bluest_b200 import _lib
+    from bluest_b200.dist import GpuEngine
+    if blu.device_count() <= 0:
+        pytest.fail("no CUDA device")
+    C = orc.wishart_cov(N, 6)
+    groups = orc.enumerate_groups(N, K)
+    L = sum(len(g) for g in groups)
+    o = orc.SapOracle(C, K, groups)
+    sizes = o.sizes[1:]
+    slices = blu.balanced_slices(sizes, 2)
+    engines = []
+    for lo, hi in slices:
+        sap = blu.SAP(C, K, [[list(g) for g in gk] for gk in groups], np.ones(L), verbose=False)
+        e = GpuEngine(sap)
+        e.set_slice(lo, hi)
+        engines.append(e)
+    for m in (orc.dense_m(L, 3), orc.sparse_m(L, N, 3)):
+        full = len(o.support(m)) == N
+        tol = 1e-12 if full else 1e-9
+        bufs = [e.shard_phi(m) for e in engines]
+        for e in engines:
+            e.sap.sync()
+        total = bufs[0].clone() + bufs[1].clone()              # the all-reduce
+        for b in bufs:
+            b.copy_(total)
+        torch.cuda.synchronize()
+        for e in engines:
+            e.shard_finish(0.0, True, True)
+            e.sap.sync()
+        NP = engines[0].NP
+        # the all-gather of U, V rows and of the gradient slices
+        for name in ("u_buffer", "v_buffer"):
+            t0 = getattr(engines[0], name)().view(-1, NP)
+            t1 = getattr(engines[1], name)().view(-1, NP)
+            (lo0, hi0), (lo1, hi1) = slices
+            t0[lo1:hi1] = t1[lo1:hi1]
+            t1[lo0:hi0] = t0[lo0:hi0]
+        g = torch.cat([engines[0].grad_buffer()[slices[0][0]:slices[0][1]], engines[1].grad_buffer()[slices[1][0]:slices[1][1]]]).cpu().numpy()
+        torch.cuda.synchronize()
+        panels = []
+        for e, (lo, hi) in zip(engines, slices):
+            e.shard_hess()
+            e.sap.sync()
+            ld = 16 * ((L + 15) // 16)
+            panels.append(e.hess_panel()[: (hi - lo) * ld].view(hi - lo, ld)[:, :L].cpu().numpy())
+        H = np.vstack(panels)
+        vo, go, Ho = o.variance_GH(m, hess_mode="factored")
+        for e in engines:
+            v, fl = e.result()
+            assert abs(v - vo) <= 1e-12 * vo
+        assert maxrel(g, go) < tol
+        assert maxrel(H, Ho) < tol
+    for e in engines:
+        e.sap.close()

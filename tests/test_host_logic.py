@@ -1,0 +1,81 @@
+"""Host-side integer logic of the package (group enumeration, unions, mappings, indicator vectors,
+slice balancing) against the golden vectors of the reference -- bit-exact, CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import bluest_b200 as blu
+import oracle as orc
+from conftest import GOLDEN
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.mark.parametrize("tag,N,K", [("complete_N4_K4", 4, 4), ("complete_N6_K3", 6, 3)])
+def test_complete_graph_enumeration(tag, N, K):
+    d = _load("enumeration.npz")
+    groups = blu.enumerate_groups(N, K)
+    cl = blu.enumerate_cliques(np.ones((N, N)), K)
+    for k in range(K):
+        assert np.array_equal(np.array(groups[k], dtype=np.int64), d[f"{tag}/groups{k+1}"])
+        assert np.array_equal(np.array(cl[k], dtype=np.int64), d[f"{tag}/groups{k+1}"])
+    assert np.array_equal(np.array(blu.indicator_ES([np.array(g) for g in groups], N)), d[f"{tag}/ES"])
+    assert np.array_equal(blu.mappings(groups, [groups])[0], d[f"{tag}/mapping0"])
+
+
+def test_two_output_cliques_union_mappings():
+    d = _load("enumeration.npz")
+    tag = "two_outputs"
+    K = int(d[f"{tag}/K"]); Ks = d[f"{tag}/Ks"].tolist()
+    multi = []
+    for n in range(2):
+        mine = blu.enumerate_cliques(d[f"{tag}/adj{n}"], 4)
+        assert len(mine) == Ks[n]
+        for k in range(Ks[n]):
+            assert np.array_equal(np.array(mine[k], dtype=np.int64), d[f"{tag}/multi{n}_groups{k+1}"])
+        multi.append(mine)
+    groups = blu.union_groups(multi)
+    assert len(groups) == K
+    for k in range(K):
+        assert np.array_equal(np.array(groups[k], dtype=np.int64).reshape(-1, k + 1), d[f"{tag}/groups{k+1}"])
+    maps = blu.mappings(groups, multi)
+    for n in range(2):
+        assert np.array_equal(maps[n], d[f"{tag}/mapping{n}"])
+    assert np.array_equal(np.array(blu.indicator_ES([np.array(g) for g in groups], 6)), d[f"{tag}/ES"])
+    with pytest.raises(AssertionError):
+        blu.mappings(groups, [[[[7]]]])             # a group that is not in the union (mosap.py:60)
+
+
+def test_disconnected_component_is_filtered():
+    """blue_models.py:468: cliques outside model 0's connected component are dropped."""
+    A = np.zeros((5, 5)); A[:3, :3] = 1; A[3:, 3:] = 1
+    cl = blu.enumerate_cliques(A, 5)
+    flat = [tuple(g) for gk in cl for g in gk]
+    assert flat == [(0,), (1,), (2,), (0, 1), (0, 2), (1, 2), (0, 1, 2)]
+
+
+def test_group_costs_and_matches_oracle():
+    mc = 2.0 ** (6 - np.arange(6))
+    groups = blu.enumerate_groups(6, 3)
+    assert np.array_equal(blu.group_costs(groups, mc), orc.group_costs(groups, mc))
+    assert blu.enumerate_groups(7) == orc.enumerate_groups(7)
+
+
+@pytest.mark.parametrize("N,world", [(10, 2), (15, 8), (12, 3)])
+def test_balanced_slices(N, world):
+    from math import comb
+    sizes = [comb(N, k) for k in range(1, N + 1)]
+    sl = blu.balanced_slices(sizes, world)
+    assert sl[0][0] == 0 and sl[-1][1] == sum(sizes)
+    assert all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
+    work = np.concatenate([np.full(s, (k + 1) ** 2) for k, s in enumerate(sizes)])
+    per = [work[lo:hi].sum() for lo, hi in sl]
+    assert max(per) / (sum(per) / world) < 1.02          # within 2% of perfect balance
+
+
+def test_pinned_pool_is_lazy_on_cpu():
+    from bluest_b200 import _lib
+    assert _lib.pinned_pool.free_blocks == {} or isinstance(_lib.pinned_pool.free_blocks, dict)
