@@ -602,7 +602,7 @@ extern "C" int blu_ctx_device_ptr(blu_ctx *c, int which, void **ptr, int64_t *nb
     void *p = nullptr; int64_t n = 0;
     switch (which) {
         case BLU_BUF_M: p = c->d_m; n = 8 * c->L; break;
-        case BLU_BUF_PHI: p = c->d_phi; n = 8 * NN; break;
+        case BLU_BUF_PHI: p = c->d_phi; n = 8 * (NN + 40); break;     // + support / non-tiny indicators (sharded mode)
         case BLU_BUF_PINV: p = c->d_pinv; n = 8 * NN; break;
         case BLU_BUF_GRAD: p = c->d_grad; n = 8 * c->L; break;
         case BLU_BUF_U: { int rc = use(c); if (rc) return rc; rc = ensure_uv(c); if (rc) return rc; p = c->d_U; n = 8 * c->Lpad * c->NP; break; }

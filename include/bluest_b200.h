@@ -47,7 +47,7 @@ extern "C" {
 
 /* `which` for blu_ctx_device_ptr */
 #define BLU_BUF_M      0   /* (L)        sample vector of the last evaluation */
-#define BLU_BUF_PHI    1   /* (N,N)      Phi(m) = delta I + sum m_i Psi_i */
+#define BLU_BUF_PHI    1   /* (N*N + 40) Phi(m) = delta I + sum m_i Psi_i, then 33 SUM-reducible indicators (sharded mode) */
 #define BLU_BUF_PINV   2   /* (N,N)      pinv(Phi), symmetric */
 #define BLU_BUF_GRAD   3   /* (L)        gradient of the variance */
 #define BLU_BUF_U      4   /* (Lpad,NP)  row i = u_i = R_i^T Cinv_i R_i x, NP = 4*ceil(N/4) */

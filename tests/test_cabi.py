@@ -71,3 +71,28 @@ def test_level1_type_checks_happen_before_the_device():
         blu.cmisc.assemble_psi_c(np.zeros(9, dtype=np.float32), 3, 1, 1, np.zeros(1, dtype=np.int64), np.ones(1))
     with pytest.raises(TypeError):
         blu.cmisc.gradK_c([0.0, 0.0], 1, 2, np.zeros(2, dtype=np.int64), np.ones(2), np.ones(3))
+
+
+def test_install_patches_the_reference_in_place():
+    """bluest_b200.install(): the reference's SAP keeps its solvers, takes setup + closures from the
+    B200 class; the Level-1 names in bluest.misc are rebound.  Needs the reference checkout."""
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference checkout not present")
+    import bluest_b200 as blu
+    ns = ref_shim.load()
+    ref_sap = ns.sap.SAP
+    ref_grad = ns.misc.gradK_c
+    try:
+        hybrid = blu.install()
+        assert ns.sap.SAP is hybrid and ns.mosap.SAP is hybrid
+        assert issubclass(hybrid, ref_sap)
+        assert hybrid.__init__ is blu.SAP.__init__ and hybrid.get_variance_functions is blu.SAP.get_variance_functions
+        assert hybrid.cvxopt_solve is ref_sap.cvxopt_solve and hybrid.integer_projection is ref_sap.integer_projection
+        assert ns.misc.gradK_c is blu.cmisc.gradK_c and ns.misc.hessKQ_c is blu.cmisc.hessKQ_c
+        if blu.device_count() <= 0:
+            with pytest.raises(blu.BluError):          # no silent CPU fallback through the patched class
+                hybrid(np.eye(3), 3, blu.enumerate_groups(3), np.ones(7), verbose=False)
+    finally:
+        blu.uninstall()
+    assert ns.sap.SAP is ref_sap and ns.mosap.SAP is ref_sap and ns.misc.gradK_c is ref_grad
