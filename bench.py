@@ -37,7 +37,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-METRIC = "Psi+grad+Hessian evals/s at L=15 (32767 groups)"
+METRIC = "Psi+grad+Hessian evals/s at L=15 (32767 groups); end-to-end SAP solve time"
 UNIT = "evals/s"
 
 
@@ -60,10 +60,11 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.marks = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -72,7 +73,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Call at the start and at the end of the timed region."""
+        self.marks.append(time.perf_counter())
 
     def stop(self):
         if self.proc is None:
@@ -84,7 +89,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
+        lines = self.lines
+        if len(self.marks) >= 2:           # keep the samples taken inside the timed region (+- one period)
+            inside = [(t, ln) for t, ln in lines if self.marks[0] - 0.03 <= t <= self.marks[-1] + 0.03]
+            if inside:
+                lines = inside
+        for _, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -254,6 +264,57 @@ def workload_config(N, L):
             "l2_policy": "every step streams the %.2f GB Hessian (>> 126 MB L2) through HBM, evicting all inputs" % (8.0 * L * L / 1e9)}
 
 
+
+# ---------------------------------------------------------------------------------------------
+# end-to-end SAP solve (second half of BASELINE's metric)
+# ---------------------------------------------------------------------------------------------
+class _CpuSap:
+    """Reference CPU closures (oracle restatement + the reference's compiled loops) behind the
+    attribute surface the shared scipy driver needs.  Test/bench infrastructure only."""
+
+    def __init__(self, C, K, groups, costs):
+        import oracle as orc
+        self.o = orc.SapOracle(C, K, groups)
+        self.L, self.N, self.costs, self.e = self.o.L, self.o.N, costs, self.o.e
+
+    def variance(self, m, delta=0):
+        return self.o.variance(m, delta)
+
+    def variance_GH(self, m, delta=0, nohess=False):
+        return self.o.variance_GH(m, delta, nohess=nohess, hess_mode="reference")
+
+    def get_max_sample_constraints(self, mm):
+        return [], []
+
+
+def sap_solve_benchmark(N=10, K=3, device=0):
+    """SAP.solve(solver="scipy"), budget mode, fixed x0, on the reference's own smoke-test shape
+    (sap.py:458-497: N=10, K=3): GPU closures vs CPU reference closures, identical driver."""
+    import bluest_b200 as blu
+    import oracle as orc
+    from bluest_b200.solvers import scipy_solve
+    C = orc.wishart_cov(N, 0)
+    groups = blu.enumerate_groups(N, K)
+    costs = blu.group_costs(groups, 2.0 ** (N - np.arange(N)))
+    L = len(costs)
+    x0 = np.ceil(10 * abs(np.random.RandomState(0).randn(L)))
+    budget = 100 * costs.max()
+    out = {"problem": "N=%d K=%d L=%d budget=%g, scipy trust-constr (sap.py:387-418), fixed x0" % (N, K, L, budget)}
+    cpu = _CpuSap(C, K, groups, costs)
+    c1 = {}
+    t0 = time.perf_counter(); r1 = scipy_solve(cpu, budget=budget, x0=x0.copy(), counters=c1); t_cpu = time.perf_counter() - t0
+    sap = blu.SAP(C, K, [[list(g) for g in gk] for gk in groups], costs, verbose=False, device=device)
+    sap.variance_GH(x0)                                  # warm-up (pinned pool, first launches)
+    c2 = {}
+    t0 = time.perf_counter(); r2 = scipy_solve(sap, budget=budget, x0=x0.copy(), counters=c2); t_gpu = time.perf_counter() - t0
+    out.update({"cpu_reference_s": t_cpu, "gpu_s": t_gpu, "cpu_evals": c1, "gpu_evals": c2,
+                "cpu_variance": float(r1.fun), "gpu_variance": float(r2.fun),
+                "allocation_maxrel_diff": float(np.max(np.abs(r1.x - r2.x)) / np.max(np.abs(r1.x))),
+                "variance_rel_diff": float(abs(r1.fun - r2.fun) / abs(r1.fun)),
+                "note": "solve time is dominated by scipy's trust-constr internals at this size, not by the closures"})
+    sap.close()
+    return out
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -294,21 +355,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         sap.eval_device(ms_dev[i % npool], 0.0, grad=True, hess=True)
     sap.sync()
     var0, flags0 = sap.last_result()
     launches_per_eval = sap.last_launches()
     sap.timing_log(args.steps)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    sampler.mark()
     e0.record(ext)
     for i in range(args.steps):
         sap.eval_device(ms_dev[i % npool], 0.0, grad=True, hess=True)
     e1.record(ext)
     barrier()
+    sampler.mark()
     clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
     phases = sap.timing_read()                     # (steps, 4) ms
@@ -373,6 +436,11 @@ def run_ours(args):
                 out["cpu_baseline"] = {"value": 1.0 / t_eval, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": desc}
             except Exception as ex:       # the baseline must never take the GPU number down with it
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+            if args.solve:
+                try:
+                    out["sap_solve"] = sap_solve_benchmark(device=local)
+                except Exception as ex:
+                    out["sap_solve"] = {"failed": repr(ex)}
         print(json.dumps(out))
     sap.close()
     if world > 1:
@@ -383,12 +451,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--models", type=int, default=15, help="number of models N (BASELINE.json calls it L)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-solve", dest="solve", action="store_false", help="skip the end-to-end SAP solve comparison")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 5)

@@ -14,6 +14,7 @@
 
 #include "blu_common.cuh"
 #include "blu_jacobi.cuh"
+#include "blu_stream.cuh"
 #include "blu_invert.cuh"
 #include "blu_phi.cuh"
 #include "blu_grad.cuh"
@@ -69,6 +70,8 @@ struct blu_ctx {
     long long H_rows = 0;              // rows allocated in d_H
     BluEvalHeader *d_hdr = nullptr, *h_hdr = nullptr;
     int grid_phi = 1, grid_grad = 1;
+    BluChunk *d_chunks = nullptr;      // work list of the owned slice (blu_stream.cuh)
+    int nchunks = 0, lutlen = 0, part_rows = 0;
     bool have_inv = false;
     std::vector<char> inv_set;         // per class: inverses present
     long long lo = 0, hi = 0;          // owned slice of the flat enumeration
@@ -130,12 +133,52 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     cudaFree(c->d_cls); cudaFree(c->d_gidx); cudaFree(c->d_gmask); cudaFree(c->d_lut); cudaFree(c->d_cinv);
     cudaFree(c->d_C); cudaFree(c->d_m); cudaFree(c->d_part); cudaFree(c->d_phi); cudaFree(c->d_pinv);
     cudaFree(c->d_x); cudaFree(c->d_S); cudaFree(c->d_grad); cudaFree(c->d_U); cudaFree(c->d_V); cudaFree(c->d_H);
-    cudaFree(c->d_hdr);
+    cudaFree(c->d_hdr); cudaFree(c->d_chunks);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->evlog) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+    return BLU_OK;
+}
+
+// Work list of the streaming kernels: chunks of consecutive groups of one class inside [lo,hi).
+static int build_chunks(blu_ctx *c)
+{
+    std::vector<BluChunk> ch;
+    // chunk payload: up to a full stage, but small enough that every resident warp gets ~3 chunks
+    long long total = 0;
+    for (const BluClass &ci : c->cls) {
+        const long long i0 = std::max<long long>(c->lo - ci.goff, 0), i1 = std::min<long long>(c->hi - ci.goff, ci.Lk);
+        if (i1 > i0) total += (i1 - i0) * ci.T;
+    }
+    const long long cap = std::max<long long>(96, std::min<long long>(BLU_CHUNK_DOUBLES, total / ((long long)c->nsm * BLU_STREAM_WARPS * 2 * 3)));
+    for (size_t ic = 0; ic < c->cls.size(); ++ic) {
+        const BluClass &ci = c->cls[ic];
+        const long long i0 = std::max<long long>(c->lo - ci.goff, 0), i1 = std::min<long long>(c->hi - ci.goff, ci.Lk);
+        if (i1 <= i0) continue;
+        const int G = (int)std::max<long long>(1, std::min<long long>(32, cap / ci.T));
+        for (long long i = i0; i < i1; i += G) {
+            BluChunk b; b.cls = (int)ic; b.g = (int)std::min<long long>(G, i1 - i); b.i0 = i;
+            ch.push_back(b);
+        }
+    }
+    if (c->d_chunks) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->d_chunks)); c->d_chunks = nullptr; }
+    c->nchunks = (int)ch.size();
+    CUDA_TRY(cudaMalloc(&c->d_chunks, sizeof(BluChunk) * std::max<size_t>(ch.size(), 1)));
+    if (!ch.empty()) CUDA_TRY(cudaMemcpyAsync(c->d_chunks, ch.data(), sizeof(BluChunk) * ch.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // launch geometry: ~4 chunks per warp, at most two CTAs per SM for the Phi kernel (its partial
+    // tiles are reduced by one CTA afterwards), a few more for the gradient kernels
+    const long long want = std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS * 3 - 1) / (BLU_STREAM_WARPS * 3));
+    c->grid_phi = (int)std::min<long long>(want, (long long)c->nsm * 2);
+    c->grid_grad = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS - 1) / BLU_STREAM_WARPS), (long long)c->nsm * 3);
+    if (c->grid_phi > c->part_rows) {
+        if (c->d_part) CUDA_TRY(cudaFree(c->d_part));
+        c->d_part = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_part, sizeof(double) * (size_t)c->N * c->N * c->grid_phi));
+        c->part_rows = c->grid_phi;
+    }
     return BLU_OK;
 }
 
@@ -215,22 +258,18 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
     CTX_TRY(cudaMalloc(&c->d_gidx, std::max<long long>(ioff, 1)));
     CTX_TRY(cudaMalloc(&c->d_gmask, sizeof(unsigned) * L));
     CTX_TRY(cudaMalloc(&c->d_lut, sizeof(uint16_t) * lut.size()));
-    CTX_TRY(cudaMalloc(&c->d_cinv, sizeof(double) * std::max<long long>(coff, 1)));
-    CTX_TRY(cudaMemsetAsync(c->d_cinv, 0, sizeof(double) * std::max<long long>(coff, 1), c->stream));
+    CTX_TRY(cudaMalloc(&c->d_cinv, sizeof(double) * (std::max<long long>(coff, 1) + 16)));   // + slack for 16-byte rounded bulk copies
+    CTX_TRY(cudaMemsetAsync(c->d_cinv, 0, sizeof(double) * (std::max<long long>(coff, 1) + 16), c->stream));
     CTX_TRY(cudaMemcpyAsync(c->d_cls, c->cls.data(), sizeof(BluClass) * c->cls.size(), cudaMemcpyHostToDevice, c->stream));
     CTX_TRY(cudaMemcpyAsync(c->d_gidx, gidx.data(), gidx.size(), cudaMemcpyHostToDevice, c->stream));
     CTX_TRY(cudaMemcpyAsync(c->d_gmask, gmask.data(), sizeof(unsigned) * L, cudaMemcpyHostToDevice, c->stream));
     CTX_TRY(cudaMemcpyAsync(c->d_lut, lut.data(), sizeof(uint16_t) * lut.size(), cudaMemcpyHostToDevice, c->stream));
 
-    // launch geometry: enough warps to cover the groups, capped at a few CTAs per SM
-    const long long want = (L + BLU_PHI_WARPS * 4 - 1) / (BLU_PHI_WARPS * 4);
-    c->grid_phi = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->nsm * 2));
-    c->grid_grad = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->nsm * 8));
+    c->lutlen = (int)lut.size();
 
     const size_t NN = (size_t)N * N;
     CTX_TRY(cudaMalloc(&c->d_C, sizeof(double) * NN));
     CTX_TRY(cudaMalloc(&c->d_m, sizeof(double) * L));
-    CTX_TRY(cudaMalloc(&c->d_part, sizeof(double) * NN * c->grid_phi));
     CTX_TRY(cudaMalloc(&c->d_phi, sizeof(double) * (NN + 40)));   // + SUM-reducible support / non-tiny indicators
     CTX_TRY(cudaMalloc(&c->d_pinv, sizeof(double) * NN));
     CTX_TRY(cudaMalloc(&c->d_x, sizeof(double) * BLU_MAX_MODELS));
@@ -242,10 +281,22 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
     memset(c->h_hdr, 0, sizeof(BluEvalHeader));
     // opt in to large dynamic shared memory where needed
     CTX_TRY(cudaFuncSetAttribute(blu_phi_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_FIN_SEG * 1024 * 8));
-    CTX_TRY(cudaFuncSetAttribute(blu_phi_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_PHI_WARPS * 1024 * 8));
-    CTX_TRY(cudaFuncSetAttribute(blu_gradu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1024 + BLU_GRAD_WARPS * 528) * 8));
+    {
+        const int ncl = (int)c->cls.size();
+        CTX_TRY(cudaFuncSetAttribute(blu_phi_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)blu_stream_smem_bytes(BLU_STREAM_WARPS * 1024, 32, 6000)));
+        CTX_TRY(cudaFuncSetAttribute(blu_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)blu_stream_smem_bytes(0, 32, 6000)));
+        CTX_TRY(cudaFuncSetAttribute(blu_gradu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)blu_stream_smem_bytes(1024, 32, 6000)));
+        (void)ncl;
+    }
     CTX_TRY(cudaStreamSynchronize(c->stream));
 #undef CTX_TRY
+    {
+        int rc2 = build_chunks(c);
+        if (rc2) { blu_ctx_destroy(c); return rc2; }
+    }
     *out = c;
     return BLU_OK;
 }
@@ -409,8 +460,8 @@ extern "C" int blu_ctx_assemble_psi(blu_ctx *c, double *psi)
 static int launch_phi(blu_ctx *c, const double *d_m, double delta, int mode)
 {
     const int NN = c->N * c->N;
-    blu_phi_partial_kernel<<<c->grid_phi, BLU_PHI_WARPS * 32, sizeof(double) * NN * BLU_PHI_WARPS, c->stream>>>(
-        c->d_cls, (int)c->cls.size(), c->N, c->d_gidx, c->d_cinv, c->d_lut, d_m, c->lo, c->hi, c->d_part, c->d_hdr);
+    blu_phi_partial_kernel<<<c->grid_phi, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(BLU_STREAM_WARPS * NN, (int)c->cls.size(), c->lutlen), c->stream>>>(
+        c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr);
     KERNEL_CHECK(c);
     blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
         c->N, c->grid_phi, c->d_part, delta, mode, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr);
@@ -432,17 +483,16 @@ static int ensure_uv(blu_ctx *c)
 static int launch_grad(blu_ctx *c, int want_uv)
 {
     if (!want_uv) {
-        blu_grad_kernel<<<c->grid_grad, BLU_GRAD_WARPS * 32, 0, c->stream>>>(
-            c->d_cls, (int)c->cls.size(), c->N, c->d_gidx, c->d_cinv, c->d_lut, c->d_x, c->lo, c->hi, c->d_grad);
+        blu_grad_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(0, (int)c->cls.size(), c->lutlen), c->stream>>>(
+            c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_grad);
         KERNEL_CHECK(c);
         return BLU_OK;
     }
     int rc = ensure_uv(c);
     if (rc) return rc;
-    const size_t smem = sizeof(double) * ((size_t)c->N * c->N + (size_t)BLU_GRAD_WARPS * c->Tmax);
-    blu_gradu_kernel<<<c->grid_grad, BLU_GRAD_WARPS * 32, smem, c->stream>>>(
-        c->d_cls, (int)c->cls.size(), c->N, c->NP, c->Tmax, c->d_gidx, c->d_gmask, c->d_cinv, c->d_x, c->d_S,
-        c->lo, c->hi, c->d_grad, c->d_U, c->d_V);
+    blu_gradu_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->N * c->N, (int)c->cls.size(), c->lutlen), c->stream>>>(
+        c->d_cls, (int)c->cls.size(), c->N, c->NP, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_S,
+        c->d_grad, c->d_U, c->d_V);
     KERNEL_CHECK(c);
     return BLU_OK;
 }
@@ -709,8 +759,10 @@ extern "C" int blu_ctx_set_slice(blu_ctx *c, int64_t lo, int64_t hi)
 {
     if (!c) return fail(BLU_ERR_ARG, "null context");
     if (lo < 0 || hi > c->L || lo > hi) return fail(BLU_ERR_ARG, "slice [%lld,%lld) outside [0,%lld]", (long long)lo, (long long)hi, c->L);
+    int rc = use(c);
+    if (rc) return rc;
     c->lo = lo; c->hi = hi;
-    return BLU_OK;
+    return build_chunks(c);
 }
 
 extern "C" int blu_shard_phi(blu_ctx *c, const double *d_m)

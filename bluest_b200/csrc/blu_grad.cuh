@@ -6,83 +6,162 @@
 // so that the Hessian of misc.py:497-503 is  H = U S U^T = U V^T  (SURVEY.md 0.3), which
 // blu_hess.cuh forms with FP64 tensor-core MMAs.
 //
-// blu_grad_kernel   (no Hessian wanted): lane-per-packed-entry streaming, one shuffle-tree sum per
-//                   group -- a pure HBM stream of the packed inverses.
-// blu_gradu_kernel  (Hessian / U wanted): the group's packed block is staged in the warp's shared
-//                   memory slice, lane j forms row j of Cinv_i x[g_i], rows are scattered to model
+// Both kernels stream chunks of consecutive groups through the warp-private bulk-async ring of
+// blu_stream.cuh.
+// blu_grad_kernel   (no Hessian wanted): lane-per-packed-entry, one shuffle-tree sum per group -- a
+//                   pure HBM stream of the packed inverses.
+// blu_gradu_kernel  (Hessian / U wanted): lane j forms row j of Cinv_i x[g_i] from the staged block,
+//                   rows are scattered to model
 //                   positions via the membership mask and multiplied by S; U and V rows (NP doubles,
 //                   one 128-byte line at N <= 16) are written coalesced.
 // x and S are broadcast once per CTA into registers / shared memory.
 #pragma once
 #include "blu_common.cuh"
+#include "blu_stream.cuh"
 
-#define BLU_GRAD_WARPS 8
-
-__global__ void __launch_bounds__(BLU_GRAD_WARPS * 32)
-blu_grad_kernel(const BluClass *__restrict__ cls, int ncls, int N, const uint8_t *__restrict__ gidx,
-                const double *__restrict__ cinv, const uint16_t *__restrict__ lut,
-                const double *__restrict__ xrow, long long lo, long long hi, double *__restrict__ grad)
+// Consume one staged chunk for the gradient: lane g keeps -x_g^T Cinv_g x_g of group g.
+template <int S>
+__device__ __forceinline__ double blu_grad_chunk(const double *__restrict__ base, const unsigned short *__restrict__ lt, int T, int ng,
+                                                 const unsigned char *__restrict__ ids, double xv, int lane)
 {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const double xv = lane < N ? xrow[lane] : 0.0;
-    const long long gw = (long long)blockIdx.x * BLU_GRAD_WARPS + w;
-    const long long nw = (long long)gridDim.x * BLU_GRAD_WARPS;
-    for (int c = 0; c < ncls; ++c) {
-        const BluClass ci = cls[c];
-        const int k = ci.k, T = ci.T;
-        const uint16_t *lt = lut + ci.lutoff;
-        long long i0 = lo > ci.goff ? lo - ci.goff : 0;
-        long long i1 = hi < ci.goff + ci.Lk ? hi - ci.goff : ci.Lk;
-        for (long long i = i0 + gw; i < i1; i += nw) {
-            const int gv = lane < k ? (int)gidx[ci.ioff + i * k + lane] : 0;
-            const double xg = blu_shfl(xv, gv);
-            const double *cp = cinv + ci.coff + i * T;
-            double sum = 0.0;
-            for (int e0 = 0; e0 < T; e0 += 32) {
-                const int e = e0 + lane;
-                const bool ok = e < T;
-                const unsigned jl = ok ? lt[e] : 0u;
-                const double v = ok ? cp[e] : 0.0;
-                const int j = jl >> 8, l = jl & 255u;
-                const double xa = blu_shfl(xg, j), xb = blu_shfl(xg, l);
-                const double wgt = (j == l) ? 1.0 : 2.0;
-                sum += wgt * (xa * v * xb);
-            }
-            sum = blu_warp_sum(sum);
-            if (lane == 0) grad[ci.goff + i] = -sum;
+    int ja[S], la[S];
+    double wg[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int e = s * 32 + lane;
+        const unsigned jl = e < T ? lt[e] : 0u;
+        ja[s] = jl >> 8; la[s] = jl & 255u;
+        wg[s] = e < T ? ((ja[s] == la[s]) ? 1.0 : 2.0) : 0.0;
+    }
+    double mine = 0.0;
+    for (int g = 0; g < ng; ++g) {
+        const int gv = ids[g * 32 + lane];
+        const double xg = blu_shfl(xv, gv);
+        const double *cp = base + g * T;
+        double sum = 0.0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int e = s * 32 + lane;
+            const double v = e < T ? cp[e] : 0.0;
+            const double xa = blu_shfl(xg, ja[s]), xb = blu_shfl(xg, la[s]);
+            sum += wg[s] * (xa * v * xb);
         }
+        sum = blu_warp_sum(sum);
+        if (lane == g) mine = -sum;
+    }
+    return mine;
+}
+__device__ __forceinline__ double blu_grad_chunk_any(const double *__restrict__ base, const unsigned short *__restrict__ lt, int T, int ng,
+                                                     const unsigned char *__restrict__ ids, double xv, int lane)
+{
+    double mine = 0.0;
+    for (int g = 0; g < ng; ++g) {
+        const int gv = ids[g * 32 + lane];
+        const double xg = blu_shfl(xv, gv);
+        const double *cp = base + g * T;
+        double sum = 0.0;
+        for (int e0 = 0; e0 < T; e0 += 32) {
+            const int e = e0 + lane;
+            const bool ok = e < T;
+            const unsigned jl = ok ? lt[e] : 0u;
+            const double v = ok ? cp[e] : 0.0;
+            const int j = jl >> 8, l = jl & 255u;
+            const double xa = blu_shfl(xg, j), xb = blu_shfl(xg, l);
+            sum += ((j == l) ? 1.0 : 2.0) * (xa * v * xb);
+        }
+        sum = blu_warp_sum(sum);
+        if (lane == g) mine = -sum;
+    }
+    return mine;
+}
+
+// extra shared doubles: none
+__global__ void __launch_bounds__(BLU_STREAM_WARPS * 32)
+blu_grad_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks,
+                const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
+                const unsigned *__restrict__ gmask, const double *__restrict__ xrow, double *__restrict__ grad)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const BluStreamSmem sm = blu_stream_carve(smraw, 0, ncls, lutlen);
+    const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ids = sm.ids + w * 32 * 32;
+    const double xv = lane < N ? xrow[lane] : 0.0;
+    const int gw = blockIdx.x * BLU_STREAM_WARPS + w;
+    const int nw = gridDim.x * BLU_STREAM_WARPS;
+
+    int c = gw;
+    BluChunkRegs cur, nxt;
+    BluChunk dnext;
+    if (c < nchunks) cur = blu_prefetch_chunk(chunks[c], sm.cls, cinv, nullptr, gmask, ws, 0, lane);
+    if (c + nw < nchunks) dnext = chunks[c + nw];
+    for (int it = 0; c < nchunks; c += nw, ++it) {
+        const int s = it & 1;
+        if (c + nw < nchunks) nxt = blu_prefetch_chunk(dnext, sm.cls, cinv, nullptr, gmask, ws, s ^ 1, lane);
+        if (c + 2 * nw < nchunks) dnext = chunks[c + 2 * nw];
+        const BluClass ci = sm.cls[cur.cls];
+        const int T = ci.T;
+        const unsigned short *lt = sm.lut + ci.lutoff;
+        blu_mbar_wait(ws.bar[s], (unsigned)((it >> 1) & 1));
+        const double *base = ws.stage[s] + cur.skew;
+        blu_expand_ids(cur.mask, ci.k, ids, lane);
+        double mine;                                      // lane g keeps the result of group g
+        switch ((T + 31) >> 5) {
+            case 1: mine = blu_grad_chunk<1>(base, lt, T, cur.g, ids, xv, lane); break;
+            case 2: mine = blu_grad_chunk<2>(base, lt, T, cur.g, ids, xv, lane); break;
+            case 3: mine = blu_grad_chunk<3>(base, lt, T, cur.g, ids, xv, lane); break;
+            case 4: mine = blu_grad_chunk<4>(base, lt, T, cur.g, ids, xv, lane); break;
+            case 5: mine = blu_grad_chunk<5>(base, lt, T, cur.g, ids, xv, lane); break;
+            case 6: mine = blu_grad_chunk<6>(base, lt, T, cur.g, ids, xv, lane); break;
+            case 7: mine = blu_grad_chunk<7>(base, lt, T, cur.g, ids, xv, lane); break;
+            case 8: mine = blu_grad_chunk<8>(base, lt, T, cur.g, ids, xv, lane); break;
+            default: mine = blu_grad_chunk_any(base, lt, T, cur.g, ids, xv, lane); break;
+        }
+        if (lane < cur.g) grad[ci.goff + cur.i0 + lane] = mine;          // coalesced
+        __syncwarp();
+        cur = nxt;
     }
 }
 
-// dynamic shared memory: N*N doubles (S) + BLU_GRAD_WARPS * Tmax doubles (staging)
-__global__ void __launch_bounds__(BLU_GRAD_WARPS * 32)
-blu_gradu_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, int Tmax,
-                 const uint8_t *__restrict__ gidx, const unsigned *__restrict__ gmask,
-                 const double *__restrict__ cinv, const double *__restrict__ xrow,
-                 const double *__restrict__ S, long long lo, long long hi,
+// extra shared doubles: N*N (S)
+__global__ void __launch_bounds__(BLU_STREAM_WARPS * 32)
+blu_gradu_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, const BluChunk *__restrict__ chunks, int nchunks,
+                 const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
+                 const unsigned *__restrict__ gmask, const double *__restrict__ xrow, const double *__restrict__ S,
                  double *__restrict__ grad, double *__restrict__ U, double *__restrict__ V)
 {
-    extern __shared__ double sm[];
-    double *sS = sm;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *st = sm + N * N + w * Tmax;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const BluStreamSmem sm = blu_stream_carve(smraw, N * N, ncls, lutlen);
+    double *sS = sm.extra;
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) sS[t] = S[t];
-    __syncthreads();
+    const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);       // ends with __syncthreads
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ids = sm.ids + w * 32 * 32;
     const double xv = lane < N ? xrow[lane] : 0.0;
-    const long long gw = (long long)blockIdx.x * BLU_GRAD_WARPS + w;
-    const long long nw = (long long)gridDim.x * BLU_GRAD_WARPS;
-    for (int c = 0; c < ncls; ++c) {
-        const BluClass ci = cls[c];
+    const int gw = blockIdx.x * BLU_STREAM_WARPS + w;
+    const int nw = gridDim.x * BLU_STREAM_WARPS;
+
+    int c = gw;
+    BluChunkRegs cur, nxt;
+    BluChunk dnext;
+    if (c < nchunks) cur = blu_prefetch_chunk(chunks[c], sm.cls, cinv, nullptr, gmask, ws, 0, lane);
+    if (c + nw < nchunks) dnext = chunks[c + nw];
+    for (int it = 0; c < nchunks; c += nw, ++it) {
+        const int s = it & 1;
+        if (c + nw < nchunks) nxt = blu_prefetch_chunk(dnext, sm.cls, cinv, nullptr, gmask, ws, s ^ 1, lane);
+        if (c + 2 * nw < nchunks) dnext = chunks[c + 2 * nw];
+        const BluClass ci = sm.cls[cur.cls];
         const int k = ci.k, T = ci.T;
-        long long i0 = lo > ci.goff ? lo - ci.goff : 0;
-        long long i1 = hi < ci.goff + ci.Lk ? hi - ci.goff : ci.Lk;
-        for (long long i = i0 + gw; i < i1; i += nw) {
-            const double *cp = cinv + ci.coff + i * T;
-            for (int e = lane; e < T; e += 32) st[e] = cp[e];
-            const int gv = lane < k ? (int)gidx[ci.ioff + i * k + lane] : 0;
-            const unsigned mask = gmask[ci.goff + i];
+        blu_mbar_wait(ws.bar[s], (unsigned)((it >> 1) & 1));
+        const double *base = ws.stage[s] + cur.skew;
+        blu_expand_ids(cur.mask, k, ids, lane);
+        double mine = 0.0;
+        for (int g = 0; g < cur.g; ++g) {
+            const unsigned mask = __shfl_sync(BLU_FULL, cur.mask, g);
+            const int gv = ids[g * 32 + lane];
             const double xg = blu_shfl(xv, gv);
-            __syncwarp();
+            const double *st = base + g * T;
+            // lane j < k: row j of Cinv_i x[g_i]
             const int j = lane < k ? lane : k - 1;
             double y = 0.0;
             for (int l = 0; l < k; ++l) {
@@ -91,7 +170,8 @@ blu_gradu_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, int 
                 y += st[blu_pk(k, a, b)] * xl;
             }
             const double gs = blu_warp_sum(lane < k ? xg * y : 0.0);
-            // scatter rows of Cinv_i x[g_i] to model slots
+            if (lane == g) mine = -gs;
+            // scatter rows to model slots, then v = S u
             const bool in = (mask >> lane) & 1u;
             const int pos = __popc(mask & ((1u << lane) - 1u));
             const double ysrc = blu_shfl(y, pos);
@@ -101,14 +181,15 @@ blu_gradu_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, int 
                 const double ub = blu_shfl(ua, b);
                 if (lane < N) va += sS[lane * N + b] * ub;
             }
-            const long long row = ci.goff + i;
-            if (lane == 0) grad[row] = -gs;
+            const long long row = ci.goff + cur.i0 + g;
             if (lane < NP) {
                 U[row * NP + lane] = ua;
                 V[row * NP + lane] = lane < N ? va : 0.0;
             }
-            __syncwarp();
         }
+        if (lane < cur.g) grad[ci.goff + cur.i0 + lane] = mine;
+        __syncwarp();
+        cur = nxt;
     }
 }
 

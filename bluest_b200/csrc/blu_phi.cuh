@@ -2,7 +2,8 @@
 // GEMV psi@m of misc.py:459-461 / the sparse loop objectiveK_c, cmisc.cpp:25-40), followed by the
 // N x N pseudo-inverse and the variance (misc.py:463-477, 487-490).
 //
-// blu_phi_partial_kernel: each warp streams whole groups of the packed inverse array; lane e of a
+// blu_phi_partial_kernel: each warp streams chunks of consecutive groups of the packed inverse
+// array through its shared-memory ring (bulk async copies, blu_stream.cuh); lane e of a
 // 32-entry step owns packed entry (j,l) of the group and adds m_i * Cinv_i[j,l] into the warp's
 // PRIVATE N x N accumulator tile in shared memory at (g[j], g[l]).  Inside one group all targets
 // are distinct, so the read-modify-write needs no atomics; groups are separated by __syncwarp().
@@ -20,8 +21,7 @@
 #pragma once
 #include "blu_common.cuh"
 #include "blu_jacobi.cuh"
-
-#define BLU_PHI_WARPS 16
+#include "blu_stream.cuh"
 
 struct BluEvalHeader {          // small device-side status block of a context
     unsigned supp;              // support mask (OR)
@@ -30,50 +30,116 @@ struct BluEvalHeader {          // small device-side status block of a context
     double scal[8];             // [0] variance [1] max|m| [2] sweeps [3] lambda_max [4] var (full pinv)
 };
 
-__global__ void __launch_bounds__(BLU_PHI_WARPS * 32)
-blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N,
-                       const uint8_t *__restrict__ gidx, const double *__restrict__ cinv,
-                       const uint16_t *__restrict__ lut, const double *__restrict__ m,
-                       long long lo, long long hi,          // owned slice of the flat enumeration
+// Consume one staged chunk for the Phi accumulation.  S = ceil(T/32) steps per group, fully
+// unrolled; the lane's (j,l) pairs are fixed for the whole chunk and live in registers.
+template <int S>
+__device__ __forceinline__ void blu_phi_chunk(const double *__restrict__ base, const unsigned short *__restrict__ lt, int T, int ng,
+                                              unsigned live, double mreg, const unsigned char *__restrict__ ids,
+                                              double *__restrict__ acc, int N, int lane)
+{
+    int ja[S], la[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int e = s * 32 + lane;
+        const unsigned jl = e < T ? lt[e] : 0u;
+        ja[s] = jl >> 8; la[s] = jl & 255u;
+    }
+    for (int g = 0; g < ng; ++g) {
+        if (!((live >> g) & 1u)) continue;                // m_i == 0 contributes exact zeros
+        const double mi = blu_shfl(mreg, g);
+        const int gv = ids[g * 32 + lane];
+        const double *cp = base + g * T;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int e = s * 32 + lane;
+            const bool ok = e < T;
+            const double v = ok ? cp[e] : 0.0;
+            const int a = __shfl_sync(BLU_FULL, gv, ja[s]);
+            const int b = __shfl_sync(BLU_FULL, gv, la[s]);
+            if (ok) acc[a * N + b] += mi * v;
+        }
+        __syncwarp();
+    }
+}
+// generic step count (k > 22)
+__device__ __forceinline__ void blu_phi_chunk_any(const double *__restrict__ base, const unsigned short *__restrict__ lt, int T, int ng,
+                                                  unsigned live, double mreg, const unsigned char *__restrict__ ids,
+                                                  double *__restrict__ acc, int N, int lane)
+{
+    for (int g = 0; g < ng; ++g) {
+        if (!((live >> g) & 1u)) continue;
+        const double mi = blu_shfl(mreg, g);
+        const int gv = ids[g * 32 + lane];
+        const double *cp = base + g * T;
+        for (int e0 = 0; e0 < T; e0 += 32) {
+            const int e = e0 + lane;
+            const bool ok = e < T;
+            const unsigned jl = ok ? lt[e] : 0u;
+            const double v = ok ? cp[e] : 0.0;
+            const int a = __shfl_sync(BLU_FULL, gv, jl >> 8);
+            const int b = __shfl_sync(BLU_FULL, gv, jl & 255u);
+            if (ok) acc[a * N + b] += mi * v;
+        }
+        __syncwarp();
+    }
+}
+
+// `chunks` lists the work of this launch (whole context or the owned slice); see blu_stream.cuh.
+__global__ void __launch_bounds__(BLU_STREAM_WARPS * 32)
+blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks,
+                       const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
+                       const unsigned *__restrict__ gmask, const double *__restrict__ m,
                        double *__restrict__ part, BluEvalHeader *hdr)
 {
-    extern __shared__ double sacc[];                 // BLU_PHI_WARPS tiles of N*N
+    extern __shared__ __align__(16) unsigned char smraw[];
     const int NN = N * N;
+    const BluStreamSmem sm = blu_stream_carve(smraw, BLU_STREAM_WARPS * NN, ncls, lutlen);
+    const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *acc = sacc + w * NN;
+    double *acc = sm.extra + w * NN;                     // this warp's private N x N tile
+    unsigned char *ids = sm.ids + w * 32 * 32;
     for (int t = lane; t < NN; t += 32) acc[t] = 0.0;
     __syncwarp();
 
     unsigned supp = 0u;
     double mymax = 0.0;
-    const long long gw = (long long)blockIdx.x * BLU_PHI_WARPS + w;
-    const long long nw = (long long)gridDim.x * BLU_PHI_WARPS;
+    const int gw = blockIdx.x * BLU_STREAM_WARPS + w;
+    const int nw = gridDim.x * BLU_STREAM_WARPS;
 
-    for (int c = 0; c < ncls; ++c) {
-        const BluClass ci = cls[c];
-        const int k = ci.k, T = ci.T;
-        const uint16_t *lt = lut + ci.lutoff;
-        long long i0 = lo > ci.goff ? lo - ci.goff : 0;
-        long long i1 = hi < ci.goff + ci.Lk ? hi - ci.goff : ci.Lk;
-        for (long long i = i0 + gw; i < i1; i += nw) {
-            const double mi = m[ci.goff + i];
-            const double am = fabs(mi);
-            mymax = fmax(mymax, am);
-            if (mi == 0.0) continue;                  // warp-uniform
-            const int gv = lane < k ? (int)gidx[ci.ioff + i * k + lane] : 0;
-            if (am > 1.0e-6 && lane < k) supp |= 1u << gv;
-            const double *cp = cinv + ci.coff + i * T;
-            for (int e0 = 0; e0 < T; e0 += 32) {
-                const int e = e0 + lane;
-                const bool ok = e < T;
-                const unsigned jl = ok ? lt[e] : 0u;
-                const double v = ok ? cp[e] : 0.0;
-                const int a = __shfl_sync(BLU_FULL, gv, jl >> 8);
-                const int b = __shfl_sync(BLU_FULL, gv, jl & 255u);
-                if (ok) acc[a * N + b] += mi * v;
+    int c = gw;
+    BluChunkRegs cur, nxt;
+    BluChunk dnext;                                       // descriptor of chunk c + nw, fetched one round early
+    if (c < nchunks) cur = blu_prefetch_chunk(chunks[c], sm.cls, cinv, m, gmask, ws, 0, lane);
+    if (c + nw < nchunks) dnext = chunks[c + nw];
+    for (int it = 0; c < nchunks; c += nw, ++it) {
+        const int s = it & 1;
+        if (c + nw < nchunks) nxt = blu_prefetch_chunk(dnext, sm.cls, cinv, m, gmask, ws, s ^ 1, lane);
+        if (c + 2 * nw < nchunks) dnext = chunks[c + 2 * nw];
+        const BluClass ci = sm.cls[cur.cls];
+        const int T = ci.T;
+        const unsigned short *lt = sm.lut + ci.lutoff;
+        const double am = fabs(cur.m);
+        mymax = fmax(mymax, am);
+        if (am > 1.0e-6) supp |= cur.mask;
+        const unsigned live = __ballot_sync(BLU_FULL, cur.m != 0.0);
+        blu_mbar_wait(ws.bar[s], (unsigned)((it >> 1) & 1));
+        const double *base = ws.stage[s] + cur.skew;
+        if (live) {
+            blu_expand_ids(cur.mask, ci.k, ids, lane);
+            switch ((T + 31) >> 5) {
+                case 1: blu_phi_chunk<1>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
+                case 2: blu_phi_chunk<2>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
+                case 3: blu_phi_chunk<3>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
+                case 4: blu_phi_chunk<4>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
+                case 5: blu_phi_chunk<5>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
+                case 6: blu_phi_chunk<6>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
+                case 7: blu_phi_chunk<7>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
+                case 8: blu_phi_chunk<8>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
+                default: blu_phi_chunk_any(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
             }
-            __syncwarp();
         }
+        __syncwarp();                                     // stage s fully consumed before it is refilled
+        cur = nxt;
     }
     supp = __reduce_or_sync(BLU_FULL, supp);
 #pragma unroll
@@ -84,10 +150,10 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N,
     }
     __syncthreads();
     for (int t = threadIdx.x; t < NN; t += blockDim.x) {
-        double s = 0.0;
+        double sum = 0.0;
 #pragma unroll
-        for (int ww = 0; ww < BLU_PHI_WARPS; ++ww) s += sacc[ww * NN + t];
-        part[(long long)blockIdx.x * NN + t] = s;
+        for (int ww = 0; ww < BLU_STREAM_WARPS; ++ww) sum += sm.extra[ww * NN + t];
+        part[(long long)blockIdx.x * NN + t] = sum;
     }
 }
 

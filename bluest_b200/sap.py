@@ -258,34 +258,9 @@ class SAP(object):
 
     def scipy_solve(self, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000):
         """sap.py:378-418 -- same constraints, tolerances and callbacks; the callbacks are the GPU closures."""
-        from scipy.optimize import Bounds, LinearConstraint, NonlinearConstraint, minimize
-        if budget is None and eps is None:
-            raise ValueError("Need to specify either budget or RMSE tolerance")
-        delta = 0
-        L = int(self.L)
-        w = self.costs
-        e = self.e
-        es, rhs = self.get_max_sample_constraints(max_model_samples)
-        constraint1 = Bounds(0.0 * np.ones((L,)), np.inf * np.ones((L,)), keep_feasible=True)
-        constraint3 = LinearConstraint(e, 1, np.inf, keep_feasible=True)
-        constraint4 = [LinearConstraint(ee, -np.inf, rr) for ee, rr in zip(es, rhs)]
-        opts = {"factorization_method": None, "disp": False, "maxiter": maxiter, "verbose": 3 * int(self.verbose)}
-        if budget is not None:
-            constraint2 = LinearConstraint(w, -np.inf, budget)
-            if x0 is None:
-                x0 = np.ceil(10 * abs(np.random.randn(L)))
-            res = minimize(lambda x: self.variance_GH(x, nohess=True, delta=delta)[:-1], x0, jac=True,
-                           hess=lambda x: self.variance_GH(x, delta=delta)[-1], bounds=constraint1,
-                           constraints=[constraint2, constraint3] + constraint4, method="trust-constr", options=opts, tol=1.0e-8)
-        else:
-            epsq = eps ** 2
-            constraint2 = NonlinearConstraint(lambda x: self.variance(x, delta=delta), epsq, epsq,
-                                              jac=lambda x: self.variance_GH(x, nohess=True, delta=delta)[1],
-                                              hess=lambda x, p: self.variance_GH(x, delta=delta)[2] * p)
-            if x0 is None:
-                x0 = np.ceil(eps ** -2 * np.random.rand(L))
-            wn = w / np.linalg.norm(w)
-            res = minimize(lambda x: [wn @ x, wn], x0, jac=True, hessp=lambda x, p: np.zeros((len(x),)), bounds=constraint1,
-                           constraints=[constraint2, constraint3] + constraint4, method="trust-constr", options=opts, tol=1.0e-10)
+        from .solvers import scipy_solve
+        self.scipy_counters = {}
+        res = scipy_solve(self, budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, maxiter=maxiter,
+                          verbose=self.verbose, counters=self.scipy_counters)
         self.scipy_result = res
         return res.x

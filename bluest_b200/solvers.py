@@ -1,0 +1,54 @@
+"""Host-side solver driver kept from the reference (sap.py:378-418): scipy ``trust-constr`` iterating
+on the objective closures.  Works on any object exposing ``L, costs, e, variance, variance_GH,
+get_max_sample_constraints`` -- the B200-backed SAP in production, an oracle-backed stand-in when
+bench.py times the CPU reference with the identical driver."""
+import numpy as np
+
+
+def scipy_solve(problem, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000, verbose=False, counters=None):
+    from scipy.optimize import Bounds, LinearConstraint, NonlinearConstraint, minimize
+    if budget is None and eps is None:
+        raise ValueError("Need to specify either budget or RMSE tolerance")
+    delta = 0
+    L = int(problem.L)
+    w = problem.costs
+    e = problem.e
+    es, rhs = problem.get_max_sample_constraints(max_model_samples)
+    cnt = counters if counters is not None else {}
+    cnt.setdefault("f", 0); cnt.setdefault("g", 0); cnt.setdefault("H", 0)
+
+    def fg(x):
+        cnt["g"] += 1
+        return problem.variance_GH(x, nohess=True, delta=delta)[:-1]
+
+    def hess(x):
+        cnt["H"] += 1
+        return problem.variance_GH(x, delta=delta)[-1]
+
+    def var(x):
+        cnt["f"] += 1
+        return problem.variance(x, delta=delta)
+
+    def jac(x):
+        cnt["g"] += 1
+        return problem.variance_GH(x, nohess=True, delta=delta)[1]
+
+    constraint1 = Bounds(0.0 * np.ones((L,)), np.inf * np.ones((L,)), keep_feasible=True)
+    constraint3 = LinearConstraint(e, 1, np.inf, keep_feasible=True)
+    constraint4 = [LinearConstraint(ee, -np.inf, rr) for ee, rr in zip(es, rhs)]
+    opts = {"factorization_method": None, "disp": False, "maxiter": maxiter, "verbose": 3 * int(verbose)}
+    if budget is not None:
+        constraint2 = LinearConstraint(w, -np.inf, budget)
+        if x0 is None:
+            x0 = np.ceil(10 * abs(np.random.randn(L)))
+        res = minimize(fg, x0, jac=True, hess=hess, bounds=constraint1, constraints=[constraint2, constraint3] + constraint4,
+                       method="trust-constr", options=opts, tol=1.0e-8)
+    else:
+        epsq = eps ** 2
+        constraint2 = NonlinearConstraint(var, epsq, epsq, jac=jac, hess=lambda x, p: hess(x) * p)
+        if x0 is None:
+            x0 = np.ceil(eps ** -2 * np.random.rand(L))
+        wn = w / np.linalg.norm(w)
+        res = minimize(lambda x: [wn @ x, wn], x0, jac=True, hessp=lambda x, p: np.zeros((len(x),)), bounds=constraint1,
+                       constraints=[constraint2, constraint3] + constraint4, method="trust-constr", options=opts, tol=1.0e-10)
+    return res
