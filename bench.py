@@ -448,6 +448,77 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_shard(args):
+    """Group-sharded evaluation of ONE problem across the ranks: contiguous
+    work-balanced slices, NCCL all-reduce of the partial Phi, all-gather of U/V rows, each rank
+    writes its own Hessian row panel.  Strong scaling: total work fixed as N grows."""
+    import torch
+    import torch.distributed as dist
+    import bluest_b200 as blu
+    import oracle as orc
+    from bluest_b200.dist import GpuEngine, ShardedEvaluator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N = args.models
+    hess = not args.nohess
+    C = orc.wishart_cov(N, 0)
+    groups = blu.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    sizes = [len(g) for g in groups]
+    sap = blu.SAP(C, N, groups, np.ones(L), verbose=False, device=local)
+    eng = GpuEngine(sap)
+    ev = ShardedEvaluator(eng, sizes, rank, world, dist=dist if world > 1 else None)
+    ms_dev = [torch.from_numpy(orc.dense_m(L, j)).to("cuda:%d" % local) for j in range(4)]
+    ext = torch.cuda.ExternalStream(sap.stream(), device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        r = ev.evaluate(ms_dev[i % 4], 0.0, grad=True, hess=hess, gather_grad=args.gather_grad)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for i in range(args.steps):
+        with torch.cuda.stream(ext):
+            pass
+        r = ev.evaluate_async(ms_dev[i % 4], 0.0, grad=True, hess=hess, gather_grad=args.gather_grad)
+    e1.record(ext)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    var, flags = sap.last_result()
+    if rank == 0:
+        S_inv = sum(len(g) * (k + 1) ** 2 for k, g in enumerate(groups))
+        algo = 16.0 * S_inv + 24.0 * L + ((16.0 * N * L + 8.0 * L * L) if hess else 0.0)
+        peak, peak_src = peaks()
+        per = float(t[0]) / args.steps
+        out = {"metric": METRIC, "value": args.steps / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "impl": "ours",
+               "config": {"workload": "group-sharded evaluation, %d models, %d groups, %s" % (N, L, "dense Hessian row panels" if hess else "no Hessian"),
+                          "models": N, "groups": L, "parallelism": "group-shard x%d, NCCL all-reduce of N^2+33 doubles%s" % (world, " + all-gather of U,V" if hess else ""),
+                          "slices": [list(sl) for sl in ev.slices], "hessian_row_panels": [list(sl) for sl in ev.row_slices]},
+               "roofline": {"bound": "hbm", "achieved": algo / (per * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                            "frac": algo / (per * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + " x n_gpus",
+                            "algorithmic_bytes_per_eval": algo},
+               "variance_check": var}
+        print(json.dumps(out))
+    sap.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -458,10 +529,16 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-solve", dest="solve", action="store_false", help="skip the end-to-end SAP solve comparison")
+    ap.add_argument("--mode", default="sweep", choices=["sweep", "shard"], help="sweep: independent instances per GPU (default); shard: one problem, groups sharded")
+    ap.add_argument("--nohess", action="store_true", help="shard mode: Phi + variance + gradient only (e.g. --models 20)")
+    ap.add_argument("--gather-grad", action="store_true", help="shard mode: all-gather the gradient slices")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 5)
         run_reference(args)
+    elif args.mode == "shard":
+        args.warmup = max(args.warmup, 3)
+        run_shard(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

@@ -518,15 +518,16 @@ static void launch_hess_t(blu_ctx *c, bool sym, const double *Ua, long long Lrow
     }
 }
 
-static int launch_hess(blu_ctx *c, bool sym)
+static int launch_hess(blu_ctx *c, bool sym, long long rlo = 0, long long rhi = 0)
 {
-    const long long rows = sym ? c->L : (c->hi - c->lo);
+    const long long rows = sym ? c->L : (rhi - rlo);
+    if (rows <= 0) return BLU_OK;
     if (!c->d_H || c->H_rows < rows) {
         if (c->d_H) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->d_H)); c->d_H = nullptr; }
         CUDA_TRY(cudaMalloc(&c->d_H, sizeof(double) * (size_t)rows * (size_t)c->ldH));
         c->H_rows = rows;
     }
-    const double *Ua = c->d_U + (sym ? 0 : c->lo * c->NP);
+    const double *Ua = c->d_U + (sym ? 0 : rlo * c->NP);
     switch (c->NCH) {
         case 1: launch_hess_t<1>(c, sym, Ua, rows, c->d_H); break;
         case 2: launch_hess_t<2>(c, sym, Ua, rows, c->d_H); break;
@@ -788,12 +789,13 @@ extern "C" int blu_shard_finish(blu_ctx *c, double delta, int want_grad, int wan
     return BLU_OK;
 }
 
-extern "C" int blu_shard_hess(blu_ctx *c)
+extern "C" int blu_shard_hess(blu_ctx *c, int64_t row_lo, int64_t row_hi)
 {
     int rc = use(c);
     if (rc) return rc;
     if (!c->d_U) return fail(BLU_ERR_STATE, "U/V not computed");
-    return launch_hess(c, false);
+    if (row_lo < 0 || row_hi > c->L || row_lo > row_hi) return fail(BLU_ERR_ARG, "row panel [%lld,%lld) outside [0,%lld]", (long long)row_lo, (long long)row_hi, c->L);
+    return launch_hess(c, false, row_lo, row_hi);
 }
 
 // --------------------------------------------------------------------------------------------

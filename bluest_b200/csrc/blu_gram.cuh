@@ -35,22 +35,22 @@ blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab
     double acc[NPAIR][2];
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) { acc[p][0] = 0.0; acc[p][1] = 0.0; }
-    for (long long s = s0; s < s1; s += 8) {
-        double f[2][NT];
+    for (long long s = s0; s < s1; s += 16) {
+        double f[4][NT];                       // 4 x 4 samples in flight before the first MMA issues
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 4; ++h) {
             const long long row = s + 4 * h + ks;
             const bool rok = row < s1;
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const int col = 8 * t + cq;
                 double v = 0.0;
-                if (rok) v = (col < N) ? Y[row * N + col] : (col == N ? 1.0 : 0.0);
+                if (rok) v = (col < N) ? __ldcs(Y + row * N + col) : (col == N ? 1.0 : 0.0);
                 f[h][t] = v;
             }
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 4; ++h) {
             int p = 0;
 #pragma unroll
             for (int ti = 0; ti < NT; ++ti)
@@ -82,19 +82,37 @@ blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab
     }
 }
 
-// Fixed-order reduction over CTAs + covariance formula.  One CTA.
-__global__ void blu_gram_finish_kernel(const double *__restrict__ part, int nparts, int NPG, int N, long long n,
-                                       double *__restrict__ s1, double *__restrict__ S2, double *__restrict__ Chat)
+// Fixed-order reduction over CTAs + covariance formula.  One CTA; the partial tiles are summed in
+// BLU_GRAM_SEG interleaved segments (independent loads in flight), then the segments in order.
+#define BLU_GRAM_SEG 16
+__global__ void __launch_bounds__(1024)
+blu_gram_finish_kernel(const double *__restrict__ part, int nparts, int NPG, int N, long long n,
+                       double *__restrict__ s1, double *__restrict__ S2, double *__restrict__ Chat)
 {
-    extern __shared__ double G[];        // NPG*NPG
-    for (int t = threadIdx.x; t < NPG * NPG; t += blockDim.x) {
-        const int r = t / NPG, c = t - r * NPG;
+    extern __shared__ double gsm[];       // BLU_GRAM_SEG * NPG*NPG staging, then G = first NPG*NPG
+    const int E = NPG * NPG;
+    for (int t = threadIdx.x; t < E * BLU_GRAM_SEG; t += blockDim.x) {
+        const int seg = t / E, e = t - seg * E;
+        const int r = e / NPG, c = e - r * NPG;
         double sum = 0.0;
         if ((r >> 3) <= (c >> 3))
-            for (int p = 0; p < nparts; ++p) sum += part[(long long)p * NPG * NPG + t];
-        G[t] = sum;
+            for (int p = seg; p < nparts; p += BLU_GRAM_SEG) sum += part[(long long)p * E + e];
+        gsm[t] = sum;
     }
     __syncthreads();
+    double tot[2] = {0.0, 0.0};
+    int idx = 0;
+    for (int e = threadIdx.x; e < E; e += blockDim.x, ++idx) {
+        double sum = 0.0;
+#pragma unroll
+        for (int seg = 0; seg < BLU_GRAM_SEG; ++seg) sum += gsm[seg * E + e];
+        tot[idx & 1] = sum;                 // E <= 1600 <= 2 * blockDim
+    }
+    __syncthreads();
+    idx = 0;
+    for (int e = threadIdx.x; e < E; e += blockDim.x, ++idx) gsm[e] = tot[idx & 1];
+    __syncthreads();
+    const double *G = gsm;
     const double dn = (double)n;
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
         const int r = t / N, c = t - r * N;
@@ -126,10 +144,10 @@ static int blu_gram_run(const double *Y, long long n, int N, int y_on_device, do
     cudaGetDeviceProperties(&prop, dev);
     const long long warps_wanted = (n + 255) / 256;                       // >= 256 samples per warp
     int grid = (int)std::max<long long>(1, std::min<long long>((warps_wanted + BLU_GRAM_WARPS - 1) / BLU_GRAM_WARPS,
-                                                                  (long long)prop.multiProcessorCount * 4));
+                                                                  (long long)prop.multiProcessorCount * 2));
     const long long nwarps = (long long)grid * BLU_GRAM_WARPS;
     long long slab = (n + nwarps - 1) / nwarps;
-    slab = ((slab + 7) / 8) * 8;
+    slab = ((slab + 15) / 16) * 16;
     double *dY = nullptr, *d_part = nullptr, *d_out = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -161,7 +179,11 @@ static int blu_gram_run(const double *Y, long long n, int N, int y_on_device, do
         default: e = blu_gram_launch<5>(dY, n, N, grid, slab, d_part, st); break;
     }
     if (e != cudaSuccess) return done(BLU_ERR_CUDA);
-    blu_gram_finish_kernel<<<1, 256, sizeof(double) * NPG * NPG, st>>>(d_part, grid, NPG, N, n, d_out, d_out + N, d_out + N + N * N);
+    {
+        const int fsm = (int)(sizeof(double) * NPG * NPG * BLU_GRAM_SEG);
+        if ((e = cudaFuncSetAttribute(blu_gram_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return done(BLU_ERR_CUDA);
+        blu_gram_finish_kernel<<<1, 1024, fsm, st>>>(d_part, grid, NPG, N, n, d_out, d_out + N, d_out + N + N * N);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return done(BLU_ERR_CUDA);
     cudaEventRecord(e1, st);
     std::vector<double> h((size_t)(2 * N * N + N));

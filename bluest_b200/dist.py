@@ -7,7 +7,7 @@ inverses of that slice only.  One evaluation is three local phases with two smal
     ALL-REDUCE     N*N (+33 indicator) doubles                  <- the one real exchange of the path
     shard_finish   delta*I, pinv, variance (redundant on every rank); gradient, U, V of the slice
     ALL-GATHER     U, V rows (N*L doubles each) -- only when the dense Hessian is wanted
-    shard_hess     rows [lo,hi) of H against all columns        (kernel 3b, local; H stays sharded)
+    shard_hess     an equal-rows panel of H against all columns (kernel 3b, local; H stays sharded)
 
 The choreography is engine-agnostic: ``GpuEngine`` drives a ``blu_ctx`` through the C ABI and
 ``torch.distributed`` (NCCL over NVLink); the CPU tests plug a numpy engine into the same class and
@@ -32,6 +32,10 @@ class ShardedEvaluator:
         self.slices = balanced_slices(list(sizes), world)
         self.lo, self.hi = self.slices[rank]
         self.max_rows = max(hi - lo for lo, hi in self.slices)
+        # Hessian row panels: equal row counts (equal bytes written), independent of the group slices
+        cuts = [(self.L * r) // world for r in range(world + 1)]
+        self.row_slices = [(cuts[r], cuts[r + 1]) for r in range(world)]
+        self.rlo, self.rhi = self.row_slices[rank]
         engine.set_slice(self.lo, self.hi)
 
     # -- collectives (no-ops at world == 1) --------------------------------------------------
@@ -70,10 +74,26 @@ class ShardedEvaluator:
             if hess:
                 self._all_gather_rows(e.u_buffer(), e.NP)
                 self._all_gather_rows(e.v_buffer(), e.NP)
-                e.shard_hess()
+                e.shard_hess(self.rlo, self.rhi)
         var, flags = e.result()
-        out.update(var=var, flags=flags, lo=self.lo, hi=self.hi)
+        out.update(var=var, flags=flags, lo=self.lo, hi=self.hi, rlo=self.rlo, rhi=self.rhi)
         return out
+
+    def evaluate_async(self, m, delta=0.0, grad=True, hess=False, gather_grad=True):
+        """Same as evaluate() but without the final read-back of (var, flags): nothing on the host
+        waits for the device, so evaluations can be queued back to back."""
+        e = self.engine
+        with e.stream_context():
+            buf = e.shard_phi(m)
+            self._all_reduce(buf)
+            e.shard_finish(delta, grad or hess, hess)
+            if grad and gather_grad:
+                self._all_gather_rows(e.grad_buffer(), 1)
+            if hess:
+                self._all_gather_rows(e.u_buffer(), e.NP)
+                self._all_gather_rows(e.v_buffer(), e.NP)
+                e.shard_hess(self.rlo, self.rhi)
+        return None
 
 
 class GpuEngine:
@@ -109,8 +129,8 @@ class GpuEngine:
     def shard_finish(self, delta, want_grad, want_uv):
         _lib.check(_lib.lib().blu_shard_finish(self.sap._ctx, float(delta), int(bool(want_grad)), int(bool(want_uv))))
 
-    def shard_hess(self):
-        _lib.check(_lib.lib().blu_shard_hess(self.sap._ctx))
+    def shard_hess(self, rlo, rhi):
+        _lib.check(_lib.lib().blu_shard_hess(self.sap._ctx, int(rlo), int(rhi)))
 
     def grad_buffer(self):
         return self.sap.device_buffer(_lib.BUF_GRAD)

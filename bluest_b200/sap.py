@@ -122,7 +122,9 @@ class SAP(object):
         def variance_GH(m, delta=0, nohess=False):
             var = ctypes.c_double(0.0); fl = ctypes.c_uint(0)
             grad = np.empty(L)
-            hess = None if nohess else _lib.pinned_pool.empty((L, L))
+            # page-locked destination only where it pays (pinning costs ~0.1 ms/MB once; a pageable D2H of a
+            # big Hessian runs several times slower than the 57 GB/s of a pinned one)
+            hess = None if nohess else (_lib.pinned_pool.empty((L, L)) if L * L * 8 >= (32 << 20) else np.empty((L, L)))
             hp = None if nohess else ctypes.c_void_p(hess.ctypes.data)
             check(lib().blu_variance_GH(ctx, dptr(self._m(m)), float(delta), ctypes.byref(var), dptr(grad), hp, ctypes.byref(fl)))
             if fl.value & _lib.FLAG_TINY:

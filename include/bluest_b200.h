@@ -137,11 +137,14 @@ int blu_ctx_last_launches(blu_ctx *ctx);
  *   (all-reduce BLU_BUF_PHI across ranks)
  *   blu_shard_finish   delta*I, pinv, variance on the reduced Phi; grad and U,V rows of the slice
  *   (all-gather U,V rows)
- *   blu_shard_hess     rows [lo,hi) of the Hessian against all L columns. */
+ *   blu_shard_hess     rows [row_lo,row_hi) of the Hessian against all L columns.  Once U,V are
+ *                      gathered any rank can produce any rows, so the row panels are balanced by
+ *                      row count (equal bytes written) independently of the group slices, which
+ *                      are balanced by k^2 work. */
 int blu_ctx_set_slice(blu_ctx *ctx, int64_t lo, int64_t hi);
 int blu_shard_phi(blu_ctx *ctx, const double *d_m);
 int blu_shard_finish(blu_ctx *ctx, double delta, int want_grad, int want_uv);
-int blu_shard_hess(blu_ctx *ctx);
+int blu_shard_hess(blu_ctx *ctx, int64_t row_lo, int64_t row_hi);
 
 /* Page-locked host memory for large results (the dense Hessian): pageable destinations make
  * the D2H copy several times slower. */

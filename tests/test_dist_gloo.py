@@ -76,9 +76,9 @@ class NumpyEngine:
             V[self.lo:self.hi, :N] = Uall[self.lo:self.hi] @ (2 * P)
             self.U.copy_(torch.from_numpy(U.ravel())); self.V.copy_(torch.from_numpy(V.ravel()))
 
-    def shard_hess(self):
+    def shard_hess(self, rlo, rhi):
         U = self.U.numpy().reshape(-1, self.NP); V = self.V.numpy().reshape(-1, self.NP)
-        self.H = U[self.lo:self.hi] @ V.T
+        self.H = U[rlo:rhi] @ V.T
 
     def grad_buffer(self): return self.grad
     def u_buffer(self): return self.U
@@ -103,7 +103,7 @@ def _worker(rank, world, port, N, K, ret):
         for name, m in (("dense", orc.dense_m(o.L, 2)), ("sparse", orc.sparse_m(o.L, N, 2)), ("tiny", 0.01 * np.ones(o.L))):
             r = ev.evaluate(m, delta=0.0, grad=True, hess=(name != "tiny"))
             e = ev.engine
-            out[name] = dict(var=r["var"], flags=r["flags"], lo=r["lo"], hi=r["hi"],
+            out[name] = dict(var=r["var"], flags=r["flags"], lo=r["lo"], hi=r["hi"], rlo=r["rlo"], rhi=r["rhi"],
                              grad=e.grad.numpy().copy(), H=getattr(e, "H", None) if name != "tiny" else None)
         ret[rank] = out
     finally:
@@ -130,7 +130,7 @@ def test_sharded_evaluation_world2(N, K):
             tol = 1e-12 if name == "dense" else 1e-9
             assert np.max(np.abs(res["grad"] - g)) <= tol * np.max(np.abs(g))       # gathered: full length on every rank
             rows.append(res["H"])
-            assert res["H"].shape == (res["hi"] - res["lo"], o.L)
+            assert res["H"].shape == (res["rhi"] - res["rlo"], o.L)
         Hcat = np.vstack(rows)
         assert np.max(np.abs(Hcat - H)) <= (1e-12 if name == "dense" else 1e-9) * np.max(np.abs(H))
     for r in range(world):
