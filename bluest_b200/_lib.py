@@ -44,6 +44,9 @@ SIGNATURES = {
     "blu_ctx_timing_log": (c_int, [p_void, c_int]),
     "blu_ctx_timing_read": (c_int, [p_void, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(c_int)]),
     "blu_ctx_set_slice": (c_int, [p_void, c_i64, c_i64]),
+    "blu_ctx_peer_handle": (c_int, [p_void, p_void]),
+    "blu_ctx_peer_connect": (c_int, [p_void, c_int, c_int, p_void]),
+    "blu_shard_eval_fused": (c_int, [p_void, p_void, c_dbl, c_int, c_int]),
     "blu_shard_phi": (c_int, [p_void, p_void]),
     "blu_shard_finish": (c_int, [p_void, c_dbl, c_int, c_int]),
     "blu_shard_hess": (c_int, [p_void, c_i64, c_i64]),

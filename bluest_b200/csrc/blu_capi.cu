@@ -79,6 +79,10 @@ struct blu_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
     int launches = 0;
+    BluXchg *d_xchg = nullptr;         // this rank's exchange buffer (CUDA IPC shared)
+    BluPeers peers{};                  // peers as mapped here; world == 0: not connected
+    std::vector<void *> ipc_opened;
+    unsigned long long epoch = 0;
     std::vector<cudaEvent_t> evlog;    // optional per-evaluation event log (4 events per evaluation)
     int evlog_n = 0;
 };
@@ -134,6 +138,8 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     cudaFree(c->d_C); cudaFree(c->d_m); cudaFree(c->d_part); cudaFree(c->d_phi); cudaFree(c->d_pinv);
     cudaFree(c->d_x); cudaFree(c->d_S); cudaFree(c->d_grad); cudaFree(c->d_U); cudaFree(c->d_V); cudaFree(c->d_H);
     cudaFree(c->d_hdr); cudaFree(c->d_chunks);
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(c->d_xchg);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->evlog) if (e) cudaEventDestroy(e);
@@ -464,7 +470,7 @@ static int launch_phi(blu_ctx *c, const double *d_m, double delta, int mode)
         c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr);
     KERNEL_CHECK(c);
     blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
-        c->N, c->grid_phi, c->d_part, delta, mode, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr);
+        c->N, c->grid_phi, c->d_part, delta, mode, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr, c->peers, c->epoch);
     KERNEL_CHECK(c);
     return BLU_OK;
 }
@@ -783,7 +789,7 @@ extern "C" int blu_shard_finish(blu_ctx *c, double delta, int want_grad, int wan
     const int NN = c->N * c->N;
     // BLU_BUF_PHI now holds the all-reduced upper-triangle sum; supp / max|m| were reduced by the host
     blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
-        c->N, 0, c->d_part, delta, 1, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr);
+        c->N, 0, c->d_part, delta, 1, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr, c->peers, c->epoch);
     KERNEL_CHECK(c);
     if (want_grad || want_uv) return launch_grad(c, want_uv);
     return BLU_OK;
@@ -796,6 +802,62 @@ extern "C" int blu_shard_hess(blu_ctx *c, int64_t row_lo, int64_t row_hi)
     if (!c->d_U) return fail(BLU_ERR_STATE, "U/V not computed");
     if (row_lo < 0 || row_hi > c->L || row_lo > row_hi) return fail(BLU_ERR_ARG, "row panel [%lld,%lld) outside [0,%lld]", (long long)row_lo, (long long)row_hi, c->L);
     return launch_hess(c, false, row_lo, row_hi);
+}
+
+// ---- fused multi-GPU path: all-reduce of the partial Phi over NVLink peer memory ---------------
+extern "C" int blu_ctx_peer_handle(blu_ctx *c, void *handle64)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!handle64) return fail(BLU_ERR_ARG, "null handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!c->d_xchg) {
+        CUDA_TRY(cudaMalloc(&c->d_xchg, sizeof(BluXchg)));
+        CUDA_TRY(cudaMemset(c->d_xchg, 0, sizeof(BluXchg)));
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->d_xchg));
+    memcpy(handle64, &h, 64);
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_peer_connect(blu_ctx *c, int world, int rank, const void *handles)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (world < 1 || world > BLU_MAX_PEERS || rank < 0 || rank >= world) return fail(BLU_ERR_ARG, "bad world/rank %d/%d", world, rank);
+    if (!c->d_xchg) return fail(BLU_ERR_STATE, "call blu_ctx_peer_handle first");
+    if (world > 1 && !handles) return fail(BLU_ERR_ARG, "null handles");
+    if (c->N * c->N + 40 > BLU_XCHG_DOUBLES) return fail(BLU_ERR_ARG, "N too large for the exchange slot");
+    BluPeers p{};
+    p.world = world; p.rank = rank;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { p.peer[r] = c->d_xchg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+        void *ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->ipc_opened.push_back(ptr);
+        p.peer[r] = (BluXchg *)ptr;
+    }
+    c->peers = p;
+    c->epoch = 0;
+    return BLU_OK;
+}
+
+extern "C" int blu_shard_eval_fused(blu_ctx *c, const double *d_m, double delta, int want_grad, int want_uv)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->have_inv) return fail(BLU_ERR_STATE, "inverses not set");
+    if (c->peers.world < 1) return fail(BLU_ERR_STATE, "peers not connected: call blu_ctx_peer_connect first");
+    if (!d_m) d_m = c->d_m;
+    c->launches = 0;
+    c->epoch += 1;                    // every rank counts its evaluations the same way
+    rc = launch_phi(c, d_m, delta, 3);
+    if (rc) return rc;
+    if (want_grad || want_uv) return launch_grad(c, want_uv);
+    return BLU_OK;
 }
 
 // --------------------------------------------------------------------------------------------

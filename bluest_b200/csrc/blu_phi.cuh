@@ -219,15 +219,34 @@ __device__ __forceinline__ int blu_block_pinv(const double *phi, int N, const in
 }
 
 #define BLU_FIN_THREADS 512
+#define BLU_MAX_PEERS 16
+#define BLU_XCHG_DOUBLES 1088                 // N*N + 40 <= 1064 doubles per slot
+
+// One rank's exchange buffer for the fused (peer-memory) all-reduce of the partial Phi:
+// two slots (epoch parity) of raw upper-triangle sums + SUM-reducible indicators, and the epoch
+// each slot was last published for.  Lives in cudaMalloc memory shared through CUDA IPC, so the
+// finish kernel of every rank reads every other rank's slot directly over NVLink.
+struct BluXchg {
+    double data[2][BLU_XCHG_DOUBLES];
+    unsigned long long ready[2];
+};
+struct BluPeers {
+    BluXchg *peer[BLU_MAX_PEERS];             // peer[r] = rank r's buffer as mapped in THIS process
+    int world, rank;
+};
 #define BLU_FIN_SEG 8
 
 // mode 0: reduce + mirror + delta only (get_phi).  mode 1: + pinv, x, S, variance.
 // mode 2: reduce only, no mirror/delta (partial Phi of a group slice, before the all-reduce).
 // nparts == 0: Phi already sits in `phi` as an un-mirrored upper-triangle sum (after all-reduce).
+// mode 3: fused multi-GPU path -- reduce the local CTA partials, publish them in this rank's exchange
+//         slot, wait for every peer's slot of the same epoch, sum all ranks in rank order (every rank
+//         gets the bit-identical Phi), then continue exactly like mode 1.  One kernel does the
+//         local reduction, the all-reduce over NVLink peer memory and the pseudo-inverse.
 __global__ void __launch_bounds__(BLU_FIN_THREADS)
 blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double delta, int mode,
                       double *__restrict__ phi, double *__restrict__ pinv, double *__restrict__ xrow,
-                      double *__restrict__ S, BluEvalHeader *hdr)
+                      double *__restrict__ S, BluEvalHeader *hdr, BluPeers peers, unsigned long long epoch)
 {
     __shared__ double A[BLU_JMAX * BLU_JLD], V[BLU_JMAX * BLU_JLD], Ph[BLU_JMAX * BLU_JLD];
     extern __shared__ double red[];              // BLU_FIN_SEG x N*N staging for the partial sums
@@ -257,6 +276,37 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
         for (int e = tid; e < NN; e += nthr) Ph[(e / N) * BLU_JLD + (e % N)] = phi[e];
     }
     __syncthreads();
+    if (mode == 3) {
+        const int slot = (int)(epoch & 1ull);
+        BluXchg *mine = peers.peer[peers.rank];
+        const unsigned sp = hdr->supp;
+        const double mx = __longlong_as_double((long long)hdr->maxbits);
+        for (int e = tid; e < NN; e += nthr) mine->data[slot][e] = Ph[(e / N) * BLU_JLD + (e % N)];
+        if (tid < 32) mine->data[slot][NN + tid] = (sp >> tid) & 1u ? 1.0 : 0.0;
+        if (tid == 32) mine->data[slot][NN + 32] = mx >= 0.05 ? 1.0 : 0.0;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            hdr->supp = 0u; hdr->maxbits = 0ull;
+            *((volatile unsigned long long *)&mine->ready[slot]) = epoch;       // publish
+            __threadfence_system();
+        }
+        if (tid < peers.world) {                                                // wait for every rank
+            volatile unsigned long long *flag = (volatile unsigned long long *)&peers.peer[tid]->ready[slot];
+            while (*flag < epoch) { }
+        }
+        __syncthreads();
+        for (int e = tid; e < NN + 33; e += nthr) {
+            double sum = 0.0;
+            for (int r = 0; r < peers.world; ++r) sum += __ldcv(&peers.peer[r]->data[slot][e]);   // rank order, uncached
+            phi[e] = sum;
+        }
+        __syncthreads();
+        for (int e = tid; e < NN; e += nthr) Ph[(e / N) * BLU_JLD + (e % N)] = phi[e];
+        __syncthreads();
+        nparts = 0;                           // from here on: the all-reduced path of mode 1
+        mode = 1;
+    }
     if (mode == 2) {
         // partial of a group slice: raw upper-triangle sums, followed by SUM-reducible encodings
         // of the support mask (32 indicators) and of "max|m| >= 0.05" (1 indicator)

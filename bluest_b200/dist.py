@@ -22,10 +22,12 @@ from .groups import balanced_slices
 
 
 class ShardedEvaluator:
-    def __init__(self, engine, sizes, rank, world, dist=None, group=None):
+    def __init__(self, engine, sizes, rank, world, dist=None, group=None, fused=False):
         """engine: object with shard_phi / shard_finish / shard_hess / buffers (see GpuEngine).
-        sizes = [L1..LK]."""
+        sizes = [L1..LK].  fused=True: the Phi all-reduce runs inside the finish kernel over NVLink
+        peer memory (engine.connect_peers) instead of a separate NCCL call."""
         self.engine = engine
+        self.fused = bool(fused)
         self.rank, self.world = rank, world
         self.dist, self.group = dist, group
         self.L = int(sum(sizes))
@@ -37,6 +39,17 @@ class ShardedEvaluator:
         self.row_slices = [(cuts[r], cuts[r + 1]) for r in range(world)]
         self.rlo, self.rhi = self.row_slices[rank]
         engine.set_slice(self.lo, self.hi)
+        if self.fused:
+            engine.connect_peers(rank, world, dist, group)
+
+    def _phi_exchange_finish(self, m, delta, want_grad, want_uv):
+        e = self.engine
+        if self.fused:
+            e.shard_eval_fused(m, delta, want_grad, want_uv)       # one kernel: reduce + NVLink all-reduce + pinv
+        else:
+            buf = e.shard_phi(m)                                  # (N*N + 40) partial sums + indicators
+            self._all_reduce(buf)
+            e.shard_finish(delta, want_grad, want_uv)
 
     # -- collectives (no-ops at world == 1) --------------------------------------------------
     def _all_reduce(self, t):
@@ -65,9 +78,7 @@ class ShardedEvaluator:
         own slice is valid) and the own Hessian row panel when hess=True."""
         e = self.engine
         with e.stream_context():
-            buf = e.shard_phi(m)                    # (N*N + 40) partial sums + indicators
-            self._all_reduce(buf)
-            e.shard_finish(delta, grad or hess, hess)
+            self._phi_exchange_finish(m, delta, grad or hess, hess)
             out = {}
             if grad and gather_grad:
                 self._all_gather_rows(e.grad_buffer(), 1)
@@ -84,9 +95,7 @@ class ShardedEvaluator:
         waits for the device, so evaluations can be queued back to back."""
         e = self.engine
         with e.stream_context():
-            buf = e.shard_phi(m)
-            self._all_reduce(buf)
-            e.shard_finish(delta, grad or hess, hess)
+            self._phi_exchange_finish(m, delta, grad or hess, hess)
             if grad and gather_grad:
                 self._all_gather_rows(e.grad_buffer(), 1)
             if hess:
@@ -113,6 +122,29 @@ class GpuEngine:
 
     def set_slice(self, lo, hi):
         _lib.check(_lib.lib().blu_ctx_set_slice(self.sap._ctx, int(lo), int(hi)))
+
+    def connect_peers(self, rank, world, dist=None, group=None):
+        """Exchange the CUDA-IPC handles of the per-rank exchange buffers and map the peers."""
+        h = ctypes.create_string_buffer(64)
+        _lib.check(_lib.lib().blu_ctx_peer_handle(self.sap._ctx, h))
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(h.raw), group=group)
+            blob = b"".join(handles)
+        else:
+            blob = bytes(h.raw)
+        _lib.check(_lib.lib().blu_ctx_peer_connect(self.sap._ctx, int(world), int(rank), blob))
+
+    def _m_ptr(self, m):
+        if m is None:
+            return None
+        if hasattr(m, "data_ptr"):
+            return ctypes.c_void_p(int(m.data_ptr()))
+        self.sap.device_buffer(_lib.BUF_M).copy_(self.torch.from_numpy(np.ascontiguousarray(m, dtype=np.float64)), non_blocking=True)
+        return None
+
+    def shard_eval_fused(self, m, delta, want_grad, want_uv):
+        _lib.check(_lib.lib().blu_shard_eval_fused(self.sap._ctx, self._m_ptr(m), float(delta), int(bool(want_grad)), int(bool(want_uv))))
 
     def shard_phi(self, m):
         if m is not None:

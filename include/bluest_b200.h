@@ -140,8 +140,21 @@ int blu_ctx_last_launches(blu_ctx *ctx);
  *   blu_shard_hess     rows [row_lo,row_hi) of the Hessian against all L columns.  Once U,V are
  *                      gathered any rank can produce any rows, so the row panels are balanced by
  *                      row count (equal bytes written) independently of the group slices, which
- *                      are balanced by k^2 work. */
+ *                      are balanced by k^2 work.
+ *
+ * Fused variant (one process per GPU on one NVLink box): the all-reduce is done INSIDE the finish
+ * kernel over peer memory -- every rank publishes its partial Phi in a CUDA-IPC shared slot and reads
+ * the other ranks' slots directly over NVLink, in rank order (bit-identical Phi on all ranks):
+ *   blu_ctx_peer_handle    64-byte cudaIpcMemHandle_t of this rank's exchange buffer
+ *   (exchange the handles between the processes with any host-side all-gather)
+ *   blu_ctx_peer_connect   map the peers' buffers (handles = world x 64 bytes, rank order)
+ *   blu_shard_eval_fused   partial Phi -> [local reduce + NVLink all-reduce + pinv + variance] ->
+ *                          gradient (and U,V) of the slice; every rank must call it the same number
+ *                          of times (the epoch counter is the call count). */
 int blu_ctx_set_slice(blu_ctx *ctx, int64_t lo, int64_t hi);
+int blu_ctx_peer_handle(blu_ctx *ctx, void *handle64);
+int blu_ctx_peer_connect(blu_ctx *ctx, int world, int rank, const void *handles);
+int blu_shard_eval_fused(blu_ctx *ctx, const double *d_m, double delta, int want_grad, int want_uv);
 int blu_shard_phi(blu_ctx *ctx, const double *d_m);
 int blu_shard_finish(blu_ctx *ctx, double delta, int want_grad, int want_uv);
 int blu_shard_hess(blu_ctx *ctx, int64_t row_lo, int64_t row_hi);

@@ -1,0 +1,95 @@
+"""Fused peer-memory all-reduce (blu_shard_eval_fused): world=1 on one GPU must reproduce the plain
+evaluation bit for bit; with >= 2 GPUs two processes exchange their partial Phi over NVLink inside
+the finish kernel and must agree with the oracle and with each other exactly."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from conftest import maxrel
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fused_world1_equals_plain():
+    import torch
+    import bluest_b200 as blu
+    from bluest_b200 import _lib
+    from bluest_b200.dist import GpuEngine, ShardedEvaluator
+    N = 11
+    C = orc.wishart_cov(N, 2)
+    groups = orc.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    sizes = [len(g) for g in groups]
+    sap = blu.SAP(C, N, [[list(g) for g in gk] for gk in groups], np.ones(L), verbose=False)
+    ref = blu.SAP(C, N, [[list(g) for g in gk] for gk in groups], np.ones(L), verbose=False)
+    ev = ShardedEvaluator(GpuEngine(sap), sizes, 0, 1, fused=True)
+    for m in (orc.dense_m(L, 1), orc.sparse_m(L, N, 1), 0.01 * np.ones(L)):
+        r = ev.evaluate(m, 0.0, grad=True, hess=False)
+        res = ref.variance_GH(m, nohess=True)
+        if len(res) == 2:
+            assert r["flags"] & 1 and np.isinf(r["var"])
+            continue
+        assert r["var"] == res[0]
+        g = sap.device_buffer(_lib.BUF_GRAD).cpu().numpy()
+        assert np.array_equal(g, res[1])
+    sap.close(); ref.close()
+
+
+def _worker(rank, world, port, N, ret):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import bluest_b200 as blu
+    from bluest_b200 import _lib
+    from bluest_b200.dist import GpuEngine, ShardedEvaluator
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        C = orc.wishart_cov(N, 2)
+        groups = orc.enumerate_groups(N)
+        L = sum(len(g) for g in groups)
+        sap = blu.SAP(C, N, [[list(g) for g in gk] for gk in groups], np.ones(L), verbose=False, device=rank)
+        ev = ShardedEvaluator(GpuEngine(sap), [len(g) for g in groups], rank, world, dist=dist, fused=True)
+        out = []
+        for seed in range(3):
+            m = orc.dense_m(L, seed) if seed < 2 else orc.sparse_m(L, N, seed)
+            r = ev.evaluate(m, 0.0, grad=True, hess=True, gather_grad=True)
+            ld = 16 * ((L + 15) // 16)
+            H = sap.device_buffer(_lib.BUF_HESS)[: (r["rhi"] - r["rlo"]) * ld].view(-1, ld)[:, :L].cpu().numpy()
+            out.append(dict(var=r["var"], grad=sap.device_buffer(_lib.BUF_GRAD).cpu().numpy(), H=H, rows=(r["rlo"], r["rhi"]),
+                            phi=sap.device_buffer(_lib.BUF_PHI)[: N * N].cpu().numpy()))
+        ret[rank] = out
+        sap.close()
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_fused_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    N, world = 12, 2
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 300, N, ret), nprocs=world, join=True)
+    C = orc.wishart_cov(N, 2)
+    groups = orc.enumerate_groups(N)
+    o = orc.SapOracle(C, N, groups)
+    for seed in range(3):
+        m = orc.dense_m(o.L, seed) if seed < 2 else orc.sparse_m(o.L, N, seed)
+        v, g, H = o.variance_GH(m, hess_mode="factored")
+        tol = 1e-12 if seed < 2 else 1e-9
+        a, b = ret[0][seed], ret[1][seed]
+        assert a["var"] == b["var"] and np.array_equal(a["phi"], b["phi"])       # rank-order sum: identical on all ranks
+        assert abs(a["var"] - v) <= 1e-12 * v
+        assert np.array_equal(a["grad"], b["grad"]) and maxrel(a["grad"], g) < tol
+        Hcat = np.vstack([a["H"], b["H"]])
+        assert maxrel(Hcat, H) < tol
