@@ -71,7 +71,7 @@ struct blu_ctx {
     BluEvalHeader *d_hdr = nullptr, *h_hdr = nullptr;
     int grid_phi = 1, grid_grad = 1;
     BluChunk *d_chunks = nullptr;      // work list of the owned slice (blu_stream.cuh)
-    int nchunks = 0, lutlen = 0, part_rows = 0;
+    int nchunks = 0, lutlen = 0, part_rows = 0, phi_warps = BLU_PHI_WARPS;
     bool have_inv = false;
     std::vector<char> inv_set;         // per class: inverses present
     long long lo = 0, hi = 0;          // owned slice of the flat enumeration
@@ -177,7 +177,9 @@ static int build_chunks(blu_ctx *c)
     // launch geometry: ~4 chunks per warp, at most two CTAs per SM for the Phi kernel (its partial
     // tiles are reduced by one CTA afterwards), a few more for the gradient kernels
     const long long want = std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS * 3 - 1) / (BLU_STREAM_WARPS * 3));
-    c->grid_phi = (int)std::min<long long>(want, (long long)c->nsm * 2);
+    c->phi_warps = blu_stream_smem_bytes(BLU_PHI_WARPS * c->N * c->N, (int)c->cls.size(), c->lutlen, BLU_PHI_WARPS) <= 200 * 1024 ? BLU_PHI_WARPS : 8;
+    c->grid_phi = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + c->phi_warps * 3 - 1) / (c->phi_warps * 3)),
+                                           (long long)c->nsm * (BLU_PHI_WARPS / c->phi_warps));
     c->grid_grad = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS - 1) / BLU_STREAM_WARPS), (long long)c->nsm * 3);
     if (c->grid_phi > c->part_rows) {
         if (c->d_part) CUDA_TRY(cudaFree(c->d_part));
@@ -290,7 +292,7 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
     {
         const int ncl = (int)c->cls.size();
         CTX_TRY(cudaFuncSetAttribute(blu_phi_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)blu_stream_smem_bytes(BLU_STREAM_WARPS * 1024, 32, 6000)));
+                                     220 * 1024));
         CTX_TRY(cudaFuncSetAttribute(blu_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)blu_stream_smem_bytes(0, 32, 6000)));
         CTX_TRY(cudaFuncSetAttribute(blu_gradu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -466,7 +468,7 @@ extern "C" int blu_ctx_assemble_psi(blu_ctx *c, double *psi)
 static int launch_phi(blu_ctx *c, const double *d_m, double delta, int mode)
 {
     const int NN = c->N * c->N;
-    blu_phi_partial_kernel<<<c->grid_phi, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(BLU_STREAM_WARPS * NN, (int)c->cls.size(), c->lutlen), c->stream>>>(
+    blu_phi_partial_kernel<<<c->grid_phi, c->phi_warps * 32, blu_stream_smem_bytes(c->phi_warps * NN, (int)c->cls.size(), c->lutlen, c->phi_warps), c->stream>>>(
         c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr);
     KERNEL_CHECK(c);
     blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(

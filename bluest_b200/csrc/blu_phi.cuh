@@ -23,6 +23,8 @@
 #include "blu_jacobi.cuh"
 #include "blu_stream.cuh"
 
+#define BLU_PHI_WARPS 16            // one CTA per SM: half as many partial tiles for the finish kernel
+
 struct BluEvalHeader {          // small device-side status block of a context
     unsigned supp;              // support mask (OR)
     unsigned flags;             // BLU_FLAG_* of the last evaluation
@@ -85,7 +87,7 @@ __device__ __forceinline__ void blu_phi_chunk_any(const double *__restrict__ bas
 }
 
 // `chunks` lists the work of this launch (whole context or the owned slice); see blu_stream.cuh.
-__global__ void __launch_bounds__(BLU_STREAM_WARPS * 32)
+__global__ void __launch_bounds__(BLU_PHI_WARPS * 32)
 blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks,
                        const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
                        const unsigned *__restrict__ gmask, const double *__restrict__ m,
@@ -93,7 +95,8 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int NN = N * N;
-    const BluStreamSmem sm = blu_stream_carve(smraw, BLU_STREAM_WARPS * NN, ncls, lutlen);
+    const int nwarps = blockDim.x >> 5;                  // 16 normally, 8 when N is large (shared-memory budget)
+    const BluStreamSmem sm = blu_stream_carve(smraw, nwarps * NN, ncls, lutlen, nwarps);
     const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *acc = sm.extra + w * NN;                     // this warp's private N x N tile
@@ -103,8 +106,8 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
 
     unsigned supp = 0u;
     double mymax = 0.0;
-    const int gw = blockIdx.x * BLU_STREAM_WARPS + w;
-    const int nw = gridDim.x * BLU_STREAM_WARPS;
+    const int gw = blockIdx.x * nwarps + w;
+    const int nw = gridDim.x * nwarps;
 
     int c = gw;
     BluChunkRegs cur, nxt;
@@ -151,8 +154,7 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
     __syncthreads();
     for (int t = threadIdx.x; t < NN; t += blockDim.x) {
         double sum = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < BLU_STREAM_WARPS; ++ww) sum += sm.extra[ww * NN + t];
+        for (int ww = 0; ww < nwarps; ++ww) sum += sm.extra[ww * NN + t];
         part[(long long)blockIdx.x * NN + t] = sum;
     }
 }
@@ -262,7 +264,13 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
         for (int t = tid; t < NN * BLU_FIN_SEG; t += nthr) {
             const int seg = t / NN, e = t - seg * NN;
             double s = 0.0;
-            for (int p = seg; p < nparts; p += BLU_FIN_SEG) s += part[(long long)p * NN + e];
+            int p = seg;
+            for (; p + 3 * BLU_FIN_SEG < nparts; p += 4 * BLU_FIN_SEG) {       // 4 loads in flight, same association every run
+                const double a0 = part[(long long)p * NN + e], a1 = part[(long long)(p + BLU_FIN_SEG) * NN + e];
+                const double a2 = part[(long long)(p + 2 * BLU_FIN_SEG) * NN + e], a3 = part[(long long)(p + 3 * BLU_FIN_SEG) * NN + e];
+                s += a0; s += a1; s += a2; s += a3;
+            }
+            for (; p < nparts; p += BLU_FIN_SEG) s += part[(long long)p * NN + e];
             red[seg * NN + e] = s;
         }
         __syncthreads();

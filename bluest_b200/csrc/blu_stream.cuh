@@ -107,25 +107,25 @@ struct BluStreamSmem {
     unsigned char *ids;
 };
 
-__host__ __device__ __forceinline__ size_t blu_stream_smem_bytes(int extra_doubles, int ncls, int lutlen)
+__host__ __device__ __forceinline__ size_t blu_stream_smem_bytes(int extra_doubles, int ncls, int lutlen, int warps = BLU_STREAM_WARPS)
 {
-    size_t b = sizeof(double) * ((size_t)BLU_STREAM_WARPS * 2 * BLU_STAGE_DOUBLES + extra_doubles);
+    size_t b = sizeof(double) * ((size_t)warps * 2 * BLU_STAGE_DOUBLES + extra_doubles);
     b += sizeof(BluClass) * ncls;
     b += ((sizeof(unsigned short) * lutlen + 7) / 8) * 8;
-    b += sizeof(unsigned long long) * BLU_STREAM_WARPS * 2;
-    b += BLU_STREAM_WARPS * 32 * 32;
+    b += sizeof(unsigned long long) * warps * 2;
+    b += warps * 32 * 32;
     return b;
 }
 
-__device__ __forceinline__ BluStreamSmem blu_stream_carve(unsigned char *raw, int extra_doubles, int ncls, int lutlen)
+__device__ __forceinline__ BluStreamSmem blu_stream_carve(unsigned char *raw, int extra_doubles, int ncls, int lutlen, int warps = BLU_STREAM_WARPS)
 {
     BluStreamSmem s;
     s.stages = reinterpret_cast<double *>(raw);
-    s.extra = s.stages + (size_t)BLU_STREAM_WARPS * 2 * BLU_STAGE_DOUBLES;
+    s.extra = s.stages + (size_t)warps * 2 * BLU_STAGE_DOUBLES;
     s.cls = reinterpret_cast<BluClass *>(s.extra + extra_doubles);
     s.lut = reinterpret_cast<unsigned short *>(s.cls + ncls);
     s.bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(s.lut) + ((sizeof(unsigned short) * lutlen + 7) / 8) * 8);
-    s.ids = reinterpret_cast<unsigned char *>(s.bars + BLU_STREAM_WARPS * 2);
+    s.ids = reinterpret_cast<unsigned char *>(s.bars + warps * 2);
     return s;
 }
 

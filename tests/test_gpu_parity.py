@@ -337,3 +337,19 @@ def test_determinism(blu):
         b = sap.variance_GH(m)
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
         assert np.array_equal(sap.get_phi(m), sap.get_phi(m))
+
+
+@pytest.mark.parametrize("N,K", [(24, 2), (32, 2), (32, 3)])
+def test_many_models_small_groups(blu, N, K):
+    """Largest supported model counts (32-bit membership masks, shared-memory budget of the Phi
+    kernel switches to 8 warps per CTA) with small K, as in the paper runs (M=12..32, K<=3)."""
+    C = orc.wishart_cov(N, 9)
+    groups = orc.enumerate_groups(N, K)
+    L = sum(len(g) for g in groups)
+    o = orc.SapOracle(C, K, groups)
+    sap = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False)
+    m = orc.dense_m(L, 4)
+    assert maxrel(sap.get_phi(m), o.get_phi(m)) < TOL
+    v, g, h = sap.variance_GH(m)
+    vo, go, ho = o.variance_GH(m, hess_mode="factored")
+    assert abs(v - vo) <= TOL * vo and maxrel(g, go) < TOL and maxrel(h, ho) < TOL
