@@ -297,6 +297,8 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
                                      (int)blu_stream_smem_bytes(0, 32, 6000)));
         CTX_TRY(cudaFuncSetAttribute(blu_gradu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)blu_stream_smem_bytes(1024, 32, 6000)));
+        CTX_TRY(cudaFuncSetAttribute(blu_ysum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)blu_stream_smem_bytes(BLU_STREAM_WARPS * 32, 32, 6000)));
         (void)ncl;
     }
     CTX_TRY(cudaStreamSynchronize(c->stream));
@@ -760,6 +762,45 @@ extern "C" int blu_cleanup_matrix(blu_ctx *c, const double *m, double delta, int
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_X);
     if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "cleanup_matrix: %s", cudaGetErrorString(e));
+    return BLU_OK;
+}
+
+// BLUE estimator (compute_BLUE_estimator sap.py:99-119 + PHIinvY0 misc.py:518-544)
+extern "C" int blu_blue_estimator(blu_ctx *c, const double *samples, const double *sums_flat, double *mu, double *var,
+                                  double *y_out, unsigned *flags)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!sums_flat) return fail(BLU_ERR_ARG, "null sums");
+    if ((rc = upload_m(c, samples))) return rc;
+    if ((rc = blu_eval_device(c, c->d_m, 0.0, 0, 0))) return rc;
+    double *d_sums = nullptr, *d_part = nullptr, *d_y = nullptr;
+    const size_t ns = (size_t)std::max<long long>(c->gidx_len, 1);
+    CUDA_TRY(cudaMalloc(&d_sums, sizeof(double) * ns));
+    cudaError_t e = cudaMalloc(&d_part, sizeof(double) * 32 * (size_t)c->grid_grad);
+    if (e == cudaSuccess) e = cudaMalloc(&d_y, sizeof(double) * 32);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sums, sums_flat, sizeof(double) * (size_t)c->gidx_len, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        blu_ysum_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(BLU_STREAM_WARPS * 32, (int)c->cls.size(), c->lutlen), c->stream>>>(
+            c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_sums, d_part);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) {
+        blu_ysum_finish_kernel<<<1, 32, 0, c->stream>>>(d_part, c->grid_grad, c->N, d_y, c->d_hdr);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    std::vector<double> y(32, 0.0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(y.data(), d_y, sizeof(double) * 32, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_hdr, c->d_hdr, sizeof(BluEvalHeader), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_sums); cudaFree(d_part); cudaFree(d_y);
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "blue_estimator: %s", cudaGetErrorString(e));
+    if (flags) *flags = c->h_hdr->flags;
+    if (var) *var = c->h_hdr->scal[0];
+    if (mu) *mu = (c->h_hdr->flags & BLU_FLAG_TINY) ? std::numeric_limits<double>::infinity() : c->h_hdr->scal[5];
+    if (y_out) memcpy(y_out, y.data(), sizeof(double) * c->N);
     return BLU_OK;
 }
 

@@ -251,3 +251,78 @@ __global__ void blu_psi_kernel(const BluClass *__restrict__ cls, int ncls, int N
         }
     }
 }
+
+// BLUE estimator right-hand side (compute_BLUE_estimator, sap.py:99-119):
+//     y[g_i[j]] += sum_s Cinv_i[j,s] * sums_i[s]      over all groups,
+// the same packed-inverse stream as the U factor with the per-group sample sums as the right-hand
+// side.  `sums` is flat in group order, k entries per group (same indexing as the id table).
+// Per-warp private y tiles (targets inside a group are distinct), fixed-order reductions.
+// part: (gridDim.x, 32).
+__global__ void __launch_bounds__(BLU_STREAM_WARPS * 32)
+blu_ysum_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks,
+                const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
+                const unsigned *__restrict__ gmask, const double *__restrict__ sums, double *__restrict__ part)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const BluStreamSmem sm = blu_stream_carve(smraw, BLU_STREAM_WARPS * 32, ncls, lutlen);
+    const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ids = sm.ids + w * 32 * 32;
+    double *yacc = sm.extra + w * 32;
+    yacc[lane] = 0.0;
+    __syncwarp();
+    const int gw = blockIdx.x * BLU_STREAM_WARPS + w;
+    const int nw = gridDim.x * BLU_STREAM_WARPS;
+    int c = gw;
+    BluChunkRegs cur, nxt;
+    BluChunk dnext;
+    if (c < nchunks) cur = blu_prefetch_chunk(chunks[c], sm.cls, cinv, nullptr, gmask, ws, 0, lane);
+    if (c + nw < nchunks) dnext = chunks[c + nw];
+    for (int it = 0; c < nchunks; c += nw, ++it) {
+        const int s = it & 1;
+        if (c + nw < nchunks) nxt = blu_prefetch_chunk(dnext, sm.cls, cinv, nullptr, gmask, ws, s ^ 1, lane);
+        if (c + 2 * nw < nchunks) dnext = chunks[c + 2 * nw];
+        const BluClass ci = sm.cls[cur.cls];
+        const int k = ci.k, T = ci.T;
+        blu_mbar_wait(ws.bar[s], (unsigned)((it >> 1) & 1));
+        const double *base = ws.stage[s] + cur.skew;
+        blu_expand_ids(cur.mask, k, ids, lane);
+        for (int g = 0; g < cur.g; ++g) {
+            const int gv = ids[g * 32 + lane];
+            const double sv = lane < k ? sums[ci.ioff + (cur.i0 + g) * k + lane] : 0.0;
+            const double *st = base + g * T;
+            const int j = lane < k ? lane : k - 1;
+            double y = 0.0;
+            for (int l = 0; l < k; ++l) {
+                const double sl = blu_shfl(sv, l);
+                const int a = j < l ? j : l, b = j < l ? l : j;
+                y += st[blu_pk(k, a, b)] * sl;
+            }
+            if (lane < k) yacc[gv] += y;
+            __syncwarp();
+        }
+        __syncwarp();
+        cur = nxt;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double sum = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < BLU_STREAM_WARPS; ++ww) sum += sm.extra[ww * 32 + threadIdx.x];
+        part[(long long)blockIdx.x * 32 + threadIdx.x] = sum;
+    }
+}
+
+// y = fixed-order sum of the CTA partials; mu = xsup . y  (PHIinvY0, misc.py:529-533).  One warp.
+__global__ void blu_ysum_finish_kernel(const double *__restrict__ part, int nparts, int N, double *__restrict__ y, BluEvalHeader *hdr)
+{
+    const int lane = threadIdx.x;
+    double sum = 0.0;
+    for (int p = 0; p < nparts; ++p) sum += part[(long long)p * 32 + lane];
+    if (lane < N) y[lane] = sum;
+    double prod = lane < N ? hdr->xsup[lane] * sum : 0.0;
+    // sequential, model order (the reference sums j = 0..len(y)-1 in order)
+    double mu = 0.0;
+    for (int a = 0; a < N; ++a) mu += blu_shfl(prod, a);
+    if (lane == 0) hdr->scal[5] = mu;
+}

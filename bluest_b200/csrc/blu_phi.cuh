@@ -29,7 +29,8 @@ struct BluEvalHeader {          // small device-side status block of a context
     unsigned supp;              // support mask (OR)
     unsigned flags;             // BLU_FLAG_* of the last evaluation
     unsigned long long maxbits; // bit pattern of max|m|
-    double scal[8];             // [0] variance [1] max|m| [2] sweeps [3] lambda_max [4] var (full pinv)
+    double scal[8];             // [0] variance [1] max|m| [2] sweeps [3] lambda_max [4] var (full pinv) [5] BLUE mean
+    double xsup[32];            // first row of pinv(Phi[idx,idx]) scattered to model slots (PHIinvY0, misc.py:529-533)
 };
 
 // Consume one staged chunk for the Phi accumulation.  S = ceil(T/32) steps per group, fully
@@ -400,6 +401,7 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
         // pinv(Phi[idx,idx])[0,0] is the (first supported model) diagonal entry of the block above
         const int s0 = sup ? __ffs(sup) - 1 : 0;
         if (tid == 0) { hdr->scal[0] = sup ? pinv[s0 * N + s0] : INFINITY; hdr->flags = flags; }
+        if (tid < 32) hdr->xsup[tid] = (tid < N && (sup >> tid & 1u)) ? pinv[s0 * N + tid] : 0.0;
         return;
     }
     __syncthreads();
@@ -412,4 +414,7 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
     const int nsub = ns;
     if (nsub > 0) blu_block_pinv(phi, N, sidx, nsub, A, V, Ph, diag0, &js, tid, nthr);
     if (tid == 0) { hdr->scal[0] = nsub > 0 ? Ph[0] : INFINITY; hdr->flags = flags; }
+    if (tid < 32) hdr->xsup[tid] = 0.0;
+    __syncthreads();
+    if (tid < nsub) hdr->xsup[sidx[tid]] = Ph[tid];
 }

@@ -58,18 +58,16 @@ class ShardedEvaluator:
 
     def _all_gather_rows(self, full, width):
         """Every rank has filled rows [lo,hi) of ``full`` (rows x width, row-major, flat tensor);
-        gather the other ranks' rows.  Slices are uneven, so a padded all_gather_into_tensor."""
+        fetch the other ranks' rows.  The slices are uneven (balanced by work, not by count), so
+        instead of a padded all-gather each owner broadcasts its slice IN PLACE: the views are
+        contiguous, nothing is staged or copied."""
         if self.world == 1:
             return
-        import torch
         full2 = full[: (full.numel() // width) * width].view(-1, width)
-        send = torch.zeros((self.max_rows, width), dtype=full.dtype, device=full.device)
-        send[: self.hi - self.lo] = full2[self.lo:self.hi]
-        recv = torch.empty((self.world * self.max_rows, width), dtype=full.dtype, device=full.device)
-        self.dist.all_gather_into_tensor(recv, send, group=self.group)
         for r, (lo, hi) in enumerate(self.slices):
-            if r != self.rank and hi > lo:
-                full2[lo:hi] = recv[r * self.max_rows: r * self.max_rows + (hi - lo)]
+            if hi > lo:
+                src = self.dist.get_global_rank(self.group, r) if self.group is not None else r
+                self.dist.broadcast(full2[lo:hi], src=src, group=self.group)
 
     # -- one evaluation ----------------------------------------------------------------------
     def evaluate(self, m, delta=0.0, grad=True, hess=False, gather_grad=True):

@@ -21,7 +21,7 @@ from .sap import SAP as B200SAP
 _saved = {}
 _L1 = ("assemble_psi_c", "objectiveK_c", "gradK_c", "hessKQ_c", "cleanupK_c")
 _L2_METHODS = ("__init__", "get_variance_functions", "_m", "eval_device", "upload_m", "sync", "last_result", "last_timing",
-               "timing_log", "timing_read", "last_launches", "device_ptr", "device_buffer", "stream", "close", "__del__")
+               "timing_log", "timing_read", "last_launches", "device_ptr", "device_buffer", "stream", "close", "__del__", "compute_BLUE_estimator")
 
 
 def make_hybrid(ref_sap_cls):

@@ -79,3 +79,13 @@ class MOSAP(object):
             X[:, self.mappings[n]] = self.SAPS[n].get_cleanup_matrix(m[self.mappings[n]], delta=delta)
             Xs.append(X)
         return np.vstack(Xs)
+
+    def compute_BLUE_estimators(self, sums, samples):
+        """mosap.py:113-123."""
+        out = []
+        for n in range(self.n_outputs):
+            sums_n = [sums[n][item] for item in self.mappings[n]]
+            out.append(self.SAPS[n].compute_BLUE_estimator(sums_n, samples=samples[self.mappings[n]]))
+        mus = [item[0] for item in out]
+        Vars = np.array([item[1] for item in out])
+        return mus, Vars

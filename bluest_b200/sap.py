@@ -221,6 +221,25 @@ class SAP(object):
         except Exception:
             pass
 
+    def compute_BLUE_estimator(self, sums, samples=None):
+        """sap.py:99-119 + misc.py:518-544.  ``sums[i]`` = the k sample sums of group i (flat group
+        order, scalar outputs).  Returns (mu, var); inf when max|samples| < 0.05."""
+        if samples is None:
+            samples = self.samples
+        flat = np.concatenate([np.asarray(s_, dtype=np.float64).ravel() for s_ in sums]) if len(sums) else np.zeros(0)
+        expect = int(sum(self.sizes[k] * k for k in range(1, self.K + 1)))
+        if flat.size != expect:
+            raise ValueError("sums must hold k scalars per group (%d in total), got %d" % (expect, flat.size))
+        flat = np.ascontiguousarray(flat)
+        mu = ctypes.c_double(0.0); var = ctypes.c_double(0.0); fl = ctypes.c_uint(0)
+        y = np.empty(self.N)
+        check(lib().blu_blue_estimator(self._ctx, dptr(self._m(samples)), dptr(flat), ctypes.byref(mu), ctypes.byref(var), dptr(y), ctypes.byref(fl)))
+        if fl.value & _lib.FLAG_TINY:
+            return np.inf                                     # misc.py:519
+        assert not (fl.value & _lib.FLAG_NO_MODEL0)           # misc.py:527
+        self.last_y = y
+        return mu.value, var.value
+
     # ---- host orchestration kept from the reference -------------------------------------------
     def get_max_sample_constraints(self, max_model_samples):
         """sap.py:222-240."""

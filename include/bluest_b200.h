@@ -110,6 +110,14 @@ int blu_variance_GH(blu_ctx *ctx, const double *m, double delta, double *var, do
 int blu_cleanup_matrix(blu_ctx *ctx, const double *m, double delta, int mode, double *X,
                        unsigned *flags);
 
+/* BLUE estimator (compute_BLUE_estimator sap.py:99-119 + PHIinvY0 misc.py:518-544) -- the step after
+ * sampling, "next" row of the scope table.  samples: (L) sample counts; sums_flat: the per-group
+ * sample sums, k doubles per group in flat group order (sum_k Lk*k doubles).  Outputs: *mu, *var
+ * (inf with BLU_FLAG_TINY), y (N, optional) = sum_i R_i^T Cinv_i sums_i.  BLU_FLAG_NO_MODEL0 where
+ * the reference asserts. */
+int blu_blue_estimator(blu_ctx *ctx, const double *samples, const double *sums_flat, double *mu,
+                       double *var, double *y, unsigned *flags);
+
 /* Device-resident evaluation: d_m lives on the context's device (or NULL to reuse BLU_BUF_M).
  * want_grad / want_hess select the work; results stay in the context's buffers
  * (blu_ctx_device_ptr).  The call is asynchronous on the context's stream. */

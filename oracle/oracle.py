@@ -297,6 +297,33 @@ class SapOracle:
         return np.hstack(cols)
 
 
+def blue_estimator(o, sums, samples):
+    """compute_BLUE_estimator (sap.py:99-119) + PHIinvY0 (misc.py:518-544) on a SapOracle ``o``.
+    sums[i] = the k sample sums of group i (flat group order).  Returns (mu, var, y)."""
+    samples = np.asarray(samples)
+    y = np.zeros(o.N)
+    pos = 0
+    for k in range(1, o.K + 1):
+        for i in range(o.sizes[k]):
+            Ci = o.invcovs[k - 1][k * k * i:k * k * (i + 1)].reshape(k, k)
+            g = o.groups[k - 1][i]
+            si = np.asarray(sums[pos], dtype=float)
+            for j in range(k):
+                for s in range(k):
+                    y[g[j]] += Ci[j, s] * si[s]
+            pos += 1
+    if np.abs(samples).max() < 0.05:
+        return np.inf, np.inf, y
+    phi = o.get_phi(samples)
+    idx = o.support(samples)
+    assert idx.min() == 0
+    P = np.linalg.pinv(phi[np.ix_(idx, idx)])
+    mu = 0.0
+    for j in range(len(idx)):
+        mu += P[0, j] * y[idx[j]]
+    return mu, P[0, 0], y
+
+
 def pilot_covariance(Y):
     """Biased one-pass covariance of an (n, N) sample matrix, blue_models.py:333 with the
     default inner product of blue_fn.py:82-83.  Returns (s1, S2, C_hat)."""

@@ -18,6 +18,7 @@ Files written
   matern.npz      restrictions_matern covariance (M=7, cond 1.5e9), K=7: reference inverses + outputs
   enumeration.npz clique enumeration / union / mappings / ES from BLUEProblem.setup_solver code
                   path (networkx) for complete and non-complete model graphs
+  estimator.npz   SAP.compute_BLUE_estimator (sap.py:99-119) on random per-group sample sums
   pilot.npz       pilot-sample sums and C_hat computed with the reference's accumulation loop
 """
 import os
@@ -264,6 +265,29 @@ def make_enumeration(ns):
     print("enumeration.npz:", len(out), "arrays")
 
 
+def make_estimator(ns):
+    """SAP.compute_BLUE_estimator (sap.py:99-119 -> misc.PHIinvY0) on random per-group sample sums."""
+    out = {}
+    for tag, N, K, seed in [("N6K6", 6, 6, 31), ("N9K4", 9, 4, 32)]:
+        C = wishart(N, seed)
+        groups = all_groups(N, K)
+        flat = [g for gk in groups for g in gk]
+        L = len(flat)
+        rng = np.random.RandomState(seed)
+        sap = ns.sap.SAP(C.copy(), K, [[list(g) for g in gk] for gk in groups], np.ones(L), verbose=False)
+        samples = np.zeros(L, dtype=np.int64)
+        nz = rng.choice(L, size=2 * N, replace=False)
+        samples[nz] = rng.randint(1, 200, size=len(nz)); samples[0] = 50
+        sums = [samples[i] * (1.0 + 0.1 * rng.randn(len(flat[i]))) for i in range(L)]
+        mu, var = sap.compute_BLUE_estimator(sums, samples=samples)
+        out[f"{tag}/C"] = C; out[f"{tag}/K"] = np.int64(K); out[f"{tag}/samples"] = samples
+        out[f"{tag}/sums"] = np.concatenate(sums); out[f"{tag}/mu"] = np.float64(mu); out[f"{tag}/var"] = np.float64(var)
+        for k in range(K):
+            out[f"{tag}/invcovs{k+1}"] = np.asarray(sap.invcovs[k])
+        print("estimator", tag, mu, var)
+    np.savez_compressed(os.path.join(OUT, "estimator.npz"), **out)
+
+
 def make_pilot():
     """The reference accumulates the pilot sums one sample at a time (blue_fn.py:159-167, N1=1)
     and then forms C_hat = sumsc/N - outer(sumse, sumse)/N^2 (blue_models.py:333)."""
@@ -290,5 +314,6 @@ if __name__ == "__main__":
     make_hodgkin(ns)
     make_matern(ns)
     make_enumeration(ns)
+    make_estimator(ns)
     make_pilot()
     print("done")

@@ -353,3 +353,28 @@ def test_many_models_small_groups(blu, N, K):
     v, g, h = sap.variance_GH(m)
     vo, go, ho = o.variance_GH(m, hess_mode="factored")
     assert abs(v - vo) <= TOL * vo and maxrel(g, go) < TOL and maxrel(h, ho) < TOL
+
+
+@pytest.mark.parametrize("tag,N", [("N6K6", 6), ("N9K4", 9)])
+def test_blue_estimator(blu, tag, N):
+    """"next" row f3: the BLUE estimator assembled on the device against the reference's result."""
+    d = _load("estimator.npz")
+    K = int(d[f"{tag}/K"])
+    groups = orc.enumerate_groups(N, K)
+    L = sum(len(g) for g in groups)
+    flat = [g for gk in groups for g in gk]
+    sums, pos = [], 0
+    for g in flat:
+        sums.append(d[f"{tag}/sums"][pos:pos + len(g)]); pos += len(g)
+    samples = d[f"{tag}/samples"]
+    for ingest in (True, False):
+        inv = [d[f"{tag}/invcovs{k+1}"] for k in range(K)] if ingest else None
+        sap = blu.SAP(d[f"{tag}/C"], K, _copy(groups), np.ones(L), verbose=False, invcovs=inv)
+        mu, var = sap.compute_BLUE_estimator(sums, samples=samples)
+        assert abs(mu - float(d[f"{tag}/mu"])) <= 1e-11 * abs(mu)
+        assert abs(var - float(d[f"{tag}/var"])) <= 1e-11 * var
+        o = orc.SapOracle(d[f"{tag}/C"], K, groups, invcovs=[d[f"{tag}/invcovs{k+1}"] for k in range(K)])
+        assert maxrel(sap.last_y, orc.blue_estimator(o, sums, samples)[2]) < 1e-12
+        assert np.isinf(sap.compute_BLUE_estimator(sums, samples=0 * samples))
+        with pytest.raises(ValueError):
+            sap.compute_BLUE_estimator(sums[:-1], samples=samples)

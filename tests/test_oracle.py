@@ -261,3 +261,20 @@ def test_live_reference_random_cases():
             tol = TOL if full else 1e-9
             assert abs(a[0] - b[0]) <= TOL * abs(b[0])
             assert maxrel(a[1], b[1]) < tol and maxrel(a[2], b[2]) < tol
+
+
+@pytest.mark.parametrize("tag,N", [("N6K6", 6), ("N9K4", 9)])
+def test_blue_estimator_matches_reference(tag, N):
+    """"next" row f3: compute_BLUE_estimator (sap.py:99-119) + PHIinvY0 (misc.py:518-544)."""
+    d = _load("estimator.npz")
+    K = int(d[f"{tag}/K"])
+    groups = orc.enumerate_groups(N, K)
+    inv = [d[f"{tag}/invcovs{k+1}"] for k in range(K)]
+    o = orc.SapOracle(d[f"{tag}/C"], K, groups, invcovs=inv)
+    flat = [g for gk in groups for g in gk]
+    sums, pos = [], 0
+    for g in flat:
+        sums.append(d[f"{tag}/sums"][pos:pos + len(g)]); pos += len(g)
+    mu, var, _ = orc.blue_estimator(o, sums, d[f"{tag}/samples"])
+    assert abs(mu - float(d[f"{tag}/mu"])) <= 1e-12 * abs(mu)
+    assert abs(var - float(d[f"{tag}/var"])) <= 1e-12 * var
