@@ -20,6 +20,7 @@
 #include "blu_grad.cuh"
 #include "blu_hess.cuh"
 #include "blu_gram.cuh"
+#include "blu_intproj.cuh"
 #include "blu_level1.cuh"
 
 // --------------------------------------------------------------------------------------------
@@ -801,6 +802,51 @@ extern "C" int blu_blue_estimator(blu_ctx *c, const double *samples, const doubl
     if (var) *var = c->h_hdr->scal[0];
     if (mu) *mu = (c->h_hdr->flags & BLU_FLAG_TINY) ? std::numeric_limits<double>::infinity() : c->h_hdr->scal[5];
     if (y_out) memcpy(y_out, y.data(), sizeof(double) * c->N);
+    return BLU_OK;
+}
+
+// Integer projection: batched candidate variances (misc.py:368-369)
+extern "C" int blu_candidate_variances(blu_ctx *c, const double *basephi, int LL, const int64_t *idx, const int64_t *ms,
+                                       int64_t ncand, double rcond, double *Vs)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->have_inv) return fail(BLU_ERR_STATE, "inverses not set");
+    if (!basephi || !idx || !ms || !Vs) return fail(BLU_ERR_ARG, "null argument");
+    if (LL < 1 || LL > BLU_IP_MAXLL) return fail(BLU_ERR_ARG, "LL=%d outside [1,%d] (misc.py:320 brute-forces at most 24 dimensions)", LL, BLU_IP_MAXLL);
+    if (ncand < 1) return BLU_OK;
+    for (int t = 0; t < LL; ++t)
+        if (idx[t] < 0 || idx[t] >= c->L) return fail(BLU_ERR_ARG, "group id %lld outside [0,%lld)", (long long)idx[t], c->L);
+    const int N = c->N, NN = N * N;
+    const size_t smem = sizeof(double) * ((size_t)LL * NN + NN + (size_t)BLU_IP_WARPS * N * (N + 1));
+    if (smem > 220 * 1024) return fail(BLU_ERR_ARG, "N=%d with LL=%d candidates groups exceeds the shared-memory budget", N, LL);
+    double *d_base = nullptr, *d_psis = nullptr, *d_V = nullptr;
+    long long *d_idx = nullptr, *d_ms = nullptr;
+    cudaError_t e = cudaMalloc(&d_base, sizeof(double) * NN);
+    if (e == cudaSuccess) e = cudaMalloc(&d_psis, sizeof(double) * (size_t)LL * NN);
+    if (e == cudaSuccess) e = cudaMalloc(&d_V, sizeof(double) * (size_t)ncand);
+    if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(long long) * LL);
+    if (e == cudaSuccess) e = cudaMalloc(&d_ms, sizeof(long long) * (size_t)LL * (size_t)ncand);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_base, basephi, sizeof(double) * NN, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, idx, sizeof(long long) * LL, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ms, ms, sizeof(long long) * (size_t)LL * (size_t)ncand, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        blu_ip_expand_kernel<<<LL, 128, 0, c->stream>>>(c->d_cls, (int)c->cls.size(), N, LL, d_idx, c->d_gidx, c->d_cinv, d_psis);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(blu_ip_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        const long long warps = (ncand + 31) / 32;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((warps + BLU_IP_WARPS - 1) / BLU_IP_WARPS, (long long)c->nsm * 8));
+        blu_ip_candidates_kernel<<<grid, BLU_IP_WARPS * 32, smem, c->stream>>>(N, LL, d_base, d_psis, d_ms, ncand, rcond, d_V);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Vs, d_V, sizeof(double) * (size_t)ncand, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_base); cudaFree(d_psis); cudaFree(d_V); cudaFree(d_idx); cudaFree(d_ms);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BLU_ERR_NOMEM : BLU_ERR_CUDA, "candidate_variances: %s", cudaGetErrorString(e));
     return BLU_OK;
 }
 

@@ -241,6 +241,11 @@ class SAP(object):
         return mu.value, var.value
 
     # ---- host orchestration kept from the reference -------------------------------------------
+    def integer_projection(self, samples, budget=None, eps=None, max_model_samples=None):
+        """sap.py:145-187; the candidate variances are evaluated in one batched device call."""
+        from .intproj import integer_projection
+        return integer_projection(self, samples, budget=budget, eps=eps, max_model_samples=max_model_samples)
+
     def get_max_sample_constraints(self, max_model_samples):
         """sap.py:222-240."""
         if max_model_samples is None:
@@ -270,7 +275,7 @@ class SAP(object):
             self.samples = None
             return None
         if not continuous_relaxation:
-            raise NotImplementedError("integer projection (misc.py:313-413) stays with the reference host code")
+            samples = self.integer_projection(samples, budget=budget, eps=eps, max_model_samples=max_model_samples)
         self.samples = samples
         self.budget = budget
         self.eps = eps

@@ -118,6 +118,13 @@ int blu_cleanup_matrix(blu_ctx *ctx, const double *m, double delta, int mode, do
 int blu_blue_estimator(blu_ctx *ctx, const double *samples, const double *sums_flat, double *mu,
                        double *var, double *y, unsigned *flags);
 
+/* Integer projection, batched candidate evaluation ("next" row; misc.py:368-369 inside
+ * best_closest_integer_solution_BLUE): for every column c of ms (LL, ncand; int64, row-major -- the
+ * floor/ceil combinations of the LL <= 24 groups idx[]) form Phi_c = basephi + sum_t ms[t,c] Psi_idx[t]
+ * and return Vs[c] = pinv(Phi_c, hermitian, rcond)[0,0].  basephi is (N,N) = psi @ baseval. */
+int blu_candidate_variances(blu_ctx *ctx, const double *basephi, int LL, const int64_t *idx,
+                            const int64_t *ms, int64_t ncand, double rcond, double *Vs);
+
 /* Device-resident evaluation: d_m lives on the context's device (or NULL to reuse BLU_BUF_M).
  * want_grad / want_hess select the work; results stay in the context's buffers
  * (blu_ctx_device_ptr).  The call is asynchronous on the context's stream. */

@@ -19,6 +19,7 @@ Files written
   enumeration.npz clique enumeration / union / mappings / ES from BLUEProblem.setup_solver code
                   path (networkx) for complete and non-complete model graphs
   estimator.npz   SAP.compute_BLUE_estimator (sap.py:99-119) on random per-group sample sums
+  intproj.npz     get_feasible_integer_bounds / best_closest_integer_solution_BLUE (misc.py:141-165,313-382)
   pilot.npz       pilot-sample sums and C_hat computed with the reference's accumulation loop
 """
 import os
@@ -288,6 +289,38 @@ def make_estimator(ns):
     np.savez_compressed(os.path.join(OUT, "estimator.npz"), **out)
 
 
+def make_intproj(ns):
+    """best_closest_integer_solution_BLUE (misc.py:313-382) in budget and eps mode."""
+    out = {}
+    for tag, N, K, seed in [("N6K6", 6, 6, 41), ("N8K3", 8, 3, 42)]:
+        C = wishart(N, seed)
+        groups = all_groups(N, K)
+        flat = [g for gk in groups for g in gk]
+        L = len(flat)
+        model_costs = 2.0 ** (N - np.arange(N))
+        w = np.array([model_costs[g].sum() for g in flat])
+        sap = ns.sap.SAP(C.copy(), K, [[list(g) for g in gk] for gk in groups], w, verbose=False)
+        rng = np.random.RandomState(seed)
+        sol = np.zeros(L)
+        nz = rng.choice(L, size=N + 3, replace=False)
+        sol[nz] = 0.3 + 40 * rng.rand(len(nz)); sol[0] = 2.6
+        out[f"{tag}/C"] = C; out[f"{tag}/K"] = np.int64(K); out[f"{tag}/w"] = w; out[f"{tag}/sol"] = sol
+        for k in range(K):
+            out[f"{tag}/invcovs{k+1}"] = np.asarray(sap.invcovs[k])
+        lb, ub, idx = ns.misc.get_feasible_integer_bounds(sol, N, e=sap.e)
+        out[f"{tag}/lb"] = lb; out[f"{tag}/ub"] = ub; out[f"{tag}/idx"] = idx
+        budget = float(w @ np.round(sol)) * 1.01
+        val, fval = ns.misc.best_closest_integer_solution_BLUE(sol, sap.psi, w, sap.e, budget=budget)
+        out[f"{tag}/budget"] = np.float64(budget); out[f"{tag}/budget_val"] = val; out[f"{tag}/budget_fval"] = np.float64(fval)
+        eps = float(np.sqrt(sap.variance(np.round(sol).astype(int)) * 1.02))
+        val2, fval2 = ns.misc.best_closest_integer_solution_BLUE(sol, sap.psi, w, sap.e, eps=eps)
+        out[f"{tag}/eps"] = np.float64(eps); out[f"{tag}/eps_val"] = val2; out[f"{tag}/eps_fval"] = np.float64(fval2)
+        ip = sap.integer_projection(sol, budget=budget)
+        out[f"{tag}/projection_budget"] = np.asarray(ip)
+        print("intproj", tag, len(idx), fval, fval2, int(np.abs(val - val2).sum()))
+    np.savez_compressed(os.path.join(OUT, "intproj.npz"), **out)
+
+
 def make_pilot():
     """The reference accumulates the pilot sums one sample at a time (blue_fn.py:159-167, N1=1)
     and then forms C_hat = sumsc/N - outer(sumse, sumse)/N^2 (blue_models.py:333)."""
@@ -315,5 +348,6 @@ if __name__ == "__main__":
     make_matern(ns)
     make_enumeration(ns)
     make_estimator(ns)
+    make_intproj(ns)
     make_pilot()
     print("done")

@@ -378,3 +378,37 @@ def test_blue_estimator(blu, tag, N):
         assert np.isinf(sap.compute_BLUE_estimator(sums, samples=0 * samples))
         with pytest.raises(ValueError):
             sap.compute_BLUE_estimator(sums[:-1], samples=samples)
+
+
+@pytest.mark.parametrize("tag,N", [("N6K6", 6), ("N8K3", 8)])
+def test_integer_projection(blu, tag, N):
+    """"next" row f2: integer allocations bit-exact with the reference's brute-force projection, the
+    batched candidate variances against numpy's hermitian pinv."""
+    from bluest_b200 import intproj
+    d = _load("intproj.npz")
+    K = int(d[f"{tag}/K"])
+    groups = orc.enumerate_groups(N, K)
+    L = sum(len(g) for g in groups)
+    inv = [d[f"{tag}/invcovs{k+1}"] for k in range(K)]
+    sap = blu.SAP(d[f"{tag}/C"], K, _copy(groups), d[f"{tag}/w"], verbose=False, invcovs=inv)
+    sol = d[f"{tag}/sol"]
+    val, fval = intproj.best_closest_integer_solution_BLUE(sap, sol, budget=float(d[f"{tag}/budget"]))
+    assert np.array_equal(val, d[f"{tag}/budget_val"])
+    assert abs(fval - float(d[f"{tag}/budget_fval"])) <= 1e-10 * fval
+    val, fval = intproj.best_closest_integer_solution_BLUE(sap, sol, eps=float(d[f"{tag}/eps"]))
+    assert np.array_equal(val, d[f"{tag}/eps_val"])
+    assert abs(fval - float(d[f"{tag}/eps_fval"])) <= 1e-10 * fval
+    assert np.array_equal(sap.integer_projection(sol, budget=float(d[f"{tag}/budget"])), d[f"{tag}/projection_budget"])
+    # every candidate, including structurally singular ones (models no candidate touches)
+    o = orc.SapOracle(d[f"{tag}/C"], K, groups, invcovs=inv)
+    lb, ub, idx = intproj.feasible_integer_bounds(sol, N, e=sap.e)
+    ms = intproj._combinations(lb, ub)
+    base = np.round(sol).astype(int); base[idx] = 0
+    Vs = intproj.candidate_variances(sap, base, idx, ms)
+    phis = (o.get_phi(base).reshape(-1, 1) + o.psi[:, idx] @ ms).T.reshape(-1, N, N)
+    ref = np.linalg.pinv(phis, hermitian=True, rcond=1e-10)[:, 0, 0]
+    assert maxrel(Vs, ref) < 1e-10
+    # only model 0's singleton group sampled: every other model has a zero row
+    idx1 = np.array([0]); ms1 = np.array([[1, 2, 5]])
+    V1 = intproj.candidate_variances(sap, np.zeros(L, dtype=int), idx1, ms1)
+    assert maxrel(V1, d[f"{tag}/C"][0, 0] / np.array([1.0, 2.0, 5.0])) < 1e-12

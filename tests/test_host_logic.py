@@ -79,3 +79,33 @@ def test_balanced_slices(N, world):
 def test_pinned_pool_is_lazy_on_cpu():
     from bluest_b200 import _lib
     assert _lib.pinned_pool.free_blocks == {} or isinstance(_lib.pinned_pool.free_blocks, dict)
+
+
+@pytest.mark.parametrize("tag,N", [("N6K6", 6), ("N8K3", 8)])
+def test_integer_projection_host_logic(tag, N, monkeypatch):
+    """Row f2: candidate enumeration / filtering / tie-breaking against the reference's result, with the
+    device call replaced by a numpy stand-in built on the oracle (CPU-only check of the host logic)."""
+    from bluest_b200 import intproj
+    d = _load("intproj.npz")
+    K = int(d[f"{tag}/K"])
+    groups = orc.enumerate_groups(N, K)
+    o = orc.SapOracle(d[f"{tag}/C"], K, groups, invcovs=[d[f"{tag}/invcovs{k+1}"] for k in range(K)])
+    sol = d[f"{tag}/sol"]
+    lb, ub, idx = intproj.feasible_integer_bounds(sol, N, e=o.e)
+    assert np.array_equal(lb, d[f"{tag}/lb"]) and np.array_equal(ub, d[f"{tag}/ub"]) and np.array_equal(idx, d[f"{tag}/idx"])
+
+    class FakeSap:
+        pass
+    sap = FakeSap()
+    sap.N, sap.costs, sap.e, sap.L = N, d[f"{tag}/w"], o.e, o.L
+    sap.get_max_sample_constraints = lambda mm: ([], [])
+
+    def fake_candidates(sap_, base, idx_, ms, rcond=1e-10):
+        phis = np.stack([o.get_phi(base) + sum(ms[t, c] * o.psi[:, idx_[t]].reshape(N, N) for t in range(len(idx_))) for c in range(ms.shape[1])])
+        return np.linalg.pinv(phis, hermitian=True, rcond=rcond)[:, 0, 0]
+    monkeypatch.setattr(intproj, "candidate_variances", fake_candidates)
+    val, fval = intproj.best_closest_integer_solution_BLUE(sap, sol, budget=float(d[f"{tag}/budget"]))
+    assert np.array_equal(val, d[f"{tag}/budget_val"]) and abs(fval - float(d[f"{tag}/budget_fval"])) <= 1e-10 * fval
+    val, fval = intproj.best_closest_integer_solution_BLUE(sap, sol, eps=float(d[f"{tag}/eps"]))
+    assert np.array_equal(val, d[f"{tag}/eps_val"]) and abs(fval - float(d[f"{tag}/eps_fval"])) <= 1e-10 * fval
+    assert np.array_equal(intproj.integer_projection(sap, sol, budget=float(d[f"{tag}/budget"])), d[f"{tag}/projection_budget"])
