@@ -4,9 +4,9 @@ What a BLUEST maintainer would do by hand done at run time:
 
 * Level 2: ``bluest.sap.SAP`` / ``bluest.mosap.SAP`` become a hybrid class that keeps every
   host-side method of the reference's SAP (``solve``, ``cvxopt_solve``, ``cvxpy_solve``,
-  ``ipopt_solve``, ``scipy_solve``, ``integer_projection``, ``compute_BLUE_estimator`` ...) and
-  takes ``__init__``, ``get_variance_functions``, ``psi`` and ``invcovs`` from
-  ``bluest_b200.SAP`` -- so ``BLUEProblem.setup_solver`` / ``MOSAP`` run unmodified on the GPU closures.
+  ``ipopt_solve``, ``scipy_solve``, ``get_max_sample_constraints`` ...) and takes ``__init__``,
+  ``get_variance_functions``, ``psi``, ``invcovs``, ``integer_projection`` and
+  ``compute_BLUE_estimator`` from ``bluest_b200.SAP`` -- so ``BLUEProblem.setup_solver`` / ``MOSAP`` run unmodified on the GPU closures.
 * Level 1: the five ``_cmisc_bluest`` routines bound in ``bluest.misc`` are replaced by
   ``bluest_b200.cmisc``.
 
@@ -21,7 +21,7 @@ from .sap import SAP as B200SAP
 _saved = {}
 _L1 = ("assemble_psi_c", "objectiveK_c", "gradK_c", "hessKQ_c", "cleanupK_c")
 _L2_METHODS = ("__init__", "get_variance_functions", "_m", "eval_device", "upload_m", "sync", "last_result", "last_timing",
-               "timing_log", "timing_read", "last_launches", "device_ptr", "device_buffer", "stream", "close", "__del__", "compute_BLUE_estimator")
+               "timing_log", "timing_read", "last_launches", "device_ptr", "device_buffer", "stream", "close", "__del__", "compute_BLUE_estimator", "integer_projection")
 
 
 def make_hybrid(ref_sap_cls):

@@ -20,6 +20,7 @@ Files written
                   path (networkx) for complete and non-complete model graphs
   estimator.npz   SAP.compute_BLUE_estimator (sap.py:99-119) on random per-group sample sums
   intproj.npz     get_feasible_integer_bounds / best_closest_integer_solution_BLUE (misc.py:141-165,313-382)
+  solve.npz       SAP.solve(solver="scipy") end to end: continuous solution and integer allocation
   pilot.npz       pilot-sample sums and C_hat computed with the reference's accumulation loop
 """
 import os
@@ -321,6 +322,34 @@ def make_intproj(ns):
     np.savez_compressed(os.path.join(OUT, "intproj.npz"), **out)
 
 
+def make_solve(ns):
+    """End-to-end SAP.solve(solver="scipy") of the reference (the only solver runnable without
+    cvxopt/cvxpy/ipopt): continuous solution and integer allocation from a fixed x0."""
+    out = {}
+    C5 = np.array([[2.53500581, 2.3583669, 2.36312599, 1.66331444, 0.72897923],
+                   [2.3583669, 2.27345322, 2.07702441, 1.67029559, 0.80520217],
+                   [2.36312599, 2.07702441, 2.40127866, 1.37242096, 0.47072499],
+                   [1.66331444, 1.67029559, 1.37242096, 1.29027193, 0.67275196],
+                   [0.72897923, 0.80520217, 0.47072499, 0.67275196, 1.56637342]])
+    for tag, C, K, seed in [("tutorial", C5, 5, 51), ("N6K3", wishart(6, 52), 3, 52)]:
+        N = C.shape[0]
+        groups = all_groups(N, K)
+        flat = [g for gk in groups for g in gk]
+        L = len(flat)
+        model_costs = 2.0 ** (N - np.arange(N))
+        w = np.array([model_costs[g].sum() for g in flat])
+        sap = ns.sap.SAP(C.copy(), K, [[list(g) for g in gk] for gk in groups], w, verbose=False)
+        x0 = np.ceil(10 * abs(np.random.RandomState(seed).randn(L)))
+        budget = 100.0 * w.max()
+        cont = sap.solve(budget=budget, solver="scipy", x0=x0.copy(), continuous_relaxation=True)
+        ints = sap.solve(budget=budget, solver="scipy", x0=x0.copy(), continuous_relaxation=False)
+        out[f"{tag}/C"] = C; out[f"{tag}/K"] = np.int64(K); out[f"{tag}/w"] = w; out[f"{tag}/x0"] = x0
+        out[f"{tag}/budget"] = np.float64(budget); out[f"{tag}/continuous"] = cont; out[f"{tag}/integer"] = np.asarray(ints)
+        out[f"{tag}/variance"] = np.float64(sap.variance(ints)); out[f"{tag}/cost"] = np.float64(ints @ w)
+        print("solve", tag, L, float(sap.variance(ints)), float(ints @ w), int((ints > 0).sum()))
+    np.savez_compressed(os.path.join(OUT, "solve.npz"), **out)
+
+
 def make_pilot():
     """The reference accumulates the pilot sums one sample at a time (blue_fn.py:159-167, N1=1)
     and then forms C_hat = sumsc/N - outer(sumse, sumse)/N^2 (blue_models.py:333)."""
@@ -349,5 +378,6 @@ if __name__ == "__main__":
     make_enumeration(ns)
     make_estimator(ns)
     make_intproj(ns)
+    make_solve(ns)
     make_pilot()
     print("done")

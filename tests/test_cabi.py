@@ -88,7 +88,8 @@ def test_install_patches_the_reference_in_place():
         assert ns.sap.SAP is hybrid and ns.mosap.SAP is hybrid
         assert issubclass(hybrid, ref_sap)
         assert hybrid.__init__ is blu.SAP.__init__ and hybrid.get_variance_functions is blu.SAP.get_variance_functions
-        assert hybrid.cvxopt_solve is ref_sap.cvxopt_solve and hybrid.integer_projection is ref_sap.integer_projection
+        assert hybrid.cvxopt_solve is ref_sap.cvxopt_solve and hybrid.solve is ref_sap.solve
+        assert hybrid.integer_projection is blu.SAP.integer_projection and hybrid.compute_BLUE_estimator is blu.SAP.compute_BLUE_estimator
         assert ns.misc.gradK_c is blu.cmisc.gradK_c and ns.misc.hessKQ_c is blu.cmisc.hessKQ_c
         if blu.device_count() <= 0:
             with pytest.raises(blu.BluError):          # no silent CPU fallback through the patched class
