@@ -4,6 +4,8 @@
 // blu_invert.cuh / blu_phi.cuh / blu_grad.cuh / blu_hess.cuh / blu_gram.cuh / blu_level1.cuh.
 // There is no CPU fallback: without a CUDA device every entry point fails with BLU_ERR_NODEVICE.
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -80,6 +82,8 @@ struct blu_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
     int launches = 0;
+    std::vector<cudaEvent_t> panel_ev; // one event per Hessian row panel (symmetric download)
+    bool sym_download = false;         // measured slower on the GPU box's host (mirroring 4.3 GB costs more than the PCIe time it saves)
     BluXchg *d_xchg = nullptr;         // this rank's exchange buffer (CUDA IPC shared)
     BluPeers peers{};                  // peers as mapped here; world == 0: not connected
     std::vector<void *> ipc_opened;
@@ -144,6 +148,7 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->evlog) if (e) cudaEventDestroy(e);
+    for (auto &e : c->panel_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return BLU_OK;
@@ -657,6 +662,17 @@ extern "C" int blu_ctx_last_timing(blu_ctx *c, float *ms)
 
 extern "C" int blu_ctx_last_launches(blu_ctx *c) { return c ? c->launches : 0; }
 
+// Options: "sym_download" (default 0) -- copy only the upper block-triangle of the dense Hessian
+// over PCIe and mirror it on the host with threads.  Off by default: on the B200 box's host the
+// mirroring of 4.3 GB (16 threads, ~52 GB/s effective) costs more than the 75 ms of PCIe time it
+// saves (6.1 vs 6.6 evaluations/s end to end); worth enabling on hosts with more memory bandwidth.
+extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
+{
+    if (!c || !name) return fail(BLU_ERR_ARG, "null argument");
+    if (!strcmp(name, "sym_download")) { c->sym_download = value != 0; return BLU_OK; }
+    return fail(BLU_ERR_ARG, "unknown option %s", name);
+}
+
 extern "C" int blu_ctx_device_ptr(blu_ctx *c, int which, void **ptr, int64_t *nbytes)
 {
     if (!c || !ptr) return fail(BLU_ERR_ARG, "null argument");
@@ -710,6 +726,72 @@ extern "C" int blu_variance(blu_ctx *c, const double *m, double delta, double *v
     return blu_ctx_last_result(c, var, flags);
 }
 
+// --------------------------------------------------------------------------------------------
+// Dense Hessian to the host.  H is exactly symmetric, so only the block-upper triangle crosses
+// PCIe (row panels, columns >= the panel's first row); host threads mirror each panel into the
+// lower triangle (blocked 64 x 64 transposes) while the next panel is still in flight.  Halves the
+// PCIe bytes of the one transfer that dominates the end-to-end evaluation (8 L^2 bytes at 57 GB/s).
+// --------------------------------------------------------------------------------------------
+static void mirror_chunk(double *H, long long L, long long r0, long long r1, long long c0, long long c1)
+{
+    // H[c][r] = H[r][c] for r in [r0,r1), c in [c0,c1)   (c0 >= r1: strictly right of the diagonal block)
+    alignas(64) double buf[64][64];
+    for (long long rb = r0; rb < r1; rb += 64) {
+        const int nr = (int)std::min<long long>(64, r1 - rb);
+        for (long long cb = c0; cb < c1; cb += 64) {
+            const int nc = (int)std::min<long long>(64, c1 - cb);
+            for (int i = 0; i < nr; ++i) {
+                const double *src = H + (rb + i) * L + cb;
+                for (int j = 0; j < nc; ++j) buf[j][i] = src[j];
+            }
+            for (int j = 0; j < nc; ++j) memcpy(H + (cb + j) * L + rb, buf[j], sizeof(double) * nr);
+        }
+    }
+}
+
+static int download_hessian_symmetric(blu_ctx *c, double *hess)
+{
+    const long long L = c->L;
+    const long long PH = 1024;                                   // panel height (rows)
+    const int npan = (int)((L + PH - 1) / PH);
+    while ((int)c->panel_ev.size() < npan) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->panel_ev.push_back(e); }
+    for (int p = 0; p < npan; ++p) {
+        const long long r0 = p * PH, r1 = std::min<long long>(L, r0 + PH);
+        CUDA_TRY(cudaMemcpy2DAsync(hess + r0 * L + r0, sizeof(double) * L, c->d_H + r0 * c->ldH + r0, sizeof(double) * c->ldH,
+                                   sizeof(double) * (L - r0), (size_t)(r1 - r0), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaEventRecord(c->panel_ev[p], c->stream));
+    }
+    const int nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::atomic<int>> ready(npan), next(npan);
+    for (int p = 0; p < npan; ++p) { ready[p].store(0); next[p].store(0); }
+    const long long CW = 512;                                     // columns per work item
+    auto worker = [&]() {
+        for (int p = 0; p < npan; ++p) {
+            const long long r0 = p * PH, r1 = std::min<long long>(L, r0 + PH);
+            const int nitems = (int)((L - r1 + CW - 1) / CW);
+            if (nitems <= 0) continue;
+            while (ready[p].load(std::memory_order_acquire) == 0) std::this_thread::yield();
+            for (;;) {
+                const int it = next[p].fetch_add(1);
+                if (it >= nitems) break;
+                const long long c0 = r1 + it * CW, c1 = std::min<long long>(L, c0 + CW);
+                mirror_chunk(hess, L, r0, r1, c0, c1);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+    cudaError_t err = cudaSuccess;
+    for (int p = 0; p < npan; ++p) {
+        if (err == cudaSuccess) err = cudaEventSynchronize(c->panel_ev[p]);
+        ready[p].store(1, std::memory_order_release);              // on error too: never leave the workers spinning
+    }
+    for (auto &t : pool) t.join();
+    if (err != cudaSuccess) return fail(BLU_ERR_CUDA, "Hessian download: %s", cudaGetErrorString(err));
+    // the diagonal blocks arrived whole; the strictly-lower part of each diagonal block was copied too
+    return BLU_OK;
+}
+
 extern "C" int blu_variance_GH(blu_ctx *c, const double *m, double delta, double *var, double *grad,
                                double *hess, unsigned *flags)
 {
@@ -730,6 +812,7 @@ extern "C" int blu_variance_GH(blu_ctx *c, const double *m, double delta, double
         return BLU_OK;
     }
     if (hess) {
+        if (c->L >= 4096 && c->sym_download) return download_hessian_symmetric(c, hess);
         CUDA_TRY(cudaMemcpy2DAsync(hess, sizeof(double) * c->L, c->d_H, sizeof(double) * c->ldH, sizeof(double) * c->L,
                                    (size_t)c->L, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));

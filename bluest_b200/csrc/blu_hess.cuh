@@ -22,7 +22,9 @@
 #include "blu_common.cuh"
 
 #define BLU_HT 64              // tile edge
+#ifndef BLU_HSB
 #define BLU_HSB 16             // super-block edge in tiles (rasterisation)
+#endif
 #define BLU_HLDN 72            // staging pitch, normal tile   (72*8 B: rows 2 apart never share a bank phase)
 #define BLU_HLDT 66            // staging pitch, transposed tile
 #define BLU_HESS_SMEM ((BLU_HT * BLU_HLDN + BLU_HT * BLU_HLDT) * 8)

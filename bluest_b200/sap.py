@@ -175,13 +175,17 @@ class SAP(object):
     def timing_log(self, capacity):
         """Log the phase events of the next ``capacity`` device evaluations (no sync in between)."""
         check(lib().blu_ctx_timing_log(self._ctx, int(capacity)))
+        self._timing_cap = int(capacity)
 
     def timing_read(self):
         """(n,4) array of ms: [phi+pinv, grad/U, Hessian, total] per logged evaluation."""
-        cap = 4096
+        cap = max(1, getattr(self, "_timing_cap", 1))
         buf = (ctypes.c_float * (4 * cap))(); n = ctypes.c_int(0)
         check(lib().blu_ctx_timing_read(self._ctx, buf, ctypes.byref(n)))
         return np.array(buf[:4 * n.value], dtype=np.float64).reshape(n.value, 4)
+
+    def set_option(self, name, value):
+        check(lib().blu_ctx_set_option(self._ctx, name.encode(), int(value)))
 
     def last_launches(self):
         return int(lib().blu_ctx_last_launches(self._ctx))

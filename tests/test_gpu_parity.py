@@ -432,3 +432,23 @@ def test_end_to_end_scipy_solve_matches_reference(blu, tag):
     assert np.array_equal(ints, d[f"{tag}/integer"])
     assert abs(sap.variance(ints) - float(d[f"{tag}/variance"])) <= 1e-12 * float(d[f"{tag}/variance"])
     assert sap.tot_cost == float(d[f"{tag}/cost"])
+
+
+def test_symmetric_hessian_download_equals_plain(blu):
+    """L >= 4096: only the upper block-triangle crosses PCIe, host threads mirror it -- must equal
+    the plain full copy bit for bit (panel edges, ragged last panel/column block)."""
+    N, K = 14, 6            # L = 6475... use K=7 for L >= 4096
+    K = 7
+    C = orc.wishart_cov(N, 8)
+    groups = orc.enumerate_groups(N, K)
+    L = sum(len(g) for g in groups)
+    assert L >= 4096 and L % 64 != 0
+    sap = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False)
+    m = orc.dense_m(L, 5)
+    sap.set_option("sym_download", 1)
+    v1, g1, H1 = sap.variance_GH(m)
+    sap.set_option("sym_download", 0)
+    v2, g2, H2 = sap.variance_GH(m)
+    assert v1 == v2 and np.array_equal(g1, g2)
+    assert np.array_equal(H1, H2)
+    assert np.array_equal(H1, H1.T)
