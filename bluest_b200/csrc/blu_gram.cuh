@@ -6,7 +6,7 @@
 // Y is the (n, N) row-major sample matrix.  The model axis is padded to NT tiles of 8 columns with
 // one extra column of ones at index N, so the column sums come out of the same contraction:
 // G = [Y 1]^T [Y 1]  =>  S2 = G[:N,:N], s1 = G[:N, N].
-// A warp walks its contiguous slab of samples 4 at a time: the fragment of tile t held by a lane
+// A warp walks its contiguous slab of samples (bulk-async staged through shared memory) 4 at a time: the fragment of tile t held by a lane
 // (sample lane&3, column 8t + lane>>2) is at once the A operand (row = column index, k = sample)
 // and the B operand (k = sample, col = column index) of mma.m8n8k4.f64, so every loaded double is
 // used NT times.  Only tile pairs ti <= tj are accumulated.  Reduction: warps -> CTA in shared
@@ -16,47 +16,77 @@
 #include <string>
 #include "blu_common.cuh"
 #include "blu_hess.cuh"
+#include "blu_stream.cuh"
 
 #define BLU_GRAM_WARPS 8
 
+#define BLU_GRAM_STAGE_DOUBLES 544           // >= 16 samples x 32 models + skew/round-up slack
+
+// Each warp owns a contiguous slab of samples and streams it through a private two-stage
+// shared-memory ring with bulk asynchronous copies (cp.async.bulk + mbarrier, as blu_stream.cuh):
+// a stage holds `spc` samples (spc*N doubles, one contiguous span of Y).  Fragments are read
+// from shared memory; nothing in the MMA loop waits on a global load.
 template <int NT>
 __global__ void __launch_bounds__(BLU_GRAM_WARPS * 32)
-blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab, double *__restrict__ part)
+blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab, int spc, double *__restrict__ part)
 {
     constexpr int NPG = 8 * NT;
     constexpr int NPAIR = NT * (NT + 1) / 2;
-    extern __shared__ double sred_raw[];                  // BLU_GRAM_WARPS x NPG*NPG
-    double (*sred)[NPG * NPG] = reinterpret_cast<double (*)[NPG * NPG]>(sred_raw);
+    extern __shared__ __align__(16) double gsm_raw[];   // [WARPS][2][STAGE] stages | [WARPS][NPG*NPG] reduction | barriers
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *stage0 = gsm_raw + (size_t)(2 * w) * BLU_GRAM_STAGE_DOUBLES;
+    double *stage1 = stage0 + BLU_GRAM_STAGE_DOUBLES;
+    double *sred = gsm_raw + (size_t)2 * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES + (size_t)w * NPG * NPG;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(gsm_raw + (size_t)2 * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES
+                                                                      + (size_t)BLU_GRAM_WARPS * NPG * NPG) + 2 * w;
+    if (lane == 0) { blu_mbar_init(&bars[0], 1); blu_mbar_init(&bars[1], 1); blu_mbar_fence_init(); }
+    __syncwarp();
     const int ks = lane & 3, cq = lane >> 2;
     const long long gw = (long long)blockIdx.x * BLU_GRAM_WARPS + w;
-    long long s0 = gw * slab, s1 = s0 + slab;
+    const long long s0 = gw * slab;
+    long long s1 = s0 + slab;
     if (s1 > n) s1 = n;
     double acc[NPAIR][2];
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) { acc[p][0] = 0.0; acc[p][1] = 0.0; }
-    for (long long s = s0; s < s1; s += 16) {
-        double f[4][NT];                       // 4 x 4 samples in flight before the first MMA issues
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const long long row = s + 4 * h + ks;
-            const bool rok = row < s1;
+
+    auto issue = [&](long long sb, int st) -> int {       // copy samples [sb, sb+cnt) into stage st; returns the skew
+        const long long cnt = (s1 - sb) < spc ? (s1 - sb) : spc;
+        const unsigned long long addr = (unsigned long long)(Y + sb * N);
+        const int skew = (int)((addr & 15ull) >> 3);
+        if (lane == 0) {
+            const unsigned bytes = (unsigned)(((skew + cnt * N) * 8 + 15) & ~15ll);
+            blu_mbar_expect_tx(&bars[st], bytes);
+            blu_bulk_g2s(st ? stage1 : stage0, (const void *)(addr & ~15ull), bytes, &bars[st]);
+        }
+        return skew;
+    };
+    int skew_cur = 0, skew_nxt = 0;
+    if (s0 < s1) skew_cur = issue(s0, 0);
+    int it = 0;
+    for (long long sb = s0; sb < s1; sb += spc, ++it) {
+        const int st = it & 1;
+        if (sb + spc < s1) skew_nxt = issue(sb + spc, st ^ 1);
+        blu_mbar_wait(&bars[st], (unsigned)((it >> 1) & 1));
+        const double *base = (st ? stage1 : stage0) + skew_cur;
+        const int cnt = (int)((s1 - sb) < spc ? (s1 - sb) : spc);
+        for (int r0 = 0; r0 < cnt; r0 += 4) {
+            const int row = r0 + ks;
+            const bool rok = row < cnt;
+            double f[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const int col = 8 * t + cq;
-                double v = 0.0;
-                if (rok) v = (col < N) ? __ldcs(Y + row * N + col) : (col == N ? 1.0 : 0.0);
-                f[h][t] = v;
+                f[t] = rok ? ((col < N) ? base[row * N + col] : (col == N ? 1.0 : 0.0)) : 0.0;
             }
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
             int p = 0;
 #pragma unroll
             for (int ti = 0; ti < NT; ++ti)
 #pragma unroll
-                for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[p][0], acc[p][1], f[h][ti], f[h][tj]); ++p; }
+                for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[p][0], acc[p][1], f[ti], f[tj]); ++p; }
         }
+        __syncwarp();                                   // stage consumed before it is refilled
+        skew_cur = skew_nxt;
     }
     // warp tile -> shared (C fragment: row lane>>2, cols 2*(lane&3)+{0,1})
     {
@@ -66,18 +96,19 @@ blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab
 #pragma unroll
             for (int tj = ti; tj < NT; ++tj) {
                 const int r = 8 * ti + cq, c = 8 * tj + 2 * ks;
-                sred[w][r * NPG + c] = acc[p][0];
-                sred[w][r * NPG + c + 1] = acc[p][1];
+                sred[r * NPG + c] = acc[p][0];
+                sred[r * NPG + c + 1] = acc[p][1];
                 ++p;
             }
     }
     __syncthreads();
+    const double *sall = gsm_raw + (size_t)2 * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES;
     for (int t = threadIdx.x; t < NPG * NPG; t += blockDim.x) {
         const int r = t / NPG, c = t - r * NPG;
         if ((r >> 3) > (c >> 3)) continue;                  // lower tiles are never produced
         double sum = 0.0;
 #pragma unroll
-        for (int ww = 0; ww < BLU_GRAM_WARPS; ++ww) sum += sred[ww][t];
+        for (int ww = 0; ww < BLU_GRAM_WARPS; ++ww) sum += sall[(size_t)ww * NPG * NPG + t];
         part[(long long)blockIdx.x * NPG * NPG + t] = sum;
     }
 }
@@ -128,10 +159,12 @@ blu_gram_finish_kernel(const double *__restrict__ part, int nparts, int NPG, int
 template <int NT>
 static cudaError_t blu_gram_launch(const double *dY, long long n, int N, int grid, long long slab, double *d_part, cudaStream_t st)
 {
-    const size_t smem = sizeof(double) * BLU_GRAM_WARPS * (8 * NT) * (8 * NT);
+    const int spc = (512 / N) & ~3;                      // samples per stage: multiple of 4, <= 512 doubles
+    const size_t smem = sizeof(double) * ((size_t)2 * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES + (size_t)BLU_GRAM_WARPS * (8 * NT) * (8 * NT))
+                        + sizeof(unsigned long long) * 2 * BLU_GRAM_WARPS;
     cudaError_t e = cudaFuncSetAttribute(blu_gram_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    blu_gram_kernel<NT><<<grid, BLU_GRAM_WARPS * 32, smem, st>>>(dY, n, N, slab, d_part);
+    blu_gram_kernel<NT><<<grid, BLU_GRAM_WARPS * 32, smem, st>>>(dY, n, N, slab, spc, d_part);
     return cudaGetLastError();
 }
 
