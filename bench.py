@@ -472,7 +472,8 @@ def run_shard(args):
     sizes = [len(g) for g in groups]
     sap = blu.SAP(C, N, groups, np.ones(L), verbose=False, device=local)
     eng = GpuEngine(sap)
-    ev = ShardedEvaluator(eng, sizes, rank, world, dist=dist if world > 1 else None, fused=not args.nccl_phi)
+    ev = ShardedEvaluator(eng, sizes, rank, world, dist=dist if world > 1 else None, fused=not args.nccl_phi,
+                          replicate_front=hess and not args.shard_front)
     ms_dev = [torch.from_numpy(orc.dense_m(L, j)).to("cuda:%d" % local) for j in range(4)]
     ext = torch.cuda.ExternalStream(sap.stream(), device=local)
 
@@ -506,7 +507,8 @@ def run_shard(args):
                "warmup": args.warmup, "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "impl": "ours",
                "config": {"workload": "group-sharded evaluation, %d models, %d groups, %s" % (N, L, "dense Hessian row panels" if hess else "no Hessian"),
-                          "models": N, "groups": L, "parallelism": "group-shard x%d, %s of N^2+33 doubles%s" % (world, "NCCL all-reduce" if args.nccl_phi else "in-kernel NVLink peer-memory all-reduce (fused with the pinv kernel)", " + NCCL all-gather of U,V" if hess else ""),
+                          "models": N, "groups": L, "parallelism": ("Hessian row panels x%d, front end (Phi, pinv, grad, U, V: ~90 us) replicated per rank, no collective" % world) if ev.replicate_front else
+                                         "group-shard x%d, %s of N^2+33 doubles%s" % (world, "NCCL all-reduce" if args.nccl_phi else "in-kernel NVLink peer-memory all-reduce (fused with the pinv kernel)", " + NCCL broadcast of U,V slices" if hess else ""),
                           "slices": [list(sl) for sl in ev.slices], "hessian_row_panels": [list(sl) for sl in ev.row_slices]},
                "roofline": {"bound": "hbm", "achieved": algo / (per * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                             "frac": algo / (per * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + " x n_gpus",
@@ -532,6 +534,7 @@ def main():
     ap.add_argument("--mode", default="sweep", choices=["sweep", "shard"], help="sweep: independent instances per GPU (default); shard: one problem, groups sharded")
     ap.add_argument("--nohess", action="store_true", help="shard mode: Phi + variance + gradient only (e.g. --models 20)")
     ap.add_argument("--gather-grad", action="store_true", help="shard mode: all-gather the gradient slices")
+    ap.add_argument("--shard-front", action="store_true", help="shard mode with Hessian: also shard Phi/grad/U,V by groups and exchange U,V (default: replicate the cheap front end, shard only the Hessian rows)")
     ap.add_argument("--nccl-phi", action="store_true", help="shard mode: NCCL all-reduce of the partial Phi instead of the fused peer-memory kernel")
     args = ap.parse_args()
     if args.impl == "reference":

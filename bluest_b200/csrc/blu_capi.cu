@@ -530,7 +530,8 @@ static void launch_hess_t(blu_ctx *c, bool sym, const double *Ua, long long Lrow
     } else {
         const int nTr = (int)((Lrows + BLU_HT - 1) / BLU_HT);
         dim3 grid((unsigned)nTc, (unsigned)nTr);
-        blu_hess_kernel<NCH, false><<<grid, 128, BLU_HESS_SMEM, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
+        // row panels stage only the normal orientation: half the shared memory, more CTAs per SM
+        blu_hess_kernel<NCH, false><<<grid, 128, BLU_HT * BLU_HLDN * 8, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
     }
 }
 
@@ -574,7 +575,7 @@ extern "C" int blu_eval_device(blu_ctx *c, const double *d_m, double delta, int 
     CUDA_TRY(cudaEventRecord(ev[1], c->stream));
     if (want_grad || want_hess) { rc = launch_grad(c, want_hess); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(ev[2], c->stream));
-    if (want_hess) { rc = launch_hess(c, true); if (rc) return rc; }
+    if (want_hess == 1) { rc = launch_hess(c, true); if (rc) return rc; }      // 2: U,V only (row panels follow via blu_shard_hess)
     CUDA_TRY(cudaEventRecord(ev[3], c->stream));
     c->timed = (ev == c->ev);
     return BLU_OK;

@@ -36,7 +36,7 @@ __device__ __forceinline__ void blu_dmma(double &c0, double &c1, double a, doubl
 }
 
 template <int NCH, bool SYM>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, SYM ? 3 : 5)
 blu_hess_kernel(const double *__restrict__ U, const double *__restrict__ V, long long Lrows,
                 long long Lcols, long long ldH, double *__restrict__ H, int nT, int tI0)
 {

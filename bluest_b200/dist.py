@@ -22,12 +22,16 @@ from .groups import balanced_slices
 
 
 class ShardedEvaluator:
-    def __init__(self, engine, sizes, rank, world, dist=None, group=None, fused=False):
+    def __init__(self, engine, sizes, rank, world, dist=None, group=None, fused=False, replicate_front=False):
         """engine: object with shard_phi / shard_finish / shard_hess / buffers (see GpuEngine).
         sizes = [L1..LK].  fused=True: the Phi all-reduce runs inside the finish kernel over NVLink
         peer memory (engine.connect_peers) instead of a separate NCCL call."""
         self.engine = engine
         self.fused = bool(fused)
+        # replicate_front: every rank evaluates Phi, pinv, gradient and U,V for ALL groups (tens of
+        # microseconds where a dense Hessian exists at all, N <= 17) and only the Hessian -- the
+        # 8 L^2-byte part -- is split into row panels: no collective in the whole evaluation.
+        self.replicate_front = bool(replicate_front)
         self.rank, self.world = rank, world
         self.dist, self.group = dist, group
         self.L = int(sum(sizes))
@@ -38,9 +42,13 @@ class ShardedEvaluator:
         cuts = [(self.L * r) // world for r in range(world + 1)]
         self.row_slices = [(cuts[r], cuts[r + 1]) for r in range(world)]
         self.rlo, self.rhi = self.row_slices[rank]
-        engine.set_slice(self.lo, self.hi)
-        if self.fused:
-            engine.connect_peers(rank, world, dist, group)
+        if self.replicate_front:
+            self.slices = [(0, self.L)] * world
+            self.lo, self.hi = 0, self.L
+        else:
+            engine.set_slice(self.lo, self.hi)
+            if self.fused:
+                engine.connect_peers(rank, world, dist, group)
 
     def _phi_exchange_finish(self, m, delta, want_grad, want_uv):
         e = self.engine
@@ -75,6 +83,13 @@ class ShardedEvaluator:
         var, flags, and -- as the engine's buffers -- grad (full length if gather_grad, else only the
         own slice is valid) and the own Hessian row panel when hess=True."""
         e = self.engine
+        if self.replicate_front:
+            with e.stream_context():
+                e.eval_full(m, delta, grad, hess)
+                if hess:
+                    e.shard_hess(self.rlo, self.rhi)
+            var, flags = e.result()
+            return dict(var=var, flags=flags, lo=self.lo, hi=self.hi, rlo=self.rlo, rhi=self.rhi)
         with e.stream_context():
             self._phi_exchange_finish(m, delta, grad or hess, hess)
             out = {}
@@ -92,6 +107,12 @@ class ShardedEvaluator:
         """Same as evaluate() but without the final read-back of (var, flags): nothing on the host
         waits for the device, so evaluations can be queued back to back."""
         e = self.engine
+        if self.replicate_front:
+            with e.stream_context():
+                e.eval_full(m, delta, grad, hess)
+                if hess:
+                    e.shard_hess(self.rlo, self.rhi)
+            return None
         with e.stream_context():
             self._phi_exchange_finish(m, delta, grad or hess, hess)
             if grad and gather_grad:
@@ -140,6 +161,11 @@ class GpuEngine:
             return ctypes.c_void_p(int(m.data_ptr()))
         self.sap.device_buffer(_lib.BUF_M).copy_(self.torch.from_numpy(np.ascontiguousarray(m, dtype=np.float64)), non_blocking=True)
         return None
+
+    def eval_full(self, m, delta, want_grad, want_uv):
+        """Whole-problem evaluation on this rank (no slice): Phi, pinv, variance, gradient and, if
+        want_uv, the U,V factors -- but not the Hessian."""
+        _lib.check(_lib.lib().blu_eval_device(self.sap._ctx, self._m_ptr(m), float(delta), int(bool(want_grad)), 2 if want_uv else 0))
 
     def shard_eval_fused(self, m, delta, want_grad, want_uv):
         _lib.check(_lib.lib().blu_shard_eval_fused(self.sap._ctx, self._m_ptr(m), float(delta), int(bool(want_grad)), int(bool(want_uv))))

@@ -126,7 +126,8 @@ int blu_candidate_variances(blu_ctx *ctx, const double *basephi, int LL, const i
                             const int64_t *ms, int64_t ncand, double rcond, double *Vs);
 
 /* Device-resident evaluation: d_m lives on the context's device (or NULL to reuse BLU_BUF_M).
- * want_grad / want_hess select the work; results stay in the context's buffers
+ * want_grad / want_hess select the work (want_hess == 2: the U,V factors only, no Hessian -- the
+ * caller then asks for row panels with blu_shard_hess); results stay in the context's buffers
  * (blu_ctx_device_ptr).  The call is asynchronous on the context's stream. */
 int blu_eval_device(blu_ctx *ctx, const double *d_m, double delta, int want_grad, int want_hess);
 int blu_ctx_sync(blu_ctx *ctx);

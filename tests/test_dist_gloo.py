@@ -76,6 +76,11 @@ class NumpyEngine:
             V[self.lo:self.hi, :N] = Uall[self.lo:self.hi] @ (2 * P)
             self.U.copy_(torch.from_numpy(U.ravel())); self.V.copy_(torch.from_numpy(V.ravel()))
 
+    def eval_full(self, m, delta, want_grad, want_uv):
+        self.set_slice(0, self.o.L)
+        self.shard_phi(m)
+        self.shard_finish(delta, want_grad, want_uv)
+
     def shard_hess(self, rlo, rhi):
         U = self.U.numpy().reshape(-1, self.NP); V = self.V.numpy().reshape(-1, self.NP)
         self.H = U[rlo:rhi] @ V.T
@@ -86,7 +91,7 @@ class NumpyEngine:
     def result(self): return self.var, self.flags
 
 
-def _worker(rank, world, port, N, K, ret):
+def _worker(rank, world, port, N, K, ret, replicate=False):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -98,7 +103,7 @@ def _worker(rank, world, port, N, K, ret):
         C = orc.wishart_cov(N, 4)
         groups = orc.enumerate_groups(N, K)
         o = orc.SapOracle(C, K, groups)
-        ev = ShardedEvaluator(NumpyEngine(o), o.sizes[1:], rank, world, dist=dist)
+        ev = ShardedEvaluator(NumpyEngine(o), o.sizes[1:], rank, world, dist=dist, replicate_front=replicate)
         out = {}
         for name, m in (("dense", orc.dense_m(o.L, 2)), ("sparse", orc.sparse_m(o.L, N, 2)), ("tiny", 0.01 * np.ones(o.L))):
             r = ev.evaluate(m, delta=0.0, grad=True, hess=(name != "tiny"))
@@ -110,14 +115,14 @@ def _worker(rank, world, port, N, K, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("N,K", [(7, 7), (8, 4)])
-def test_sharded_evaluation_world2(N, K):
+@pytest.mark.parametrize("N,K,replicate", [(7, 7, False), (8, 4, False), (7, 7, True)])
+def test_sharded_evaluation_world2(N, K, replicate):
     import oracle as orc
     world = 2
     port = 29500 + (os.getpid() % 2000)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, N, K, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, N, K, ret, replicate), nprocs=world, join=True)
     C = orc.wishart_cov(N, 4)
     groups = orc.enumerate_groups(N, K)
     o = orc.SapOracle(C, K, groups)
@@ -135,4 +140,6 @@ def test_sharded_evaluation_world2(N, K):
         assert np.max(np.abs(Hcat - H)) <= (1e-12 if name == "dense" else 1e-9) * np.max(np.abs(H))
     for r in range(world):
         assert ret[r]["tiny"]["flags"] & 1 and np.isinf(ret[r]["tiny"]["var"])
-    assert ret[0]["dense"]["hi"] == ret[1]["dense"]["lo"]
+    if not replicate:
+        assert ret[0]["dense"]["hi"] == ret[1]["dense"]["lo"]
+    assert ret[0]["dense"]["rhi"] == ret[1]["dense"]["rlo"]
