@@ -6,7 +6,13 @@ G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 def raw(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: a .ncu-rep, or the CSV of its raw page (``ncu -i x.ncu-rep --page raw --csv > x.raw.csv``)."""
+    if rep.endswith(".ncu-rep") and not os.path.isfile(rep):
+        rep = rep[:-8] + ".raw.csv"
+    if rep.endswith(".csv"):
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(txt.splitlines()))
     return r[0], r[1], r[2:]
 
@@ -66,9 +72,9 @@ json.dump({"kernel": "blu_hess_kernel<4,true>", "dram_bytes_per_launch": traffic
            "dram_write_bytes": sum(wr) / len(wr) * scale[uw], "algorithmic_bytes_per_launch": 8.0 * 32767 * 32767,
            "source": "profiles/%s_hess_kernel.md (ncu --set full --clock-control none, 2 launches)" % tag},
           open(os.path.join(P, "hess_kernel_traffic.json"), "w"), indent=1)
-if os.path.isfile(os.path.join(G, "%s_small.ncu-rep" % tag)):
+if os.path.isfile(os.path.join(G, "%s_small.ncu-rep" % tag)) or os.path.isfile(os.path.join(G, "%s_small.raw.csv" % tag)):
     summarize(os.path.join(G, "%s_small.ncu-rep" % tag), "%s: ncu --set full, setup + streaming kernels (N=15)" % tag, "%s_stream_kernels.md" % tag)
-if os.path.isfile(os.path.join(G, "%s_stream20.ncu-rep" % tag)):
-    summarize(os.path.join(G, "%s_stream20.ncu-rep" % tag), "%s: ncu --set full, Phi / gradient streaming kernels at N=20 (L=1048575), before the per-group overhead cut" % tag, "%s_stream_kernels_N20.md" % tag)
+if os.path.isfile(os.path.join(G, "%s_stream20.ncu-rep" % tag)) or os.path.isfile(os.path.join(G, "%s_stream20.raw.csv" % tag)):
+    summarize(os.path.join(G, "%s_stream20.ncu-rep" % tag), "%s: ncu --set full, Phi / gradient streaming kernels at N=20 (L=1048575)" % tag, "%s_stream_kernels_N20.md" % tag)
 print(open(os.path.join(P, "%s_launches.md" % tag)).read())
 print(open(os.path.join(P, "hess_kernel_traffic.json")).read())
