@@ -75,6 +75,7 @@ struct blu_ctx {
     int grid_phi = 1, grid_grad = 1;
     BluChunk *d_chunks = nullptr;      // work list of the owned slice (blu_stream.cuh)
     int nchunks = 0, lutlen = 0, part_rows = 0, phi_warps = BLU_PHI_WARPS;
+    int sd = BLU_CHUNK_DOUBLES + 4;    // stage size (doubles) of the streaming kernels
     bool have_inv = false;
     std::vector<char> inv_set;         // per class: inverses present
     long long lo = 0, hi = 0;          // owned slice of the flat enumeration
@@ -164,7 +165,12 @@ static int build_chunks(blu_ctx *c)
         const long long i0 = std::max<long long>(c->lo - ci.goff, 0), i1 = std::min<long long>(c->hi - ci.goff, ci.Lk);
         if (i1 > i0) total += (i1 - i0) * ci.T;
     }
-    const long long cap = std::max<long long>(96, std::min<long long>(BLU_CHUNK_DOUBLES, total / ((long long)c->nsm * BLU_STREAM_WARPS * 2 * 3)));
+    // stage payload: at least the largest group block, at most ~2 KB beyond it (small stages = more CTAs/SM)
+    // (big problems amortise the per-chunk overhead better with full 4 KB chunks than they gain from occupancy)
+    const long long share = total / ((long long)c->nsm * BLU_STREAM_WARPS * 2 * 3);
+    const long long maxpay = std::min<long long>(BLU_CHUNK_DOUBLES, std::max<long long>(std::max<long long>(((long long)c->Tmax + 15) / 16 * 16, 272), share));
+    const long long cap = std::max<long long>(std::max<long long>(96, c->Tmax), std::min<long long>(maxpay, total / ((long long)c->nsm * BLU_STREAM_WARPS * 2 * 3)));
+    c->sd = (int)(((maxpay + 4) + 1) / 2 * 2);
     for (size_t ic = 0; ic < c->cls.size(); ++ic) {
         const BluClass &ci = c->cls[ic];
         const long long i0 = std::max<long long>(c->lo - ci.goff, 0), i1 = std::min<long long>(c->hi - ci.goff, ci.Lk);
@@ -183,10 +189,10 @@ static int build_chunks(blu_ctx *c)
     // launch geometry: ~4 chunks per warp, at most two CTAs per SM for the Phi kernel (its partial
     // tiles are reduced by one CTA afterwards), a few more for the gradient kernels
     const long long want = std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS * 3 - 1) / (BLU_STREAM_WARPS * 3));
-    c->phi_warps = blu_stream_smem_bytes(BLU_PHI_WARPS * c->N * c->N, (int)c->cls.size(), c->lutlen, BLU_PHI_WARPS) <= 200 * 1024 ? BLU_PHI_WARPS : 8;
+    c->phi_warps = blu_stream_smem_bytes(c->sd, BLU_PHI_WARPS * c->N * c->N, (int)c->cls.size(), c->lutlen, BLU_PHI_WARPS) <= 200 * 1024 ? BLU_PHI_WARPS : 8;
     c->grid_phi = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + c->phi_warps * 3 - 1) / (c->phi_warps * 3)),
                                            (long long)c->nsm * (BLU_PHI_WARPS / c->phi_warps));
-    c->grid_grad = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS - 1) / BLU_STREAM_WARPS), (long long)c->nsm * 3);
+    c->grid_grad = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS - 1) / BLU_STREAM_WARPS), (long long)c->nsm * 5);
     if (c->grid_phi > c->part_rows) {
         if (c->d_part) CUDA_TRY(cudaFree(c->d_part));
         c->d_part = nullptr;
@@ -300,11 +306,11 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
         CTX_TRY(cudaFuncSetAttribute(blu_phi_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      220 * 1024));
         CTX_TRY(cudaFuncSetAttribute(blu_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)blu_stream_smem_bytes(0, 32, 6000)));
+                                     (int)blu_stream_smem_bytes(BLU_CHUNK_DOUBLES + 4, 0, 32, 6000)));
         CTX_TRY(cudaFuncSetAttribute(blu_gradu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)blu_stream_smem_bytes(1024, 32, 6000)));
+                                     (int)blu_stream_smem_bytes(BLU_CHUNK_DOUBLES + 4, 1024, 32, 6000)));
         CTX_TRY(cudaFuncSetAttribute(blu_ysum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)blu_stream_smem_bytes(BLU_STREAM_WARPS * 32, 32, 6000)));
+                                     (int)blu_stream_smem_bytes(BLU_CHUNK_DOUBLES + 4, BLU_STREAM_WARPS * 32, 32, 6000)));
         (void)ncl;
     }
     CTX_TRY(cudaStreamSynchronize(c->stream));
@@ -476,8 +482,8 @@ extern "C" int blu_ctx_assemble_psi(blu_ctx *c, double *psi)
 static int launch_phi(blu_ctx *c, const double *d_m, double delta, int mode)
 {
     const int NN = c->N * c->N;
-    blu_phi_partial_kernel<<<c->grid_phi, c->phi_warps * 32, blu_stream_smem_bytes(c->phi_warps * NN, (int)c->cls.size(), c->lutlen, c->phi_warps), c->stream>>>(
-        c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr);
+    blu_phi_partial_kernel<<<c->grid_phi, c->phi_warps * 32, blu_stream_smem_bytes(c->sd, c->phi_warps * NN, (int)c->cls.size(), c->lutlen, c->phi_warps), c->stream>>>(
+        c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr);
     KERNEL_CHECK(c);
     blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
         c->N, c->grid_phi, c->d_part, delta, mode, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr, c->peers, c->epoch);
@@ -499,15 +505,15 @@ static int ensure_uv(blu_ctx *c)
 static int launch_grad(blu_ctx *c, int want_uv)
 {
     if (!want_uv) {
-        blu_grad_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(0, (int)c->cls.size(), c->lutlen), c->stream>>>(
-            c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_grad);
+        blu_grad_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->sd, 0, (int)c->cls.size(), c->lutlen), c->stream>>>(
+            c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_grad);
         KERNEL_CHECK(c);
         return BLU_OK;
     }
     int rc = ensure_uv(c);
     if (rc) return rc;
-    blu_gradu_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->N * c->N, (int)c->cls.size(), c->lutlen), c->stream>>>(
-        c->d_cls, (int)c->cls.size(), c->N, c->NP, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_S,
+    blu_gradu_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->sd, c->N * c->N, (int)c->cls.size(), c->lutlen), c->stream>>>(
+        c->d_cls, (int)c->cls.size(), c->N, c->NP, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_S,
         c->d_grad, c->d_U, c->d_V);
     KERNEL_CHECK(c);
     return BLU_OK;
@@ -866,8 +872,8 @@ extern "C" int blu_blue_estimator(blu_ctx *c, const double *samples, const doubl
     if (e == cudaSuccess) e = cudaMalloc(&d_y, sizeof(double) * 32);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_sums, sums_flat, sizeof(double) * (size_t)c->gidx_len, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-        blu_ysum_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(BLU_STREAM_WARPS * 32, (int)c->cls.size(), c->lutlen), c->stream>>>(
-            c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_sums, d_part);
+        blu_ysum_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->sd, BLU_STREAM_WARPS * 32, (int)c->cls.size(), c->lutlen), c->stream>>>(
+            c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_sums, d_part);
         e = cudaGetLastError();
         c->launches++;
     }

@@ -77,13 +77,13 @@ __device__ __forceinline__ double blu_grad_chunk_any(const double *__restrict__ 
 
 // extra shared doubles: none
 __global__ void __launch_bounds__(BLU_STREAM_WARPS * 32)
-blu_grad_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks,
+blu_grad_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks, int sd,
                 const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
                 const unsigned *__restrict__ gmask, const double *__restrict__ xrow, double *__restrict__ grad)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    const BluStreamSmem sm = blu_stream_carve(smraw, 0, ncls, lutlen);
-    const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);
+    const BluStreamSmem sm = blu_stream_carve(smraw, sd, 0, ncls, lutlen);
+    const BluWarpStream ws = blu_stream_begin(sm, sd, cls, ncls, lut, lutlen);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *ids = sm.ids + w * 32 * 32;
     const double xv = lane < N ? xrow[lane] : 0.0;
@@ -125,16 +125,16 @@ blu_grad_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChun
 
 // extra shared doubles: N*N (S)
 __global__ void __launch_bounds__(BLU_STREAM_WARPS * 32)
-blu_gradu_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, const BluChunk *__restrict__ chunks, int nchunks,
+blu_gradu_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, const BluChunk *__restrict__ chunks, int nchunks, int sd,
                  const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
                  const unsigned *__restrict__ gmask, const double *__restrict__ xrow, const double *__restrict__ S,
                  double *__restrict__ grad, double *__restrict__ U, double *__restrict__ V)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    const BluStreamSmem sm = blu_stream_carve(smraw, N * N, ncls, lutlen);
+    const BluStreamSmem sm = blu_stream_carve(smraw, sd, N * N, ncls, lutlen);
     double *sS = sm.extra;
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) sS[t] = S[t];
-    const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);       // ends with __syncthreads
+    const BluWarpStream ws = blu_stream_begin(sm, sd, cls, ncls, lut, lutlen);       // ends with __syncthreads
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *ids = sm.ids + w * 32 * 32;
     const double xv = lane < N ? xrow[lane] : 0.0;
@@ -259,13 +259,13 @@ __global__ void blu_psi_kernel(const BluClass *__restrict__ cls, int ncls, int N
 // Per-warp private y tiles (targets inside a group are distinct), fixed-order reductions.
 // part: (gridDim.x, 32).
 __global__ void __launch_bounds__(BLU_STREAM_WARPS * 32)
-blu_ysum_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks,
+blu_ysum_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks, int sd,
                 const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
                 const unsigned *__restrict__ gmask, const double *__restrict__ sums, double *__restrict__ part)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    const BluStreamSmem sm = blu_stream_carve(smraw, BLU_STREAM_WARPS * 32, ncls, lutlen);
-    const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);
+    const BluStreamSmem sm = blu_stream_carve(smraw, sd, BLU_STREAM_WARPS * 32, ncls, lutlen);
+    const BluWarpStream ws = blu_stream_begin(sm, sd, cls, ncls, lut, lutlen);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *ids = sm.ids + w * 32 * 32;
     double *yacc = sm.extra + w * 32;

@@ -89,7 +89,7 @@ __device__ __forceinline__ void blu_phi_chunk_any(const double *__restrict__ bas
 
 // `chunks` lists the work of this launch (whole context or the owned slice); see blu_stream.cuh.
 __global__ void __launch_bounds__(BLU_PHI_WARPS * 32)
-blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks,
+blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks, int sd,
                        const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
                        const unsigned *__restrict__ gmask, const double *__restrict__ m,
                        double *__restrict__ part, BluEvalHeader *hdr)
@@ -97,8 +97,8 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
     extern __shared__ __align__(16) unsigned char smraw[];
     const int NN = N * N;
     const int nwarps = blockDim.x >> 5;                  // 16 normally, 8 when N is large (shared-memory budget)
-    const BluStreamSmem sm = blu_stream_carve(smraw, nwarps * NN, ncls, lutlen, nwarps);
-    const BluWarpStream ws = blu_stream_begin(sm, cls, ncls, lut, lutlen);
+    const BluStreamSmem sm = blu_stream_carve(smraw, sd, nwarps * NN, ncls, lutlen, nwarps);
+    const BluWarpStream ws = blu_stream_begin(sm, sd, cls, ncls, lut, lutlen);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *acc = sm.extra + w * NN;                     // this warp's private N x N tile
     unsigned char *ids = sm.ids + w * 32 * 32;

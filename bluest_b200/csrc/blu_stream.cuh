@@ -15,8 +15,9 @@
 #pragma once
 #include "blu_common.cuh"
 
-#define BLU_CHUNK_DOUBLES 544                       // payload capacity of one stage (>= T_32 = 528)
-#define BLU_STAGE_DOUBLES (BLU_CHUNK_DOUBLES + 4)   // + skew + 16-byte round-up
+#define BLU_CHUNK_DOUBLES 544                       // largest payload of one stage (>= T_32 = 528)
+// The stage size is a per-context run-time value `sd` (doubles) = chunk payload + 4 (skew + 16-byte
+// round-up): contexts whose largest group block is small get small stages, hence more CTAs per SM.
 
 struct BluChunk {
     int cls;          // index into the class table
@@ -94,7 +95,7 @@ __device__ __forceinline__ BluChunkRegs blu_prefetch_chunk(const BluChunk ch, co
 }
 
 // Shared-memory carve-up common to the streaming kernels:
-//   [stages  WARPS x 2 x BLU_STAGE_DOUBLES doubles][extra doubles (kernel specific)]
+//   [stages  WARPS x 2 x sd doubles][extra doubles (kernel specific)]
 //   [class table][(j,l) LUT u16][mbarriers WARPS x 2][member-id scratch WARPS x 32 groups x 32 bytes]
 #define BLU_STREAM_WARPS 8
 
@@ -107,9 +108,9 @@ struct BluStreamSmem {
     unsigned char *ids;
 };
 
-__host__ __device__ __forceinline__ size_t blu_stream_smem_bytes(int extra_doubles, int ncls, int lutlen, int warps = BLU_STREAM_WARPS)
+__host__ __device__ __forceinline__ size_t blu_stream_smem_bytes(int sd, int extra_doubles, int ncls, int lutlen, int warps = BLU_STREAM_WARPS)
 {
-    size_t b = sizeof(double) * ((size_t)warps * 2 * BLU_STAGE_DOUBLES + extra_doubles);
+    size_t b = sizeof(double) * ((size_t)warps * 2 * sd + extra_doubles);
     b += sizeof(BluClass) * ncls;
     b += ((sizeof(unsigned short) * lutlen + 7) / 8) * 8;
     b += sizeof(unsigned long long) * warps * 2;
@@ -117,11 +118,11 @@ __host__ __device__ __forceinline__ size_t blu_stream_smem_bytes(int extra_doubl
     return b;
 }
 
-__device__ __forceinline__ BluStreamSmem blu_stream_carve(unsigned char *raw, int extra_doubles, int ncls, int lutlen, int warps = BLU_STREAM_WARPS)
+__device__ __forceinline__ BluStreamSmem blu_stream_carve(unsigned char *raw, int sd, int extra_doubles, int ncls, int lutlen, int warps = BLU_STREAM_WARPS)
 {
     BluStreamSmem s;
     s.stages = reinterpret_cast<double *>(raw);
-    s.extra = s.stages + (size_t)warps * 2 * BLU_STAGE_DOUBLES;
+    s.extra = s.stages + (size_t)warps * 2 * sd;
     s.cls = reinterpret_cast<BluClass *>(s.extra + extra_doubles);
     s.lut = reinterpret_cast<unsigned short *>(s.cls + ncls);
     s.bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(s.lut) + ((sizeof(unsigned short) * lutlen + 7) / 8) * 8);
@@ -130,15 +131,15 @@ __device__ __forceinline__ BluStreamSmem blu_stream_carve(unsigned char *raw, in
 }
 
 // Block-wide prologue: class table + LUT into shared memory, barriers initialised.
-__device__ __forceinline__ BluWarpStream blu_stream_begin(const BluStreamSmem &s, const BluClass *__restrict__ cls, int ncls,
+__device__ __forceinline__ BluWarpStream blu_stream_begin(const BluStreamSmem &s, int sd, const BluClass *__restrict__ cls, int ncls,
                                                           const unsigned short *__restrict__ lut, int lutlen)
 {
     for (int t = threadIdx.x; t < ncls; t += blockDim.x) s.cls[t] = cls[t];
     for (int t = threadIdx.x; t < lutlen; t += blockDim.x) s.lut[t] = lut[t];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     BluWarpStream ws;
-    ws.stage[0] = s.stages + (size_t)(2 * w) * BLU_STAGE_DOUBLES;
-    ws.stage[1] = s.stages + (size_t)(2 * w + 1) * BLU_STAGE_DOUBLES;
+    ws.stage[0] = s.stages + (size_t)(2 * w) * sd;
+    ws.stage[1] = s.stages + (size_t)(2 * w + 1) * sd;
     ws.bar[0] = s.bars + 2 * w;
     ws.bar[1] = s.bars + 2 * w + 1;
     if (lane == 0) { blu_mbar_init(ws.bar[0], 1); blu_mbar_init(ws.bar[1], 1); blu_mbar_fence_init(); }

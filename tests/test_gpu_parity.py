@@ -452,3 +452,86 @@ def test_symmetric_hessian_download_equals_plain(blu):
     assert v1 == v2 and np.array_equal(g1, g2)
     assert np.array_equal(H1, H2)
     assert np.array_equal(H1, H1.T)
+
+
+def test_degenerate_shapes(blu):
+    """N=1, a single group, K=1 (singletons only), L=1."""
+    sap = blu.SAP(np.array([[2.5]]), 1, [[[0]]], np.ones(1), verbose=False)
+    assert abs(sap.variance(np.array([4.0])) - 2.5 / 4.0) < 1e-15
+    v, g, h = sap.variance_GH(np.array([4.0]))
+    assert abs(v - 0.625) < 1e-15 and abs(g[0] + 2.5 / 16.0) < 1e-15 and abs(h[0, 0] - 2 * 2.5 / 64.0) < 1e-15
+    # singletons only: Phi is diagonal, variance of model 0 is C00/m0 whatever the other models do
+    C = orc.wishart_cov(5, 1)
+    groups = orc.enumerate_groups(5, 1)
+    sap = blu.SAP(C, 1, _copy(groups), np.ones(5), verbose=False)
+    m = np.array([3.0, 1.0, 2.0, 5.0, 4.0])
+    o = orc.SapOracle(C, 1, groups)
+    assert abs(sap.variance(m) - C[0, 0] / 3.0) <= 1e-14
+    v, g, h = sap.variance_GH(m); vo, go, ho = o.variance_GH(m)
+    assert abs(v - vo) <= 1e-14 * vo and maxrel(g, go) < 1e-13 and maxrel(h, ho) < 1e-13
+
+
+def test_nan_entries_outside_cliques_are_never_read(blu):
+    """blue_models.py:166-179: C holds NaN where two models cannot be coupled; no admissible group
+    contains such a pair, so NaN must not leak into any result."""
+    N = 6
+    C = orc.wishart_cov(N, 4)
+    A = np.ones((N, N)); A[0, 5] = A[5, 0] = 0; A[2, 4] = A[4, 2] = 0
+    Cn = C.copy(); Cn[A == 0] = np.nan
+    groups = blu.enumerate_cliques(A, 4)
+    L = sum(len(g) for g in groups)
+    sap = blu.SAP(Cn, len(groups), _copy(groups), np.ones(L), verbose=False)
+    o = orc.SapOracle(C, len(groups), groups)          # the oracle sees finite values at the never-read places
+    m = orc.dense_m(L, 2)
+    v, g, h = sap.variance_GH(m); vo, go, ho = o.variance_GH(m)
+    assert np.isfinite(v) and np.all(np.isfinite(g)) and np.all(np.isfinite(h))
+    assert abs(v - vo) <= TOL * vo and maxrel(g, go) < TOL and maxrel(h, ho) < TOL
+    assert sap.n_fallback == 0
+
+
+def test_indefinite_phi_takes_the_jacobi_route(blu):
+    """Negative sample counts (a solver probing outside the bounds) make Phi indefinite: the
+    Gauss-Jordan fast path must refuse and the Jacobi pseudo-inverse must match numpy's pinv."""
+    N = 6
+    C = orc.wishart_cov(N, 5)
+    groups = orc.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    sap = blu.SAP(C, N, _copy(groups), np.ones(L), verbose=False)
+    o = orc.SapOracle(C, N, groups)
+    rng = np.random.RandomState(0)
+    m = 3.0 * rng.randn(L)
+    phi = o.get_phi(m)
+    assert np.linalg.eigvalsh(phi).min() < 0 < np.linalg.eigvalsh(phi).max()
+    v, g, h = sap.variance_GH(m); vo, go, ho = o.variance_GH(m, hess_mode="factored")
+    cond = np.linalg.cond(phi)
+    tol = max(TOL, 100 * cond * np.finfo(float).eps)
+    assert abs(v - vo) <= tol * abs(vo) and maxrel(g, go) < tol and maxrel(h, ho) < tol
+
+
+def test_delta_regularisation_with_sparse_m(blu):
+    """delta > 0 (ipopt's 1e-6, MOSAP's 1e-15: sap.py:426, mosap.py:567) on a sparse allocation."""
+    N = 7
+    C = orc.wishart_cov(N, 6)
+    groups = orc.enumerate_groups(N, 4)
+    L = sum(len(g) for g in groups)
+    sap = blu.SAP(C, 4, _copy(groups), np.ones(L), verbose=False)
+    o = orc.SapOracle(C, 4, groups)
+    m = np.zeros(L); m[0] = 5; m[N] = 3; m[20] = 7          # only a few models sampled
+    for delta in (1e-6, 1e-3):
+        assert maxrel(sap.get_phi(m, delta), o.get_phi(m, delta)) < TOL
+        v, g, h = sap.variance_GH(m, delta); vo, go, ho = o.variance_GH(m, delta, hess_mode="factored")
+        cond = np.linalg.cond(o.get_phi(m, delta))
+        tol = max(TOL, 100 * cond * np.finfo(float).eps)
+        assert abs(v - vo) <= tol * vo and maxrel(g, go) < tol and maxrel(h, ho) < tol
+
+
+def test_argument_errors(blu):
+    from bluest_b200 import BluError
+    C = orc.wishart_cov(4, 1)
+    with pytest.raises(BluError):
+        blu.SAP(C, 2, [[[0], [1]], [[1, 0]]], np.ones(3), verbose=False)       # unsorted group
+    with pytest.raises(BluError):
+        blu.SAP(C, 1, [[[0], [7]]], np.ones(2), verbose=False)                 # model id out of range
+    sap = blu.SAP(C, 2, [[[0], [1]], [[0, 1]]], np.ones(3), verbose=False)
+    with pytest.raises(ValueError):
+        sap.variance(np.ones(5))                                                # wrong length
