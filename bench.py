@@ -315,6 +315,59 @@ def sap_solve_benchmark(N=10, K=3, device=0):
     sap.close()
     return out
 
+
+def secondary_configs(device=0):
+    """The other BASELINE.json configs, measured briefly (device-resident, CUDA events; not bench lines)."""
+    import torch
+    import bluest_b200 as blu
+    import oracle as orc
+    out = {}
+    # config 5: 20 models, all 1 048 575 groups, Phi + variance + gradient (no dense Hessian exists), 1 GPU
+    N = 20
+    groups = blu.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    sap = blu.SAP(orc.wishart_cov(N, 0), N, groups, np.ones(L), verbose=False, device=device)
+    m = torch.from_numpy(orc.dense_m(L, 0)).to("cuda:%d" % device)
+    for _ in range(3):
+        sap.eval_device(m, 0.0, grad=True, hess=False)
+    sap.timing_log(20)
+    for _ in range(20):
+        sap.eval_device(m, 0.0, grad=True, hess=False)
+    ph = sap.timing_read()
+    t = float(np.median(ph[:, 3])) * 1e-3
+    S_inv = N * (N + 1) * 2 ** (N - 2)
+    algo = 16.0 * S_inv + 24.0 * L
+    peak, _ = peaks()
+    out["n20_nohess"] = {"models": N, "groups": L, "us_per_eval": t * 1e6, "evals_per_s": 1.0 / t,
+                         "algorithmic_GBps": algo / t / 1e9, "roofline_frac": algo / t / 1e9 / peak}
+    sap.close()
+    del groups
+    # config 5b: pilot covariance, 1e6 samples x 20 models (device-resident Y)
+    Y = torch.randn((10 ** 6, 20), dtype=torch.float64, device="cuda:%d" % device)
+    best = min(blu.pilot_covariance(Y, return_ms=True)[3] for _ in range(5))
+    out["pilot_gram_1e6x20"] = {"kernel_us": best * 1e3, "GBps": 8.0 * 1e6 * 20 / (best * 1e-3) / 1e9, "roofline_frac": 8.0 * 1e6 * 20 / (best * 1e-3) / 1e9 / peak}
+    del Y
+    # config 4: MOSAP, 4 outputs x 10 models (1023 groups each), host API, outputs evaluated concurrently
+    N, No = 10, 4
+    groups = blu.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    mos = blu.MOSAP([orc.wishart_cov(N, 10 + n) for n in range(No)], N, [N] * No, [[list(g) for g in gk] for gk in groups],
+                    [[[list(g) for g in gk] for gk in groups] for _ in range(No)], np.ones(L), [np.ones(L)] * No, verbose=False, device=device)
+    mh = orc.dense_m(L, 0)
+    res = {}
+    for name, fn in (("variances", lambda: mos.variances(mh)), ("variance_GH_nohess", lambda: mos.variance_GH(mh, nohess=True)),
+                     ("variance_GH_dense_hessians", lambda: mos.variance_GH(mh))):
+        for _ in range(3):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(30):
+            fn()
+        res[name + "_us"] = (time.perf_counter() - t0) / 30 * 1e6
+    out["mosap_4x10_host_api"] = res
+    for sp in mos.SAPS:
+        sp.close()
+    return out
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -441,6 +494,12 @@ def run_ours(args):
                     out["sap_solve"] = sap_solve_benchmark(device=local)
                 except Exception as ex:
                     out["sap_solve"] = {"failed": repr(ex)}
+            if args.extras:
+                try:
+                    sap.close()
+                    out["secondary_configs"] = secondary_configs(device=local)
+                except Exception as ex:
+                    out["secondary_configs"] = {"failed": repr(ex)}
         print(json.dumps(out))
     sap.close()
     if world > 1:
@@ -531,6 +590,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-solve", dest="solve", action="store_false", help="skip the end-to-end SAP solve comparison")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the brief measurements of the other BASELINE configs")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "shard"], help="sweep: independent instances per GPU (default); shard: one problem, groups sharded")
     ap.add_argument("--nohess", action="store_true", help="shard mode: Phi + variance + gradient only (e.g. --models 20)")
     ap.add_argument("--gather-grad", action="store_true", help="shard mode: all-gather the gradient slices")

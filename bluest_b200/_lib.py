@@ -33,6 +33,8 @@ SIGNATURES = {
     "blu_get_phi": (c_int, [p_void, p_dbl, c_dbl, p_dbl]),
     "blu_variance": (c_int, [p_void, p_dbl, c_dbl, p_dbl, ctypes.POINTER(c_uint)]),
     "blu_variance_GH": (c_int, [p_void, p_dbl, c_dbl, p_dbl, p_dbl, p_void, ctypes.POINTER(c_uint)]),
+    "blu_variance_GH_begin": (c_int, [p_void, p_dbl, c_dbl, c_int, p_void]),
+    "blu_variance_GH_end": (c_int, [p_void, p_dbl, p_dbl, ctypes.POINTER(c_uint)]),
     "blu_cleanup_matrix": (c_int, [p_void, p_dbl, c_dbl, c_int, p_dbl, ctypes.POINTER(c_uint)]),
     "blu_blue_estimator": (c_int, [p_void, p_dbl, p_dbl, p_dbl, p_dbl, p_dbl, ctypes.POINTER(c_uint)]),
     "blu_candidate_variances": (c_int, [p_void, p_dbl, c_int, p_i64, p_i64, c_i64, c_dbl, p_dbl]),
@@ -149,8 +151,10 @@ class PinnedPool:
         return arr
 
     def _give_back(self, n, blk):
+        # keep at least two blocks per size, and as many as fit in 256 MB (a MOSAP evaluation hands out
+        # one Hessian per output; freeing and re-pinning them every call would cost milliseconds)
         lst = self.free_blocks.setdefault(n, [])
-        if len(lst) < 2:
+        if len(lst) < 2 or (len(lst) + 1) * n <= (256 << 20):
             lst.append(blk)
         else:
             blk.free()

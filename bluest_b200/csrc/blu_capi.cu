@@ -83,6 +83,9 @@ struct blu_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
     int launches = 0;
+    double *h_m = nullptr, *h_grad = nullptr;   // pinned staging for m and the gradient (async begin/end pair)
+    double *pend_hess = nullptr;       // host destination of the pending evaluation's Hessian
+    bool pending = false;
     std::vector<cudaEvent_t> panel_ev; // one event per Hessian row panel (symmetric download)
     bool sym_download = false;         // measured slower on the GPU box's host (mirroring 4.3 GB costs more than the PCIe time it saves)
     BluXchg *d_xchg = nullptr;         // this rank's exchange buffer (CUDA IPC shared)
@@ -147,6 +150,8 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->d_xchg);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    if (c->h_m) cudaFreeHost(c->h_m);
+    if (c->h_grad) cudaFreeHost(c->h_grad);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->evlog) if (e) cudaEventDestroy(e);
     for (auto &e : c->panel_ev) if (e) cudaEventDestroy(e);
@@ -724,13 +729,14 @@ extern "C" int blu_get_phi(blu_ctx *c, const double *m, double delta, double *ph
     return BLU_OK;
 }
 
+extern "C" int blu_variance_GH_begin(blu_ctx *c, const double *m, double delta, int want_grad, double *hess);
+extern "C" int blu_variance_GH_end(blu_ctx *c, double *var, double *grad, unsigned *flags);
+
 extern "C" int blu_variance(blu_ctx *c, const double *m, double delta, double *var, unsigned *flags)
 {
-    int rc = use(c);
+    int rc = blu_variance_GH_begin(c, m, delta, 0, nullptr);
     if (rc) return rc;
-    if ((rc = upload_m(c, m))) return rc;
-    if ((rc = blu_eval_device(c, c->d_m, delta, 0, 0))) return rc;
-    return blu_ctx_last_result(c, var, flags);
+    return blu_variance_GH_end(c, var, nullptr, flags);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -799,32 +805,63 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
     return BLU_OK;
 }
 
-extern "C" int blu_variance_GH(blu_ctx *c, const double *m, double delta, double *var, double *grad,
-                               double *hess, unsigned *flags)
+// Split evaluation: _begin queues H2D of m (through pinned staging), the kernels and the D2H of the
+// small results on the context's stream and returns at once; _end waits and hands the results over.
+// Contexts have their own streams, so several outputs (MOSAP) or instances overlap on the device.
+extern "C" int blu_variance_GH_begin(blu_ctx *c, const double *m, double delta, int want_grad, double *hess)
 {
     int rc = use(c);
     if (rc) return rc;
-    if (!grad) return fail(BLU_ERR_ARG, "null grad");
-    if ((rc = upload_m(c, m))) return rc;
-    if ((rc = blu_eval_device(c, c->d_m, delta, 1, hess != nullptr))) return rc;
+    if (!m) return fail(BLU_ERR_ARG, "null m");
+    if (c->pending) return fail(BLU_ERR_STATE, "an evaluation is already pending on this context");
+    if (!c->h_m) {
+        CUDA_TRY(cudaHostAlloc(&c->h_m, sizeof(double) * c->L, cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc(&c->h_grad, sizeof(double) * c->L, cudaHostAllocDefault));
+    }
+    memcpy(c->h_m, m, sizeof(double) * c->L);
+    CUDA_TRY(cudaMemcpyAsync(c->d_m, c->h_m, sizeof(double) * c->L, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = blu_eval_device(c, c->d_m, delta, want_grad || hess != nullptr, hess != nullptr))) return rc;
     // small results first; the Hessian D2H (the long pole) is queued behind them on the same stream
     CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, sizeof(BluEvalHeader), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(grad, c->d_grad, sizeof(double) * c->L, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (want_grad || hess) CUDA_TRY(cudaMemcpyAsync(c->h_grad, c->d_grad, sizeof(double) * c->L, cudaMemcpyDeviceToHost, c->stream));
+    if (hess && !(c->L >= 4096 && c->sym_download))
+        CUDA_TRY(cudaMemcpy2DAsync(hess, sizeof(double) * c->L, c->d_H, sizeof(double) * c->ldH, sizeof(double) * c->L,
+                                   (size_t)c->L, cudaMemcpyDeviceToHost, c->stream));
+    c->pend_hess = hess;
+    c->pending = true;
+    return BLU_OK;
+}
+
+extern "C" int blu_variance_GH_end(blu_ctx *c, double *var, double *grad, unsigned *flags)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->pending) return fail(BLU_ERR_STATE, "no pending evaluation");
+    c->pending = false;
+    double *hess = c->pend_hess;
+    c->pend_hess = nullptr;
+    if (hess && c->L >= 4096 && c->sym_download) {
+        if ((rc = download_hessian_symmetric(c, hess))) return rc;
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
     const unsigned fl = c->h_hdr->flags;
     if (var) *var = c->h_hdr->scal[0];
     if (flags) *flags = fl;
-    if (fl & BLU_FLAG_TINY) {
-        for (long long i = 0; i < c->L; ++i) grad[i] = std::numeric_limits<double>::infinity();
-        return BLU_OK;
-    }
-    if (hess) {
-        if (c->L >= 4096 && c->sym_download) return download_hessian_symmetric(c, hess);
-        CUDA_TRY(cudaMemcpy2DAsync(hess, sizeof(double) * c->L, c->d_H, sizeof(double) * c->ldH, sizeof(double) * c->L,
-                                   (size_t)c->L, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (grad) {
+        if (fl & BLU_FLAG_TINY) for (long long i = 0; i < c->L; ++i) grad[i] = std::numeric_limits<double>::infinity();
+        else memcpy(grad, c->h_grad, sizeof(double) * c->L);
     }
     return BLU_OK;
+}
+
+extern "C" int blu_variance_GH(blu_ctx *c, const double *m, double delta, double *var, double *grad,
+                               double *hess, unsigned *flags)
+{
+    if (!grad) return fail(BLU_ERR_ARG, "null grad");
+    int rc = blu_variance_GH_begin(c, m, delta, 1, hess);
+    if (rc) return rc;
+    return blu_variance_GH_end(c, var, grad, flags);
 }
 
 extern "C" int blu_cleanup_matrix(blu_ctx *c, const double *m, double delta, int mode, double *X, unsigned *flags)

@@ -63,13 +63,32 @@ class MOSAP(object):
         return budget, eps
 
     def variances(self, m, delta=0):
-        return [self.SAPS[n].variance(m[self.mappings[n]], delta=delta) for n in range(self.n_outputs)]
+        """mosap.py:86-89; the outputs are evaluated concurrently (one stream per context)."""
+        from . import _lib
+        for n in range(self.n_outputs):
+            self.SAPS[n].variance_GH_begin(m[self.mappings[n]], delta=delta, nohess=True, grad=False)
+        out = []
+        for n in range(self.n_outputs):
+            var, _, _, fl = self.SAPS[n].variance_GH_end()
+            if fl & _lib.FLAG_TINY:
+                out.append(np.inf)
+                continue
+            assert not (fl & _lib.FLAG_NO_MODEL0)             # misc.py:470
+            out.append(var)
+        return out
 
     def variance_GH(self, m, nohess=False, delta=0):
-        out = [self.SAPS[n].variance_GH(m[self.mappings[n]], nohess=nohess, delta=delta) for n in range(self.n_outputs)]
-        variances = [item[0] for item in out]
-        gradients = [item[1] for item in out]
-        hessians = [item[2] for item in out]
+        """mosap.py:91-100; all outputs in flight at once, results collected in output order."""
+        from . import _lib
+        for n in range(self.n_outputs):
+            self.SAPS[n].variance_GH_begin(m[self.mappings[n]], delta=delta, nohess=nohess)
+        variances, gradients, hessians = [], [], []
+        for n in range(self.n_outputs):
+            var, grad, hess, fl = self.SAPS[n].variance_GH_end()
+            if fl & _lib.FLAG_TINY:
+                # the reference's SAP returns a 2-tuple here and its MOSAP then fails on item[2]
+                raise IndexError("tuple index out of range (max|m| < 0.05: misc.py:484 returns a 2-tuple)")
+            variances.append(var); gradients.append(grad); hessians.append(hess)
         return variances, gradients, hessians
 
     def get_cleanup_matrices(self, m, delta=0):

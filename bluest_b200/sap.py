@@ -124,7 +124,7 @@ class SAP(object):
             grad = np.empty(L)
             # page-locked destination only where it pays (pinning costs ~0.1 ms/MB once; a pageable D2H of a
             # big Hessian runs several times slower than the 57 GB/s of a pinned one)
-            hess = None if nohess else (_lib.pinned_pool.empty((L, L)) if L * L * 8 >= (32 << 20) else np.empty((L, L)))
+            hess = None if nohess else (_lib.pinned_pool.empty((L, L)) if L * L * 8 >= (1 << 20) else np.empty((L, L)))
             hp = None if nohess else ctypes.c_void_p(hess.ctypes.data)
             check(lib().blu_variance_GH(ctx, dptr(self._m(m)), float(delta), ctypes.byref(var), dptr(grad), hp, ctypes.byref(fl)))
             if fl.value & _lib.FLAG_TINY:
@@ -142,6 +142,22 @@ class SAP(object):
         self.variance = variance
         self.variance_GH = variance_GH
         self.get_cleanup_matrix = get_cleanup_matrix
+
+    # ---- split evaluation (several contexts in flight at once, used by MOSAP) -----------------
+    def variance_GH_begin(self, m, delta=0, nohess=False, grad=True):
+        L = int(self.L)
+        hess = None if nohess else (_lib.pinned_pool.empty((L, L)) if L * L * 8 >= (1 << 20) else np.empty((L, L)))
+        hp = None if hess is None else ctypes.c_void_p(hess.ctypes.data)
+        check(lib().blu_variance_GH_begin(self._ctx, dptr(self._m(m)), float(delta), int(bool(grad)), hp))
+        self._pending = (hess, grad)
+
+    def variance_GH_end(self):
+        hess, want_grad = self._pending
+        self._pending = None
+        var = ctypes.c_double(0.0); fl = ctypes.c_uint(0)
+        grad = np.empty(int(self.L)) if want_grad else None
+        check(lib().blu_variance_GH_end(self._ctx, ctypes.byref(var), None if grad is None else dptr(grad), ctypes.byref(fl)))
+        return var.value, grad, hess, fl.value
 
     # ---- device-resident interface (no host round trip of the big arrays) ---------------------
     def eval_device(self, d_m=None, delta=0.0, grad=True, hess=False):

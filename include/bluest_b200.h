@@ -103,6 +103,14 @@ int blu_variance(blu_ctx *ctx, const double *m, double delta, double *var, unsig
 int blu_variance_GH(blu_ctx *ctx, const double *m, double delta, double *var, double *grad,
                     double *hess, unsigned *flags);
 
+/* Split form of blu_variance / blu_variance_GH: _begin queues the upload, the kernels and the
+ * downloads on the context's stream and returns immediately; _end waits and delivers.  Contexts own
+ * their streams, so the outputs of a MOSAP (mosap.py:91-100 loops over them) overlap on the device.
+ * m is copied into pinned staging inside _begin (the caller's buffer may be reused at once); hess
+ * (may be NULL) must stay valid until _end. */
+int blu_variance_GH_begin(blu_ctx *ctx, const double *m, double delta, int want_grad, double *hess);
+int blu_variance_GH_end(blu_ctx *ctx, double *var, double *grad, unsigned *flags);
+
 /* get_cleanup_matrix (misc.py:507-516): X is (N,L) row-major.  mode 0 reproduces the reference's
  * assignment semantics (cmisc.cpp:51, only l = k-1 survives); mode 1 returns the intended
  * X[:,i] = u_i.  Returns BLU_ERR_ARG-free status with BLU_FLAG_TINY when the reference would
