@@ -287,34 +287,62 @@ class _CpuSap:
         return [], []
 
 
-def sap_solve_benchmark(N=10, K=3, device=0):
-    """SAP.solve(solver="scipy"), budget mode, fixed x0, on the reference's own smoke-test shape
-    (sap.py:458-497: N=10, K=3): GPU closures vs CPU reference closures, identical driver."""
+class _TimedClosures:
+    """Wraps a SAP-like object and accumulates the time spent inside its closures."""
+
+    def __init__(self, p):
+        self.p, self.t, self.n = p, 0.0, 0
+        self.L, self.costs, self.e = p.L, p.costs, p.e
+
+    def variance(self, m, delta=0):
+        t0 = time.perf_counter(); r = self.p.variance(m, delta); self.t += time.perf_counter() - t0; self.n += 1
+        return r
+
+    def variance_GH(self, m, delta=0, nohess=False):
+        t0 = time.perf_counter(); r = self.p.variance_GH(m, delta=delta, nohess=nohess); self.t += time.perf_counter() - t0; self.n += 1
+        return r
+
+    def get_max_sample_constraints(self, mm):
+        return [], []
+
+
+def sap_solve_benchmark(N=10, K=4, device=0):
+    """SAP.solve(solver="scipy"), budget mode, fixed x0 (10 models, groups of up to 4 -- the reference's
+    smoke test, sap.py:458-497, uses N=10, K=3): GPU closures vs CPU reference closures, identical
+    driver.  BLAS is pinned to one thread for both arms: trust-constr's small dense factorisations run
+    several times SLOWER on 16 oversubscribed threads, which otherwise swamps the comparison."""
     import bluest_b200 as blu
     import oracle as orc
     from bluest_b200.solvers import scipy_solve
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        import contextlib
+        threadpool_limits = lambda limits=None: contextlib.nullcontext()
     C = orc.wishart_cov(N, 0)
     groups = blu.enumerate_groups(N, K)
     costs = blu.group_costs(groups, 2.0 ** (N - np.arange(N)))
     L = len(costs)
     x0 = np.ceil(10 * abs(np.random.RandomState(0).randn(L)))
     budget = 100 * costs.max()
-    out = {"problem": "N=%d K=%d L=%d budget=%g, scipy trust-constr (sap.py:387-418), fixed x0" % (N, K, L, budget)}
-    cpu = _CpuSap(C, K, groups, costs)
-    c1 = {}
-    t0 = time.perf_counter(); r1 = scipy_solve(cpu, budget=budget, x0=x0.copy(), counters=c1); t_cpu = time.perf_counter() - t0
+    out = {"problem": "N=%d K=%d L=%d budget=%g, scipy trust-constr (sap.py:387-418), fixed x0, BLAS threads=1" % (N, K, L, budget)}
+    cpu = _TimedClosures(_CpuSap(C, K, groups, costs))
     sap = blu.SAP(C, K, [[list(g) for g in gk] for gk in groups], costs, verbose=False, device=device)
+    gpu = _TimedClosures(sap)
     sap.variance_GH(x0)                                  # warm-up (pinned pool, first launches)
-    c2 = {}
-    t0 = time.perf_counter(); r2 = scipy_solve(sap, budget=budget, x0=x0.copy(), counters=c2); t_gpu = time.perf_counter() - t0
-    out.update({"cpu_reference_s": t_cpu, "gpu_s": t_gpu, "cpu_evals": c1, "gpu_evals": c2,
+    with threadpool_limits(limits=1):
+        c1 = {}
+        t0 = time.perf_counter(); r1 = scipy_solve(cpu, budget=budget, x0=x0.copy(), counters=c1); t_cpu = time.perf_counter() - t0
+        c2 = {}
+        t0 = time.perf_counter(); r2 = scipy_solve(gpu, budget=budget, x0=x0.copy(), counters=c2); t_gpu = time.perf_counter() - t0
+    out.update({"cpu_reference_s": t_cpu, "gpu_s": t_gpu, "cpu_closure_s": cpu.t, "gpu_closure_s": gpu.t,
+                "closure_calls": gpu.n, "cpu_evals": c1, "gpu_evals": c2,
                 "cpu_variance": float(r1.fun), "gpu_variance": float(r2.fun),
                 "allocation_maxrel_diff": float(np.max(np.abs(r1.x - r2.x)) / np.max(np.abs(r1.x))),
                 "variance_rel_diff": float(abs(r1.fun - r2.fun) / abs(r1.fun)),
-                "note": "solve time is dominated by scipy's trust-constr internals at this size, not by the closures"})
+                "note": "what is left of the solve time after the closures is scipy's trust-constr itself (host, out of scope)"})
     sap.close()
     return out
-
 
 def secondary_configs(device=0):
     """The other BASELINE.json configs, measured briefly (device-resident, CUDA events; not bench lines)."""
