@@ -10,7 +10,7 @@ from .groups import (balanced_slices, enumerate_cliques, enumerate_groups, group
 from .sap import SAP                                    # noqa: F401
 from .mosap import MOSAP, BLUESTError                   # noqa: F401
 from .pilot import pilot_covariance                     # noqa: F401
-from . import cmisc, intproj                            # noqa: F401
+from . import cmisc, intproj, io                        # noqa: F401
 from .dist import ShardedEvaluator, GpuEngine          # noqa: F401
 from .install import install, uninstall                # noqa: F401
 

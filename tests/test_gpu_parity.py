@@ -535,3 +535,17 @@ def test_argument_errors(blu):
     sap = blu.SAP(C, 2, [[[0], [1]], [[0, 1]]], np.ones(3), verbose=False)
     with pytest.raises(ValueError):
         sap.variance(np.ones(5))                                                # wrong length
+
+
+def test_setup_from_graph_file_reproduces_hodgkin_huxley(blu):
+    """From the reference-format graph file to the per-output variances of the stored K=7 allocation
+    (BASELINE.md section 2), through the clique enumeration / union / MOSAP path."""
+    from bluest_b200 import io
+    g = io.load_graph_data(os.path.join(GOLDEN, "hh_graph_data.npz"))
+    mos = io.setup_mosap(g, K=7)
+    d = _load("hodgkin.npz")
+    assert int(mos.L) == len(d["samples"]) == 3301
+    Vs = mos.variances(d["samples"])
+    for n in range(5):
+        assert abs(Vs[n] - float(d[f"variance{n}"])) <= 1e-5 * Vs[n]
+    assert abs(d["samples"] @ mos.costs - float(d["total_cost"])) < 1e-6

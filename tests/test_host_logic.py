@@ -109,3 +109,21 @@ def test_integer_projection_host_logic(tag, N, monkeypatch):
     val, fval = intproj.best_closest_integer_solution_BLUE(sap, sol, eps=float(d[f"{tag}/eps"]))
     assert np.array_equal(val, d[f"{tag}/eps_val"]) and abs(fval - float(d[f"{tag}/eps_fval"])) <= 1e-10 * fval
     assert np.array_equal(intproj.integer_projection(sap, sol, budget=float(d[f"{tag}/budget"])), d[f"{tag}/projection_budget"])
+
+
+def test_graph_data_file_roundtrip(tmp_path):
+    """Row f4: the reference's .npz graph format (blue_models.py:265-299) and the covariance view of
+    get_covariance (blue_models.py:166-179)."""
+    from bluest_b200 import io
+    g = io.load_graph_data(os.path.join(GOLDEN, "hh_graph_data.npz"))
+    d = _load("hodgkin.npz")
+    assert g["M"] == 12 and g["n_outputs"] == 5 and len(g["C"]) == 5
+    for n in range(5):
+        assert np.array_equal(g["C"][n], d[f"C{n}"])           # complete graph: no NaN / inf to translate
+    assert np.array_equal(g["costs"], d["costs"])
+    A = g["adjacency"][0].copy(); A[0, 5] = A[5, 0] = 0.0; A[1, 2] = A[2, 1] = np.inf
+    io.save_graph_data(str(tmp_path / "g.npz"), g["costs"], [A], g["SG"][:1])
+    h = io.load_graph_data(str(tmp_path / "g.npz"))
+    assert np.isnan(h["C"][0][0, 5]) and h["C"][0][1, 2] == 0.0 and h["M"] == 12
+    with pytest.raises(ValueError):
+        io.load_graph_data(str(tmp_path / "g.npz"), n_outputs=3)
