@@ -1,0 +1,80 @@
+"""Parity at BASELINE.json's full size (15 models, all 32767 groups): the oracle still finishes the
+setup, Phi, variance and gradient in seconds, so those are compared in full; the 8.59 GB Hessian is
+checked through size-independent properties (exact symmetry, sampled rows against the factored form
+built from the oracle's U and pinv, directional finite differences of the gradient)."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from conftest import maxrel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def problem():
+    import bluest_b200 as blu
+    if blu.device_count() <= 0:
+        pytest.fail("no CUDA device")
+    N = 15
+    C = orc.wishart_cov(N, 0)
+    groups = orc.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    o = orc.SapOracle(C, N, groups)
+    sap = blu.SAP(C, N, [[list(g) for g in gk] for gk in groups], np.ones(L), verbose=False)
+    yield N, L, o, sap
+    sap.close()
+
+
+def test_group_enumeration_and_inverses_full_size(problem):
+    N, L, o, sap = problem
+    assert L == 2 ** N - 1 == 32767 and sap.n_fallback == 0
+    flat = np.concatenate([g.ravel() for g in sap.groups])
+    assert np.array_equal(flat, np.concatenate([g.ravel() for g in o.groups]))          # bit-exact indexing
+    for k in range(N):
+        assert maxrel(sap.invcovs[k], o.invcovs[k]) < TOL
+
+
+def test_phi_variance_gradient_full_size(problem):
+    N, L, o, sap = problem
+    m1, m2 = orc.dense_m(L, 0), orc.dense_m(L, 1)
+    assert maxrel(sap.get_phi(m1), o.get_phi(m1)) < TOL
+    # linearity of Phi in m (delta = 0)
+    assert maxrel(sap.get_phi(2.5 * m1 - 0.5 * m2), 2.5 * sap.get_phi(m1) - 0.5 * sap.get_phi(m2)) < 1e-13
+    vo, go, _ = o.variance_GH(m1, nohess=True)
+    v, g, _ = sap.variance_GH(m1, nohess=True)
+    assert abs(v - vo) <= TOL * vo and maxrel(g, go) < TOL
+    assert abs(sap.variance(m1) - o.variance(m1)) <= TOL * vo
+    ms = orc.sparse_m(L, N, 3)
+    vo, go, _ = o.variance_GH(ms, nohess=True)
+    v, g, _ = sap.variance_GH(ms, nohess=True)
+    assert abs(v - vo) <= TOL * vo and maxrel(g, go) < 1e-9
+
+
+def test_dense_hessian_full_size_properties(problem):
+    N, L, o, sap = problem
+    m = orc.dense_m(L, 0)
+    v, g, H = sap.variance_GH(m)
+    assert H.shape == (L, L)
+    # exact symmetry of the full 8.59 GB matrix (blockwise to bound the temporaries)
+    for r0 in range(0, L, 4096):
+        blk = H[r0:r0 + 4096]
+        assert np.array_equal(blk, H[:, r0:r0 + 4096].T)
+    # sampled rows against 2 U^T pinv(Phi) U from the oracle
+    P = np.linalg.pinv(o.get_phi(m))
+    U = o.ufactor(np.ascontiguousarray(P[0]))              # (N, L)
+    rows = np.array([0, 1, 14, 15, 119, 120, 4095, 4096, 16383, 20000, 32703, 32704, 32766])
+    ref = 2.0 * (U[:, rows].T @ P @ U)
+    assert maxrel(H[rows], ref) < TOL
+    assert maxrel(np.diag(H), 2.0 * np.einsum("al,ab,bl->l", U, P, U)) < TOL
+    # the gradient is the derivative of the variance, the Hessian of the gradient (central differences)
+    rng = np.random.RandomState(5)
+    d = rng.randn(L); d /= np.linalg.norm(d)
+    h = 1e-3
+    vp, gp, _ = sap.variance_GH(m + h * d, nohess=True)
+    vm, gm, _ = sap.variance_GH(m - h * d, nohess=True)
+    assert abs((vp - vm) / (2 * h) - g @ d) <= 1e-6 * abs(g @ d)
+    Hd = H @ d
+    assert maxrel((gp - gm) / (2 * h), Hd) < 1e-5
+    del H
