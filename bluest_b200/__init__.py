@@ -5,7 +5,7 @@ native routines; everything numerical runs in hand-written CUDA behind libbluest
 (include/bluest_b200.h).  No CPU fallback: importing works anywhere, calling needs a GPU.
 """
 from ._lib import BluError, device_count, lib          # noqa: F401
-from .groups import (balanced_slices, enumerate_cliques, enumerate_groups, group_costs,     # noqa: F401
+from .groups import (balanced_slices, stream_cost, enumerate_cliques, enumerate_groups, group_costs,     # noqa: F401
                      indicator_ES, mappings, union_groups)
 from .sap import SAP                                    # noqa: F401
 from .mosap import MOSAP, BLUESTError                   # noqa: F401

@@ -77,6 +77,7 @@ struct blu_ctx {
     int nchunks = 0, lutlen = 0, part_rows = 0, phi_warps = BLU_PHI_WARPS;
     int sd = BLU_CHUNK_DOUBLES + 4;    // stage size (doubles) of the streaming kernels
     bool have_inv = false;
+    bool hess_attr_done[2] = {false, false};
     std::vector<char> inv_set;         // per class: inverses present
     long long lo = 0, hi = 0;          // owned slice of the flat enumeration
     cudaStream_t stream = nullptr;
@@ -527,11 +528,10 @@ static int launch_grad(blu_ctx *c, int want_uv)
 template <int NCH>
 static void launch_hess_t(blu_ctx *c, bool sym, const double *Ua, long long Lrows, double *H)
 {
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[sym]) {
+    if (!c->hess_attr_done[sym]) {          // per context: function attributes are per device
         if (sym) cudaFuncSetAttribute(blu_hess_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM);
         else cudaFuncSetAttribute(blu_hess_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM);
-        attr_done[sym] = true;
+        c->hess_attr_done[sym] = true;
     }
     const int nTc = (int)((c->L + BLU_HT - 1) / BLU_HT);
     if (sym) {

@@ -252,6 +252,7 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
                       double *__restrict__ S, BluEvalHeader *hdr, BluPeers peers, unsigned long long epoch)
 {
     __shared__ double A[BLU_JMAX * BLU_JLD], V[BLU_JMAX * BLU_JLD], Ph[BLU_JMAX * BLU_JLD];
+    __shared__ double Pm[BLU_JMAX * BLU_JMAX];   // the finished Phi (mirrored, + delta), N x N dense: everything below reads this copy
     extern __shared__ double red[];              // BLU_FIN_SEG x N*N staging for the partial sums
     __shared__ BluJacobiScratch js;
     __shared__ int sidx[BLU_JMAX];
@@ -335,6 +336,7 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
         double v = Ph[lo * BLU_JLD + hi];
         if (r == c) v += delta;
         phi[e] = v;
+        Pm[e] = v;
     }
     __syncthreads();
     unsigned supp;
@@ -369,7 +371,7 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
     // in every regular evaluation and is inverted by Gauss-Jordan; Jacobi only if that fails.
     if (tid < 32) {
         bool nz = false;
-        if (tid < N) for (int c = 0; c < N; ++c) nz = nz || (phi[tid * N + c] != 0.0);
+        if (tid < N) for (int c = 0; c < N; ++c) nz = nz || (Pm[tid * N + c] != 0.0);
         const unsigned am = __ballot_sync(BLU_FULL, nz);
         if (tid == 0) {
             int cnt = 0;
@@ -382,7 +384,7 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
     const int na = ns;
     const unsigned active = amask;
     if (tid == 0) js.lmax = 0.0;
-    int sweeps = blu_block_pinv(phi, N, sidx, na, A, V, Ph, diag0, &js, tid, nthr);
+    int sweeps = blu_block_pinv(Pm, N, sidx, na, A, V, Ph, diag0, &js, tid, nthr);
     for (int e = tid; e < NN; e += nthr) {
         const int r = e / N, c = e - r * N;
         double v = 0.0;
@@ -412,7 +414,7 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
     }
     __syncthreads();
     const int nsub = ns;
-    if (nsub > 0) blu_block_pinv(phi, N, sidx, nsub, A, V, Ph, diag0, &js, tid, nthr);
+    if (nsub > 0) blu_block_pinv(Pm, N, sidx, nsub, A, V, Ph, diag0, &js, tid, nthr);
     if (tid == 0) { hdr->scal[0] = nsub > 0 ? Ph[0] : INFINITY; hdr->flags = flags; }
     if (tid < 32) hdr->xsup[tid] = 0.0;
     __syncthreads();

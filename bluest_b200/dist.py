@@ -18,11 +18,11 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .groups import balanced_slices
+from .groups import balanced_slices, stream_cost
 
 
 class ShardedEvaluator:
-    def __init__(self, engine, sizes, rank, world, dist=None, group=None, fused=False, replicate_front=False):
+    def __init__(self, engine, sizes, rank, world, dist=None, group=None, fused=False, replicate_front=False, weight=stream_cost):
         """engine: object with shard_phi / shard_finish / shard_hess / buffers (see GpuEngine).
         sizes = [L1..LK].  fused=True: the Phi all-reduce runs inside the finish kernel over NVLink
         peer memory (engine.connect_peers) instead of a separate NCCL call."""
@@ -35,7 +35,7 @@ class ShardedEvaluator:
         self.rank, self.world = rank, world
         self.dist, self.group = dist, group
         self.L = int(sum(sizes))
-        self.slices = balanced_slices(list(sizes), world)
+        self.slices = balanced_slices(list(sizes), world, weight=weight)
         self.lo, self.hi = self.slices[rank]
         self.max_rows = max(hi - lo for lo, hi in self.slices)
         # Hessian row panels: equal row counts (equal bytes written), independent of the group slices

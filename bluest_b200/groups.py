@@ -102,10 +102,20 @@ def mappings(groups, multi_groups):
     return out
 
 
-def balanced_slices(sizes, world):
-    """Contiguous slices of the flat enumeration with equal work sum(k^2).
-    ``sizes`` = [L1..LK].  Returns ``world`` (lo, hi) pairs."""
-    work = np.concatenate([np.full(int(Lk), (k + 1) ** 2, dtype=np.float64) for k, Lk in enumerate(sizes)]) if sum(sizes) else np.zeros(0)
+def stream_cost(k):
+    """Relative cost of one group of size k in the streaming kernels (Phi, gradient): a fixed
+    per-group part plus one 32-entry step per 32 packed entries (T_k = k(k+1)/2).  Much flatter than
+    the k^2 of the reference's loops: the kernels are instruction-bound, not byte-bound, on small groups."""
+    return 2.0 + (k * (k + 1) // 2 + 31) // 32
+
+
+def balanced_slices(sizes, world, weight=None):
+    """Contiguous slices of the flat enumeration with equal work.
+    ``sizes`` = [L1..LK]; ``weight(k)`` = cost of one group of size k (default k^2, the reference's
+    inner-loop count).  Returns ``world`` (lo, hi) pairs."""
+    if weight is None:
+        weight = lambda k: float(k * k)
+    work = np.concatenate([np.full(int(Lk), weight(k + 1), dtype=np.float64) for k, Lk in enumerate(sizes)]) if sum(sizes) else np.zeros(0)
     cum = np.concatenate([[0.0], np.cumsum(work)])
     total = cum[-1]
     bounds = [0]
