@@ -20,6 +20,7 @@
 #include "blu_invert.cuh"
 #include "blu_phi.cuh"
 #include "blu_grad.cuh"
+#include "blu_soa.cuh"
 #include "blu_hess.cuh"
 #include "blu_gram.cuh"
 #include "blu_intproj.cuh"
@@ -73,6 +74,13 @@ struct blu_ctx {
     long long H_rows = 0;              // rows allocated in d_H
     BluEvalHeader *d_hdr = nullptr, *h_hdr = nullptr;
     int grid_phi = 1, grid_grad = 1;
+    double *d_soa = nullptr;           // group-interleaved (SoA tile) copy of the inverses, blu_soa.cuh
+    long long *d_soff = nullptr;       // per class: offset of its tiles in d_soa
+    std::vector<long long> soff;
+    long long soa_len = 0;
+    bool soa_valid = false, tiles_valid = false, use_soa = true;
+    BluTile *d_tiles = nullptr;
+    int ntiles = 0, grid_soa = 1;
     BluChunk *d_chunks = nullptr;      // work list of the owned slice (blu_stream.cuh)
     int nchunks = 0, lutlen = 0, part_rows = 0, phi_warps = BLU_PHI_WARPS;
     int sd = BLU_CHUNK_DOUBLES + 4;    // stage size (doubles) of the streaming kernels
@@ -147,7 +155,7 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     cudaFree(c->d_cls); cudaFree(c->d_gidx); cudaFree(c->d_gmask); cudaFree(c->d_lut); cudaFree(c->d_cinv);
     cudaFree(c->d_C); cudaFree(c->d_m); cudaFree(c->d_part); cudaFree(c->d_phi); cudaFree(c->d_pinv);
     cudaFree(c->d_x); cudaFree(c->d_S); cudaFree(c->d_grad); cudaFree(c->d_U); cudaFree(c->d_V); cudaFree(c->d_H);
-    cudaFree(c->d_hdr); cudaFree(c->d_chunks);
+    cudaFree(c->d_hdr); cudaFree(c->d_chunks); cudaFree(c->d_soa); cudaFree(c->d_soff); cudaFree(c->d_tiles);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->d_xchg);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
@@ -397,6 +405,7 @@ extern "C" int blu_ctx_set_covariance(blu_ctx *c, const double *C, double pivot_
     if (n_fallback) *n_fallback = nbad;
     std::fill(c->inv_set.begin(), c->inv_set.end(), 1);
     c->have_inv = true;
+    c->soa_valid = false;
     return BLU_OK;
 }
 
@@ -424,6 +433,7 @@ extern "C" int blu_ctx_set_invcovs(blu_ctx *c, int k, const double *invcovs_k)
     cudaFree(d_full);
     if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "set_invcovs: %s", cudaGetErrorString(e));
     c->inv_set[idx] = 1;
+    c->soa_valid = false;
     c->have_inv = std::all_of(c->inv_set.begin(), c->inv_set.end(), [](char v) { return v != 0; });
     return BLU_OK;
 }
@@ -508,8 +518,76 @@ static int ensure_uv(blu_ctx *c)
     return BLU_OK;
 }
 
+// SoA-tile copy of the inverses + tile work list of the owned slice (lazy; see blu_soa.cuh).
+static int ensure_soa(blu_ctx *c)
+{
+    if (!c->d_soa) {
+        c->soff.clear();
+        long long off = 0;
+        for (const BluClass &ci : c->cls) { c->soff.push_back(off); off += ((ci.Lk + 31) / 32) * 32 * ci.T; }
+        c->soa_len = off;
+        CUDA_TRY(cudaMalloc(&c->d_soa, sizeof(double) * std::max<long long>(off, 1)));
+        CUDA_TRY(cudaMalloc(&c->d_soff, sizeof(long long) * c->cls.size()));
+        CUDA_TRY(cudaMemcpyAsync(c->d_soff, c->soff.data(), sizeof(long long) * c->cls.size(), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if (!c->soa_valid) {
+        for (size_t ic = 0; ic < c->cls.size(); ++ic) {
+            const BluClass &ci = c->cls[ic];
+            const long long total = ((ci.Lk + 31) / 32) * 32 * ci.T;
+            const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->nsm * 16));
+            blu_soa_build_kernel<<<grid, 256, 0, c->stream>>>(c->d_cinv + ci.coff, ci.Lk, ci.T, c->d_soa + c->soff[ic]);
+            KERNEL_CHECK(c);
+        }
+        c->soa_valid = true;
+    }
+    if (!c->tiles_valid) {
+        std::vector<BluTile> tl;
+        for (size_t ic = 0; ic < c->cls.size(); ++ic) {
+            const BluClass &ci = c->cls[ic];
+            const long long i0 = std::max<long long>(c->lo - ci.goff, 0), i1 = std::min<long long>(c->hi - ci.goff, ci.Lk);
+            if (i1 <= i0) continue;
+            for (long long t = i0 / 32; t <= (i1 - 1) / 32; ++t) {
+                BluTile b; b.cls = (int)ic; b.nsub = (ci.T + BLU_SOA_E - 1) / BLU_SOA_E; b.t = t;
+                tl.push_back(b);
+            }
+        }
+        if (c->d_tiles) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->d_tiles)); c->d_tiles = nullptr; }
+        c->ntiles = (int)tl.size();
+        CUDA_TRY(cudaMalloc(&c->d_tiles, sizeof(BluTile) * std::max<size_t>(tl.size(), 1)));
+        if (!tl.empty()) CUDA_TRY(cudaMemcpyAsync(c->d_tiles, tl.data(), sizeof(BluTile) * tl.size(), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->grid_soa = (int)std::max<long long>(1, std::min<long long>(((long long)c->ntiles + BLU_SOA_WARPS - 1) / BLU_SOA_WARPS, (long long)c->nsm * 2));
+        c->tiles_valid = true;
+    }
+    return BLU_OK;
+}
+
 static int launch_grad(blu_ctx *c, int want_uv)
 {
+    // One group per lane needs at least a couple of 32-group tiles per SM to fill the machine; smaller
+    // problems (latency-bound anyway) keep the entry-per-lane kernels, which spread a group over a warp.
+    if (c->use_soa && c->hi - c->lo >= (long long)c->nsm * 2 * 32) {
+        int rc = ensure_soa(c);
+        if (rc) return rc;
+        if (want_uv && (rc = ensure_uv(c))) return rc;
+        const int ncl = (int)c->cls.size();
+        if (!want_uv) {
+            const size_t smem = blu_soa_smem_bytes(c->K, false, c->N, ncl, c->lutlen);
+            CUDA_TRY(cudaFuncSetAttribute(blu_grad_soa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blu_grad_soa_kernel<false><<<c->grid_soa, BLU_SOA_WARPS * 32, smem, c->stream>>>(
+                c->d_cls, ncl, c->N, c->NP, c->K, c->d_tiles, c->ntiles, c->d_soa, c->d_soff, c->d_lut, c->lutlen, c->d_gmask,
+                c->d_x, c->d_S, c->lo, c->hi, c->d_grad, nullptr, nullptr);
+        } else {
+            const size_t smem = blu_soa_smem_bytes(c->K, true, c->N * c->N + c->N, ncl, c->lutlen);
+            CUDA_TRY(cudaFuncSetAttribute(blu_grad_soa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blu_grad_soa_kernel<true><<<c->grid_soa, BLU_SOA_WARPS * 32, smem, c->stream>>>(
+                c->d_cls, ncl, c->N, c->NP, c->K, c->d_tiles, c->ntiles, c->d_soa, c->d_soff, c->d_lut, c->lutlen, c->d_gmask,
+                c->d_x, c->d_S, c->lo, c->hi, c->d_grad, c->d_U, c->d_V);
+        }
+        KERNEL_CHECK(c);
+        return BLU_OK;
+    }
     if (!want_uv) {
         blu_grad_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->sd, 0, (int)c->cls.size(), c->lutlen), c->stream>>>(
             c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_grad);
@@ -674,7 +752,9 @@ extern "C" int blu_ctx_last_timing(blu_ctx *c, float *ms)
 
 extern "C" int blu_ctx_last_launches(blu_ctx *c) { return c ? c->launches : 0; }
 
-// Options: "sym_download" (default 0) -- copy only the upper block-triangle of the dense Hessian
+// Options: "soa" (default 1) -- gradient / U,V kernels on the group-interleaved copy of the inverses
+// (blu_soa.cuh); 0 selects the entry-per-lane kernels of blu_grad.cuh on the group-major copy.
+//          "sym_download" (default 0) -- copy only the upper block-triangle of the dense Hessian
 // over PCIe and mirror it on the host with threads.  Off by default: on the B200 box's host the
 // mirroring of 4.3 GB (16 threads, ~52 GB/s effective) costs more than the 75 ms of PCIe time it
 // saves (6.1 vs 6.6 evaluations/s end to end); worth enabling on hosts with more memory bandwidth.
@@ -682,6 +762,7 @@ extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
 {
     if (!c || !name) return fail(BLU_ERR_ARG, "null argument");
     if (!strcmp(name, "sym_download")) { c->sym_download = value != 0; return BLU_OK; }
+    if (!strcmp(name, "soa")) { c->use_soa = value != 0; return BLU_OK; }
     return fail(BLU_ERR_ARG, "unknown option %s", name);
 }
 
@@ -985,6 +1066,7 @@ extern "C" int blu_ctx_set_slice(blu_ctx *c, int64_t lo, int64_t hi)
     int rc = use(c);
     if (rc) return rc;
     c->lo = lo; c->hi = hi;
+    c->tiles_valid = false;
     return build_chunks(c);
 }
 

@@ -151,7 +151,9 @@ int blu_ctx_last_timing(blu_ctx *ctx, float *ms);
  * floats [phi+pinv, grad/U, Hessian, total] in ms. */
 int blu_ctx_timing_log(blu_ctx *ctx, int capacity);
 int blu_ctx_timing_read(blu_ctx *ctx, float *ms, int *n);
-/* Options.  "sym_download" (default 0): blu_variance_GH moves only the upper block-triangle of the
+/* Options.  "soa" (default 1): gradient / U,V kernels read a second, group-interleaved copy of the
+ * inverses, one group per lane (0: the entry-per-lane kernels on the group-major copy).
+ * "sym_download" (default 0): blu_variance_GH moves only the upper block-triangle of the
  * (exactly symmetric) dense Hessian over PCIe and mirrors it with host threads. */
 int blu_ctx_set_option(blu_ctx *ctx, const char *name, int value);
 /* Number of kernels the last evaluation launched. */
