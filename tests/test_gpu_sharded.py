@@ -69,3 +69,40 @@ def test_two_slices_reproduce_the_full_evaluation(N, K):
         assert maxrel(H, Ho) < tol
     for e in engines:
         e.sap.close()
+
+
+def test_sliced_soa_gradient_large_class_boundaries():
+    """Group slices on a problem large enough for the lane-per-group (SoA tile) kernels: slice
+    boundaries fall inside 32-group tiles, the lanes outside the slice must stay silent."""
+    import torch
+    import bluest_b200 as blu
+    from bluest_b200 import _lib
+    from bluest_b200.dist import GpuEngine
+    N = 14
+    C = orc.wishart_cov(N, 7)
+    groups = orc.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    o = orc.SapOracle(C, N, groups)
+    m = orc.dense_m(L, 4)
+    vo, go, _ = o.variance_GH(m, nohess=True)
+    slices = [(0, 5001), (5001, 5003), (5003, L)]            # odd boundaries, a 2-group slice
+    pieces = []
+    for lo, hi in slices:
+        sap = blu.SAP(C, N, [[list(g) for g in gk] for gk in groups], np.ones(L), verbose=False)
+        e = GpuEngine(sap)
+        e.set_slice(lo, hi)
+        sap.device_buffer(_lib.BUF_GRAD).fill_(123.0)        # sentinel: nothing outside the slice may be written
+        # full Phi on this context first (slice cleared), then the sliced gradient
+        e.set_slice(0, L)
+        buf = e.shard_phi(m)
+        sap.sync()
+        e.set_slice(lo, hi)
+        e.shard_finish(0.0, True, False)
+        sap.sync()
+        g = sap.device_buffer(_lib.BUF_GRAD).cpu().numpy()
+        assert np.all(g[:lo] == 123.0) and np.all(g[hi:] == 123.0)
+        pieces.append(g[lo:hi])
+        v, _ = e.result()
+        assert abs(v - vo) <= 1e-12 * vo
+        sap.close()
+    assert maxrel(np.concatenate(pieces), go) < 1e-12
