@@ -55,6 +55,11 @@ SIGNATURES = {
     "blu_shard_phi": (c_int, [p_void, p_void]),
     "blu_shard_finish": (c_int, [p_void, c_dbl, c_int, c_int]),
     "blu_shard_hess": (c_int, [p_void, c_i64, c_i64]),
+    "blu_shard_hv_partial": (c_int, [p_void, p_void, p_void]),
+    "blu_shard_hv_apply": (c_int, [p_void, p_void, p_void]),
+    "blu_variance_GH_factored": (c_int, [p_void, p_dbl, c_dbl, p_dbl, p_dbl, ctypes.POINTER(c_uint)]),
+    "blu_hess_matvec": (c_int, [p_void, p_dbl, c_int, p_dbl]),
+    "blu_hess_matvec_device": (c_int, [p_void, p_void, p_void]),
     "blu_pilot_covariance": (c_int, [c_int, p_void, c_i64, c_int, c_int, p_dbl, p_dbl, p_dbl, ctypes.POINTER(ctypes.c_float)]),
     "blu_assemble_psi_c": (c_int, [p_dbl, c_int, c_int, c_int, p_i64, p_dbl]),
     "blu_objectiveK_c": (c_int, [p_dbl, c_int, c_int, c_int, p_dbl, p_i64, p_dbl]),

@@ -22,6 +22,7 @@
 #include "blu_grad.cuh"
 #include "blu_soa.cuh"
 #include "blu_hess.cuh"
+#include "blu_matvec.cuh"
 #include "blu_gram.cuh"
 #include "blu_intproj.cuh"
 #include "blu_level1.cuh"
@@ -101,6 +102,9 @@ struct blu_ctx {
     BluPeers peers{};                  // peers as mapped here; world == 0: not connected
     std::vector<void *> ipc_opened;
     unsigned long long epoch = 0;
+    double *d_hvpart = nullptr, *d_hvp = nullptr, *d_hvout = nullptr;   // Hessian mat-vec: CTA partials of t, staged p and H p
+    int hv_grid = 1;
+    bool uv_ready = false;             // U, V hold the factors of the last want_hess evaluation
     std::vector<cudaEvent_t> evlog;    // optional per-evaluation event log (4 events per evaluation)
     int evlog_n = 0;
 };
@@ -158,6 +162,7 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     cudaFree(c->d_hdr); cudaFree(c->d_chunks); cudaFree(c->d_soa); cudaFree(c->d_soff); cudaFree(c->d_tiles);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->d_xchg);
+    cudaFree(c->d_hvpart); cudaFree(c->d_hvp); cudaFree(c->d_hvout);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     if (c->h_m) cudaFreeHost(c->h_m);
     if (c->h_grad) cudaFreeHost(c->h_grad);
@@ -565,6 +570,7 @@ static int ensure_soa(blu_ctx *c)
 
 static int launch_grad(blu_ctx *c, int want_uv)
 {
+    if (want_uv) c->uv_ready = true;
     // One group per lane needs at least a couple of 32-group tiles per SM to fill the machine; smaller
     // problems (latency-bound anyway) keep the entry-per-lane kernels, which spread a group over a warp.
     if (c->use_soa && c->hi - c->lo >= (long long)c->nsm * 2 * 32) {
@@ -943,6 +949,122 @@ extern "C" int blu_variance_GH(blu_ctx *c, const double *m, double delta, double
     int rc = blu_variance_GH_begin(c, m, delta, 1, hess);
     if (rc) return rc;
     return blu_variance_GH_end(c, var, grad, flags);
+}
+
+// --------------------------------------------------------------------------------------------
+// Hessian as an operator: H p = V (U^T p)  (blu_matvec.cuh).  The dense (L,L) matrix of
+// misc.py:497-503 is never formed; U, V are the factors the gradient pass leaves in HBM.
+// --------------------------------------------------------------------------------------------
+static int ensure_hv(blu_ctx *c)
+{
+    if (c->d_hvpart) return BLU_OK;
+    CUDA_TRY(cudaMalloc(&c->d_hvpart, sizeof(double) * 32 * (size_t)c->nsm * 4));
+    CUDA_TRY(cudaMalloc(&c->d_hvp, sizeof(double) * c->L));
+    CUDA_TRY(cudaMalloc(&c->d_hvout, sizeof(double) * c->L));
+    return BLU_OK;
+}
+
+static int launch_hv_reduce(blu_ctx *c, const double *d_p, double *d_part, int *nparts)
+{
+    const long long rows = c->hi - c->lo;
+    const int rpp = BLU_HV_THREADS / c->NP;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + (long long)rpp * BLU_HV_UNROLL - 1) / ((long long)rpp * BLU_HV_UNROLL), (long long)c->nsm * 4));
+    blu_hv_reduce_kernel<<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_U, d_p, c->lo, c->hi, c->NP, d_part);
+    KERNEL_CHECK(c);
+    *nparts = grid;
+    return BLU_OK;
+}
+
+static int launch_hv_apply(blu_ctx *c, const double *d_part, int nparts, double *d_out)
+{
+    const long long rows = c->hi - c->lo;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + BLU_HV_THREADS - 1) / BLU_HV_THREADS, (long long)c->nsm * 8));
+    blu_hv_apply_kernel<<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_V, d_part, nparts, c->lo, c->hi, c->NP, d_out);
+    KERNEL_CHECK(c);
+    return BLU_OK;
+}
+
+static int hv_ready(blu_ctx *c)
+{
+    if (!c->uv_ready || !c->d_U) return fail(BLU_ERR_STATE, "no Hessian factors: evaluate with blu_variance_GH_factored (or blu_eval_device, want_hess != 0) first");
+    return ensure_hv(c);
+}
+
+// d_out = H d_p on the device (both (L,) doubles in HBM), asynchronous on the context's stream.
+extern "C" int blu_hess_matvec_device(blu_ctx *c, const double *d_p, double *d_out)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!d_p || !d_out) return fail(BLU_ERR_ARG, "null argument");
+    if (c->lo != 0 || c->hi != c->L) return fail(BLU_ERR_STATE, "context owns a slice: use blu_shard_hv_partial / blu_shard_hv_apply");
+    if ((rc = hv_ready(c))) return rc;
+    int np = 0;
+    if ((rc = launch_hv_reduce(c, d_p, c->d_hvpart, &np))) return rc;
+    return launch_hv_apply(c, c->d_hvpart, np, d_out);
+}
+
+// Host pointers: out[v*L + i] = (H p_v)_i for nvec vectors stored one after the other.
+extern "C" int blu_hess_matvec(blu_ctx *c, const double *p, int nvec, double *out)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!p || !out) return fail(BLU_ERR_ARG, "null argument");
+    if (nvec < 0) return fail(BLU_ERR_ARG, "negative nvec");
+    c->launches = 0;
+    for (int v = 0; v < nvec; ++v) {
+        if ((rc = hv_ready(c))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->d_hvp, p + (size_t)v * c->L, sizeof(double) * c->L, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = blu_hess_matvec_device(c, c->d_hvp, c->d_hvout))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out + (size_t)v * c->L, c->d_hvout, sizeof(double) * c->L, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));     // d_hvp / d_hvout are reused by the next vector
+    }
+    return BLU_OK;
+}
+
+// variance + gradient + Hessian FACTORS (U, V stay in HBM): the evaluation behind a Hessian operator.
+extern "C" int blu_variance_GH_factored(blu_ctx *c, const double *m, double delta, double *var, double *grad, unsigned *flags)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!m || !grad) return fail(BLU_ERR_ARG, "null argument");
+    if (c->pending) return fail(BLU_ERR_STATE, "an evaluation is already pending on this context");
+    if ((rc = upload_m(c, m))) return rc;
+    if ((rc = blu_eval_device(c, c->d_m, delta, 1, 2))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(grad, c->d_grad, sizeof(double) * c->L, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = fetch_header(c))) return rc;
+    const unsigned fl = c->h_hdr->flags;
+    if (var) *var = c->h_hdr->scal[0];
+    if (flags) *flags = fl;
+    if (fl & BLU_FLAG_TINY) {
+        c->uv_ready = false;                                       // early-out (misc.py:484): there is no Hessian
+        for (long long i = 0; i < c->L; ++i) grad[i] = std::numeric_limits<double>::infinity();
+    }
+    return BLU_OK;
+}
+
+// Group-sharded operator: every rank sums its own rows into t (32 doubles, zero beyond N), the host
+// side all-reduces t (N doubles: the only exchange), then every rank applies it to its own rows.
+extern "C" int blu_shard_hv_partial(blu_ctx *c, const double *d_p, double *d_t)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!d_p || !d_t) return fail(BLU_ERR_ARG, "null argument");
+    if ((rc = hv_ready(c))) return rc;
+    int np = 0;
+    if ((rc = launch_hv_reduce(c, d_p, c->d_hvpart, &np))) return rc;
+    // fold the CTA partials into one vector with the apply kernel's fixed-order prologue (no rows)
+    blu_hv_fold_kernel<<<1, BLU_HV_THREADS, 0, c->stream>>>(c->d_hvpart, np, d_t);
+    KERNEL_CHECK(c);
+    return BLU_OK;
+}
+
+extern "C" int blu_shard_hv_apply(blu_ctx *c, const double *d_t, double *d_out)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!d_t || !d_out) return fail(BLU_ERR_ARG, "null argument");
+    if ((rc = hv_ready(c))) return rc;
+    return launch_hv_apply(c, d_t, 1, d_out);
 }
 
 extern "C" int blu_cleanup_matrix(blu_ctx *c, const double *m, double delta, int mode, double *X, unsigned *flags)

@@ -131,6 +131,19 @@ class SAP(object):
                 return np.inf, grad                             # 2-tuple, misc.py:484 (grad is inf*ones)
             return var.value, grad, hess
 
+        def variance_GH_operator(m, delta=0):
+            """``variance_GH`` with the Hessian returned as a ``scipy.sparse.linalg.LinearOperator``:
+            same (var, grad, hess) triple and the same 2-tuple early-out as misc.py:479-505, but
+            ``hess`` stays factored in HBM (H = V U^T) and ``hess @ p`` costs two passes over
+            L x N doubles on the device instead of 8 L^2 bytes over PCIe.  The operator is valid until the next
+            evaluation of this SAP that asks for a Hessian."""
+            var = ctypes.c_double(0.0); fl = ctypes.c_uint(0)
+            grad = np.empty(L)
+            check(lib().blu_variance_GH_factored(ctx, dptr(self._m(m)), float(delta), ctypes.byref(var), dptr(grad), ctypes.byref(fl)))
+            if fl.value & _lib.FLAG_TINY:
+                return np.inf, grad
+            return var.value, grad, self.hess_operator()
+
         def get_cleanup_matrix(m, delta=0, corrected=False):
             X = np.empty((N, L)); fl = ctypes.c_uint(0)
             check(lib().blu_cleanup_matrix(ctx, dptr(self._m(m)), float(delta), 1 if corrected else 0, dptr(X), ctypes.byref(fl)))
@@ -141,6 +154,7 @@ class SAP(object):
         self.get_phi = get_phi
         self.variance = variance
         self.variance_GH = variance_GH
+        self.variance_GH_operator = variance_GH_operator
         self.get_cleanup_matrix = get_cleanup_matrix
 
     # ---- split evaluation (several contexts in flight at once, used by MOSAP) -----------------
@@ -158,6 +172,33 @@ class SAP(object):
         grad = np.empty(int(self.L)) if want_grad else None
         check(lib().blu_variance_GH_end(self._ctx, ctypes.byref(var), None if grad is None else dptr(grad), ctypes.byref(fl)))
         return var.value, grad, hess, fl.value
+
+    # ---- Hessian as an operator ---------------------------------------------------------------
+    def hess_matvec(self, p):
+        """H @ p for the Hessian of the last factored evaluation; p (L,) or (L,nvec)."""
+        L = int(self.L)
+        p = np.asarray(p, dtype=np.float64)
+        if p.ndim == 1:
+            pv = f64(p, L, "p"); nvec = 1
+        else:
+            if p.shape[0] != L:
+                raise ValueError("p has %d rows, expected %d" % (p.shape[0], L))
+            pv = np.ascontiguousarray(p.T); nvec = p.shape[1]
+        out = np.empty((nvec, L))
+        check(lib().blu_hess_matvec(self._ctx, dptr(pv), nvec, dptr(out)))
+        return out[0] if p.ndim == 1 else np.ascontiguousarray(out.T)
+
+    def hess_operator(self):
+        """LinearOperator over the factors resident in HBM (symmetric: rmatvec = matvec)."""
+        from scipy.sparse.linalg import LinearOperator
+        L = int(self.L)
+        return LinearOperator((L, L), matvec=self.hess_matvec, rmatvec=self.hess_matvec, matmat=self.hess_matvec,
+                              rmatmat=self.hess_matvec, dtype=np.float64)
+
+    def hess_matvec_device(self, d_p, d_out):
+        """Asynchronous ``d_out = H @ d_p`` with both vectors in HBM (torch tensors or raw pointers)."""
+        ptr = lambda t: ctypes.c_void_p(int(t.data_ptr()) if hasattr(t, "data_ptr") else int(t))
+        check(lib().blu_hess_matvec_device(self._ctx, ptr(d_p), ptr(d_out)))
 
     # ---- device-resident interface (no host round trip of the big arrays) ---------------------
     def eval_device(self, d_m=None, delta=0.0, grad=True, hess=False):
@@ -281,7 +322,7 @@ class SAP(object):
                 rhs.append(int(np.round(max_model_samples[i])))
         return es, rhs
 
-    def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=True, max_model_samples=None, solver_params=None):
+    def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=True, max_model_samples=None, solver_params=None, hess="dense"):
         """Host-side driver kept from sap.py:189-220.  Only ``solver="scipy"`` (trust-constr
         iterating on the GPU closures) is provided here; the SDP solvers (cvxopt / cvxpy) and
         ipopt are third-party host code that consume ``self.psi`` and are not part of this package."""
@@ -290,7 +331,7 @@ class SAP(object):
         if solver != "scipy":
             raise ValueError("bluest_b200.SAP.solve provides solver='scipy'; for 'cvxopt'/'cvxpy'/'ipopt' hand "
                              "`sap.psi`, `sap.variance`, `sap.variance_GH` to the reference's own drivers (INTEGRATION.md)")
-        samples = self.scipy_solve(budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples)
+        samples = self.scipy_solve(budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, hess=hess)
         if samples is None:
             self.samples = None
             return None
@@ -302,11 +343,13 @@ class SAP(object):
         self.tot_cost = samples @ self.costs
         return samples
 
-    def scipy_solve(self, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000):
-        """sap.py:378-418 -- same constraints, tolerances and callbacks; the callbacks are the GPU closures."""
+    def scipy_solve(self, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000, hess="dense"):
+        """sap.py:378-418 -- same constraints, tolerances and callbacks; the callbacks are the GPU closures.
+        ``hess="operator"`` hands trust-constr the factored Hessian as a LinearOperator (it only ever
+        multiplies by it) instead of the dense (L,L) array."""
         from .solvers import scipy_solve
         self.scipy_counters = {}
         res = scipy_solve(self, budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, maxiter=maxiter,
-                          verbose=self.verbose, counters=self.scipy_counters)
+                          verbose=self.verbose, counters=self.scipy_counters, hess=hess)
         self.scipy_result = res
         return res.x

@@ -5,7 +5,18 @@ bench.py times the CPU reference with the identical driver."""
 import numpy as np
 
 
-def scipy_solve(problem, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000, verbose=False, counters=None):
+def _scaled(op, p):
+    """p * H for a LinearOperator H (the eps-mode constraint Hessian of sap.py:415)."""
+    from scipy.sparse.linalg import LinearOperator
+    mv = lambda v: p * op.matvec(v)
+    return LinearOperator(op.shape, matvec=mv, rmatvec=mv, dtype=op.dtype)
+
+
+def scipy_solve(problem, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000, verbose=False, counters=None,
+                hess="dense"):
+    """``hess``: "dense" -- the reference's callbacks (sap.py:410,416: a dense (L,L) array per Hessian
+    evaluation); "operator" -- ``problem.variance_GH_operator`` (Hessian factored in HBM, handed to
+    trust-constr as a LinearOperator; its projected-CG only multiplies by it)."""
     from scipy.optimize import Bounds, LinearConstraint, NonlinearConstraint, minimize
     if budget is None and eps is None:
         raise ValueError("Need to specify either budget or RMSE tolerance")
@@ -21,8 +32,14 @@ def scipy_solve(problem, budget=None, eps=None, x0=None, max_model_samples=None,
         cnt["g"] += 1
         return problem.variance_GH(x, nohess=True, delta=delta)[:-1]
 
+    if hess not in ("dense", "operator"):
+        raise ValueError("hess must be 'dense' or 'operator'")
+    hess_mode = hess
+
     def hess(x):
         cnt["H"] += 1
+        if hess_mode == "operator":
+            return problem.variance_GH_operator(x, delta=delta)[-1]
         return problem.variance_GH(x, delta=delta)[-1]
 
     def var(x):
@@ -45,7 +62,7 @@ def scipy_solve(problem, budget=None, eps=None, x0=None, max_model_samples=None,
                        method="trust-constr", options=opts, tol=1.0e-8)
     else:
         epsq = eps ** 2
-        constraint2 = NonlinearConstraint(var, epsq, epsq, jac=jac, hess=lambda x, p: hess(x) * p)
+        constraint2 = NonlinearConstraint(var, epsq, epsq, jac=jac, hess=lambda x, p: hess(x) * p if hess_mode == "dense" else _scaled(hess(x), p))
         if x0 is None:
             x0 = np.ceil(eps ** -2 * np.random.rand(L))
         wn = w / np.linalg.norm(w)

@@ -111,6 +111,18 @@ int blu_variance_GH(blu_ctx *ctx, const double *m, double delta, double *var, do
 int blu_variance_GH_begin(blu_ctx *ctx, const double *m, double delta, int want_grad, double *hess);
 int blu_variance_GH_end(blu_ctx *ctx, double *var, double *grad, unsigned *flags);
 
+/* The Hessian as an operator (replaces the dense result of hessKQ_c cmisc.cpp:74-97 + `hess += hess.T`
+ * misc.py:497-503 wherever the caller only multiplies by it: scipy trust-constr's projected CG,
+ * sap.py:410).  blu_variance_GH_factored = variance_GH with the Hessian kept FACTORED in HBM
+ * (H = V U^T, U and V (L,NP)); blu_hess_matvec then returns out[v] = H p[v] for nvec host vectors
+ * of length L stored back to back.  BLU_ERR_STATE when no factors are resident (never evaluated,
+ * or the last factored evaluation took the BLU_FLAG_TINY early-out).  The _device form takes HBM
+ * pointers and is asynchronous on the context's stream. */
+int blu_variance_GH_factored(blu_ctx *ctx, const double *m, double delta, double *var, double *grad,
+                             unsigned *flags);
+int blu_hess_matvec(blu_ctx *ctx, const double *p, int nvec, double *out);
+int blu_hess_matvec_device(blu_ctx *ctx, const double *d_p, double *d_out);
+
 /* get_cleanup_matrix (misc.py:507-516): X is (N,L) row-major.  mode 0 reproduces the reference's
  * assignment semantics (cmisc.cpp:51, only l = k-1 survives); mode 1 returns the intended
  * X[:,i] = u_i.  Returns BLU_ERR_ARG-free status with BLU_FLAG_TINY when the reference would
@@ -187,6 +199,13 @@ int blu_shard_eval_fused(blu_ctx *ctx, const double *d_m, double delta, int want
 int blu_shard_phi(blu_ctx *ctx, const double *d_m);
 int blu_shard_finish(blu_ctx *ctx, double delta, int want_grad, int want_uv);
 int blu_shard_hess(blu_ctx *ctx, int64_t row_lo, int64_t row_hi);
+/* Sharded Hessian operator (N = 20: the dense matrix is 8.8 TB and cannot exist).  p, out are (L,)
+ * in HBM, only the owned rows [lo,hi) are read / written:
+ *   blu_shard_hv_partial   d_t[0..31] = sum over owned rows of p_i u_i (zero beyond N)
+ *   (all-reduce d_t across ranks: N doubles, the only exchange)
+ *   blu_shard_hv_apply     d_out[i] = v_i . t for the owned rows */
+int blu_shard_hv_partial(blu_ctx *ctx, const double *d_p, double *d_t);
+int blu_shard_hv_apply(blu_ctx *ctx, const double *d_t, double *d_out);
 
 /* Page-locked host memory for large results (the dense Hessian): pageable destinations make
  * the D2H copy several times slower. */

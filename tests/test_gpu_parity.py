@@ -556,3 +556,64 @@ def test_setup_from_graph_file_reproduces_hodgkin_huxley(blu):
     for n in range(5):
         assert abs(Vs[n] - float(d[f"variance{n}"])) <= 1e-5 * Vs[n]
     assert abs(d["samples"] @ mos.costs - float(d["total_cost"])) < 1e-6
+
+
+@pytest.mark.parametrize("N,K,seed", [(6, 6, 0), (10, 10, 1), (12, 5, 2), (13, 13, 3), (9, 4, 4)])
+def test_hessian_operator_equals_dense_hessian(blu, N, K, seed):
+    """variance_GH_operator: same variance / gradient, and hess @ p equals the reference's dense Hessian
+    (oracle: the loop nest of cmisc.cpp:74-97 on small cases, its factored identity otherwise) times p --
+    single vectors, blocks of vectors, dense and sparse m (singular Phi)."""
+    C = orc.wishart_cov(N, seed)
+    groups = orc.enumerate_groups(N, K)
+    L = sum(len(g) for g in groups)
+    o = orc.SapOracle(C, K, groups)
+    sap = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False)
+    rng = np.random.RandomState(seed)
+    for m in (orc.dense_m(L, seed), orc.sparse_m(L, N, seed)):
+        full = len(o.support(m)) == N
+        tol = TOL if full else 1e-9
+        vo, go, ho = o.variance_GH(m, hess_mode="reference" if L <= 300 else "factored")
+        v, g, op = sap.variance_GH_operator(m)
+        assert abs(v - vo) <= TOL * vo and maxrel(g, go) < tol
+        assert op.shape == (L, L)
+        p = rng.randn(L)
+        assert maxrel(op @ p, ho @ p) < tol
+        assert maxrel(op.matvec(p), op.rmatvec(p)) == 0.0                     # symmetric operator
+        P = rng.randn(L, 3)
+        assert maxrel(op @ P, ho @ P) < tol
+        e0 = np.zeros(L); e0[L // 2] = 1.0
+        assert maxrel(op @ e0, ho[:, L // 2]) < tol                            # a column of H
+        # the operator and the dense closure of the same SAP agree, and the operator is reproducible
+        _, _, hd = sap.variance_GH(m)
+        assert maxrel(sap.hess_matvec(p), hd @ p) < tol
+        assert np.array_equal(sap.hess_matvec(p), sap.hess_matvec(p))
+    # early-out keeps the reference's 2-tuple (misc.py:484) and leaves no operator behind
+    out = sap.variance_GH_operator(0.01 * np.ones(L))
+    assert len(out) == 2 and out[0] == np.inf and np.all(np.isinf(out[1]))
+    with pytest.raises(blu.BluError):
+        sap.hess_matvec(np.ones(L))
+    sap2 = blu.SAP(C, K, _copy(groups), np.ones(L), verbose=False)
+    with pytest.raises(blu.BluError):
+        sap2.hess_matvec(np.ones(L))                                           # never evaluated
+    with pytest.raises(ValueError):
+        sap.hess_matvec(np.ones(L + 1))
+
+
+@pytest.mark.parametrize("tag", ["tutorial", "N6K3"])
+def test_scipy_solve_with_hessian_operator_matches_dense(blu, tag):
+    """trust-constr only multiplies by the Hessian: handing it the factored operator must walk the
+    same iterates as the reference's dense callbacks (same evaluation counts, same allocation)."""
+    d = _load("solve.npz")
+    C = d[f"{tag}/C"]; K = int(d[f"{tag}/K"]); N = C.shape[0]
+    groups = orc.enumerate_groups(N, K)
+    sap = blu.SAP(C, K, _copy(groups), d[f"{tag}/w"], verbose=False)
+    budget = float(d[f"{tag}/budget"])
+    dense = sap.solve(budget=budget, solver="scipy", x0=d[f"{tag}/x0"].copy())
+    cd = dict(sap.scipy_counters)
+    oper = sap.solve(budget=budget, solver="scipy", x0=d[f"{tag}/x0"].copy(), hess="operator")
+    co = dict(sap.scipy_counters)
+    assert maxrel(oper, dense) < 5e-3
+    assert abs(sap.variance(oper) - sap.variance(dense)) <= 1e-4 * sap.variance(dense)      # trust-constr stops at gtol on a flat objective
+    assert abs(co["H"] - cd["H"]) <= max(3, cd["H"] // 5)
+    vr = orc.SapOracle(C, K, groups).variance(d[f"{tag}/continuous"])
+    assert abs(sap.variance(oper) - vr) <= 1e-4 * vr
