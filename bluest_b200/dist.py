@@ -9,6 +9,13 @@ inverses of that slice only.  One evaluation is three local phases with two smal
     ALL-GATHER     U, V rows (N*L doubles each) -- only when the dense Hessian is wanted
     shard_hess     an equal-rows panel of H against all columns (kernel 3b, local; H stays sharded)
 
+The Hessian OPERATOR needs no gather at all (and is the only form of the Hessian at N = 20):
+
+    evaluate_factors(m)        U, V rows of the own slice stay on their rank
+    hess_matvec(p):  hv_partial   t_r = sum over own rows of p_i u_i            (local)
+                     ALL-REDUCE   32 doubles
+                     hv_apply     (H p)_i = v_i . t for the own rows            (local)
+
 The choreography is engine-agnostic: ``GpuEngine`` drives a ``blu_ctx`` through the C ABI and
 ``torch.distributed`` (NCCL over NVLink); the CPU tests plug a numpy engine into the same class and
 run it under gloo with world_size 2.
@@ -103,6 +110,32 @@ class ShardedEvaluator:
         out.update(var=var, flags=flags, lo=self.lo, hi=self.hi, rlo=self.rlo, rhi=self.rhi)
         return out
 
+    def evaluate_factors(self, m, delta=0.0):
+        """Variance, gradient (own slice) and the U, V rows of the own slice: everything
+        ``hess_matvec`` needs.  No gather -- the factors stay sharded."""
+        e = self.engine
+        with e.stream_context():
+            if self.replicate_front:
+                e.eval_full(m, delta, True, True)
+            else:
+                self._phi_exchange_finish(m, delta, True, True)
+        var, flags = e.result()
+        return dict(var=var, flags=flags, lo=self.lo, hi=self.hi)
+
+    def hess_matvec(self, p, gather=True):
+        """H @ p with the Hessian factored and sharded by rows.  p: full-length vector (every rank
+        passes the same values; device tensor, or numpy for a CPU engine).  Returns the engine's
+        output buffer: rows [lo,hi) valid, all rows when ``gather``."""
+        e = self.engine
+        with e.stream_context():
+            t = e.hv_partial(p)                                    # 32 doubles
+            if not self.replicate_front:
+                self._all_reduce(t)
+            out = e.hv_apply(t)
+            if gather and not self.replicate_front:
+                self._all_gather_rows(out, 1)
+        return out
+
     def evaluate_async(self, m, delta=0.0, grad=True, hess=False, gather_grad=True):
         """Same as evaluate() but without the final read-back of (var, flags): nothing on the host
         waits for the device, so evaluations can be queued back to back."""
@@ -187,6 +220,24 @@ class GpuEngine:
 
     def shard_hess(self, rlo, rhi):
         _lib.check(_lib.lib().blu_shard_hess(self.sap._ctx, int(rlo), int(rhi)))
+
+    def hv_partial(self, p):
+        """t = sum over the owned rows of p_i u_i  ->  (32,) device tensor (zero beyond N)."""
+        torch = self.torch
+        if not hasattr(self, "_hv_t"):
+            dev = "cuda:%d" % self.sap.device
+            self._hv_t = torch.zeros(32, dtype=torch.float64, device=dev)
+            self._hv_out = torch.zeros(int(self.sap.L), dtype=torch.float64, device=dev)
+            self._hv_p = torch.zeros(int(self.sap.L), dtype=torch.float64, device=dev)
+        if not hasattr(p, "data_ptr"):
+            self._hv_p.copy_(torch.from_numpy(np.ascontiguousarray(p, dtype=np.float64)), non_blocking=True)
+            p = self._hv_p
+        _lib.check(_lib.lib().blu_shard_hv_partial(self.sap._ctx, ctypes.c_void_p(int(p.data_ptr())), ctypes.c_void_p(int(self._hv_t.data_ptr()))))
+        return self._hv_t
+
+    def hv_apply(self, t):
+        _lib.check(_lib.lib().blu_shard_hv_apply(self.sap._ctx, ctypes.c_void_p(int(t.data_ptr())), ctypes.c_void_p(int(self._hv_out.data_ptr()))))
+        return self._hv_out
 
     def grad_buffer(self):
         return self.sap.device_buffer(_lib.BUF_GRAD)

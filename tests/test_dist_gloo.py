@@ -85,6 +85,20 @@ class NumpyEngine:
         U = self.U.numpy().reshape(-1, self.NP); V = self.V.numpy().reshape(-1, self.NP)
         self.H = U[rlo:rhi] @ V.T
 
+    def hv_partial(self, p):
+        U = self.U.numpy().reshape(-1, self.NP)
+        t = np.zeros(32)
+        t[:self.NP] = np.asarray(p)[self.lo:self.hi] @ U[self.lo:self.hi]
+        self.t = torch.from_numpy(t)
+        return self.t
+
+    def hv_apply(self, t):
+        V = self.V.numpy().reshape(-1, self.NP)
+        out = np.zeros(self.o.L)
+        out[self.lo:self.hi] = V[self.lo:self.hi] @ t.numpy()[:self.NP]
+        self.hv = torch.from_numpy(out)
+        return self.hv
+
     def grad_buffer(self): return self.grad
     def u_buffer(self): return self.U
     def v_buffer(self): return self.V
@@ -110,6 +124,13 @@ def _worker(rank, world, port, N, K, ret, replicate=False):
             e = ev.engine
             out[name] = dict(var=r["var"], flags=r["flags"], lo=r["lo"], hi=r["hi"], rlo=r["rlo"], rhi=r["rhi"],
                              grad=e.grad.numpy().copy(), H=getattr(e, "H", None) if name != "tiny" else None)
+        # Hessian operator: factors stay sharded, one 32-double all-reduce per product
+        m = orc.dense_m(o.L, 2)
+        r = ev.evaluate_factors(m)
+        p = np.random.RandomState(7).randn(o.L)
+        hp = ev.hess_matvec(p, gather=True).numpy().copy()
+        own = ev.hess_matvec(p, gather=False).numpy().copy()
+        out["operator"] = dict(var=r["var"], hp=hp, own=own[r["lo"]:r["hi"]], lo=r["lo"], hi=r["hi"])
         ret[rank] = out
     finally:
         dist.destroy_process_group()
@@ -138,6 +159,14 @@ def test_sharded_evaluation_world2(N, K, replicate):
             assert res["H"].shape == (res["rhi"] - res["rlo"], o.L)
         Hcat = np.vstack(rows)
         assert np.max(np.abs(Hcat - H)) <= (1e-12 if name == "dense" else 1e-9) * np.max(np.abs(H))
+    m = orc.dense_m(o.L, 2)
+    v, g, H = o.variance_GH(m, hess_mode="factored")
+    p = np.random.RandomState(7).randn(o.L)
+    for r in range(world):
+        res = ret[r]["operator"]
+        assert abs(res["var"] - v) <= 1e-12 * abs(v)
+        assert np.max(np.abs(res["hp"] - H @ p)) <= 1e-12 * np.max(np.abs(H @ p))        # gathered: all rows on every rank
+        assert np.max(np.abs(res["own"] - (H @ p)[res["lo"]:res["hi"]])) <= 1e-12 * np.max(np.abs(H @ p))
     for r in range(world):
         assert ret[r]["tiny"]["flags"] & 1 and np.isinf(ret[r]["tiny"]["var"])
     if not replicate:

@@ -78,3 +78,69 @@ def test_dense_hessian_full_size_properties(problem):
     Hd = H @ d
     assert maxrel((gp - gm) / (2 * h), Hd) < 1e-5
     del H
+
+
+def test_hessian_operator_full_size(problem):
+    """15 models: the operator must reproduce the dense 8.59 GB Hessian times p without forming it."""
+    N, L, o, sap = problem
+    m = orc.dense_m(L, 0)
+    P = np.linalg.pinv(o.get_phi(m))
+    U = o.ufactor(np.ascontiguousarray(P[0]))
+    vo, go, _ = o.variance_GH(m, nohess=True)
+    v, g, op = sap.variance_GH_operator(m)
+    assert abs(v - vo) <= TOL * vo and maxrel(g, go) < TOL
+    rng = np.random.RandomState(11)
+    for _ in range(3):
+        p = rng.randn(L)
+        assert maxrel(op @ p, 2.0 * (U.T @ (P @ (U @ p)))) < TOL
+    # H is positive semi-definite (2 U^T pinv(Phi) U): p^T H p >= 0, and = 0 never for random p
+    p = rng.randn(L)
+    assert p @ (op @ p) > 0
+    # directional second derivative of the variance
+    d = rng.randn(L); d /= np.linalg.norm(d)
+    h = 1e-3
+    _, gp, _ = sap.variance_GH(m + h * d, nohess=True)
+    _, gm, _ = sap.variance_GH(m - h * d, nohess=True)
+    v2, g2, op2 = sap.variance_GH_operator(m)
+    assert maxrel((gp - gm) / (2 * h), op2 @ d) < 1e-5
+
+
+def test_hessian_operator_20_models():
+    """20 models, 1 048 575 groups: the dense Hessian (8.8 TB) cannot exist; the operator is checked
+    against central differences of the gradient and against the oracle's factors on sampled rows."""
+    import bluest_b200 as blu
+    N = 20
+    C = orc.wishart_cov(N, 0)
+    groups = blu.enumerate_groups(N)
+    L = sum(len(g) for g in groups)
+    assert L == 2 ** N - 1
+    sap = blu.SAP(C, N, groups, np.ones(L), verbose=False)
+    m = orc.dense_m(L, 0)
+    v, g, op = sap.variance_GH_operator(m)
+    rng = np.random.RandomState(3)
+    d = rng.randn(L); d /= np.linalg.norm(d)
+    Hd = op @ d
+    h = 1e-2
+    _, gp, _ = sap.variance_GH(m + h * d, nohess=True)
+    _, gm, _ = sap.variance_GH(m - h * d, nohess=True)
+    assert maxrel((gp - gm) / (2 * h), Hd) < 1e-5
+    assert d @ Hd > 0
+    # factors against numpy on the device's own Phi: U rows of sampled groups, t = U^T d, V = 2 U pinv(Phi)
+    phi = sap.get_phi(m)
+    P = np.linalg.pinv(phi)
+    x = P[0]
+    Ud = sap.device_buffer(blu._lib.BUF_U).cpu().numpy()
+    NP = 4 * ((N + 3) // 4)
+    Ud = Ud[: (Ud.size // NP) * NP].reshape(-1, NP)[:L, :N]
+    flat_rows = [0, 19, 20, 209, 210, 524287, 524288, 1048574]
+    inv = sap.invcovs
+    for i in flat_rows:
+        k = int(np.searchsorted(sap.cumsizes, i, side="right"))
+        j = i - int(sap.cumsizes[k - 1])
+        grp = np.asarray(sap.groups[k - 1][j])
+        Ci = inv[k - 1][j * k * k:(j + 1) * k * k].reshape(k, k)
+        u = np.zeros(N); u[grp] = Ci @ x[grp]
+        assert maxrel(Ud[i], u) < 1e-11
+    t = Ud.T @ d
+    assert maxrel(Hd[flat_rows], 2.0 * (Ud[flat_rows] @ (P @ t))) < 1e-11
+    sap.close()
