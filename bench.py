@@ -257,6 +257,14 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def _hess_d2h_bytes(L, panel=1024):
+    """Bytes of the dense Hessian that cross PCIe (symmetric download, blu_capi.cu): per 1024-row panel
+    the columns from the panel's first row on; everything when L < 4096."""
+    if L < 4096:
+        return 8 * L * L
+    return sum(8 * (min(L, r0 + panel) - r0) * (L - r0) for r0 in range(0, L, panel))
+
+
 def workload_config(N, L):
     return {"workload": "single-output MLBLUE, %d models, all %d groups (K=N), Wishart covariance seed 0, m=1+10*rand: "
                         "Phi + pinv + variance + gradient + dense (L,L) Hessian per evaluation" % (N, L),
@@ -302,15 +310,21 @@ class _TimedClosures:
         t0 = time.perf_counter(); r = self.p.variance_GH(m, delta=delta, nohess=nohess); self.t += time.perf_counter() - t0; self.n += 1
         return r
 
+    def variance_GH_operator(self, m, delta=0):
+        t0 = time.perf_counter(); r = self.p.variance_GH_operator(m, delta=delta); self.t += time.perf_counter() - t0; self.n += 1
+        return r
+
     def get_max_sample_constraints(self, mm):
         return [], []
 
 
-def sap_solve_benchmark(N=10, K=4, device=0):
-    """SAP.solve(solver="scipy"), budget mode, fixed x0 (10 models, groups of up to 4 -- the reference's
-    smoke test, sap.py:458-497, uses N=10, K=3): GPU closures vs CPU reference closures, identical
-    driver.  BLAS is pinned to one thread for both arms: trust-constr's small dense factorisations run
-    several times SLOWER on 16 oversubscribed threads, which otherwise swamps the comparison."""
+def sap_solve_benchmark(N=10, K=4, device=0, large=True):
+    """SAP.solve(solver="scipy"), budget mode, fixed FEASIBLE x0 (10 models, groups of up to 4 -- the
+    reference's smoke test, sap.py:458-497, uses N=10, K=3; its default x0 violates the budget and
+    trust-constr then stops with the constraint unmet, so x0 is made feasible here).  Arms, identical
+    driver: CPU reference closures, GPU closures with the reference's dense callbacks, GPU closures
+    with the Hessian operator + sparse constraint rows.  BLAS is pinned to one thread for all arms:
+    trust-constr's small dense factorisations run several times SLOWER on 16 oversubscribed threads."""
     import bluest_b200 as blu
     import oracle as orc
     from bluest_b200.solvers import scipy_solve
@@ -324,25 +338,73 @@ def sap_solve_benchmark(N=10, K=4, device=0):
     costs = blu.group_costs(groups, 2.0 ** (N - np.arange(N)))
     L = len(costs)
     x0 = np.ceil(10 * abs(np.random.RandomState(0).randn(L)))
-    budget = 100 * costs.max()
-    out = {"problem": "N=%d K=%d L=%d budget=%g, scipy trust-constr (sap.py:387-418), fixed x0, BLAS threads=1" % (N, K, L, budget)}
+    budget = float(x0 @ costs) / 0.9
+    out = {"problem": "N=%d K=%d L=%d budget=%g (x0 feasible), scipy trust-constr (sap.py:387-418), fixed x0, BLAS threads=1" % (N, K, L, budget)}
     cpu = _TimedClosures(_CpuSap(C, K, groups, costs))
     sap = blu.SAP(C, K, [[list(g) for g in gk] for gk in groups], costs, verbose=False, device=device)
     gpu = _TimedClosures(sap)
+    gpu2 = _TimedClosures(sap)
     sap.variance_GH(x0)                                  # warm-up (pinned pool, first launches)
+    sap.variance_GH_operator(x0)[2] @ x0
     with threadpool_limits(limits=1):
         c1 = {}
         t0 = time.perf_counter(); r1 = scipy_solve(cpu, budget=budget, x0=x0.copy(), counters=c1); t_cpu = time.perf_counter() - t0
         c2 = {}
         t0 = time.perf_counter(); r2 = scipy_solve(gpu, budget=budget, x0=x0.copy(), counters=c2); t_gpu = time.perf_counter() - t0
-    out.update({"cpu_reference_s": t_cpu, "gpu_s": t_gpu, "cpu_closure_s": cpu.t, "gpu_closure_s": gpu.t,
-                "closure_calls": gpu.n, "cpu_evals": c1, "gpu_evals": c2,
-                "cpu_variance": float(r1.fun), "gpu_variance": float(r2.fun),
+        c3 = {}
+        t0 = time.perf_counter(); r3 = scipy_solve(gpu2, budget=budget, x0=x0.copy(), counters=c3, hess="operator", sparse_constraints=True); t_op = time.perf_counter() - t0
+    out.update({"cpu_reference_s": t_cpu, "gpu_s": t_gpu, "gpu_operator_sparse_s": t_op,
+                "cpu_closure_s": cpu.t, "gpu_closure_s": gpu.t, "gpu_operator_closure_s": gpu2.t,
+                "closure_calls": gpu.n, "cpu_evals": c1, "gpu_evals": c2, "gpu_operator_evals": c3,
+                "status": [int(r1.status), int(r2.status), int(r3.status)], "iterations": [int(r1.nit), int(r2.nit), int(r3.nit)],
+                "cpu_variance": float(r1.fun), "gpu_variance": float(r2.fun), "gpu_operator_variance": float(r3.fun),
                 "allocation_maxrel_diff": float(np.max(np.abs(r1.x - r2.x)) / np.max(np.abs(r1.x))),
                 "variance_rel_diff": float(abs(r1.fun - r2.fun) / abs(r1.fun)),
                 "note": "what is left of the solve time after the closures is scipy's trust-constr itself (host, out of scope)"})
     sap.close()
+    if large:
+        out["large"] = sap_solve_large(device=device)
     return out
+
+
+def sap_solve_large(N=15, device=0):
+    """The BASELINE size end to end: 15 models, all 32767 groups, budget mode, solved with the same scipy
+    driver using the Hessian OPERATOR (factors in HBM) and sparse constraint rows.  The reference's own
+    callbacks cannot run this size: every Hessian evaluation is ~1 h of hessKQ_c on one core and its
+    dense-constraint driver needs an 8.6 GB identity plus O(L^3) QR factorisations per iteration."""
+    import bluest_b200 as blu
+    import oracle as orc
+    from bluest_b200.solvers import scipy_solve
+    C = orc.wishart_cov(N, 0)
+    groups = blu.enumerate_groups(N)
+    costs = blu.group_costs(groups, 2.0 ** (N - np.arange(N)))
+    L = len(costs)
+    x0 = np.ceil(10 * abs(np.random.RandomState(0).randn(L)))
+    budget = float(x0 @ costs) / 0.9
+    sap = blu.SAP(C, N, groups, costs, verbose=False, device=device)
+    tc = _TimedClosures(sap)
+    mv = {"n": 0, "t": 0.0}
+    orig = sap.hess_matvec
+
+    def timed_mv(p):
+        t0 = time.perf_counter(); r = orig(p); mv["t"] += time.perf_counter() - t0; mv["n"] += 1
+        return r
+    sap.hess_matvec = timed_mv
+    sap.variance_GH_operator(x0)[2] @ x0
+    mv["n"], mv["t"] = 0, 0.0
+    cnt = {}
+    t0 = time.perf_counter()
+    r = scipy_solve(tc, budget=budget, x0=x0.copy(), counters=cnt, hess="operator", sparse_constraints=True)
+    t = time.perf_counter() - t0
+    v0 = sap.variance(x0)
+    out = {"problem": "N=%d K=%d L=%d budget=%g, trust-constr, Hessian operator + sparse constraint rows" % (N, N, L, budget),
+           "gpu_s": t, "closure_s": tc.t, "closure_calls": tc.n, "hess_matvecs": mv["n"], "hess_matvec_s": mv["t"],
+           "evals": cnt, "status": int(r.status), "iterations": int(r.nit), "variance_x0": float(v0), "variance": float(r.fun),
+           "cost": float(r.x @ costs), "budget": budget, "constr_violation": float(r.constr_violation),
+           "note": "closure_s + hess_matvec_s is all the time spent in this package; the rest is scipy's sparse LU / projected CG on the host"}
+    sap.close()
+    return out
+
 
 def secondary_configs(device=0):
     """The other BASELINE.json configs, measured briefly (device-resident, CUDA events; not bench lines)."""
@@ -475,6 +537,25 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     barrier()
 
+    # ---- the same evaluation with the Hessian delivered as an operator (factors stay in HBM) ------
+    pvec = np.random.RandomState(1).randn(L)
+    for i in range(3):
+        v, g, op = sap.variance_GH_operator(pinned_m[i % npool].numpy()); op @ pvec
+    barrier()
+    op_steps = max(20, args.steps)
+    t0 = time.perf_counter()
+    for i in range(op_steps):
+        v, g, op = sap.variance_GH_operator(pinned_m[i % npool].numpy())
+        hp = op @ pvec
+        chk += v + hp[0]
+    torch.cuda.synchronize()
+    e2e_op_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(op_steps):
+        hp = op @ pvec
+    mv_s = (time.perf_counter() - t0) / op_steps
+    barrier()
+
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -505,8 +586,15 @@ def run_ours(args):
                "phases_ms": {"phi_pinv": float(np.mean(phases[:, 0])), "grad_uv": float(np.mean(phases[:, 1])),
                              "hessian": hess_ms, "eval_total": float(np.mean(phases[:, 3]))},
                "e2e": {"value": world * e2e_steps / e2e_s_max, "unit": UNIT, "steps": e2e_steps,
-                       "h2d_bytes_per_step": 8 * L, "d2h_bytes_per_step": 8 * L * L + 8 * L + 8,
-                       "api": "SAP.variance_GH(m) -> (var, grad (L,), hess (L,L)) numpy, pinned host buffers"},
+                       "h2d_bytes_per_step": 8 * L, "d2h_bytes_per_step": _hess_d2h_bytes(L) + 8 * L + 8,
+                       "host_bytes_delivered_per_step": 8 * L * L + 8 * L + 8,
+                       "api": "SAP.variance_GH(m) -> (var, grad (L,), hess (L,L)) numpy, pinned host buffers; the dense Hessian "
+                              "crosses PCIe as its upper block-triangle (1024-row panels) and host threads mirror the lower one"},
+               "e2e_operator": {"value": world * op_steps / e2e_op_s, "unit": UNIT, "steps": op_steps,
+                                "h2d_bytes_per_step": 16 * L, "d2h_bytes_per_step": 16 * L + 8,
+                                "hess_matvec_us": mv_s * 1e6,
+                                "api": "SAP.variance_GH_operator(m) -> (var, grad, LinearOperator) + one hess @ p; the dense matrix is never formed "
+                                       "(rank 0's rate x ranks; not the headline: the reference API returns the dense array)"},
                "gpu_launches": launches_per_eval * args.steps,
                "launches_per_eval": launches_per_eval,
                "clocks": clocks, "setup_s": setup_s, "variance_check": var0}

@@ -5,6 +5,7 @@
 // There is no CPU fallback: without a CUDA device every entry point fails with BLU_ERR_NODEVICE.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <cmath>
 #include <cstdarg>
@@ -17,7 +18,7 @@
 #include "blu_common.cuh"
 #include "blu_jacobi.cuh"
 #include "blu_stream.cuh"
-#include "blu_invert.cuh"
+#include "blu_launch.h"
 #include "blu_phi.cuh"
 #include "blu_grad.cuh"
 #include "blu_soa.cuh"
@@ -97,7 +98,7 @@ struct blu_ctx {
     double *pend_hess = nullptr;       // host destination of the pending evaluation's Hessian
     bool pending = false;
     std::vector<cudaEvent_t> panel_ev; // one event per Hessian row panel (symmetric download)
-    bool sym_download = false;         // measured slower on the GPU box's host (mirroring 4.3 GB costs more than the PCIe time it saves)
+    bool sym_download = true;          // dense Hessian to the host: upper block-triangle over PCIe, lower mirrored by host threads
     BluXchg *d_xchg = nullptr;         // this rank's exchange buffer (CUDA IPC shared)
     BluPeers peers{};                  // peers as mapped here; world == 0: not connected
     std::vector<void *> ipc_opened;
@@ -345,28 +346,6 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
 // --------------------------------------------------------------------------------------------
 // kernel (1): inverses
 // --------------------------------------------------------------------------------------------
-template <int K>
-static void launch_invert(blu_ctx *c, const BluClass &ci, unsigned char *d_flag, double pivtol)
-{
-    constexpr int G = 32 / BluSub<K>::value;
-    const long long warps = (ci.Lk + G - 1) / G;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((warps + 3) / 4, (long long)c->nsm * 16));
-    blu_invert_groups_kernel<K><<<grid, 128, 0, c->stream>>>(c->d_C, c->N, c->d_gidx + ci.ioff, ci.Lk,
-                                                             c->d_cinv + ci.coff, d_flag + ci.goff, pivtol);
-}
-
-static void launch_invert_k(blu_ctx *c, const BluClass &ci, unsigned char *d_flag, double pivtol)
-{
-    switch (ci.k) {
-#define CASE(K) case K: launch_invert<K>(c, ci, d_flag, pivtol); break;
-        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
-        CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
-        CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24)
-        CASE(25) CASE(26) CASE(27) CASE(28) CASE(29) CASE(30) CASE(31) CASE(32)
-#undef CASE
-    }
-}
-
 extern "C" int blu_ctx_set_covariance(blu_ctx *c, const double *C, double pivot_rtol, int64_t *n_fallback)
 {
     int rc = use(c);
@@ -379,7 +358,7 @@ extern "C" int blu_ctx_set_covariance(blu_ctx *c, const double *C, double pivot_
     CUDA_TRY(cudaMalloc(&d_flag, (size_t)c->L));
     CUDA_TRY(cudaMemsetAsync(d_flag, 0, (size_t)c->L, c->stream));
     for (const BluClass &ci : c->cls) {
-        launch_invert_k(c, ci, d_flag, pivot_rtol);
+        blu_launch_invert_class(ci.k, c->nsm, c->stream, c->d_C, c->N, c->d_gidx + ci.ioff, ci.Lk, c->d_cinv + ci.coff, d_flag + ci.goff, pivot_rtol);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { cudaFree(d_flag); return fail(BLU_ERR_CUDA, "invert kernel (k=%d): %s", ci.k, cudaGetErrorString(e)); }
         c->launches++;
@@ -399,8 +378,7 @@ extern "C" int blu_ctx_set_covariance(blu_ctx *c, const double *C, double pivot_
         long long *d_todo = nullptr;
         CUDA_TRY(cudaMalloc(&d_todo, sizeof(long long) * todo.size()));
         CUDA_TRY(cudaMemcpyAsync(d_todo, todo.data(), sizeof(long long) * todo.size(), cudaMemcpyHostToDevice, c->stream));
-        blu_pinv_groups_kernel<<<(unsigned)todo.size(), 256, 0, c->stream>>>(c->d_C, c->N, ci.k, c->d_gidx + ci.ioff, d_todo,
-                                                                              c->d_cinv + ci.coff, 1.0e-15);
+        blu_launch_pinv_groups((unsigned)todo.size(), c->stream, c->d_C, c->N, ci.k, c->d_gidx + ci.ioff, d_todo, c->d_cinv + ci.coff, 1.0e-15);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         cudaFree(d_todo);
@@ -430,7 +408,7 @@ extern "C" int blu_ctx_set_invcovs(blu_ctx *c, int k, const double *invcovs_k)
     if (e == cudaSuccess) {
         const long long total = ci.Lk * ci.T;
         const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->nsm * 8));
-        blu_pack_invcovs_kernel<<<grid, 256, 0, c->stream>>>(d_full, k, ci.Lk, c->d_cinv + ci.coff);
+        blu_launch_pack_invcovs(grid, c->stream, d_full, k, ci.Lk, c->d_cinv + ci.coff);
         e = cudaGetLastError();
         c->launches++;
     }
@@ -457,7 +435,7 @@ extern "C" int blu_ctx_get_invcovs(blu_ctx *c, int k, double *invcovs_k)
     double *d_full = nullptr;
     CUDA_TRY(cudaMalloc(&d_full, sizeof(double) * n));
     const int grid = (int)std::max<long long>(1, std::min<long long>(((long long)n + 255) / 256, (long long)c->nsm * 8));
-    blu_unpack_invcovs_kernel<<<grid, 256, 0, c->stream>>>(c->d_cinv + ci.coff, k, ci.Lk, d_full);
+    blu_launch_unpack_invcovs(grid, c->stream, c->d_cinv + ci.coff, k, ci.Lk, d_full);
     cudaError_t e = cudaGetLastError();
     c->launches++;
     if (e == cudaSuccess) e = cudaMemcpyAsync(invcovs_k, d_full, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
@@ -760,10 +738,11 @@ extern "C" int blu_ctx_last_launches(blu_ctx *c) { return c ? c->launches : 0; }
 
 // Options: "soa" (default 1) -- gradient / U,V kernels on the group-interleaved copy of the inverses
 // (blu_soa.cuh); 0 selects the entry-per-lane kernels of blu_grad.cuh on the group-major copy.
-//          "sym_download" (default 0) -- copy only the upper block-triangle of the dense Hessian
-// over PCIe and mirror it on the host with threads.  Off by default: on the B200 box's host the
-// mirroring of 4.3 GB (16 threads, ~52 GB/s effective) costs more than the 75 ms of PCIe time it
-// saves (6.1 vs 6.6 evaluations/s end to end); worth enabling on hosts with more memory bandwidth.
+//          "sym_download" (default 1) -- copy only the upper block-triangle of the dense Hessian
+// over PCIe and mirror it on the host with threads (streaming stores, blu_hostmirror.cpp) while later
+// panels are in flight.  On the B200 box (16 host cores, PCIe 57 GB/s) one N = 15 evaluation end to
+// end takes 97-125 ms instead of 152-170 ms; the limit is the host's memory bandwidth (4.3 GB of DMA
+// writes + 8.6 GB of mirror traffic).  0 = one plain 2-D copy of all 8 L^2 bytes.
 extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
 {
     if (!c || !name) return fail(BLU_ERR_ARG, "null argument");
@@ -832,23 +811,6 @@ extern "C" int blu_variance(blu_ctx *c, const double *m, double delta, double *v
 // lower triangle (blocked 64 x 64 transposes) while the next panel is still in flight.  Halves the
 // PCIe bytes of the one transfer that dominates the end-to-end evaluation (8 L^2 bytes at 57 GB/s).
 // --------------------------------------------------------------------------------------------
-static void mirror_chunk(double *H, long long L, long long r0, long long r1, long long c0, long long c1)
-{
-    // H[c][r] = H[r][c] for r in [r0,r1), c in [c0,c1)   (c0 >= r1: strictly right of the diagonal block)
-    alignas(64) double buf[64][64];
-    for (long long rb = r0; rb < r1; rb += 64) {
-        const int nr = (int)std::min<long long>(64, r1 - rb);
-        for (long long cb = c0; cb < c1; cb += 64) {
-            const int nc = (int)std::min<long long>(64, c1 - cb);
-            for (int i = 0; i < nr; ++i) {
-                const double *src = H + (rb + i) * L + cb;
-                for (int j = 0; j < nc; ++j) buf[j][i] = src[j];
-            }
-            for (int j = 0; j < nc; ++j) memcpy(H + (cb + j) * L + rb, buf[j], sizeof(double) * nr);
-        }
-    }
-}
-
 static int download_hessian_symmetric(blu_ctx *c, double *hess)
 {
     const long long L = c->L;
@@ -875,18 +837,24 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
                 const int it = next[p].fetch_add(1);
                 if (it >= nitems) break;
                 const long long c0 = r1 + it * CW, c1 = std::min<long long>(L, c0 + CW);
-                mirror_chunk(hess, L, r0, r1, c0, c1);
+                blu_host_mirror_block(hess, L, r0, r1, c0, c1);
             }
         }
+        blu_host_store_fence();                                     // streaming stores visible before join
     };
+    const bool dbg = getenv("BLU_DEBUG_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
     for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
     cudaError_t err = cudaSuccess;
     for (int p = 0; p < npan; ++p) {
         if (err == cudaSuccess) err = cudaEventSynchronize(c->panel_ev[p]);
         ready[p].store(1, std::memory_order_release);              // on error too: never leave the workers spinning
+        if (dbg && (p == 0 || p == npan / 2 || p == npan - 1))
+            fprintf(stderr, "[blu] panel %d arrived at %.1f ms\n", p, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     }
     for (auto &t : pool) t.join();
+    if (dbg) fprintf(stderr, "[blu] mirror done at %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     if (err != cudaSuccess) return fail(BLU_ERR_CUDA, "Hessian download: %s", cudaGetErrorString(err));
     // the diagonal blocks arrived whole; the strictly-lower part of each diagonal block was copied too
     return BLU_OK;

@@ -1,0 +1,18 @@
+// blu_launch.h -- host entry points shared between the translation units of libbluest_b200.so
+// (internal; the public boundary is include/bluest_b200.h).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+// blu_invert_tu.cu
+void blu_launch_invert_class(int k, int nsm, cudaStream_t stream, const double *d_C, int N, const uint8_t *gidx, long long Lk,
+                             double *cinv, unsigned char *flag, double pivtol);
+void blu_launch_pinv_groups(unsigned ngroups, cudaStream_t stream, const double *d_C, int N, int k, const uint8_t *gidx,
+                            const long long *d_todo, double *cinv, double rcond);
+void blu_launch_pack_invcovs(int grid, cudaStream_t stream, const double *d_full, int k, long long Lk, double *cinv);
+void blu_launch_unpack_invcovs(int grid, cudaStream_t stream, const double *cinv, int k, long long Lk, double *d_full);
+
+// blu_hostmirror.cpp: H[c][r] = H[r][c] for r in [r0,r1), c in [c0,c1) of a dense row-major (L,L) host
+// matrix, written with streaming stores (no read-for-ownership of the destination lines).
+void blu_host_mirror_block(double *H, long long L, long long r0, long long r1, long long c0, long long c1);
+void blu_host_store_fence();

@@ -322,7 +322,7 @@ class SAP(object):
                 rhs.append(int(np.round(max_model_samples[i])))
         return es, rhs
 
-    def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=True, max_model_samples=None, solver_params=None, hess="dense"):
+    def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=True, max_model_samples=None, solver_params=None, hess="dense", sparse_constraints=False):
         """Host-side driver kept from sap.py:189-220.  Only ``solver="scipy"`` (trust-constr
         iterating on the GPU closures) is provided here; the SDP solvers (cvxopt / cvxpy) and
         ipopt are third-party host code that consume ``self.psi`` and are not part of this package."""
@@ -331,7 +331,7 @@ class SAP(object):
         if solver != "scipy":
             raise ValueError("bluest_b200.SAP.solve provides solver='scipy'; for 'cvxopt'/'cvxpy'/'ipopt' hand "
                              "`sap.psi`, `sap.variance`, `sap.variance_GH` to the reference's own drivers (INTEGRATION.md)")
-        samples = self.scipy_solve(budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, hess=hess)
+        samples = self.scipy_solve(budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, hess=hess, sparse_constraints=sparse_constraints)
         if samples is None:
             self.samples = None
             return None
@@ -343,13 +343,13 @@ class SAP(object):
         self.tot_cost = samples @ self.costs
         return samples
 
-    def scipy_solve(self, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000, hess="dense"):
+    def scipy_solve(self, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=1000, hess="dense", sparse_constraints=False):
         """sap.py:378-418 -- same constraints, tolerances and callbacks; the callbacks are the GPU closures.
         ``hess="operator"`` hands trust-constr the factored Hessian as a LinearOperator (it only ever
         multiplies by it) instead of the dense (L,L) array."""
         from .solvers import scipy_solve
         self.scipy_counters = {}
         res = scipy_solve(self, budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, maxiter=maxiter,
-                          verbose=self.verbose, counters=self.scipy_counters, hess=hess)
+                          verbose=self.verbose, counters=self.scipy_counters, hess=hess, sparse_constraints=sparse_constraints)
         self.scipy_result = res
         return res.x

@@ -165,8 +165,9 @@ int blu_ctx_timing_log(blu_ctx *ctx, int capacity);
 int blu_ctx_timing_read(blu_ctx *ctx, float *ms, int *n);
 /* Options.  "soa" (default 1): gradient / U,V kernels read a second, group-interleaved copy of the
  * inverses, one group per lane (0: the entry-per-lane kernels on the group-major copy).
- * "sym_download" (default 0): blu_variance_GH moves only the upper block-triangle of the
- * (exactly symmetric) dense Hessian over PCIe and mirrors it with host threads. */
+ * "sym_download" (default 1, used when L >= 4096): blu_variance_GH moves only the upper
+ * block-triangle of the (exactly symmetric) dense Hessian over PCIe and mirrors it with host threads
+ * (0: one plain copy of all 8 L^2 bytes). */
 int blu_ctx_set_option(blu_ctx *ctx, const char *name, int value);
 /* Number of kernels the last evaluation launched. */
 int blu_ctx_last_launches(blu_ctx *ctx);

@@ -127,3 +127,58 @@ def test_graph_data_file_roundtrip(tmp_path):
     assert np.isnan(h["C"][0][0, 5]) and h["C"][0][1, 2] == 0.0 and h["M"] == 12
     with pytest.raises(ValueError):
         io.load_graph_data(str(tmp_path / "g.npz"), n_outputs=3)
+
+
+class _OracleProblem:
+    """Oracle-backed stand-in with the attribute surface of bluest_b200.SAP that the shared scipy driver
+    needs (the GPU tests run the same driver on the real SAP)."""
+
+    def __init__(self, N, K, seed=0):
+        self.o = orc.SapOracle(orc.wishart_cov(N, seed), K, orc.enumerate_groups(N, K))
+        self.L, self.N, self.e = self.o.L, N, self.o.e
+        from bluest_b200.groups import enumerate_groups, group_costs
+        self.costs = group_costs(enumerate_groups(N, K), 2.0 ** (N - np.arange(N)))
+
+    def variance(self, m, delta=0):
+        return self.o.variance(m, delta)
+
+    def variance_GH(self, m, delta=0, nohess=False):
+        return self.o.variance_GH(m, delta, nohess=nohess, hess_mode="factored")
+
+    def variance_GH_operator(self, m, delta=0):
+        from scipy.sparse.linalg import LinearOperator
+        v, g, _ = self.o.variance_GH(m, delta, nohess=True)
+        P = np.linalg.pinv(self.o.get_phi(m, delta))
+        U = self.o.ufactor(np.ascontiguousarray(P[0]))
+        mv = lambda p: 2.0 * (U.T @ (P @ (U @ p)))
+        return v, g, LinearOperator((self.L, self.L), matvec=mv, rmatvec=mv, dtype=np.float64)
+
+    def get_max_sample_constraints(self, mm):
+        return [], []
+
+
+@pytest.mark.parametrize("mode", ["budget", "eps"])
+def test_scipy_driver_operator_and_sparse_constraints_walk_the_same_iterates(mode):
+    """solvers.scipy_solve: the reference's dense driver (sap.py:387-418), the Hessian-operator driver
+    and the sparse-constraint driver must reach the same allocation from the same feasible x0."""
+    from bluest_b200.solvers import scipy_solve
+    p = _OracleProblem(6, 4)
+    x0 = np.ceil(10 * abs(np.random.RandomState(0).randn(p.L)))
+    if mode == "budget":
+        kw = dict(budget=float(x0 @ p.costs) / 0.9)
+    else:
+        kw = dict(eps=float(np.sqrt(p.variance(x0))))
+    ref = scipy_solve(p, x0=x0.copy(), **kw)
+    for opts in (dict(hess="operator"), dict(sparse_constraints=True), dict(hess="operator", sparse_constraints=True)):
+        cnt = {}
+        r = scipy_solve(p, x0=x0.copy(), counters=cnt, **opts, **kw)
+        assert r.status == ref.status
+        if mode == "budget":
+            assert abs(r.fun - ref.fun) <= 1e-4 * abs(ref.fun)          # gtol stop on a flat objective
+            assert abs(r.x @ p.costs - ref.x @ p.costs) <= 1e-4 * kw["budget"]
+        else:
+            assert abs(p.variance(r.x) - kw["eps"] ** 2) <= 1e-6 * kw["eps"] ** 2
+            assert abs(r.x @ p.costs - ref.x @ p.costs) <= 1e-3 * (ref.x @ p.costs)
+        assert cnt["H"] > 0
+    with pytest.raises(ValueError):
+        scipy_solve(p, x0=x0, hess="banded", **kw)
