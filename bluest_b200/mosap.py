@@ -108,3 +108,120 @@ class MOSAP(object):
         mus = [item[0] for item in out]
         Vars = np.array([item[1] for item in out])
         return mus, Vars
+
+    # ---- host orchestration kept from the reference -------------------------------------------
+    def output_indicators(self):
+        """Per output n the (L,) vector that is ``e`` on the groups of output n and 0 elsewhere
+        (mosap.py:136-141, 577-581)."""
+        E = np.zeros((self.n_outputs, int(self.L)))
+        for n in range(self.n_outputs):
+            E[n, self.mappings[n]] = self.e[self.mappings[n]]
+        return E
+
+    def get_max_sample_constraints(self, max_model_samples):
+        """mosap.py:333-351."""
+        if max_model_samples is None:
+            return [], []
+        if not isinstance(max_model_samples, np.ndarray) or len(max_model_samples) != self.N:
+            raise ValueError("The maximum number of model samples must be prescribed as a numpy array of the same length as the number of models.")
+        if max_model_samples[0] < 1:
+            raise ValueError("The high-fidelity model must be sampled at least once.")
+        es, rhs = [], []
+        for i in range(self.N):
+            if np.isfinite(max_model_samples[i]):
+                es.append(self.ES[i])
+                rhs.append(int(np.round(max_model_samples[i])))
+        return es, rhs
+
+    def cleanup_solution(self, m, delta=0, tol=0):
+        """mosap.py:125-211: walk along null-space directions of the stacked cleanup matrices that do
+        not increase the cost, as far as positivity and the coverage constraints allow, while the
+        largest output variance does not get worse -- a sparser allocation of the same quality.
+        Like the reference it zeroes the entries of the caller's ``m`` that lie below ``tol``."""
+        from scipy.linalg import null_space
+        w = self.costs
+        E = self.output_indicators()
+        worst = lambda x: max(self.variances(x, delta=delta))
+        idx = np.argwhere(m > tol).flatten()
+        V0 = worst(m)
+        smax = 0
+        while len(idx) > self.N:
+            idx = np.argwhere(m > tol).flatten()
+            m[m < tol] = 0
+            wr, Er = w[idx], E[:, idx]
+            X = self.get_cleanup_matrices(m, delta=delta)[:, idx]
+            NN = null_space(X)
+            vals = wr @ NN
+            signs = np.sign(vals)
+            NN[:, signs > 0] *= -1                     # orient every direction so that it does not raise the cost
+            vals[signs > 0] *= -1
+            NN, vals = NN[:, abs(signs) > 0], vals[abs(signs) > 0]
+            order = np.argsort(abs(vals))[::-1]        # steepest cost decrease first
+            if len(vals) == 0:
+                break
+            em = Er @ m[idx]
+            for i in order:
+                t = NN[:, i]
+                evals = Er @ t
+                neg = np.argwhere(evals < 0).flatten()
+                s1 = np.inf if len(neg) == 0 else min(abs(em[neg] - 1) / abs(evals[neg]))
+                neg = np.argwhere(t < 0).flatten()
+                s2 = np.inf if len(neg) == 0 else min(m[idx][neg] / abs(t[neg]))
+                smax = max(min(s1, s2), 0)
+                if smax > 5 * tol:
+                    step = np.zeros_like(m); step[idx] = t
+                    mnew = m + smax * step
+                    V = worst(mnew)
+                    if V < V0 or abs(V - V0) / abs(V0) < 1.0e-4:
+                        m = mnew.copy()
+                        break
+                    smax = 0
+            if smax <= 5 * tol:
+                break
+        m[m < tol] = 0
+        return m
+
+    def integer_projection(self, samples, budget=None, eps=None, max_model_samples=None):
+        """mosap.py:213-292; the candidate variances of every output come from one batched device call each."""
+        from .intproj import integer_projection_multi
+        return integer_projection_multi(self, samples, budget=budget, eps=eps, max_model_samples=max_model_samples)
+
+    def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=False, max_model_samples=None,
+              solver_params=None, hess="dense", sparse_constraints=False):
+        """mosap.py:294-331.  ``solver="scipy"`` only (trust-constr on the GPU closures); the SDP
+        solvers and ipopt are third-party host code consuming ``SAPS[n].psi``."""
+        if budget is None and eps is None:
+            raise ValueError("Need to specify either budget or RMSE tolerance")
+        if solver != "scipy":
+            raise ValueError("bluest_b200.MOSAP.solve provides solver='scipy'; for 'cvxopt'/'cvxpy'/'ipopt' hand the SAPS' "
+                             "`psi` / closures to the reference's own drivers (INTEGRATION.md)")
+        samples = self.scipy_solve(budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, hess=hess,
+                                   sparse_constraints=sparse_constraints)
+        if samples is None:
+            self.samples = None
+            return None
+        if not continuous_relaxation:
+            try:
+                samples = self.integer_projection(samples, budget=budget, eps=eps, max_model_samples=max_model_samples)
+            except AssertionError as ex:
+                print(str(ex))
+                self.samples = None
+                return None
+        self.samples = samples
+        self.budget = budget
+        self.eps = eps
+        self.tot_cost = samples @ self.costs
+        for n in range(self.n_outputs):
+            self.SAPS[n].samples = samples[self.mappings[n]]
+        return samples
+
+    def scipy_solve(self, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=5000, hess="dense", sparse_constraints=False,
+                    reference_eps_bound=True):
+        """mosap.py:555-610 (see solvers.scipy_solve_multi for ``reference_eps_bound``)."""
+        from .solvers import scipy_solve_multi
+        self.scipy_counters = {}
+        res = scipy_solve_multi(self, budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, maxiter=maxiter,
+                                verbose=self.verbose, counters=self.scipy_counters, hess=hess, sparse_constraints=sparse_constraints,
+                                reference_eps_bound=reference_eps_bound)
+        self.scipy_result = res
+        return res.x

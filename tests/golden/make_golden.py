@@ -21,6 +21,8 @@ Files written
   estimator.npz   SAP.compute_BLUE_estimator (sap.py:99-119) on random per-group sample sums
   intproj.npz     get_feasible_integer_bounds / best_closest_integer_solution_BLUE (misc.py:141-165,313-382)
   solve.npz       SAP.solve(solver="scipy") end to end: continuous solution and integer allocation
+  mosap.npz       MOSAP cleanup matrices / cleanup_solution, multi-output integer projection (brute force and
+                  randomised, misc.py:177-311), MOSAP.integer_projection, MOSAP.scipy_solve from a fixed x0
   pilot.npz       pilot-sample sums and C_hat computed with the reference's accumulation loop
 """
 import os
@@ -350,6 +352,121 @@ def make_solve(ns):
     np.savez_compressed(os.path.join(OUT, "solve.npz"), **out)
 
 
+def make_mosap(ns):
+    """Multi-output host orchestration of the reference (mosap.py:125-331, 555-610; misc.py:177-311):
+    cleanup matrices and cleanup_solution, the brute-force and the randomised integer projection,
+    MOSAP.integer_projection and MOSAP.scipy_solve from a fixed x0.  np.random is seeded before every
+    call that draws from it (misc.py:203-213)."""
+    import contextlib
+    import io
+    out = {}
+    quiet = lambda: contextlib.redirect_stdout(io.StringIO())
+
+    def build(tag, Cs, K, Ks, groups, multi_groups, model_costs):
+        flat = [g for gk in groups for g in gk]
+        L = len(flat)
+        w = np.array([model_costs[list(g)].sum() for g in flat])
+        mw = [np.array([model_costs[list(g)].sum() for gk in mg for g in gk]) for mg in multi_groups]
+        mosap = ns.mosap.MOSAP([c.copy() for c in Cs], K, list(Ks), [[list(g) for g in gk] for gk in groups],
+                               [[[list(g) for g in gk] for gk in mg] for mg in multi_groups], w, mw, verbose=False)
+        out[f"{tag}/K"] = np.int64(K); out[f"{tag}/Ks"] = np.array(Ks, dtype=np.int64); out[f"{tag}/w"] = w
+        out[f"{tag}/n_outputs"] = np.int64(len(Cs))
+        for n, c in enumerate(Cs):
+            out[f"{tag}/C{n}"] = c
+        for k in range(K):
+            out[f"{tag}/groups{k+1}"] = np.array(groups[k], dtype=np.int64).reshape(-1, k + 1)
+        for n, mg in enumerate(multi_groups):
+            for k in range(Ks[n]):
+                out[f"{tag}/multi{n}_groups{k+1}"] = np.array(mg[k], dtype=np.int64).reshape(-1, k + 1)
+        return mosap, w, L
+
+    def projections(tag, mosap, w, L, sol, name):
+        N = mosap.N
+        out[f"{tag}/{name}_sol"] = sol
+        psis = [mosap.SAPS[n].psi for n in range(mosap.n_outputs)]
+        lb, ub, idx = ns.misc.get_feasible_integer_bounds(sol, N, e=mosap.e)
+        out[f"{tag}/{name}_idx"] = idx
+        budget = float(w @ np.round(sol)) * 1.01
+        vr = np.array(mosap.variances(np.round(sol).astype(int)))
+        eps = np.sqrt(vr * 1.05)
+        out[f"{tag}/{name}_budget"] = np.float64(budget); out[f"{tag}/{name}_eps"] = eps
+        with quiet():
+            np.random.seed(1234)
+            val, fval = ns.misc.best_closest_integer_solution_BLUE_multi(sol.copy(), psis, w, mosap.e, mosap.mappings, budget=budget)
+            np.random.seed(1234)
+            val2, fval2 = ns.misc.best_closest_integer_solution_BLUE_multi(sol.copy(), psis, w, mosap.e, mosap.mappings, eps=eps)
+            np.random.seed(1234)
+            ipb = mosap.integer_projection(sol.copy(), budget=budget)
+            np.random.seed(1234)
+            ipe = mosap.integer_projection(sol.copy(), eps=eps)
+            # max-sample caps that bind: model 1 at most ceil(half of what the budget projection uses)
+            caps = np.inf * np.ones(N); caps[1] = max(1.0, np.ceil(0.5 * (np.array(mosap.ES[1]) @ ipb)))
+            np.random.seed(1234)
+            ipc = mosap.integer_projection(sol.copy(), budget=budget, max_model_samples=caps)
+        out[f"{tag}/{name}_budget_val"] = val; out[f"{tag}/{name}_budget_fval"] = np.float64(fval)
+        out[f"{tag}/{name}_eps_val"] = val2; out[f"{tag}/{name}_eps_fval"] = np.float64(fval2)
+        out[f"{tag}/{name}_projection_budget"] = np.asarray(ipb); out[f"{tag}/{name}_projection_eps"] = np.asarray(ipe)
+        out[f"{tag}/{name}_caps"] = caps; out[f"{tag}/{name}_projection_caps"] = np.asarray(ipc)
+        print("mosap", tag, name, "LL", len(idx), fval, fval2, int(ipb.sum()), int(ipe.sum()), int(ipc.sum()))
+
+    # ---- case A: two outputs on different coupling graphs (non-trivial mappings), from enumeration.npz
+    d = np.load(os.path.join(OUT, "enumeration.npz"))
+    tag = "two_outputs"
+    K = int(d[f"{tag}/K"]); Ks = d[f"{tag}/Ks"].tolist()
+    groups = [d[f"{tag}/groups{k+1}"].tolist() for k in range(K)]
+    multi = [[d[f"{tag}/multi{n}_groups{k+1}"].tolist() for k in range(Ks[n])] for n in range(2)]
+    N = 6
+    mosap, w, L = build(tag, [wishart(N, 61), wishart(N, 62)], K, Ks, groups, multi, 2.0 ** (N - np.arange(N)))
+    rng = np.random.RandomState(63)
+    sol = np.zeros(L); nz = rng.choice(L, size=N + 2, replace=False)
+    sol[nz] = 0.3 + 30 * rng.rand(len(nz)); sol[0] = 3.4
+    projections(tag, mosap, w, L, sol, "small")
+    m = np.zeros(L); nz = rng.choice(L, size=3 * N, replace=False); m[nz] = 1 + 20 * rng.rand(len(nz)); m[0] = 5.0
+    out[f"{tag}/cleanup_m"] = m
+    out[f"{tag}/cleanup_X"] = mosap.get_cleanup_matrices(m.copy())
+    with quiet():
+        out[f"{tag}/cleanup_result"] = mosap.cleanup_solution(m.copy())
+    out[f"{tag}/cleanup_variances_before"] = np.array(mosap.variances(m)); out[f"{tag}/cleanup_variances_after"] = np.array(mosap.variances(out[f"{tag}/cleanup_result"]))
+
+    # ---- case B: three outputs sharing all groups of 8 models up to size 3 (BASELINE config 4 style): more than
+    #      15 rounding candidates, so the reference randomises (misc.py:196-224)
+    tag = "shared_N8K3"
+    N, K, No = 8, 3, 3
+    groups = all_groups(N, K)
+    mosap, w, L = build(tag, [wishart(N, 70 + n) for n in range(No)], K, [K] * No, groups, [groups] * No, 2.0 ** (N - np.arange(N)))
+    rng = np.random.RandomState(73)
+    flat = [g for gk in groups for g in gk]
+    with0 = np.array([i for i, g in enumerate(flat) if 0 in g]); without0 = np.array([i for i, g in enumerate(flat) if 0 not in g])
+    sol = np.zeros(L)
+    sol[rng.choice(without0, size=11, replace=False)] = 10.3 + 30 * rng.rand(11)      # the 9 largest entries avoid model 0 ...
+    sol[rng.choice(with0, size=8, replace=False)] = 1.2 + 3 * rng.rand(8)             # ... and 8 more candidates contain it: LL = 17 > 15
+    projections(tag, mosap, w, L, sol, "big")
+
+    # ---- case C: scipy trust-constr driver, three outputs sharing the groups of 5 models up to size 3
+    tag = "solve_N5K3"
+    N, K, No = 5, 3, 3
+    groups = all_groups(N, K)
+    mosap, w, L = build(tag, [wishart(N, 80 + n) for n in range(No)], K, [K] * No, groups, [groups] * No, 2.0 ** (N - np.arange(N)))
+    x0 = np.ceil(10 * abs(np.random.RandomState(83).randn(L)))
+    budget = float(x0 @ w) / 0.9
+    x0b = np.concatenate([[max(mosap.variances(x0, delta=1.0e-15))], x0])
+    with quiet():
+        cont_b = mosap.scipy_solve(budget=budget, x0=x0b.copy())
+    eps = np.sqrt(np.array(mosap.variances(x0)) * 1.5)
+    with quiet():
+        cont_e = mosap.scipy_solve(eps=eps, x0=x0.copy())
+        np.random.seed(1234)
+        int_b = mosap.integer_projection(cont_b.copy(), budget=budget)
+        np.random.seed(1234)
+        int_e = mosap.integer_projection(cont_e.copy(), eps=eps)
+    out[f"{tag}/x0"] = x0; out[f"{tag}/budget"] = np.float64(budget); out[f"{tag}/eps"] = eps
+    out[f"{tag}/continuous_budget"] = cont_b; out[f"{tag}/continuous_eps"] = cont_e
+    out[f"{tag}/integer_budget"] = np.asarray(int_b); out[f"{tag}/integer_eps"] = np.asarray(int_e)
+    out[f"{tag}/variances_budget"] = np.array(mosap.variances(cont_b)); out[f"{tag}/variances_eps"] = np.array(mosap.variances(cont_e))
+    print("mosap solve", max(mosap.variances(cont_b)), float(cont_b @ w), budget, np.array(mosap.variances(cont_e)) / eps ** 2, float(cont_e @ w))
+    np.savez_compressed(os.path.join(OUT, "mosap.npz"), **out)
+
+
 def make_pilot():
     """The reference accumulates the pilot sums one sample at a time (blue_fn.py:159-167, N1=1)
     and then forms C_hat = sumsc/N - outer(sumse, sumse)/N^2 (blue_models.py:333)."""
@@ -379,5 +496,6 @@ if __name__ == "__main__":
     make_estimator(ns)
     make_intproj(ns)
     make_solve(ns)
+    make_mosap(ns)
     make_pilot()
     print("done")

@@ -617,3 +617,91 @@ def test_scipy_solve_with_hessian_operator_matches_dense(blu, tag):
     assert abs(co["H"] - cd["H"]) <= max(3, cd["H"] // 5)
     vr = orc.SapOracle(C, K, groups).variance(d[f"{tag}/continuous"])
     assert abs(sap.variance(oper) - vr) <= 1e-4 * vr
+
+
+def _mosap_case(blu, d, tag):
+    K = int(d[f"{tag}/K"]); Ks = d[f"{tag}/Ks"].tolist(); No = int(d[f"{tag}/n_outputs"])
+    groups = [d[f"{tag}/groups{k+1}"].tolist() for k in range(K)]
+    multi = [[d[f"{tag}/multi{n}_groups{k+1}"].tolist() for k in range(Ks[n])] for n in range(No)]
+    w = d[f"{tag}/w"]
+    where = {tuple(g): i for i, g in enumerate(g for gk in groups for g in gk)}
+    mw = [np.array([w[where[tuple(g)]] for gk in mg for g in gk]) for mg in multi]
+    return blu.MOSAP([d[f"{tag}/C{n}"] for n in range(No)], K, Ks, _copy(groups), [_copy(mg) for mg in multi], w, mw, verbose=False)
+
+
+@pytest.mark.parametrize("tag,name", [("two_outputs", "small"), ("shared_N8K3", "big")])
+def test_multi_output_integer_projection(blu, tag, name):
+    """mosap.py:213-292 / misc.py:177-311 on the device: brute force (<= 15 groups) and the seeded
+    randomised search (> 15): integer allocations bit-exact with the reference's."""
+    from bluest_b200 import intproj
+    d = _load("mosap.npz")
+    mos = _mosap_case(blu, d, tag)
+    sol = d[f"{tag}/{name}_sol"]
+    budget = float(d[f"{tag}/{name}_budget"]); eps = d[f"{tag}/{name}_eps"]
+    np.random.seed(1234)
+    val, fval = intproj.best_closest_integer_solution_BLUE_multi(mos, sol.copy(), budget=budget)
+    assert np.array_equal(val, d[f"{tag}/{name}_budget_val"]) and abs(fval - float(d[f"{tag}/{name}_budget_fval"])) <= 1e-10 * fval
+    np.random.seed(1234)
+    val, fval = intproj.best_closest_integer_solution_BLUE_multi(mos, sol.copy(), eps=eps)
+    assert np.array_equal(val, d[f"{tag}/{name}_eps_val"]) and abs(fval - float(d[f"{tag}/{name}_eps_fval"])) <= 1e-10 * fval
+    np.random.seed(1234)
+    assert np.array_equal(mos.integer_projection(sol.copy(), budget=budget), d[f"{tag}/{name}_projection_budget"])
+    np.random.seed(1234)
+    assert np.array_equal(mos.integer_projection(sol.copy(), eps=eps), d[f"{tag}/{name}_projection_eps"])
+    np.random.seed(1234)
+    assert np.array_equal(mos.integer_projection(sol.copy(), budget=budget, max_model_samples=d[f"{tag}/{name}_caps"]), d[f"{tag}/{name}_projection_caps"])
+
+
+def test_multi_output_cleanup(blu):
+    """mosap.py:102-111, 125-211: stacked cleanup matrices and the sparsified allocation of the reference."""
+    d = _load("mosap.npz")
+    tag = "two_outputs"
+    mos = _mosap_case(blu, d, tag)
+    m = d[f"{tag}/cleanup_m"]
+    assert maxrel(mos.get_cleanup_matrices(m.copy()), d[f"{tag}/cleanup_X"]) < TOL
+    assert maxrel(mos.variances(m), d[f"{tag}/cleanup_variances_before"]) < TOL
+    out = mos.cleanup_solution(m.copy())
+    ref = d[f"{tag}/cleanup_result"]
+    assert np.array_equal(out > 0, ref > 0)
+    assert maxrel(out, ref) < 1e-8
+    assert maxrel(mos.variances(out), d[f"{tag}/cleanup_variances_after"]) < 1e-8
+
+
+def test_multi_output_scipy_solve(blu):
+    """MOSAP.scipy_solve (mosap.py:555-610) from the reference's x0: budget mode (epigraph variable) and
+    eps mode, the dense driver against the reference's continuous solution, and the operator / sparse
+    variants against the dense driver."""
+    d = _load("mosap.npz")
+    tag = "solve_N5K3"
+    mos = _mosap_case(blu, d, tag)
+    w = d[f"{tag}/w"]; x0 = d[f"{tag}/x0"]
+    budget = float(d[f"{tag}/budget"]); eps = d[f"{tag}/eps"]
+    cb = mos.scipy_solve(budget=budget, x0=x0.copy())
+    # trust-constr stops on tolerances: iterates agree to ~1e-3, the objective (largest variance) much better
+    assert abs(max(mos.variances(cb)) - max(d[f"{tag}/variances_budget"])) <= 1e-4 * max(d[f"{tag}/variances_budget"])
+    assert cb @ w <= budget * (1 + 1e-9)
+    assert maxrel(cb, d[f"{tag}/continuous_budget"]) < 2e-2
+    ce = mos.scipy_solve(eps=eps, x0=x0.copy())
+    assert abs(ce @ w - d[f"{tag}/continuous_eps"] @ w) <= 1e-3 * (d[f"{tag}/continuous_eps"] @ w)
+    assert maxrel(ce, d[f"{tag}/continuous_eps"]) < 2e-2
+    # the reference bounds every output by the LAST output's tolerance (mosap.py:605)
+    assert np.all(np.array(mos.variances(ce)) <= eps[-1] ** 2 * (1 + 1e-6))
+    cfix = mos.scipy_solve(eps=eps, x0=x0.copy(), reference_eps_bound=False)
+    assert np.all(np.array(mos.variances(cfix)) <= eps ** 2 * (1 + 1e-6))
+    for kw in (dict(hess="operator"), dict(hess="operator", sparse_constraints=True)):
+        cb2 = mos.scipy_solve(budget=budget, x0=x0.copy(), **kw)
+        assert abs(max(mos.variances(cb2)) - max(mos.variances(cb))) <= 1e-4 * max(mos.variances(cb))
+        ce2 = mos.scipy_solve(eps=eps, x0=x0.copy(), **kw)
+        assert abs(ce2 @ w - ce @ w) <= 1e-3 * (ce @ w)
+        assert mos.scipy_counters["H"] > 0
+    # full pipeline: continuous solve + integer projection; feasible and no worse than the reference's allocation
+    np.random.seed(1234)
+    ints = mos.solve(budget=budget, x0=x0.copy(), continuous_relaxation=False)
+    assert ints.dtype.kind == "i" and ints @ w <= 1.0001 * budget
+    ref_int = d[f"{tag}/integer_budget"]
+    assert max(mos.variances(ints)) <= max(mos.variances(ref_int)) * (1 + 2e-3)
+    assert np.array_equal(mos.SAPS[1].samples, ints[mos.mappings[1]])
+    with pytest.raises(ValueError):
+        mos.solve(budget=budget, solver="cvxopt")
+    with pytest.raises(ValueError):
+        mos.solve()

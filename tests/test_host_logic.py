@@ -182,3 +182,106 @@ def test_scipy_driver_operator_and_sparse_constraints_walk_the_same_iterates(mod
         assert cnt["H"] > 0
     with pytest.raises(ValueError):
         scipy_solve(p, x0=x0, hess="banded", **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-output host orchestration (mosap.py:125-331, misc.py:177-311) with oracle-backed outputs
+# ---------------------------------------------------------------------------------------------
+class _OracleOutput:
+    """Stand-in for one output's device context: the oracle behind the few SAP members MOSAP touches."""
+
+    def __init__(self, C, K, groups):
+        self.o = orc.SapOracle(C, K, groups)
+        self.N, self.L, self.e = self.o.N, self.o.L, self.o.e
+        self.samples = None
+
+    def get_phi(self, m, delta=0):
+        return self.o.get_phi(m, delta)
+
+    def variance(self, m, delta=0):
+        return self.o.variance(m, delta)
+
+    def get_cleanup_matrix(self, m, delta=0):
+        return self.o.cleanup_matrix(m, delta)
+
+
+def _oracle_mosap(d, tag):
+    """A real bluest_b200.MOSAP object (host logic under test) whose outputs are oracle stand-ins."""
+    from bluest_b200.groups import indicator_ES, mappings as build_mappings
+    K = int(d[f"{tag}/K"]); Ks = d[f"{tag}/Ks"].tolist(); No = int(d[f"{tag}/n_outputs"])
+    groups = [d[f"{tag}/groups{k+1}"].tolist() for k in range(K)]
+    multi = [[d[f"{tag}/multi{n}_groups{k+1}"].tolist() for k in range(Ks[n])] for n in range(No)]
+    mos = object.__new__(blu.MOSAP)
+    mos.verbose = False
+    mos.n_outputs = No
+    mos.C = [d[f"{tag}/C{n}"] for n in range(No)]
+    mos.N = mos.C[0].shape[0]
+    mos.K, mos.Ks, mos.costs = K, Ks, d[f"{tag}/w"]
+    mos.groups = [np.array(g, dtype=np.int64) for g in groups]
+    mos.SAPS = [_OracleOutput(mos.C[n], Ks[n], multi[n]) for n in range(No)]
+    mos.sizes = [0] + [len(g) for g in groups]
+    mos.cumsizes = np.cumsum(mos.sizes)
+    mos.L = mos.cumsizes[-1]
+    mos.ES = indicator_ES(groups, mos.N)
+    mos.e = mos.ES[0]
+    mos.mappings = build_mappings(groups, multi)
+    mos.variances = lambda m, delta=0: [mos.SAPS[n].variance(np.asarray(m)[mos.mappings[n]], delta) for n in range(No)]
+    return mos
+
+
+def _fake_candidates(sap_, base, idx_, ms, rcond=1e-10):
+    o = sap_.o
+    N = o.N
+    phis = (o.get_phi(base).reshape(-1, 1) + o.psi[:, idx_] @ ms).T.reshape(-1, N, N)
+    return np.linalg.pinv(phis, hermitian=True, rcond=rcond)[:, 0, 0]
+
+
+@pytest.mark.parametrize("tag,name", [("two_outputs", "small"), ("shared_N8K3", "big")])
+def test_multi_output_integer_projection_host_logic(tag, name, monkeypatch):
+    """misc.py:177-311 / mosap.py:213-292: brute-force (<= 15 groups) and randomised (> 15, seeded)
+    projection, the fallback ladder and the max-sample caps -- allocations equal to the reference's."""
+    from bluest_b200 import intproj
+    d = _load("mosap.npz")
+    mos = _oracle_mosap(d, tag)
+    monkeypatch.setattr(intproj, "candidate_variances", _fake_candidates)
+    sol = d[f"{tag}/{name}_sol"]
+    lb, ub, idx = intproj.feasible_integer_bounds(sol, mos.N, e=mos.e)
+    assert np.array_equal(idx, d[f"{tag}/{name}_idx"])
+    assert (len(idx) > intproj.LL_MAX_MULTI) == (name == "big")
+    budget = float(d[f"{tag}/{name}_budget"]); eps = d[f"{tag}/{name}_eps"]
+    np.random.seed(1234)
+    val, fval = intproj.best_closest_integer_solution_BLUE_multi(mos, sol.copy(), budget=budget)
+    assert np.array_equal(val, d[f"{tag}/{name}_budget_val"]) and abs(fval - float(d[f"{tag}/{name}_budget_fval"])) <= 1e-10 * fval
+    np.random.seed(1234)
+    val, fval = intproj.best_closest_integer_solution_BLUE_multi(mos, sol.copy(), eps=eps)
+    assert np.array_equal(val, d[f"{tag}/{name}_eps_val"]) and abs(fval - float(d[f"{tag}/{name}_eps_fval"])) <= 1e-10 * fval
+    np.random.seed(1234)
+    assert np.array_equal(mos.integer_projection(sol.copy(), budget=budget), d[f"{tag}/{name}_projection_budget"])
+    np.random.seed(1234)
+    assert np.array_equal(mos.integer_projection(sol.copy(), eps=eps), d[f"{tag}/{name}_projection_eps"])
+    np.random.seed(1234)
+    assert np.array_equal(mos.integer_projection(sol.copy(), budget=budget, max_model_samples=d[f"{tag}/{name}_caps"]), d[f"{tag}/{name}_projection_caps"])
+    with pytest.raises(ValueError):
+        mos.integer_projection(sol)
+    with pytest.raises(ValueError):
+        mos.get_max_sample_constraints(np.ones(mos.N + 1))
+    with pytest.raises(ValueError):
+        mos.get_max_sample_constraints(np.zeros(mos.N))
+
+
+def test_multi_output_cleanup_solution_host_logic():
+    """mosap.py:125-211: the sparsified allocation equals the reference's, its cost is not higher and
+    the largest output variance not worse."""
+    d = _load("mosap.npz")
+    tag = "two_outputs"
+    mos = _oracle_mosap(d, tag)
+    m = d[f"{tag}/cleanup_m"]
+    X = mos.get_cleanup_matrices(m.copy())
+    assert np.max(np.abs(X - d[f"{tag}/cleanup_X"])) <= 1e-12 * np.max(np.abs(d[f"{tag}/cleanup_X"]))
+    out = mos.cleanup_solution(m.copy())
+    ref = d[f"{tag}/cleanup_result"]
+    assert np.array_equal(out > 0, ref > 0)
+    assert np.max(np.abs(out - ref)) <= 1e-8 * np.max(np.abs(ref))
+    assert (out > 0).sum() < (m > 0).sum()
+    assert out @ mos.costs <= m @ mos.costs * (1 + 1e-12)
+    assert max(mos.variances(out)) <= max(d[f"{tag}/cleanup_variances_before"]) * (1 + 1e-4)
