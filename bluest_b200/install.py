@@ -21,7 +21,8 @@ from .sap import SAP as B200SAP
 _saved = {}
 _L1 = ("assemble_psi_c", "objectiveK_c", "gradK_c", "hessKQ_c", "cleanupK_c")
 _L2_METHODS = ("__init__", "get_variance_functions", "_m", "eval_device", "upload_m", "sync", "last_result", "last_timing",
-               "timing_log", "timing_read", "last_launches", "device_ptr", "device_buffer", "stream", "close", "__del__", "compute_BLUE_estimator", "integer_projection")
+               "timing_log", "timing_read", "last_launches", "device_ptr", "device_buffer", "stream", "close", "__del__", "compute_BLUE_estimator", "integer_projection",
+               "variance_GH_begin", "variance_GH_end", "hess_matvec", "hess_operator", "hess_matvec_device", "set_option")
 
 
 def make_hybrid(ref_sap_cls):

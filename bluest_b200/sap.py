@@ -322,7 +322,7 @@ class SAP(object):
                 rhs.append(int(np.round(max_model_samples[i])))
         return es, rhs
 
-    def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=True, max_model_samples=None, solver_params=None, hess="dense", sparse_constraints=False):
+    def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=False, max_model_samples=None, solver_params=None, hess="dense", sparse_constraints=False):
         """Host-side driver kept from sap.py:189-220.  Only ``solver="scipy"`` (trust-constr
         iterating on the GPU closures) is provided here; the SDP solvers (cvxopt / cvxpy) and
         ipopt are third-party host code that consume ``self.psi`` and are not part of this package."""

@@ -608,9 +608,9 @@ def test_scipy_solve_with_hessian_operator_matches_dense(blu, tag):
     groups = orc.enumerate_groups(N, K)
     sap = blu.SAP(C, K, _copy(groups), d[f"{tag}/w"], verbose=False)
     budget = float(d[f"{tag}/budget"])
-    dense = sap.solve(budget=budget, solver="scipy", x0=d[f"{tag}/x0"].copy())
+    dense = sap.solve(budget=budget, solver="scipy", x0=d[f"{tag}/x0"].copy(), continuous_relaxation=True)
     cd = dict(sap.scipy_counters)
-    oper = sap.solve(budget=budget, solver="scipy", x0=d[f"{tag}/x0"].copy(), hess="operator")
+    oper = sap.solve(budget=budget, solver="scipy", x0=d[f"{tag}/x0"].copy(), hess="operator", continuous_relaxation=True)
     co = dict(sap.scipy_counters)
     assert maxrel(oper, dense) < 5e-3
     assert abs(sap.variance(oper) - sap.variance(dense)) <= 1e-4 * sap.variance(dense)      # trust-constr stops at gtol on a flat objective
