@@ -65,6 +65,13 @@ def _worker(rank, world, port, N, ret):
             H = sap.device_buffer(_lib.BUF_HESS)[: (r["rhi"] - r["rlo"]) * ld].view(-1, ld)[:, :L].cpu().numpy()
             out.append(dict(var=r["var"], grad=sap.device_buffer(_lib.BUF_GRAD).cpu().numpy(), H=H, rows=(r["rlo"], r["rhi"]),
                             phi=sap.device_buffer(_lib.BUF_PHI)[: N * N].cpu().numpy()))
+        # sharded Hessian operator: factors stay on their rank, one 32-double NCCL all-reduce per product
+        m = orc.dense_m(L, 0)
+        r = ev.evaluate_factors(m)
+        p = torch.from_numpy(np.random.RandomState(5).randn(L)).cuda(rank)
+        hp = ev.hess_matvec(p, gather=True).cpu().numpy().copy()
+        own = ev.hess_matvec(p, gather=False).cpu().numpy()[r["lo"]:r["hi"]].copy()
+        out.append(dict(var=r["var"], hp=hp, own=own, lo=r["lo"], hi=r["hi"]))
         ret[rank] = out
         sap.close()
     finally:
@@ -93,3 +100,10 @@ def test_fused_two_gpus():
         assert np.array_equal(a["grad"], b["grad"]) and maxrel(a["grad"], g) < tol
         Hcat = np.vstack([a["H"], b["H"]])
         assert maxrel(Hcat, H) < tol
+    # operator: H p with the factors sharded over the two GPUs
+    m = orc.dense_m(o.L, 0)
+    v, g, H = o.variance_GH(m, hess_mode="factored")
+    Hp = H @ np.random.RandomState(5).randn(o.L)
+    a, b = ret[0][3], ret[1][3]
+    assert np.array_equal(a["hp"], b["hp"]) and maxrel(a["hp"], Hp) < 1e-12
+    assert a["hi"] == b["lo"] and maxrel(np.concatenate([a["own"], b["own"]]), Hp) < 1e-12
