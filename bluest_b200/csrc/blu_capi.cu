@@ -105,7 +105,7 @@ struct blu_ctx {
     unsigned long long epoch = 0;
     double *d_hvpart = nullptr, *d_hvp = nullptr, *d_hvout = nullptr;   // Hessian mat-vec: CTA partials of t, staged p and H p
     int hv_grid = 1;
-    bool uv_ready = false;             // U, V hold the factors of the last want_hess evaluation
+    bool uv_ready = false, v_ready = false;   // U (and V) hold the factors of the last want_hess evaluation
     std::vector<cudaEvent_t> evlog;    // optional per-evaluation event log (4 events per evaluation)
     int evlog_n = 0;
 };
@@ -216,7 +216,7 @@ static int build_chunks(blu_ctx *c)
     if (c->grid_phi > c->part_rows) {
         if (c->d_part) CUDA_TRY(cudaFree(c->d_part));
         c->d_part = nullptr;
-        CUDA_TRY(cudaMalloc(&c->d_part, sizeof(double) * (size_t)c->N * c->N * c->grid_phi));
+        CUDA_TRY(cudaMalloc(&c->d_part, sizeof(double) * (size_t)c->N * c->N * (c->grid_phi + 1)));   // + one row for the folded tile
         c->part_rows = c->grid_phi;
     }
     return BLU_OK;
@@ -484,8 +484,16 @@ static int launch_phi(blu_ctx *c, const double *d_m, double delta, int mode)
     blu_phi_partial_kernel<<<c->grid_phi, c->phi_warps * 32, blu_stream_smem_bytes(c->sd, c->phi_warps * NN, (int)c->cls.size(), c->lutlen, c->phi_warps), c->stream>>>(
         c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr);
     KERNEL_CHECK(c);
+    const double *part = c->d_part;
+    int nparts = c->grid_phi;
+    if (nparts > 200) {                 // many partial tiles (N >= 17): fold them with NN/32 CTAs first (d_part has one spare row); below that the extra launch costs more than it saves
+        double *folded = c->d_part + (size_t)c->part_rows * NN;
+        blu_phi_fold_kernel<<<(NN + 31) / 32, BLU_FOLD_WARPS * 32, 0, c->stream>>>(c->d_part, nparts, NN, folded);
+        KERNEL_CHECK(c);
+        part = folded; nparts = 1;
+    }
     blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
-        c->N, c->grid_phi, c->d_part, delta, mode, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr, c->peers, c->epoch);
+        c->N, nparts, part, delta, mode, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr, c->peers, c->epoch);
     KERNEL_CHECK(c);
     return BLU_OK;
 }
@@ -546,9 +554,23 @@ static int ensure_soa(blu_ctx *c)
     return BLU_OK;
 }
 
-static int launch_grad(blu_ctx *c, int want_uv)
+// V rows of the owned slice from its U rows (V = U S, S = 2 pinv(Phi)): needed by the dense Hessian
+// kernel and the sharded row panels, not by the operator.
+static int launch_v_from_u(blu_ctx *c)
 {
-    if (want_uv) c->uv_ready = true;
+    const long long total = (c->hi - c->lo) * c->NP;
+    if (total <= 0) return BLU_OK;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->nsm * 8));
+    blu_v_from_u_kernel<<<grid, 256, 0, c->stream>>>(c->d_U, c->d_S, c->N, c->NP, c->lo, c->hi, c->d_V);
+    KERNEL_CHECK(c);
+    return BLU_OK;
+}
+
+// uv: 0 = gradient only, 1 = gradient + U and V rows, 2 = gradient + U rows only (Hessian operator).
+static int launch_grad(blu_ctx *c, int uv)
+{
+    const bool want_uv = uv != 0;
+    if (want_uv) { c->uv_ready = true; c->v_ready = (uv == 1); }
     // One group per lane needs at least a couple of 32-group tiles per SM to fill the machine; smaller
     // problems (latency-bound anyway) keep the entry-per-lane kernels, which spread a group over a warp.
     if (c->use_soa && c->hi - c->lo >= (long long)c->nsm * 2 * 32) {
@@ -561,16 +583,17 @@ static int launch_grad(blu_ctx *c, int want_uv)
             CUDA_TRY(cudaFuncSetAttribute(blu_grad_soa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             blu_grad_soa_kernel<false><<<c->grid_soa, BLU_SOA_WARPS * 32, smem, c->stream>>>(
                 c->d_cls, ncl, c->N, c->NP, c->K, c->d_tiles, c->ntiles, c->d_soa, c->d_soff, c->d_lut, c->lutlen, c->d_gmask,
-                c->d_x, c->d_S, c->lo, c->hi, c->d_grad, nullptr, nullptr);
-        } else {
-            const size_t smem = blu_soa_smem_bytes(c->K, true, c->N * c->N + c->N, ncl, c->lutlen);
-            CUDA_TRY(cudaFuncSetAttribute(blu_grad_soa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            blu_grad_soa_kernel<true><<<c->grid_soa, BLU_SOA_WARPS * 32, smem, c->stream>>>(
-                c->d_cls, ncl, c->N, c->NP, c->K, c->d_tiles, c->ntiles, c->d_soa, c->d_soff, c->d_lut, c->lutlen, c->d_gmask,
-                c->d_x, c->d_S, c->lo, c->hi, c->d_grad, c->d_U, c->d_V);
+                c->d_x, c->lo, c->hi, c->d_grad, nullptr);
+            KERNEL_CHECK(c);
+            return BLU_OK;
         }
+        const size_t smem = blu_soa_smem_bytes(c->K, true, c->N, ncl, c->lutlen);
+        CUDA_TRY(cudaFuncSetAttribute(blu_grad_soa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        blu_grad_soa_kernel<true><<<c->grid_soa, BLU_SOA_WARPS * 32, smem, c->stream>>>(
+            c->d_cls, ncl, c->N, c->NP, c->K, c->d_tiles, c->ntiles, c->d_soa, c->d_soff, c->d_lut, c->lutlen, c->d_gmask,
+            c->d_x, c->lo, c->hi, c->d_grad, c->d_U);
         KERNEL_CHECK(c);
-        return BLU_OK;
+        return uv == 1 ? launch_v_from_u(c) : BLU_OK;
     }
     if (!want_uv) {
         blu_grad_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->sd, 0, (int)c->cls.size(), c->lutlen), c->stream>>>(
@@ -580,6 +603,7 @@ static int launch_grad(blu_ctx *c, int want_uv)
     }
     int rc = ensure_uv(c);
     if (rc) return rc;
+    c->v_ready = true;                  // the entry-per-lane kernel writes both factors
     blu_gradu_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->sd, c->N * c->N, (int)c->cls.size(), c->lutlen), c->stream>>>(
         c->d_cls, (int)c->cls.size(), c->N, c->NP, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_S,
         c->d_grad, c->d_U, c->d_V);
@@ -646,7 +670,7 @@ extern "C" int blu_eval_device(blu_ctx *c, const double *d_m, double delta, int 
     rc = launch_phi(c, d_m, delta, 1);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(ev[1], c->stream));
-    if (want_grad || want_hess) { rc = launch_grad(c, want_hess); if (rc) return rc; }
+    if (want_grad || want_hess) { rc = launch_grad(c, want_hess == 0 ? 0 : (want_hess == 3 ? 2 : 1)); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(ev[2], c->stream));
     if (want_hess == 1) { rc = launch_hess(c, true); if (rc) return rc; }      // 2: U,V only (row panels follow via blu_shard_hess)
     CUDA_TRY(cudaEventRecord(ev[3], c->stream));
@@ -947,7 +971,7 @@ static int launch_hv_apply(blu_ctx *c, const double *d_part, int nparts, double 
 {
     const long long rows = c->hi - c->lo;
     const int grid = (int)std::max<long long>(1, std::min<long long>((rows + BLU_HV_THREADS - 1) / BLU_HV_THREADS, (long long)c->nsm * 8));
-    blu_hv_apply_kernel<<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_V, d_part, nparts, c->lo, c->hi, c->NP, d_out);
+    blu_hv_apply_kernel<<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_U, c->d_S, c->N, d_part, nparts, c->lo, c->hi, c->NP, d_out);
     KERNEL_CHECK(c);
     return BLU_OK;
 }
@@ -997,7 +1021,7 @@ extern "C" int blu_variance_GH_factored(blu_ctx *c, const double *m, double delt
     if (!m || !grad) return fail(BLU_ERR_ARG, "null argument");
     if (c->pending) return fail(BLU_ERR_STATE, "an evaluation is already pending on this context");
     if ((rc = upload_m(c, m))) return rc;
-    if ((rc = blu_eval_device(c, c->d_m, delta, 1, 2))) return rc;
+    if ((rc = blu_eval_device(c, c->d_m, delta, 1, 3))) return rc;     // U rows only: the operator never reads V
     CUDA_TRY(cudaMemcpyAsync(grad, c->d_grad, sizeof(double) * c->L, cudaMemcpyDeviceToHost, c->stream));
     if ((rc = fetch_header(c))) return rc;
     const unsigned fl = c->h_hdr->flags;
@@ -1187,7 +1211,7 @@ extern "C" int blu_shard_hess(blu_ctx *c, int64_t row_lo, int64_t row_hi)
 {
     int rc = use(c);
     if (rc) return rc;
-    if (!c->d_U) return fail(BLU_ERR_STATE, "U/V not computed");
+    if (!c->d_U || !c->v_ready) return fail(BLU_ERR_STATE, "U/V not computed (evaluate with want_uv = 1)");
     if (row_lo < 0 || row_hi > c->L || row_lo > row_hi) return fail(BLU_ERR_ARG, "row panel [%lld,%lld) outside [0,%lld]", (long long)row_lo, (long long)row_hi, c->L);
     return launch_hess(c, false, row_lo, row_hi);
 }

@@ -113,47 +113,64 @@ blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab
     }
 }
 
-// Fixed-order reduction over CTAs + covariance formula.  One CTA; the partial tiles are summed in
-// BLU_GRAM_SEG interleaved segments (independent loads in flight), then the segments in order.
-#define BLU_GRAM_SEG 16
-__global__ void __launch_bounds__(1024)
+// Fixed-order reduction over CTAs + covariance formula, spread over E/32 CTAs: CTA b owns the 32
+// entries [32b, 32b+32) of the Gram tile; its 8 warps sum interleaved subsets of the partial tiles
+// (coalesced 256-byte rows, independent loads in flight) and are combined in warp order, so the
+// association is fixed.  The CTA that finishes last (a ticket counter: control flow only, no
+// arithmetic through atomics) turns G into s1, S2 and C_hat.  A single-CTA version of this reduction
+// took as long as the streaming kernel itself (1.4 MB of partials behind one SM's load queue).
+#define BLU_GRAM_FIN_WARPS 8
+__global__ void __launch_bounds__(BLU_GRAM_FIN_WARPS * 32)
 blu_gram_finish_kernel(const double *__restrict__ part, int nparts, int NPG, int N, long long n,
+                       double *__restrict__ G, unsigned *__restrict__ ticket,
                        double *__restrict__ s1, double *__restrict__ S2, double *__restrict__ Chat)
 {
-    extern __shared__ double gsm[];       // BLU_GRAM_SEG * NPG*NPG staging, then G = first NPG*NPG
+    __shared__ double sh[BLU_GRAM_FIN_WARPS][32];
+    __shared__ bool last;
     const int E = NPG * NPG;
-    for (int t = threadIdx.x; t < E * BLU_GRAM_SEG; t += blockDim.x) {
-        const int seg = t / E, e = t - seg * E;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 32 + lane;
+    double sum = 0.0;
+    if (e < E) {
         const int r = e / NPG, c = e - r * NPG;
-        double sum = 0.0;
-        if ((r >> 3) <= (c >> 3))
-            for (int p = seg; p < nparts; p += BLU_GRAM_SEG) sum += part[(long long)p * E + e];
-        gsm[t] = sum;
+        if ((r >> 3) <= (c >> 3)) {                              // lower tiles are never produced
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int p = w;
+            for (; p + 3 * BLU_GRAM_FIN_WARPS < nparts; p += 4 * BLU_GRAM_FIN_WARPS) {
+                a0 += part[(long long)p * E + e];
+                a1 += part[(long long)(p + BLU_GRAM_FIN_WARPS) * E + e];
+                a2 += part[(long long)(p + 2 * BLU_GRAM_FIN_WARPS) * E + e];
+                a3 += part[(long long)(p + 3 * BLU_GRAM_FIN_WARPS) * E + e];
+            }
+            for (; p < nparts; p += BLU_GRAM_FIN_WARPS) a0 += part[(long long)p * E + e];
+            sum = (a0 + a1) + (a2 + a3);
+        }
     }
+    sh[w][lane] = sum;
     __syncthreads();
-    double tot[2] = {0.0, 0.0};
-    int idx = 0;
-    for (int e = threadIdx.x; e < E; e += blockDim.x, ++idx) {
-        double sum = 0.0;
+    if (w == 0 && e < E) {
+        double g = 0.0;
 #pragma unroll
-        for (int seg = 0; seg < BLU_GRAM_SEG; ++seg) sum += gsm[seg * E + e];
-        tot[idx & 1] = sum;                 // E <= 1600 <= 2 * blockDim
+        for (int ww = 0; ww < BLU_GRAM_FIN_WARPS; ++ww) g += sh[ww][lane];
+        G[e] = g;
     }
+    __threadfence();
     __syncthreads();
-    idx = 0;
-    for (int e = threadIdx.x; e < E; e += blockDim.x, ++idx) gsm[e] = tot[idx & 1];
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    const double *G = gsm;
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0u;                          // ready for the next call on this buffer
     const double dn = (double)n;
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
         const int r = t / N, c = t - r * N;
         const int lo = r < c ? r : c, hi = r < c ? c : r;
-        const double g = G[lo * NPG + hi];                 // upper triangle holds the sums
-        const double a = G[r * NPG + N], b = G[c * NPG + N];
+        const double g = __ldcg(G + lo * NPG + hi);              // upper triangle holds the sums
+        const double a = __ldcg(G + r * NPG + N), b = __ldcg(G + c * NPG + N);
         S2[t] = g;
         Chat[t] = g / dn - (a * b) / (dn * dn);
     }
-    for (int t = threadIdx.x; t < N; t += blockDim.x) s1[t] = G[t * NPG + N];
+    for (int t = threadIdx.x; t < N; t += blockDim.x) s1[t] = __ldcg(G + t * NPG + N);
 }
 
 template <int NT>
@@ -201,7 +218,10 @@ static int blu_gram_run(const double *Y, long long n, int N, int y_on_device, do
         if ((e = cudaMemcpyAsync(dY, Y, sizeof(double) * n * N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return done(BLU_ERR_CUDA);
     }
     if ((e = cudaMalloc(&d_part, sizeof(double) * NPG * NPG * grid)) != cudaSuccess) return done(BLU_ERR_NOMEM);
-    if ((e = cudaMalloc(&d_out, sizeof(double) * (2 * N * N + N))) != cudaSuccess) return done(BLU_ERR_NOMEM);
+    if ((e = cudaMalloc(&d_out, sizeof(double) * (2 * N * N + N + NPG * NPG + 2))) != cudaSuccess) return done(BLU_ERR_NOMEM);
+    double *d_G = d_out + 2 * N * N + N;                          // reduced Gram tile, then the ticket counter
+    unsigned *d_ticket = reinterpret_cast<unsigned *>(d_G + NPG * NPG);
+    if ((e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), st)) != cudaSuccess) return done(BLU_ERR_CUDA);
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
     switch (NT) {
@@ -212,11 +232,8 @@ static int blu_gram_run(const double *Y, long long n, int N, int y_on_device, do
         default: e = blu_gram_launch<5>(dY, n, N, grid, slab, d_part, st); break;
     }
     if (e != cudaSuccess) return done(BLU_ERR_CUDA);
-    {
-        const int fsm = (int)(sizeof(double) * NPG * NPG * BLU_GRAM_SEG);
-        if ((e = cudaFuncSetAttribute(blu_gram_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm)) != cudaSuccess) return done(BLU_ERR_CUDA);
-        blu_gram_finish_kernel<<<1, 1024, fsm, st>>>(d_part, grid, NPG, N, n, d_out, d_out + N, d_out + N + N * N);
-    }
+    blu_gram_finish_kernel<<<(NPG * NPG + 31) / 32, BLU_GRAM_FIN_WARPS * 32, 0, st>>>(d_part, grid, NPG, N, n, d_G, d_ticket,
+                                                                                     d_out, d_out + N, d_out + N + N * N);
     if ((e = cudaGetLastError()) != cudaSuccess) return done(BLU_ERR_CUDA);
     cudaEventRecord(e1, st);
     std::vector<double> h((size_t)(2 * N * N + N));

@@ -4,7 +4,8 @@
 // `hess += hess.T`; with u_i = R_i^T Cinv_i R_i x and v_i = 2 pinv(Phi) u_i (the rows of the U and V
 // factors the gradient pass leaves in HBM) that matrix is H[i][j] = v_i . u_j, so
 //
-//     (H p)_i = v_i . t,      t = sum_j p_j u_j          (two passes over L x NP doubles)
+//     (H p)_i = v_i . t = u_i . (S t),      t = sum_j p_j u_j,  S = 2 pinv(Phi)
+//                                                    (two passes over the L x NP doubles of U; V is not needed)
 //
 // which is all scipy's trust-constr (projected CG, sap.py:410) or a truncated-Newton step ever asks
 // of the Hessian.  At N = 15 the dense matrix is 8.59 GB (151 ms of PCIe per evaluation); the two
@@ -12,7 +13,7 @@
 // is the only form of the Hessian.
 //
 //   blu_hv_reduce_kernel : per-CTA partial sums of t over a row range, fixed association
-//   blu_hv_apply_kernel  : fixed-order sum of the partials, then one dot product per row
+//   blu_hv_apply_kernel  : fixed-order sum of the partials, s = S t, then one dot product per row
 // Both are HBM/L2 streams of one factor (8*NP*L bytes each); no atomics, bit-reproducible.
 #pragma once
 #include "blu_common.cuh"
@@ -82,18 +83,27 @@ blu_hv_fold_kernel(const double *__restrict__ part, int nparts, double *__restri
     if (threadIdx.x < 32) t_out[threadIdx.x] = t[threadIdx.x];
 }
 
-// out[i] = V[i] . t for i in [lo,hi), t folded from `nparts` partial vectors
+// out[i] = u_i . s for i in [lo,hi), s = S t (S = 2 pinv(Phi), N x N), t folded from `nparts` partial
+// vectors: H p = U S U^T p needs the U factor only.
 __global__ void __launch_bounds__(BLU_HV_THREADS)
-blu_hv_apply_kernel(const double *__restrict__ V, const double *__restrict__ part, int nparts, long long lo, long long hi,
-                    int NP, double *__restrict__ out)
+blu_hv_apply_kernel(const double *__restrict__ U, const double *__restrict__ S, int N, const double *__restrict__ part, int nparts,
+                    long long lo, long long hi, int NP, double *__restrict__ out)
 {
     __shared__ double sh[BLU_HV_THREADS];
+    __shared__ double tt[32];
     __shared__ double t[32];
     const int tid = threadIdx.x;
-    blu_hv_fold(part, nparts, sh, t);
+    blu_hv_fold(part, nparts, sh, tt);
+    if (tid < 32) {
+        double s = 0.0;
+        if (tid < N)
+            for (int b = 0; b < N; ++b) s = fma(__ldg(S + tid * N + b), tt[b], s);
+        t[tid] = s;
+    }
+    __syncthreads();
     const int nq = NP >> 1;
     for (long long i = lo + (long long)blockIdx.x * BLU_HV_THREADS + tid; i < hi; i += (long long)gridDim.x * BLU_HV_THREADS) {
-        const double2 *row = reinterpret_cast<const double2 *>(V + i * NP);
+        const double2 *row = reinterpret_cast<const double2 *>(U + i * NP);
         double a0 = 0.0, a1 = 0.0;
         for (int q = 0; q < nq; ++q) {
             const double2 v = __ldg(row + q);

@@ -239,6 +239,39 @@ struct BluPeers {
 };
 #define BLU_FIN_SEG 8
 
+// Pre-reduction of the CTA partials for the finish kernel: CTA b owns entries [32b, 32b+32) of the
+// N x N tile, its 8 warps sum interleaved subsets of the `nparts` partial tiles (coalesced rows, four
+// independent loads in flight per thread) and are combined in warp order -- a fixed association, so
+// the result is bit-reproducible.  One CTA doing this alone (the finish kernel) is latency-bound on
+// ~1 MB of partials; spread over NN/32 CTAs it takes a few microseconds.
+#define BLU_FOLD_WARPS 8
+__global__ void __launch_bounds__(BLU_FOLD_WARPS * 32)
+blu_phi_fold_kernel(const double *__restrict__ part, int nparts, int NN, double *__restrict__ out)
+{
+    __shared__ double sh[BLU_FOLD_WARPS][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 32 + lane;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (e < NN) {
+        int p = w;
+        for (; p + 3 * BLU_FOLD_WARPS < nparts; p += 4 * BLU_FOLD_WARPS) {
+            a0 += part[(long long)p * NN + e];
+            a1 += part[(long long)(p + BLU_FOLD_WARPS) * NN + e];
+            a2 += part[(long long)(p + 2 * BLU_FOLD_WARPS) * NN + e];
+            a3 += part[(long long)(p + 3 * BLU_FOLD_WARPS) * NN + e];
+        }
+        for (; p < nparts; p += BLU_FOLD_WARPS) a0 += part[(long long)p * NN + e];
+    }
+    sh[w][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (w == 0 && e < NN) {
+        double s = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < BLU_FOLD_WARPS; ++ww) s += sh[ww][lane];
+        out[e] = s;
+    }
+}
+
 // mode 0: reduce + mirror + delta only (get_phi).  mode 1: + pinv, x, S, variance.
 // mode 2: reduce only, no mirror/delta (partial Phi of a group slice, before the all-reduce).
 // nparts == 0: Phi already sits in `phi` as an un-mirrored upper-triangle sum (after all-reduce).

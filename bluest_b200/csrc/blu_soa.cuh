@@ -76,25 +76,47 @@ struct BluSoaCursor {
     BluTile d;        // descriptor of tile q
 };
 
-// WITHU = false: gradient only.  WITHU = true: gradient + U,V rows.
+// V rows from U rows: v_i = S u_i with S = 2 pinv(Phi) (N x N, symmetric), for rows [lo,hi).  One thread
+// per (row, column): a warp covers 32 consecutive doubles of V (coalesced), S lives in shared memory,
+// the U row is read through L1.  8 NP L bytes in, 8 NP L bytes out.
+__global__ void __launch_bounds__(256)
+blu_v_from_u_kernel(const double *__restrict__ U, const double *__restrict__ S, int N, int NP, long long lo, long long hi,
+                    double *__restrict__ V)
+{
+    __shared__ double sS[BLU_MAX_MODELS_C * BLU_MAX_MODELS_C];
+    for (int t = threadIdx.x; t < N * N; t += blockDim.x) sS[t] = S[t];
+    __syncthreads();
+    const long long total = (hi - lo) * NP;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const long long r = q / NP;
+        const int a = (int)(q - r * NP);
+        const double *ur = U + (lo + r) * NP;
+        double va = 0.0;
+        if (a < N) {
+#pragma unroll 4
+            for (int b = 0; b < N; ++b) va = fma(sS[a * N + b], __ldg(ur + b), va);
+        }
+        V[(lo + r) * NP + a] = va;
+    }
+}
+
+// WITHU = false: gradient only.  WITHU = true: gradient + U rows.
 template <bool WITHU>
 __global__ void __launch_bounds__(BLU_SOA_WARPS * 32)
 blu_grad_soa_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, int K,
                     const BluTile *__restrict__ tiles, int ntiles, const double *__restrict__ soa,
                     const long long *__restrict__ soff, const unsigned short *__restrict__ lut, int lutlen,
-                    const unsigned *__restrict__ gmask, const double *__restrict__ xrow, const double *__restrict__ S,
-                    long long lo, long long hi, double *__restrict__ grad, double *__restrict__ U, double *__restrict__ V)
+                    const unsigned *__restrict__ gmask, const double *__restrict__ xrow,
+                    long long lo, long long hi, double *__restrict__ grad, double *__restrict__ U)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    const BluSoaSmem sm = blu_soa_carve(smraw, K, WITHU, WITHU ? N * N + N : N, ncls, lutlen);
+    const BluSoaSmem sm = blu_soa_carve(smraw, K, WITHU, N, ncls, lutlen);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // block prologue
     for (int t = threadIdx.x; t < ncls; t += blockDim.x) sm.cls[t] = cls[t];
     for (int t = threadIdx.x; t < lutlen; t += blockDim.x) sm.lut[t] = lut[t];
     double *sx = sm.extra;                         // x (N)
-    double *sS = sm.extra + N;                     // S (N x N), U kernel only
     for (int t = threadIdx.x; t < N; t += blockDim.x) sx[t] = xrow[t];
-    if (WITHU) for (int t = threadIdx.x; t < N * N; t += blockDim.x) sS[t] = S[t];
     double *stage[2] = {sm.stages + (size_t)(2 * w) * BLU_SOA_STAGE, sm.stages + (size_t)(2 * w + 1) * BLU_SOA_STAGE};
     unsigned long long *bar[2] = {sm.bars + 2 * w, sm.bars + 2 * w + 1};
     double *xg = sm.xg + (size_t)w * K * 32;       // xg[j*32 + lane] = x[id_j(group of lane)]
@@ -188,23 +210,21 @@ blu_grad_soa_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, i
                 double gsum = 0.0;
                 for (int j = 0; j < k; ++j) gsum = fma(xg[j * 32 + lane], yv[j * 32 + lane], gsum);
                 if (live) grad[gi] = -gsum;
-                // U row: y scattered to model slots; V row: S u.  One group per lane, NP doubles per row.
-                if (live) {
-                    double *ur = U + gi * NP, *vr = V + gi * NP;
-                    int pos = 0;
-                    for (int a = 0; a < NP; ++a) {
-                        double ua = 0.0;
-                        if (a < N && ((mask >> a) & 1u)) { ua = yv[pos * 32 + lane]; ++pos; }
-                        ur[a] = ua;
-                    }
-                    for (int a = 0; a < NP; ++a) {
-                        double va = 0.0;
-                        if (a < N) {
-                            unsigned mk = mask; int j = 0;
-                            while (mk) { const int b = __ffs(mk) - 1; va = fma(sS[a * N + b], yv[j * 32 + lane], va); mk &= mk - 1u; ++j; }
-                        }
-                        vr[a] = va;
-                    }
+                // U rows: y scattered to model slots.  The tile's 32 groups are consecutive flat indices, so
+                // their rows are ONE contiguous span of 32 NP doubles: element idx = r NP + a is produced by
+                // lane idx & 31 from row r's mask (shuffle) and y (shared), and every store instruction
+                // writes 256 contiguous bytes.  (V = U S is a separate pass over U: blu_v_from_u_kernel.)
+                __syncwarp();
+                const long long g0 = ci.goff + cd.t * 32;                   // flat index of the tile's first group
+                const int nrow = (int)((ci.Lk - cd.t * 32) < 32 ? (ci.Lk - cd.t * 32) : 32);
+                double *ub = U + g0 * NP;
+                for (int idx = lane; idx < 32 * NP; idx += 32) {
+                    const int r = idx / NP, a = idx - r * NP;
+                    const unsigned mr = __shfl_sync(BLU_FULL, mask, r);
+                    double ua = 0.0;
+                    if ((mr >> a) & 1u) ua = yv[__popc(mr & ((1u << a) - 1u)) * 32 + r];
+                    const long long gr = g0 + r;
+                    if (r < nrow && gr >= lo && gr < hi) ub[idx] = ua;
                 }
             }
             cs = 0; cq += nw;

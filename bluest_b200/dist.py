@@ -116,9 +116,9 @@ class ShardedEvaluator:
         e = self.engine
         with e.stream_context():
             if self.replicate_front:
-                e.eval_full(m, delta, True, True)
+                e.eval_full(m, delta, True, 2)                     # 2: U rows only -- the operator never reads V
             else:
-                self._phi_exchange_finish(m, delta, True, True)
+                self._phi_exchange_finish(m, delta, True, 2)
         var, flags = e.result()
         return dict(var=var, flags=flags, lo=self.lo, hi=self.hi)
 
@@ -198,10 +198,10 @@ class GpuEngine:
     def eval_full(self, m, delta, want_grad, want_uv):
         """Whole-problem evaluation on this rank (no slice): Phi, pinv, variance, gradient and, if
         want_uv, the U,V factors -- but not the Hessian."""
-        _lib.check(_lib.lib().blu_eval_device(self.sap._ctx, self._m_ptr(m), float(delta), int(bool(want_grad)), 2 if want_uv else 0))
+        _lib.check(_lib.lib().blu_eval_device(self.sap._ctx, self._m_ptr(m), float(delta), int(bool(want_grad)), {0: 0, 1: 2, 2: 3}[int(want_uv)]))
 
     def shard_eval_fused(self, m, delta, want_grad, want_uv):
-        _lib.check(_lib.lib().blu_shard_eval_fused(self.sap._ctx, self._m_ptr(m), float(delta), int(bool(want_grad)), int(bool(want_uv))))
+        _lib.check(_lib.lib().blu_shard_eval_fused(self.sap._ctx, self._m_ptr(m), float(delta), int(bool(want_grad)), int(want_uv)))
 
     def shard_phi(self, m):
         if m is not None:
@@ -216,7 +216,7 @@ class GpuEngine:
         return self.sap.device_buffer(_lib.BUF_PHI)
 
     def shard_finish(self, delta, want_grad, want_uv):
-        _lib.check(_lib.lib().blu_shard_finish(self.sap._ctx, float(delta), int(bool(want_grad)), int(bool(want_uv))))
+        _lib.check(_lib.lib().blu_shard_finish(self.sap._ctx, float(delta), int(bool(want_grad)), int(want_uv)))
 
     def shard_hess(self, rlo, rhi):
         _lib.check(_lib.lib().blu_shard_hess(self.sap._ctx, int(rlo), int(rhi)))

@@ -147,7 +147,8 @@ int blu_candidate_variances(blu_ctx *ctx, const double *basephi, int LL, const i
 
 /* Device-resident evaluation: d_m lives on the context's device (or NULL to reuse BLU_BUF_M).
  * want_grad / want_hess select the work (want_hess == 2: the U,V factors only, no Hessian -- the
- * caller then asks for row panels with blu_shard_hess); results stay in the context's buffers
+ * caller then asks for row panels with blu_shard_hess; want_hess == 3: the U factor only, all the
+ * Hessian operator needs: H p = U (S (U^T p)), S = 2 pinv(Phi)); results stay in the context's buffers
  * (blu_ctx_device_ptr).  The call is asynchronous on the context's stream. */
 int blu_eval_device(blu_ctx *ctx, const double *d_m, double delta, int want_grad, int want_hess);
 int blu_ctx_sync(blu_ctx *ctx);
@@ -178,6 +179,7 @@ int blu_ctx_last_launches(blu_ctx *ctx);
  *   blu_shard_phi      partial Phi of the slice -> BLU_BUF_PHI (N*N doubles, no delta, no pinv)
  *   (all-reduce BLU_BUF_PHI across ranks)
  *   blu_shard_finish   delta*I, pinv, variance on the reduced Phi; grad and U,V rows of the slice
+ *                      (want_uv: 0 none, 1 U and V, 2 U only -- enough for blu_shard_hv_*)
  *   (all-gather U,V rows)
  *   blu_shard_hess     rows [row_lo,row_hi) of the Hessian against all L columns.  Once U,V are
  *                      gathered any rank can produce any rows, so the row panels are balanced by

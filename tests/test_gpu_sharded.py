@@ -134,7 +134,7 @@ def test_sliced_hessian_operator(N, K, cuts):
         buf = e.shard_phi(m)                                  # full Phi on every context (slice not yet set)
         sap.sync()
         e.set_slice(lo, hi)
-        e.shard_finish(0.0, True, True)                       # gradient, U, V rows of the slice only
+        e.shard_finish(0.0, True, 2)                          # gradient and U rows of the slice only (2: no V)
         sap.sync()
         engines.append(e)
     pd = torch.from_numpy(p).cuda()

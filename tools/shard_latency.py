@@ -30,4 +30,5 @@ for w in (1, 2, 4, 8):
         t_fin = timeit(lambda: eng.shard_finish(0.0, False, False))
         t_all = timeit(lambda: (eng.shard_phi(m), eng.shard_finish(0.0, True, False)))
         t_uv = timeit(lambda: (eng.shard_phi(m), eng.shard_finish(0.0, True, True)))
-        print("N=%d world=%d rank=%d groups=%d: phi %.1f us, finish %.1f us, phi+finish+grad %.1f us, +U,V %.1f us" % (N, w, r, sl[r][1] - sl[r][0], t_phi, t_fin, t_all, t_uv))
+        t_u = timeit(lambda: (eng.shard_phi(m), eng.shard_finish(0.0, True, 2)))
+        print("N=%d world=%d rank=%d groups=%d: phi %.1f us, finish %.1f us, phi+finish+grad %.1f us, +U,V %.1f us, +U only %.1f us" % (N, w, r, sl[r][1] - sl[r][0], t_phi, t_fin, t_all, t_uv, t_u), flush=True)
