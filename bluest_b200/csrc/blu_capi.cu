@@ -21,7 +21,7 @@
 #include "blu_launch.h"
 #include "blu_phi.cuh"
 #include "blu_grad.cuh"
-#include "blu_soa.cuh"
+#include "blu_soa_types.h"
 #include "blu_hess.cuh"
 #include "blu_matvec.cuh"
 #include "blu_gram.cuh"
@@ -527,8 +527,8 @@ static int ensure_soa(blu_ctx *c)
             const BluClass &ci = c->cls[ic];
             const long long total = ((ci.Lk + 31) / 32) * 32 * ci.T;
             const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->nsm * 16));
-            blu_soa_build_kernel<<<grid, 256, 0, c->stream>>>(c->d_cinv + ci.coff, ci.Lk, ci.T, c->d_soa + c->soff[ic]);
-            KERNEL_CHECK(c);
+            CUDA_TRY(blu_launch_soa_build(grid, c->stream, c->d_cinv + ci.coff, ci.Lk, ci.T, c->d_soa + c->soff[ic]));
+            c->launches++;
         }
         c->soa_valid = true;
     }
@@ -561,8 +561,8 @@ static int launch_v_from_u(blu_ctx *c)
     const long long total = (c->hi - c->lo) * c->NP;
     if (total <= 0) return BLU_OK;
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->nsm * 8));
-    blu_v_from_u_kernel<<<grid, 256, 0, c->stream>>>(c->d_U, c->d_S, c->N, c->NP, c->lo, c->hi, c->d_V);
-    KERNEL_CHECK(c);
+    CUDA_TRY(blu_launch_v_from_u(grid, c->stream, c->d_U, c->d_S, c->N, c->NP, c->lo, c->hi, c->d_V));
+    c->launches++;
     return BLU_OK;
 }
 
@@ -577,22 +577,9 @@ static int launch_grad(blu_ctx *c, int uv)
         int rc = ensure_soa(c);
         if (rc) return rc;
         if (want_uv && (rc = ensure_uv(c))) return rc;
-        const int ncl = (int)c->cls.size();
-        if (!want_uv) {
-            const size_t smem = blu_soa_smem_bytes(c->K, false, c->N, ncl, c->lutlen);
-            CUDA_TRY(cudaFuncSetAttribute(blu_grad_soa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            blu_grad_soa_kernel<false><<<c->grid_soa, BLU_SOA_WARPS * 32, smem, c->stream>>>(
-                c->d_cls, ncl, c->N, c->NP, c->K, c->d_tiles, c->ntiles, c->d_soa, c->d_soff, c->d_lut, c->lutlen, c->d_gmask,
-                c->d_x, c->lo, c->hi, c->d_grad, nullptr);
-            KERNEL_CHECK(c);
-            return BLU_OK;
-        }
-        const size_t smem = blu_soa_smem_bytes(c->K, true, c->N, ncl, c->lutlen);
-        CUDA_TRY(cudaFuncSetAttribute(blu_grad_soa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        blu_grad_soa_kernel<true><<<c->grid_soa, BLU_SOA_WARPS * 32, smem, c->stream>>>(
-            c->d_cls, ncl, c->N, c->NP, c->K, c->d_tiles, c->ntiles, c->d_soa, c->d_soff, c->d_lut, c->lutlen, c->d_gmask,
-            c->d_x, c->lo, c->hi, c->d_grad, c->d_U);
-        KERNEL_CHECK(c);
+        CUDA_TRY(blu_launch_grad_soa(want_uv, c->grid_soa, c->stream, c->d_cls, (int)c->cls.size(), c->N, c->NP, c->K, c->d_tiles, c->ntiles,
+                                     c->d_soa, c->d_soff, c->d_gmask, c->d_x, c->lo, c->hi, c->d_grad, want_uv ? c->d_U : nullptr));
+        c->launches++;
         return uv == 1 ? launch_v_from_u(c) : BLU_OK;
     }
     if (!want_uv) {
