@@ -430,6 +430,31 @@ def secondary_configs(device=0):
     peak, _ = peaks()
     out["n20_nohess"] = {"models": N, "groups": L, "us_per_eval": t * 1e6, "evals_per_s": 1.0 / t,
                          "algorithmic_GBps": algo / t / 1e9, "roofline_frac": algo / t / 1e9 / peak}
+    # the Hessian at 20 models exists only as an operator: factored evaluation (Phi, pinv, gradient, U) + products H p
+    ext = torch.cuda.ExternalStream(sap.stream(), device=device)
+    NP = 4 * ((N + 3) // 4)
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        sap.sync()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(n):
+            fn()
+        e1.record(ext)
+        sap.sync()
+        return e0.elapsed_time(e1) / n * 1e-3
+    from bluest_b200 import _lib as _bl
+    import ctypes as _ct
+    t_fac = timed(lambda: _bl.check(_bl.lib().blu_eval_device(sap._ctx, _ct.c_void_p(int(m.data_ptr())), 0.0, 1, 3)), 20)
+    pv = torch.randn(L, dtype=torch.float64, device="cuda:%d" % device); hp = torch.empty_like(pv)
+    t_mv = timed(lambda: sap.hess_matvec_device(pv, hp), 50)
+    out["n20_operator"] = {"factored_eval_us": t_fac * 1e6, "hess_matvec_us": t_mv * 1e6,
+                           "factored_eval_algorithmic_GBps": (algo + 8.0 * NP * L) / t_fac / 1e9,
+                           "hess_matvec_GBps": (16.0 * NP * L + 16.0 * L) / t_mv / 1e9,
+                           "hess_matvec_roofline_frac": (16.0 * NP * L + 16.0 * L) / t_mv / 1e9 / peak,
+                           "note": "H p = U (S (U^T p)): two passes over the (L, NP) U factor (168 MB); the dense matrix would be 8.8 TB"}
     sap.close()
     del groups
     # config 5b: pilot covariance, 1e6 samples x 20 models (device-resident Y)

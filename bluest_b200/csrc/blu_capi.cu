@@ -937,28 +937,39 @@ extern "C" int blu_variance_GH(blu_ctx *c, const double *m, double delta, double
 static int ensure_hv(blu_ctx *c)
 {
     if (c->d_hvpart) return BLU_OK;
-    CUDA_TRY(cudaMalloc(&c->d_hvpart, sizeof(double) * 32 * (size_t)c->nsm * 4));
+    // CTA partials (32 doubles each) | folded t (32 doubles) | ticket counter
+    CUDA_TRY(cudaMalloc(&c->d_hvpart, sizeof(double) * (32 * (size_t)c->nsm * 8 + 32 + 2)));
+    CUDA_TRY(cudaMemsetAsync(c->d_hvpart, 0, sizeof(double) * (32 * (size_t)c->nsm * 8 + 32 + 2), c->stream));
     CUDA_TRY(cudaMalloc(&c->d_hvp, sizeof(double) * c->L));
     CUDA_TRY(cudaMalloc(&c->d_hvout, sizeof(double) * c->L));
     return BLU_OK;
 }
 
-static int launch_hv_reduce(blu_ctx *c, const double *d_p, double *d_part, int *nparts)
+// t (32 doubles at d_t) = sum over the owned rows of p_i u_i
+static int launch_hv_reduce(blu_ctx *c, const double *d_p, double *d_t)
 {
     const long long rows = c->hi - c->lo;
-    const int rpp = BLU_HV_THREADS / c->NP;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + (long long)rpp * BLU_HV_UNROLL - 1) / ((long long)rpp * BLU_HV_UNROLL), (long long)c->nsm * 4));
-    blu_hv_reduce_kernel<<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_U, d_p, c->lo, c->hi, c->NP, d_part);
+    const int rpp = BLU_HV_THREADS / (c->NP / 2);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + (long long)rpp * BLU_HV_UNROLL - 1) / ((long long)rpp * BLU_HV_UNROLL), (long long)c->nsm * 8));
+    unsigned *ticket = reinterpret_cast<unsigned *>(c->d_hvpart + 32 * (size_t)c->nsm * 8 + 32);
+    switch (c->NP) {
+#define HV_CASE(P) case P: blu_hv_reduce_kernel<P><<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_U, d_p, c->lo, c->hi, c->d_hvpart, ticket, d_t); break;
+        HV_CASE(4) HV_CASE(8) HV_CASE(12) HV_CASE(16) HV_CASE(20) HV_CASE(24) HV_CASE(28) HV_CASE(32)
+#undef HV_CASE
+    }
     KERNEL_CHECK(c);
-    *nparts = grid;
     return BLU_OK;
 }
 
-static int launch_hv_apply(blu_ctx *c, const double *d_part, int nparts, double *d_out)
+static int launch_hv_apply(blu_ctx *c, const double *d_t, double *d_out)
 {
     const long long rows = c->hi - c->lo;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + BLU_HV_THREADS - 1) / BLU_HV_THREADS, (long long)c->nsm * 8));
-    blu_hv_apply_kernel<<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_U, c->d_S, c->N, d_part, nparts, c->lo, c->hi, c->NP, d_out);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + BLU_HVA_THREADS - 1) / BLU_HVA_THREADS, (long long)c->nsm * 8));
+    switch (c->NP) {
+#define HV_CASE(P) case P: blu_hv_apply_kernel<P><<<grid, BLU_HVA_THREADS, 0, c->stream>>>(c->d_U, c->d_S, c->N, d_t, c->lo, c->hi, d_out); break;
+        HV_CASE(4) HV_CASE(8) HV_CASE(12) HV_CASE(16) HV_CASE(20) HV_CASE(24) HV_CASE(28) HV_CASE(32)
+#undef HV_CASE
+    }
     KERNEL_CHECK(c);
     return BLU_OK;
 }
@@ -977,9 +988,9 @@ extern "C" int blu_hess_matvec_device(blu_ctx *c, const double *d_p, double *d_o
     if (!d_p || !d_out) return fail(BLU_ERR_ARG, "null argument");
     if (c->lo != 0 || c->hi != c->L) return fail(BLU_ERR_STATE, "context owns a slice: use blu_shard_hv_partial / blu_shard_hv_apply");
     if ((rc = hv_ready(c))) return rc;
-    int np = 0;
-    if ((rc = launch_hv_reduce(c, d_p, c->d_hvpart, &np))) return rc;
-    return launch_hv_apply(c, c->d_hvpart, np, d_out);
+    double *d_t = c->d_hvpart + 32 * (size_t)c->nsm * 8;
+    if ((rc = launch_hv_reduce(c, d_p, d_t))) return rc;
+    return launch_hv_apply(c, d_t, d_out);
 }
 
 // Host pointers: out[v*L + i] = (H p_v)_i for nvec vectors stored one after the other.
@@ -1029,12 +1040,7 @@ extern "C" int blu_shard_hv_partial(blu_ctx *c, const double *d_p, double *d_t)
     if (rc) return rc;
     if (!d_p || !d_t) return fail(BLU_ERR_ARG, "null argument");
     if ((rc = hv_ready(c))) return rc;
-    int np = 0;
-    if ((rc = launch_hv_reduce(c, d_p, c->d_hvpart, &np))) return rc;
-    // fold the CTA partials into one vector with the apply kernel's fixed-order prologue (no rows)
-    blu_hv_fold_kernel<<<1, BLU_HV_THREADS, 0, c->stream>>>(c->d_hvpart, np, d_t);
-    KERNEL_CHECK(c);
-    return BLU_OK;
+    return launch_hv_reduce(c, d_p, d_t);
 }
 
 extern "C" int blu_shard_hv_apply(blu_ctx *c, const double *d_t, double *d_out)
@@ -1043,7 +1049,7 @@ extern "C" int blu_shard_hv_apply(blu_ctx *c, const double *d_t, double *d_out)
     if (rc) return rc;
     if (!d_t || !d_out) return fail(BLU_ERR_ARG, "null argument");
     if ((rc = hv_ready(c))) return rc;
-    return launch_hv_apply(c, d_t, 1, d_out);
+    return launch_hv_apply(c, d_t, d_out);
 }
 
 extern "C" int blu_cleanup_matrix(blu_ctx *c, const double *m, double delta, int mode, double *X, unsigned *flags)
