@@ -254,7 +254,7 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": desc},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def _hess_d2h_bytes(L, panel=1024):
@@ -641,7 +641,7 @@ def run_ours(args):
                     out["secondary_configs"] = secondary_configs(device=local)
                 except Exception as ex:
                     out["secondary_configs"] = {"failed": repr(ex)}
-        print(json.dumps(out))
+        emit(out)
     sap.close()
     if world > 1:
         dist.barrier()
@@ -714,14 +714,37 @@ def run_shard(args):
                             "frac": algo / (per * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + " x n_gpus",
                             "algorithmic_bytes_per_eval": algo},
                "variance_check": var}
-        print(json.dumps(out))
+        emit(out)
     sap.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route file descriptor 1 to stderr for the whole run: libraries (NCCL prints its version banner on
+    stdout at communicator creation) must not put anything next to the ONE JSON line of the contract."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -98,6 +98,7 @@ struct blu_ctx {
     double *pend_hess = nullptr;       // host destination of the pending evaluation's Hessian
     bool pending = false;
     std::vector<cudaEvent_t> panel_ev; // one event per Hessian row panel (symmetric download)
+    int mirror_threads = 0;            // 0: automatic (see download_hessian_symmetric)
     bool sym_download = true;          // dense Hessian to the host: upper block-triangle over PCIe, lower mirrored by host threads
     BluXchg *d_xchg = nullptr;         // this rank's exchange buffer (CUDA IPC shared)
     BluPeers peers{};                  // peers as mapped here; world == 0: not connected
@@ -754,11 +755,13 @@ extern "C" int blu_ctx_last_launches(blu_ctx *c) { return c ? c->launches : 0; }
 // panels are in flight.  On the B200 box (16 host cores, PCIe 57 GB/s) one N = 15 evaluation end to
 // end takes 97-125 ms instead of 152-170 ms; the limit is the host's memory bandwidth (4.3 GB of DMA
 // writes + 8.6 GB of mirror traffic).  0 = one plain 2-D copy of all 8 L^2 bytes.
+//          "mirror_threads" (default 0 = automatic: min(16, cores) / LOCAL_WORLD_SIZE, at least 2).
 extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
 {
     if (!c || !name) return fail(BLU_ERR_ARG, "null argument");
     if (!strcmp(name, "sym_download")) { c->sym_download = value != 0; return BLU_OK; }
     if (!strcmp(name, "soa")) { c->use_soa = value != 0; return BLU_OK; }
+    if (!strcmp(name, "mirror_threads")) { c->mirror_threads = value; return BLU_OK; }
     return fail(BLU_ERR_ARG, "unknown option %s", name);
 }
 
@@ -834,7 +837,14 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
                                    sizeof(double) * (L - r0), (size_t)(r1 - r0), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaEventRecord(c->panel_ev[p], c->stream));
     }
-    const int nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    // host threads for the mirroring: all cores (at most 16), shared fairly when torchrun runs one rank per GPU
+    int nthreads = c->mirror_threads;
+    if (nthreads <= 0) {
+        nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const char *lws = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lws ? atoi(lws) : 1;
+        if (ranks > 1) nthreads = std::max(2, nthreads / ranks);
+    }
     std::vector<std::atomic<int>> ready(npan), next(npan);
     for (int p = 0; p < npan; ++p) { ready[p].store(0); next[p].store(0); }
     const long long CW = 512;                                     // columns per work item

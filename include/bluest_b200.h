@@ -168,7 +168,8 @@ int blu_ctx_timing_read(blu_ctx *ctx, float *ms, int *n);
  * inverses, one group per lane (0: the entry-per-lane kernels on the group-major copy).
  * "sym_download" (default 1, used when L >= 4096): blu_variance_GH moves only the upper
  * block-triangle of the (exactly symmetric) dense Hessian over PCIe and mirrors it with host threads
- * (0: one plain copy of all 8 L^2 bytes). */
+ * (0: one plain copy of all 8 L^2 bytes).  "mirror_threads" (default 0 = automatic): host threads of
+ * that mirroring. */
 int blu_ctx_set_option(blu_ctx *ctx, const char *name, int value);
 /* Number of kernels the last evaluation launched. */
 int blu_ctx_last_launches(blu_ctx *ctx);
