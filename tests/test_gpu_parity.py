@@ -558,7 +558,7 @@ def test_setup_from_graph_file_reproduces_hodgkin_huxley(blu):
     assert abs(d["samples"] @ mos.costs - float(d["total_cost"])) < 1e-6
 
 
-@pytest.mark.parametrize("N,K,seed", [(6, 6, 0), (10, 10, 1), (12, 5, 2), (13, 13, 3), (9, 4, 4)])
+@pytest.mark.parametrize("N,K,seed", [(1, 1, 7), (3, 3, 5), (6, 6, 0), (10, 10, 1), (12, 5, 2), (13, 13, 3), (9, 4, 4), (17, 3, 6), (14, 14, 8)])
 def test_hessian_operator_equals_dense_hessian(blu, N, K, seed):
     """variance_GH_operator: same variance / gradient, and hess @ p equals the reference's dense Hessian
     (oracle: the loop nest of cmisc.cpp:74-97 on small cases, its factored identity otherwise) times p --
