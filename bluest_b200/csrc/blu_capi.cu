@@ -87,7 +87,8 @@ struct blu_ctx {
     int nchunks = 0, lutlen = 0, part_rows = 0, phi_warps = BLU_PHI_WARPS;
     int sd = BLU_CHUNK_DOUBLES + 4;    // stage size (doubles) of the streaming kernels
     bool have_inv = false;
-    bool hess_attr_done[2] = {false, false};
+    bool hess_attr_done[3] = {false, false, false};
+    bool hess_onebuf = true;           // symmetric Hessian kernel: single staging buffer, 4 CTAs per SM (blu_hess.cuh)
     std::vector<char> inv_set;         // per class: inverses present
     long long lo = 0, hi = 0;          // owned slice of the flat enumeration
     cudaStream_t stream = nullptr;
@@ -602,21 +603,24 @@ static int launch_grad(blu_ctx *c, int uv)
 template <int NCH>
 static void launch_hess_t(blu_ctx *c, bool sym, const double *Ua, long long Lrows, double *H)
 {
-    if (!c->hess_attr_done[sym]) {          // per context: function attributes are per device
-        if (sym) cudaFuncSetAttribute(blu_hess_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM);
-        else cudaFuncSetAttribute(blu_hess_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM);
-        c->hess_attr_done[sym] = true;
+    const int which = sym ? (c->hess_onebuf ? 2 : 1) : 0;
+    if (!c->hess_attr_done[which]) {          // per context: function attributes are per device
+        if (which == 2) cudaFuncSetAttribute(blu_hess_kernel<NCH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM1);
+        else if (which == 1) cudaFuncSetAttribute(blu_hess_kernel<NCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM2);
+        else cudaFuncSetAttribute(blu_hess_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLU_HESS_SMEM1);
+        c->hess_attr_done[which] = true;
     }
     const int nTc = (int)((c->L + BLU_HT - 1) / BLU_HT);
     if (sym) {
         const int nB = (nTc + BLU_HSB - 1) / BLU_HSB;
         dim3 grid(BLU_HSB * BLU_HSB, (unsigned)((long long)nB * (nB + 1) / 2));
-        blu_hess_kernel<NCH, true><<<grid, 128, BLU_HESS_SMEM, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
+        if (c->hess_onebuf) blu_hess_kernel<NCH, true, true><<<grid, 128, BLU_HESS_SMEM1, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
+        else blu_hess_kernel<NCH, true, false><<<grid, 128, BLU_HESS_SMEM2, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
     } else {
         const int nTr = (int)((Lrows + BLU_HT - 1) / BLU_HT);
         dim3 grid((unsigned)nTc, (unsigned)nTr);
         // row panels stage only the normal orientation: half the shared memory, more CTAs per SM
-        blu_hess_kernel<NCH, false><<<grid, 128, BLU_HT * BLU_HLDN * 8, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
+        blu_hess_kernel<NCH, false><<<grid, 128, BLU_HESS_SMEM1, c->stream>>>(Ua, c->d_V, Lrows, c->L, c->ldH, H, nTc, 0);
     }
 }
 
@@ -762,6 +766,7 @@ extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
     if (!strcmp(name, "sym_download")) { c->sym_download = value != 0; return BLU_OK; }
     if (!strcmp(name, "soa")) { c->use_soa = value != 0; return BLU_OK; }
     if (!strcmp(name, "mirror_threads")) { c->mirror_threads = value; return BLU_OK; }
+    if (!strcmp(name, "hess_onebuf")) { c->hess_onebuf = value != 0; return BLU_OK; }
     return fail(BLU_ERR_ARG, "unknown option %s", name);
 }
 

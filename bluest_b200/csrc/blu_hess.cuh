@@ -27,7 +27,12 @@
 #endif
 #define BLU_HLDN 72            // staging pitch, normal tile   (72*8 B: rows 2 apart never share a bank phase)
 #define BLU_HLDT 66            // staging pitch, transposed tile
-#define BLU_HESS_SMEM ((BLU_HT * BLU_HLDN + BLU_HT * BLU_HLDT) * 8)
+// Staging variants of the symmetric kernel (template parameter ONEBUF):
+//   false: normal and transposed image staged side by side (70.6 KB, 3 CTAs per SM)
+//   true : the transposed image is staged in the SAME buffer after the normal one has been stored
+//          (36.9 KB and two more barriers per tile, 4 CTAs per SM)
+#define BLU_HESS_SMEM1 (BLU_HT * BLU_HLDN * 8)
+#define BLU_HESS_SMEM2 ((BLU_HT * BLU_HLDN + BLU_HT * BLU_HLDT) * 8)
 
 __device__ __forceinline__ void blu_dmma(double &c0, double &c1, double a, double b)
 {
@@ -35,15 +40,15 @@ __device__ __forceinline__ void blu_dmma(double &c0, double &c1, double a, doubl
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int NCH, bool SYM>
-__global__ void __launch_bounds__(128, SYM ? 3 : 5)
+template <int NCH, bool SYM, bool ONEBUF = false>
+__global__ void __launch_bounds__(128, SYM ? (ONEBUF ? 4 : 3) : 5)
 blu_hess_kernel(const double *__restrict__ U, const double *__restrict__ V, long long Lrows,
                 long long Lcols, long long ldH, double *__restrict__ H, int nT, int tI0)
 {
     constexpr int NP = 4 * NCH;
     extern __shared__ double hsm[];
     double *sN = hsm;
-    double *sT = hsm + BLU_HT * BLU_HLDN;
+    double *sT = ONEBUF ? hsm : hsm + BLU_HT * BLU_HLDN;
 
     int I, J;
     if (SYM) {
@@ -114,7 +119,7 @@ blu_hess_kernel(const double *__restrict__ U, const double *__restrict__ V, long
             const int row = wy * 32 + rb * 8 + gq;
             const int col = wx * 32 + cb * 8 + 2 * s;
             *reinterpret_cast<double2 *>(sN + row * BLU_HLDN + col) = make_double2(c[rb][cb][0], c[rb][cb][1]);
-            if (offdiag) {
+            if (offdiag && !ONEBUF) {
                 sT[col * BLU_HLDT + row] = c[rb][cb][0];
                 sT[(col + 1) * BLU_HLDT + row] = c[rb][cb][1];
             }
@@ -143,6 +148,19 @@ blu_hess_kernel(const double *__restrict__ U, const double *__restrict__ V, long
         }
     }
     if (offdiag) {
+        if (ONEBUF) {
+            __syncthreads();                             // normal image read out: the buffer is free
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    const int row = wy * 32 + rb * 8 + gq;
+                    const int col = wx * 32 + cb * 8 + 2 * s;
+                    sT[col * BLU_HLDT + row] = c[rb][cb][0];
+                    sT[(col + 1) * BLU_HLDT + row] = c[rb][cb][1];
+                }
+            __syncthreads();
+        }
 #pragma unroll 4
         for (int r = w; r < BLU_HT; r += 4) {
             const long long grow = (long long)J * BLU_HT + r;
