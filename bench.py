@@ -603,7 +603,7 @@ def run_ours(args):
                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "impl": "ours",
                "config": workload_config(N, L),
-               "roofline": {"bound": "hbm", "kernel": "blu_hess_kernel<4,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+               "roofline": {"bound": "hbm", "kernel": "blu_hess_kernel<4,true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                             "avg_launch_ms": hess_ms, "peak_source": peak_src,
                             "whole_eval_frac": (8.0 * L * L + 16.0 * N * L + 16.0 * 8 * N * (N + 1) * 2 ** (N - 2) + 24.0 * L)
