@@ -871,7 +871,11 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
     const bool dbg = getenv("BLU_DEBUG_TIMING") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
-    for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+    try {
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+    } catch (...) {                                               // thread creation failed: mirror with what we have (or inline)
+    }
+    const bool inline_mirror = pool.empty();
     cudaError_t err = cudaSuccess;
     for (int p = 0; p < npan; ++p) {
         if (err == cudaSuccess) err = cudaEventSynchronize(c->panel_ev[p]);
@@ -879,6 +883,7 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
         if (dbg && (p == 0 || p == npan / 2 || p == npan - 1))
             fprintf(stderr, "[blu] panel %d arrived at %.1f ms\n", p, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     }
+    if (inline_mirror) worker();                                  // no helper thread could be started
     for (auto &t : pool) t.join();
     if (dbg) fprintf(stderr, "[blu] mirror done at %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     if (err != cudaSuccess) return fail(BLU_ERR_CUDA, "Hessian download: %s", cudaGetErrorString(err));
@@ -1189,6 +1194,7 @@ extern "C" int blu_ctx_set_slice(blu_ctx *c, int64_t lo, int64_t hi)
     if (rc) return rc;
     c->lo = lo; c->hi = hi;
     c->tiles_valid = false;
+    c->uv_ready = false; c->v_ready = false;      // factors of another slice are not this slice's factors
     return build_chunks(c);
 }
 
