@@ -61,9 +61,30 @@ def union_groups(multi_groups):
 
 
 def group_costs(groups, model_costs):
-    """blue_models.py:137-140."""
+    """blue_models.py:137-140: cost of a group = ``sum(model_costs[group])``.  Vectorised per size class,
+    adding the members in order (0 + c[g0] + c[g1] + ...) exactly like Python's ``sum``, so the result is
+    bit-identical to the reference's (a pairwise ``ndarray.sum`` would round differently from 8 members on)."""
     mc = np.asarray(model_costs)
-    return np.array([sum(mc[list(g)]) for gk in groups for g in gk])
+    out = []
+    for gk in groups:
+        arr = np.asarray(gk, dtype=np.int64)
+        if arr.size == 0:
+            continue
+        arr = arr.reshape(len(gk), -1)
+        acc = np.zeros(arr.shape[0], dtype=np.result_type(mc.dtype, np.int64) if mc.dtype.kind in "iu" else mc.dtype)
+        for j in range(arr.shape[1]):
+            acc = acc + mc[arr[:, j]]
+        out.append(acc)
+    return np.concatenate(out) if out else np.zeros(0)
+
+
+def _class_keys(gk):
+    """One integer key per group of a size class: the membership bit mask (models < 63)."""
+    arr = np.asarray(gk, dtype=np.int64)
+    if arr.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    arr = arr.reshape(len(gk), -1)
+    return np.bitwise_or.reduce(np.left_shift(np.int64(1), arr), axis=1)
 
 
 def indicator_ES(group_arrays, N):
@@ -85,20 +106,32 @@ def mappings(groups, multi_groups):
     (mosap.py:54-67); dictionary look-up instead of the reference's O(L^2) scan."""
     sizes = [0] + [len(gk) for gk in groups]
     cum = np.cumsum(sizes)
-    where = {}
+    # per size class: membership masks of the union, sorted once; every output's groups are located by
+    # binary search (the reference scans the union list for every group, mosap.py:59: O(L^2))
+    table = {}
     for k, gk in enumerate(groups):
-        for j, g in enumerate(gk):
-            where[tuple(int(v) for v in g)] = int(cum[k] + j)
+        if len(gk):
+            keys = _class_keys(gk)
+            order = np.argsort(keys, kind="stable")
+            table[len(gk[0])] = (keys[order], order, int(cum[k]))
     out = []
     for mg in multi_groups:
         pos = []
         for gk in mg:
-            for g in gk:
-                key = tuple(int(v) for v in g)
-                if key not in where:
-                    raise AssertionError("group %s of an output is missing from the union" % (key,))
-                pos.append(where[key])
-        out.append(np.array(pos, dtype=np.int64))
+            if len(gk) == 0:
+                continue
+            size = len(gk[0])
+            keys = _class_keys(gk)
+            if size not in table:
+                raise AssertionError("group %s of an output is missing from the union" % (tuple(int(v) for v in gk[0]),))
+            skeys, order, off = table[size]
+            at = np.searchsorted(skeys, keys)
+            at = np.minimum(at, len(skeys) - 1)
+            bad = skeys[at] != keys
+            if bad.any():
+                raise AssertionError("group %s of an output is missing from the union" % (tuple(int(v) for v in gk[int(np.argmax(bad))]),))
+            pos.append(off + order[at])
+        out.append(np.concatenate(pos).astype(np.int64) if pos else np.zeros(0, dtype=np.int64))
     return out
 
 
