@@ -285,3 +285,84 @@ def test_multi_output_cleanup_solution_host_logic():
     assert (out > 0).sum() < (m > 0).sum()
     assert out @ mos.costs <= m @ mos.costs * (1 + 1e-12)
     assert max(mos.variances(out)) <= max(d[f"{tag}/cleanup_variances_before"]) * (1 + 1e-4)
+
+
+def test_group_costs_and_mappings_vectorised_equal_the_reference_forms():
+    """groups.group_costs must be bit-identical to ``sum(model_costs[group])`` (blue_models.py:137-140)
+    and groups.mappings to the reference's linear scan (mosap.py:54-67), also for ragged per-output
+    group lists, integer costs and missing groups."""
+    from bluest_b200.groups import enumerate_groups, group_costs, mappings
+    rng = np.random.RandomState(0)
+    N = 11
+    groups = enumerate_groups(N, 9)
+    mc = rng.rand(N) * 10
+    ref = np.array([sum(mc[list(g)]) for gk in groups for g in gk])
+    assert np.array_equal(group_costs(groups, mc), ref)
+    mci = rng.randint(1, 100, size=N)
+    refi = np.array([sum(mci[list(g)]) for gk in groups for g in gk])
+    got = group_costs(groups, mci)
+    assert np.array_equal(got, refi) and got.dtype.kind == "i"
+    assert group_costs([[], [[0, 1]]], mc)[0] == mc[0] + mc[1]
+    # ragged outputs: random subsets of every size class, shuffled order inside a class
+    flat = [g for gk in groups for g in gk]
+    multi = []
+    for n in range(3):
+        mg = []
+        for gk in groups:
+            take = [gk[i] for i in rng.permutation(len(gk))[: max(1, len(gk) // (n + 2))]]
+            mg.append(take)
+        multi.append(mg)
+    maps = mappings(groups, multi)
+    for n in range(3):
+        want = np.array([flat.index(g) for gk in multi[n] for g in gk])
+        assert np.array_equal(maps[n], want) and maps[n].dtype == np.int64
+    with pytest.raises(AssertionError):
+        mappings(enumerate_groups(N, 2), [[[[0]], [[0, 1]], [[0, 1, 2]]]])
+    with pytest.raises(AssertionError):
+        mappings([[[0], [1]], [[0, 1]]], [[[[2]]]])
+
+
+@pytest.mark.parametrize("mode", ["budget", "eps"])
+def test_multi_output_scipy_driver_variants(mode):
+    """solvers.scipy_solve_multi on oracle-backed outputs: the dense driver of mosap.py:555-610, the
+    Hessian-operator driver and sparse constraint rows reach the same optimum; the reference's
+    eps-bound quirk (mosap.py:605) is reproduced by default and can be switched off."""
+    from bluest_b200.solvers import scipy_solve_multi
+    d = _load("mosap.npz")
+    tag = "solve_N5K3"
+    mos = _oracle_mosap(d, tag)
+    for s_ in mos.SAPS:
+        s_.variance_GH = (lambda o: (lambda m, delta=0, nohess=False: o.variance_GH(m, delta, nohess=nohess, hess_mode="factored")))(s_.o)
+
+        def make_op(o):
+            def variance_GH_operator(m, delta=0):
+                from scipy.sparse.linalg import LinearOperator
+                v, g, _ = o.variance_GH(m, delta, nohess=True)
+                P = np.linalg.pinv(o.get_phi(m, delta)); U = o.ufactor(np.ascontiguousarray(P[0]))
+                mv = lambda p: 2.0 * (U.T @ (P @ (U @ p)))
+                return v, g, LinearOperator((o.L, o.L), matvec=mv, rmatvec=mv, dtype=np.float64)
+            return variance_GH_operator
+        s_.variance_GH_operator = make_op(s_.o)
+    w = d[f"{tag}/w"]; x0 = d[f"{tag}/x0"]
+    if mode == "budget":
+        kw = dict(budget=float(d[f"{tag}/budget"]))
+        ref_x = d[f"{tag}/continuous_budget"]
+    else:
+        kw = dict(eps=d[f"{tag}/eps"])
+        ref_x = d[f"{tag}/continuous_eps"]
+    res = scipy_solve_multi(mos, x0=x0.copy(), **kw)
+    # the driver on the oracle's closures against the reference's own run (golden): same iterates up to solver tolerance
+    assert np.max(np.abs(res.x - ref_x)) <= 2e-2 * np.max(np.abs(ref_x))
+    worst = lambda x: max(mos.variances(x))
+    for opts in (dict(hess="operator"), dict(hess="operator", sparse_constraints=True)):
+        r2 = scipy_solve_multi(mos, x0=x0.copy(), **opts, **kw)
+        if mode == "budget":
+            assert abs(worst(r2.x) - worst(res.x)) <= 1e-4 * worst(res.x)
+        else:
+            assert abs(r2.x @ w - res.x @ w) <= 1e-3 * (res.x @ w)
+    if mode == "eps":
+        fixed = scipy_solve_multi(mos, x0=x0.copy(), reference_eps_bound=False, **kw)
+        assert np.all(np.array(mos.variances(fixed.x)) <= kw["eps"] ** 2 * (1 + 1e-6))
+        assert np.all(np.array(mos.variances(res.x)) <= kw["eps"][-1] ** 2 * (1 + 1e-6))
+    with pytest.raises(ValueError):
+        scipy_solve_multi(mos, x0=x0.copy(), hess="sparse", **kw)
