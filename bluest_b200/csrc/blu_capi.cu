@@ -105,6 +105,7 @@ struct blu_ctx {
     BluPeers peers{};                  // peers as mapped here; world == 0: not connected
     std::vector<void *> ipc_opened;
     unsigned long long epoch = 0;
+    double *d_Sop = nullptr;           // S = 2 pinv(Phi) of the evaluation the resident U factor belongs to (the operator's own copy)
     double *d_hvpart = nullptr, *d_hvp = nullptr, *d_hvout = nullptr;   // Hessian mat-vec: CTA partials of t, staged p and H p
     int hv_grid = 1;
     bool uv_ready = false, v_ready = false;   // U (and V) hold the factors of the last want_hess evaluation
@@ -165,7 +166,7 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     cudaFree(c->d_hdr); cudaFree(c->d_chunks); cudaFree(c->d_soa); cudaFree(c->d_soff); cudaFree(c->d_tiles);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->d_xchg);
-    cudaFree(c->d_hvpart); cudaFree(c->d_hvp); cudaFree(c->d_hvout);
+    cudaFree(c->d_hvpart); cudaFree(c->d_hvp); cudaFree(c->d_hvout); cudaFree(c->d_Sop);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     if (c->h_m) cudaFreeHost(c->h_m);
     if (c->h_grad) cudaFreeHost(c->h_grad);
@@ -508,6 +509,7 @@ static int ensure_uv(blu_ctx *c)
     CUDA_TRY(cudaMalloc(&c->d_V, sizeof(double) * n));
     CUDA_TRY(cudaMemsetAsync(c->d_U, 0, sizeof(double) * n, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->d_V, 0, sizeof(double) * n, c->stream));
+    CUDA_TRY(cudaMalloc(&c->d_Sop, sizeof(double) * (size_t)c->N * c->N));
     return BLU_OK;
 }
 
@@ -572,7 +574,14 @@ static int launch_v_from_u(blu_ctx *c)
 static int launch_grad(blu_ctx *c, int uv)
 {
     const bool want_uv = uv != 0;
-    if (want_uv) { c->uv_ready = true; c->v_ready = (uv == 1); }
+    if (want_uv) {
+        int rc0 = ensure_uv(c);
+        if (rc0) return rc0;
+        c->uv_ready = true; c->v_ready = (uv == 1);
+        // The operator H p = U S U^T p outlives this evaluation (a trust-region solver keeps multiplying by the
+        // Hessian of the last ACCEPTED iterate while it evaluates trial points): it gets its own copy of S.
+        CUDA_TRY(cudaMemcpyAsync(c->d_Sop, c->d_S, sizeof(double) * (size_t)c->N * c->N, cudaMemcpyDeviceToDevice, c->stream));
+    }
     // One group per lane needs at least a couple of 32-group tiles per SM to fill the machine; smaller
     // problems (latency-bound anyway) keep the entry-per-lane kernels, which spread a group over a warp.
     if (c->use_soa && c->hi - c->lo >= (long long)c->nsm * 2 * 32) {
@@ -986,7 +995,7 @@ static int launch_hv_apply(blu_ctx *c, const double *d_t, double *d_out)
     const long long rows = c->hi - c->lo;
     const int grid = (int)std::max<long long>(1, std::min<long long>((rows + BLU_HVA_THREADS - 1) / BLU_HVA_THREADS, (long long)c->nsm * 8));
     switch (c->NP) {
-#define HV_CASE(P) case P: blu_hv_apply_kernel<P><<<grid, BLU_HVA_THREADS, 0, c->stream>>>(c->d_U, c->d_S, c->N, d_t, c->lo, c->hi, d_out); break;
+#define HV_CASE(P) case P: blu_hv_apply_kernel<P><<<grid, BLU_HVA_THREADS, 0, c->stream>>>(c->d_U, c->d_Sop, c->N, d_t, c->lo, c->hi, d_out); break;
         HV_CASE(4) HV_CASE(8) HV_CASE(12) HV_CASE(16) HV_CASE(20) HV_CASE(24) HV_CASE(28) HV_CASE(32)
 #undef HV_CASE
     }
