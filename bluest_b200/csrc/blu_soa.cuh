@@ -132,85 +132,109 @@ struct BluSoaPipe {
     }
 };
 
-// One whole tile (32 groups of size K, one per lane) with everything in REGISTERS: the (j,l) sequence of
-// the packed entries is the same for every lane, so with the entry loop fully unrolled for a fixed K
-// the lane's x_j and y_j are statically indexed register arrays and a packed entry costs one shared
-// load (the staged value) and one or two FMAs -- no index table, no x/y traffic through shared memory.
-// Stage hand-offs happen at compile-time-known entry counts (every BLU_SOA_E entries).
+// A warp's RUN of tiles of one size class (32 groups of size K per tile, one group per lane) with
+// everything in REGISTERS: the (j,l) sequence of the packed entries is the same for every lane, so with
+// the entry loop fully unrolled for a fixed K the lane's x_j and y_j are statically indexed register
+// arrays and a packed entry costs one shared load (the staged value) and one or two FMAs -- no index
+// table, no x/y traffic through shared memory.  Stage hand-offs happen at compile-time-known entry
+// counts (every BLU_SOA_E entries).
 //
 // NOT inlined into the kernel: 2 x 32 unrolled routines in one function body make ptxas take ten
-// minutes; as separate functions they compile in well under one.  The call happens once per tile, where
-// hardly any register is live; the pipeline state is copied into registers for the duration of the tile.
+// minutes; as separate functions they compile in well under one.  One call covers all consecutive tiles
+// of the warp's sequence that belong to the same class (thousands, for the big classes), so the call
+// and the copy of the pipeline state into registers are paid once per run, not once per tile.
+struct BluSoaCursor {
+    int cq;               // index of the current tile in the tile list
+    BluTile cd;           // its descriptor
+    unsigned mask;        // the lane's membership mask in that tile
+};
+
 template <int K, bool WITHU, int NS>
-__device__ __noinline__ void blu_soa_tile(BluSoaPipe<NS> &pipe, const BluTile cd, const unsigned mask, const double *__restrict__ sx,
-                                          double *__restrict__ yv, int NP, long long lo, long long hi, double *__restrict__ grad,
-                                          double *__restrict__ U, int lane)
+__device__ __noinline__ void blu_soa_run(BluSoaPipe<NS> &pipe, BluSoaCursor &cur, const unsigned *__restrict__ gmask,
+                                         const double *__restrict__ sx, double *__restrict__ yv, int NP, long long lo, long long hi,
+                                         double *__restrict__ grad, double *__restrict__ U, int lane)
 {
     BluSoaPipe<NS> p = pipe;
-    double x[K], y[WITHU ? K : 1];
-    {
-        unsigned mk = mask;
+    int cq = cur.cq;
+    BluTile cd = cur.cd;
+    unsigned mask = cur.mask;
+    const int cls0 = cd.cls;
+    const BluClass ci = p.cls[cls0];
+    for (;;) {
+        // descriptor and membership mask of the warp's next tile, one tile ahead (an L2 hit hidden behind a whole tile)
+        BluTile cn = cd; unsigned mask_n = 0u;
+        if (cq + p.nw < p.ntiles) {
+            cn = p.tiles[cq + p.nw];
+            const BluClass cin = p.cls[cn.cls];
+            mask_n = (cn.t * 32 + lane < cin.Lk) ? gmask[cin.goff + cn.t * 32 + lane] : 0u;
+        }
+        double x[K], y[WITHU ? K : 1];
+        {
+            unsigned mk = mask;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int b = __ffs(mk) - 1;
+                x[j] = sx[b < 0 ? 0 : b];
+                if (WITHU) y[j] = 0.0;
+                mk &= mk - 1u;
+            }
+        }
+        double acc = 0.0;
+        const double *sp = nullptr;
+        int e = 0;                                     // compile-time after unrolling
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            const int b = __ffs(mk) - 1;
-            x[j] = sx[b < 0 ? 0 : b];
-            if (WITHU) y[j] = 0.0;
-            mk &= mk - 1u;
-        }
-    }
-    double acc = 0.0;
-    const double *sp = nullptr;
-    int e = 0;                                     // compile-time after unrolling
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-#pragma unroll
-        for (int l = j; l < K; ++l) {
-            if (e % BLU_SOA_E == 0) {
-                if (e > 0) __syncwarp();           // previous stage fully consumed before it is refilled
-                sp = p.next(lane);
+            for (int l = j; l < K; ++l) {
+                if (e % BLU_SOA_E == 0) {
+                    if (e > 0) __syncwarp();           // previous stage fully consumed before it is refilled
+                    sp = p.next(lane);
+                }
+                const double c = sp[(e % BLU_SOA_E) * 32 + lane];
+                if (!WITHU) {
+                    acc += ((j == l) ? 1.0 : 2.0) * (x[j] * c * x[l]);
+                } else {
+                    y[j] = fma(c, x[l], y[j]);
+                    if (j != l) y[l] = fma(c, x[j], y[l]);
+                }
+                ++e;
             }
-            const double c = sp[(e % BLU_SOA_E) * 32 + lane];
-            if (!WITHU) {
-                acc += ((j == l) ? 1.0 : 2.0) * (x[j] * c * x[l]);
-            } else {
-                y[j] = fma(c, x[l], y[j]);
-                if (j != l) y[l] = fma(c, x[j], y[l]);
-            }
-            ++e;
         }
+        __syncwarp();
+        const long long gi = ci.goff + cd.t * 32 + lane;          // flat group index of this lane
+        const bool live = (cd.t * 32 + lane < ci.Lk) && gi >= lo && gi < hi;
+        if (!WITHU) {
+            if (live) grad[gi] = -acc;
+        } else {
+            double gsum = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) { gsum = fma(x[j], y[j], gsum); yv[j * 32 + lane] = y[j]; }
+            if (live) grad[gi] = -gsum;
+            __syncwarp();
+            // U rows: y scattered to model slots.  The tile's 32 groups are consecutive flat indices, so their
+            // rows are ONE contiguous span of 32 NP doubles: element idx = r NP + a is produced by lane idx & 31
+            // from row r's mask (shuffle) and y (shared); every store instruction writes 256 contiguous bytes.
+            const long long g0 = ci.goff + cd.t * 32;
+            const int nrow = (int)((ci.Lk - cd.t * 32) < 32 ? (ci.Lk - cd.t * 32) : 32);
+            double *ub = U + g0 * NP;
+            const int dr = 32 / NP, da = 32 - dr * NP;
+            int r = lane / NP, a = lane - r * NP;
+            for (int idx = lane; idx < 32 * NP; idx += 32) {
+                const unsigned mr = __shfl_sync(BLU_FULL, mask, r);
+                double ua = 0.0;
+                if ((mr >> a) & 1u) ua = yv[__popc(mr & ((1u << a) - 1u)) * 32 + r];
+                const long long gr = g0 + r;
+                if (r < nrow && gr >= lo && gr < hi) ub[idx] = ua;
+                r += dr; a += da;
+                if (a >= NP) { a -= NP; ++r; }
+            }
+            __syncwarp();
+        }
+        cq += p.nw; cd = cn; mask = mask_n;
+        if (cq >= p.ntiles || cd.cls != cls0) break;
     }
-    __syncwarp();
-    const BluClass ci = p.cls[cd.cls];
-    const long long gi = ci.goff + cd.t * 32 + lane;          // flat group index of this lane
-    const bool live = (cd.t * 32 + lane < ci.Lk) && gi >= lo && gi < hi;
     pipe = p;
-    if (!WITHU) {
-        if (live) grad[gi] = -acc;
-        return;
-    }
-    double gsum = 0.0;
-#pragma unroll
-    for (int j = 0; j < K; ++j) { gsum = fma(x[j], y[j], gsum); yv[j * 32 + lane] = y[j]; }
-    if (live) grad[gi] = -gsum;
-    __syncwarp();
-    // U rows: y scattered to model slots.  The tile's 32 groups are consecutive flat indices, so their rows
-    // are ONE contiguous span of 32 NP doubles: element idx = r NP + a is produced by lane idx & 31 from
-    // row r's mask (shuffle) and y (shared), and every store instruction writes 256 contiguous bytes.
-    const long long g0 = ci.goff + cd.t * 32;
-    const int nrow = (int)((ci.Lk - cd.t * 32) < 32 ? (ci.Lk - cd.t * 32) : 32);
-    double *ub = U + g0 * NP;
-    const int dr = 32 / NP, da = 32 - dr * NP;
-    int r = lane / NP, a = lane - r * NP;
-    for (int idx = lane; idx < 32 * NP; idx += 32) {
-        const unsigned mr = __shfl_sync(BLU_FULL, mask, r);
-        double ua = 0.0;
-        if ((mr >> a) & 1u) ua = yv[__popc(mr & ((1u << a) - 1u)) * 32 + r];
-        const long long gr = g0 + r;
-        if (r < nrow && gr >= lo && gr < hi) ub[idx] = ua;
-        r += dr; a += da;
-        if (a >= NP) { a -= NP; ++r; }
-    }
-    __syncwarp();
+    cur.cq = cq; cur.cd = cd; cur.mask = mask;
 }
 
 // WITHU = false: gradient only.  WITHU = true: gradient + U rows (V = U S is a separate pass over U,
@@ -247,24 +271,21 @@ blu_grad_soa_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, i
     if (gw >= ntiles) return;
     p.q = gw; p.s = 0; p.d = tiles[gw];
     p.prime(lane);
-    // the lane's membership mask of a tile is fetched one tile ahead (an L2 hit hidden behind a whole tile)
-    auto tile_mask = [&](const BluTile &td) -> unsigned {
-        const BluClass ci = sm.cls[td.cls];
-        return (td.t * 32 + lane < ci.Lk) ? gmask[ci.goff + td.t * 32 + lane] : 0u;
-    };
-    BluTile cd = tiles[gw];
-    unsigned mask = tile_mask(cd);
-    for (int cq = gw; cq < ntiles; cq += p.nw) {
-        BluTile cn = cd; unsigned mask_n = 0u;
-        if (cq + p.nw < ntiles) { cn = tiles[cq + p.nw]; mask_n = tile_mask(cn); }
-        switch (sm.cls[cd.cls].k) {
-#define BLU_SOA_CASE(KK) case KK: blu_soa_tile<KK, WITHU, NS>(p, cd, mask, sx, yv, NP, lo, hi, grad, U, lane); break;
+    BluSoaCursor cur;
+    cur.cq = gw; cur.cd = tiles[gw];
+    {
+        const BluClass ci = sm.cls[cur.cd.cls];
+        cur.mask = (cur.cd.t * 32 + lane < ci.Lk) ? gmask[ci.goff + cur.cd.t * 32 + lane] : 0u;
+    }
+    while (cur.cq < ntiles) {
+        switch (sm.cls[cur.cd.cls].k) {
+#define BLU_SOA_CASE(KK) case KK: blu_soa_run<KK, WITHU, NS>(p, cur, gmask, sx, yv, NP, lo, hi, grad, U, lane); break;
             BLU_SOA_CASE(1) BLU_SOA_CASE(2) BLU_SOA_CASE(3) BLU_SOA_CASE(4) BLU_SOA_CASE(5) BLU_SOA_CASE(6) BLU_SOA_CASE(7) BLU_SOA_CASE(8)
             BLU_SOA_CASE(9) BLU_SOA_CASE(10) BLU_SOA_CASE(11) BLU_SOA_CASE(12) BLU_SOA_CASE(13) BLU_SOA_CASE(14) BLU_SOA_CASE(15) BLU_SOA_CASE(16)
             BLU_SOA_CASE(17) BLU_SOA_CASE(18) BLU_SOA_CASE(19) BLU_SOA_CASE(20) BLU_SOA_CASE(21) BLU_SOA_CASE(22) BLU_SOA_CASE(23) BLU_SOA_CASE(24)
             BLU_SOA_CASE(25) BLU_SOA_CASE(26) BLU_SOA_CASE(27) BLU_SOA_CASE(28) BLU_SOA_CASE(29) BLU_SOA_CASE(30) BLU_SOA_CASE(31) BLU_SOA_CASE(32)
 #undef BLU_SOA_CASE
+            default: return;                           // unreachable: 1 <= k <= 32
         }
-        cd = cn; mask = mask_n;
     }
 }
