@@ -13,7 +13,8 @@ from .pilot import pilot_covariance                     # noqa: F401
 from . import cmisc, intproj, io                        # noqa: F401
 from .dist import ShardedEvaluator, GpuEngine          # noqa: F401
 from .install import install, uninstall                # noqa: F401
+from .sweep import solve_sweep, split_instances        # noqa: F401
 
 __all__ = ["SAP", "MOSAP", "BLUESTError", "BluError", "pilot_covariance", "cmisc", "enumerate_groups",
            "enumerate_cliques", "union_groups", "group_costs", "indicator_ES", "mappings", "balanced_slices",
-           "device_count", "lib", "ShardedEvaluator", "GpuEngine", "install", "uninstall"]
+           "device_count", "lib", "ShardedEvaluator", "GpuEngine", "install", "uninstall", "solve_sweep", "split_instances"]

@@ -172,3 +172,84 @@ def test_sharded_evaluation_world2(N, K, replicate):
     if not replicate:
         assert ret[0]["dense"]["hi"] == ret[1]["dense"]["lo"]
     assert ret[0]["dense"]["rhi"] == ret[1]["dense"]["rlo"]
+
+
+# ---------------------------------------------------------------------------------------------
+# instance sweep (bluest_b200/sweep.py): budgets split across ranks, no data-path collective
+# ---------------------------------------------------------------------------------------------
+class _SweepProblem:
+    """Oracle-backed stand-in with the members solve_sweep touches (the GPU run uses bluest_b200.SAP)."""
+
+    def __init__(self, N, K):
+        import oracle as orc
+        from bluest_b200.groups import enumerate_groups, group_costs
+        self.o = orc.SapOracle(orc.wishart_cov(N, 0), K, orc.enumerate_groups(N, K))
+        self.L, self.N, self.e = self.o.L, N, self.o.e
+        self.costs = group_costs(enumerate_groups(N, K), 2.0 ** (N - np.arange(N)))
+
+    def variance(self, m, delta=0):
+        return self.o.variance(m, delta)
+
+    def variance_GH(self, m, delta=0, nohess=False):
+        return self.o.variance_GH(m, delta, nohess=nohess, hess_mode="factored")
+
+    def get_max_sample_constraints(self, mm):
+        return [], []
+
+    def solve(self, budget=None, eps=None, x0=None, continuous_relaxation=False, max_model_samples=None, **kw):
+        from bluest_b200.solvers import scipy_solve
+        return scipy_solve(self, budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, **kw).x
+
+
+def _sweep_setup():
+    rng = np.random.RandomState(0)
+    p = _SweepProblem(5, 3)
+    x0 = np.ceil(10 * abs(rng.randn(p.L)))
+    budgets = float(x0 @ p.costs) * np.array([1.2, 1.5, 2.0, 3.0, 5.0])
+    return x0, budgets
+
+
+def _sweep_worker(rank, world, port, ret):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from bluest_b200.sweep import solve_sweep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x0, budgets = _sweep_setup()
+        made = []
+        res = solve_sweep(lambda: made.append(1) or _SweepProblem(5, 3), budgets=budgets, x0=x0, dist=dist, continuous_relaxation=True)
+        ret[rank] = dict(res=res, contexts=len(made))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_instance_sweep_world2():
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from bluest_b200.sweep import solve_sweep, split_instances
+    assert [split_instances(5, 2, r) for r in range(2)] == [(0, 2), (2, 5)]
+    assert [split_instances(3, 4, r) for r in range(4)] == [(0, 0), (0, 1), (1, 2), (2, 3)]
+    with pytest.raises(ValueError):
+        split_instances(3, 2, 2)
+    x0, budgets = _sweep_setup()
+    serial = solve_sweep(lambda: _SweepProblem(5, 3), budgets=budgets, x0=x0, continuous_relaxation=True)
+    world = 2
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_sweep_worker, args=(world, 29900 + (os.getpid() % 90), ret), nprocs=world, join=True)
+    for r in range(world):
+        res = ret[r]["res"]
+        assert ret[r]["contexts"] == 1                                   # one context per rank, reused for its instances
+        assert [x["index"] for x in res] == list(range(len(budgets)))       # every rank holds all results, in instance order
+        assert [x["rank"] for x in res] == [0, 0, 1, 1, 1]
+        for a, b in zip(res, serial):
+            assert a["budget"] == b["budget"]
+            assert np.array_equal(a["samples"], b["samples"])               # same driver, same inputs: identical allocation
+            assert a["cost"] <= a["budget"] * (1 + 1e-9)
+    # a larger budget never gives a larger variance
+    v = [x["variance"] for x in serial]
+    assert all(v[i + 1] <= v[i] * (1 + 1e-6) for i in range(len(v) - 1))
+    with pytest.raises(ValueError):
+        solve_sweep(lambda: None, budgets=[1.0], epss=[1.0])

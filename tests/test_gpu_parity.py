@@ -718,3 +718,31 @@ def test_multi_output_scipy_solve(blu):
         mos.solve(budget=budget, solver="cvxopt")
     with pytest.raises(ValueError):
         mos.solve()
+
+
+def test_instance_sweep_single_process(blu):
+    """bluest_b200.solve_sweep (BASELINE config 3, one rank): a budget sweep on one context; allocations are
+    feasible, integer when asked, and the variance falls as the budget grows."""
+    N, K = 6, 3
+    C = orc.wishart_cov(N, 0)
+    groups = orc.enumerate_groups(N, K)
+    w = blu.group_costs(groups, 2.0 ** (N - np.arange(N)))
+    L = len(w)
+    x0 = np.ceil(10 * abs(np.random.RandomState(0).randn(L)))
+    budgets = float(x0 @ w) * np.array([1.2, 2.0, 4.0])
+    made = []
+
+    def make():
+        made.append(blu.SAP(C, K, _copy(groups), w, verbose=False))
+        return made[-1]
+    res = blu.solve_sweep(make, budgets=budgets, x0=x0, continuous_relaxation=True, solve_kwargs=dict(hess="operator", sparse_constraints=True))
+    assert len(made) == 1 and [r["index"] for r in res] == [0, 1, 2]
+    o = orc.SapOracle(C, K, groups)
+    for r in res:
+        assert r["cost"] <= r["budget"] * (1 + 1e-9)
+        assert abs(r["variance"] - o.variance(r["samples"])) <= 1e-12 * r["variance"]
+    assert res[0]["variance"] > res[1]["variance"] > res[2]["variance"]
+    ints = blu.solve_sweep(make, budgets=budgets[:1], x0=x0)
+    assert ints[0]["samples"].dtype.kind == "i" and ints[0]["cost"] <= 1.0001 * budgets[0]
+    for s_ in made:
+        s_.close()
