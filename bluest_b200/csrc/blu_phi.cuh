@@ -33,6 +33,20 @@ struct BluEvalHeader {          // small device-side status block of a context
     double xsup[32];            // first row of pinv(Phi[idx,idx]) scattered to model slots (PHIinvY0, misc.py:529-533)
 };
 
+// Explicit shared-space accesses with 32-bit addresses.  Through the generic pointers of the stream
+// structs the compiler emitted generic LD.E.64 for the staged values and rebuilt the shared window base
+// for every accumulator access (64-bit address arithmetic per group); these keep it to LDS/STS.
+__device__ __forceinline__ double blu_lds_f64(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void blu_sts_f64(unsigned addr, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
 // Consume one staged chunk for the Phi accumulation.  S = ceil(T/32) steps per group, fully
 // unrolled; the lane's (j,l) pairs are fixed for the whole chunk and live in registers.
 template <int S>
@@ -47,19 +61,24 @@ __device__ __forceinline__ void blu_phi_chunk(const double *__restrict__ base, c
         const unsigned jl = e < T ? lt[e] : 0u;
         ja[s] = jl >> 8; la[s] = jl & 255u;
     }
-    for (int g = 0; g < ng; ++g) {
+    const unsigned acc_s = blu_smem_u32(acc);
+    const unsigned ids_s = blu_smem_u32(ids) + lane;
+    unsigned cp_s = blu_smem_u32(base) + 8u * lane;       // staged entry `lane` of the current group
+    for (int g = 0; g < ng; ++g, cp_s += 8u * T) {
         if (!((live >> g) & 1u)) continue;                // m_i == 0 contributes exact zeros
         const double mi = blu_shfl(mreg, g);
-        const int gv = ids[g * 32 + lane];
-        const double *cp = base + g * T;
+        unsigned gv;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(gv) : "r"(ids_s + 32u * g) : "memory");
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            const int e = s * 32 + lane;
-            const bool ok = e < T;
-            const double v = ok ? cp[e] : 0.0;
-            const int a = __shfl_sync(BLU_FULL, gv, ja[s]);
-            const int b = __shfl_sync(BLU_FULL, gv, la[s]);
-            if (ok) acc[a * N + b] += mi * v;
+            const bool ok = s * 32 + lane < T;
+            const double v = ok ? blu_lds_f64(cp_s + 256u * s) : 0.0;
+            const int a = __shfl_sync(BLU_FULL, (int)gv, ja[s]);
+            const int b = __shfl_sync(BLU_FULL, (int)gv, la[s]);
+            if (ok) {
+                const unsigned at = acc_s + 8u * (unsigned)(a * N + b);
+                blu_sts_f64(at, fma(mi, v, blu_lds_f64(at)));
+            }
         }
         __syncwarp();
     }
