@@ -151,8 +151,15 @@ def _multi_helper(mosap, sol, budget, eps, lb, ub, idx, max_samples_info=([], []
     basees = [e[mappings[n]] @ baseval[mappings[n]] for n in range(No)]
     base_checks = [ees @ baseval for ees in ES]
 
-    # position of every brute-forced group inside each output's own group list
-    pos = [{int(g): j for j, g in enumerate(mappings[n])} for n in range(No)]
+    # position of every brute-forced group inside each output's own group list (built once per MOSAP: the
+    # randomised search calls this helper up to 250 times)
+    pos = getattr(mosap, "_intproj_positions", None)
+    if pos is None or len(pos) != No:
+        pos = [{int(g): j for j, g in enumerate(mappings[n])} for n in range(No)]
+        try:
+            mosap._intproj_positions = pos
+        except AttributeError:
+            pass
     redmaps = [np.array([i for i in range(len(idx)) if int(idx[i]) in pos[n]], dtype=int) for n in range(No)]
     idxs = [np.array([pos[n][int(g)] for g in idx if int(g) in pos[n]], dtype=np.int64) for n in range(No)]
 
