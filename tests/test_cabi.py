@@ -97,3 +97,37 @@ def test_install_patches_the_reference_in_place():
     finally:
         blu.uninstall()
     assert ns.sap.SAP is ref_sap and ns.mosap.SAP is ref_sap and ns.misc.gradK_c is ref_grad
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/bluest_b200.h must compile as C99 (no C++-isms) and a plain C
+    program must link against the library and get the loud no-device error on a CPU box."""
+    import shutil
+    import subprocess
+    from bluest_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdint.h>
+#include "bluest_b200.h"
+int main(void) {
+    blu_ctx *ctx = NULL;
+    int64_t sizes[2] = {2, 1};
+    int64_t groups[4] = {0, 1, 0, 1};
+    int rc;
+    printf("%s devices=%d\n", blu_version(), blu_device_count());
+    rc = blu_ctx_create(0, 2, 2, sizes, groups, &ctx);
+    printf("rc=%d err=%s\n", rc, blu_last_error());
+    if (rc == BLU_OK) blu_ctx_destroy(ctx);
+    return (rc == BLU_ERR_NODEVICE || rc == BLU_OK) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+           _lib.LIB_PATH, "-Wl,-rpath," + libdir]
+    subprocess.run(cmd, check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "bluest_b200" in out and "rc=" in out
