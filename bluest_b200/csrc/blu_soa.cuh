@@ -154,6 +154,10 @@ __device__ __noinline__ void blu_soa_run(BluSoaPipe<NS> &pipe, BluSoaCursor &cur
                                          const double *__restrict__ sx, double *__restrict__ yv, int NP, long long lo, long long hi,
                                          double *__restrict__ grad, double *__restrict__ U, int lane)
 {
+    // these generic pointers all point into shared memory: say so, or the staged values are read with
+    // generic LD.E.64 instead of LDS
+    __builtin_assume(__isShared(sx));
+    __builtin_assume(__isShared(yv));
     BluSoaPipe<NS> p = pipe;
     int cq = cur.cq;
     BluTile cd = cur.cd;
@@ -189,6 +193,7 @@ __device__ __noinline__ void blu_soa_run(BluSoaPipe<NS> &pipe, BluSoaCursor &cur
                 if (e % BLU_SOA_E == 0) {
                     if (e > 0) __syncwarp();           // previous stage fully consumed before it is refilled
                     sp = p.next(lane);
+                    __builtin_assume(__isShared(sp));
                 }
                 const double c = sp[(e % BLU_SOA_E) * 32 + lane];
                 if (!WITHU) {
