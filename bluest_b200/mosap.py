@@ -18,49 +18,41 @@ class MOSAP(object):
     ''' MOSAP, MultiObjectiveSampleAllocationProblem '''
 
     def __init__(self, C, K, Ks, groups, multi_groups, costs, multi_costs, verbose=True, device=0):
-        self.verbose = verbose
-        self.n_outputs = len(C)
-        self.C = C
-        self.N = C[0].shape[0]
-        self.K = K
-        self.Ks = Ks
-        self.costs = costs
-        self.multi_groups = multi_groups
-        self.multi_costs = multi_costs
-        flattened_groups = []
+        """Same arguments as mosap.py:20: per-output covariances ``C``, the union ``groups`` (size-major) and the
+        per-output ``multi_groups`` / ``multi_costs``.  ``groups[k]`` is converted to an int64 array in place
+        (mosap.py:34), one device context per output is created, and ``mappings`` ties the two numberings."""
+        self.verbose, self.n_outputs = verbose, len(C)
+        self.C, self.N = C, C[0].shape[0]
+        self.K, self.Ks = K, Ks
+        self.costs, self.multi_groups, self.multi_costs = costs, multi_groups, multi_costs
+        self.flattened_groups = [list(g) for k in range(K) for g in groups[k]]
         for k in range(K):
-            flattened_groups += [list(g) for g in groups[k]]
-            groups[k] = np.array(groups[k], dtype=np.int64)       # mosap.py:34
-        self.flattened_groups = flattened_groups
+            groups[k] = np.array(groups[k], dtype=np.int64)
         self.groups = groups
 
         self.SAPS = [SAP(C[n], Ks[n], multi_groups[n], multi_costs[n], verbose=self.verbose, device=device)
                      for n in range(self.n_outputs)]
 
-        self.sizes = [0] + [len(groupsk) for groupsk in groups]
+        self.sizes = [0] + [len(gk) for gk in groups]
         self.cumsizes = np.cumsum(self.sizes)
         self.L = self.cumsizes[-1]
         self.ES = indicator_ES(groups, self.N)
         self.e = self.ES[0]
         # m <-> groups, and m[mappings[n]] = m_n <-> multi_groups[n]   (mosap.py:54-67)
         self.mappings = build_mappings(groups, multi_groups)
-
-        self.samples = None
-        self.budget = None
-        self.eps = None
-        self.tot_cost = None
+        self.samples = self.budget = self.eps = self.tot_cost = None
 
     def check_input(self, budget, eps):
+        """mosap.py:74-84: one tolerance per output; a scalar is broadcast, a sequence of the wrong length is an error."""
         if budget is None and eps is None:
             raise ValueError("Need to specify either budget or RMSE tolerance")
-        if eps is not None:
-            try:
-                if len(eps) != self.n_outputs:
-                    raise ValueError("eps must be a scalar or an array of tolerances")
-                eps = np.array(eps)
-            except TypeError:
-                eps = np.array([eps for n in range(self.n_outputs)])
-        return budget, eps
+        if eps is None:
+            return budget, eps
+        if np.ndim(eps) == 0:
+            return budget, np.full(self.n_outputs, eps, dtype=np.asarray(eps).dtype)
+        if len(eps) != self.n_outputs:
+            raise ValueError("eps must be a scalar or an array of tolerances")
+        return budget, np.array(eps)
 
     def variances(self, m, delta=0):
         """mosap.py:86-89; the outputs are evaluated concurrently (one stream per context)."""
@@ -119,67 +111,14 @@ class MOSAP(object):
         return E
 
     def get_max_sample_constraints(self, max_model_samples):
-        """mosap.py:333-351."""
-        if max_model_samples is None:
-            return [], []
-        if not isinstance(max_model_samples, np.ndarray) or len(max_model_samples) != self.N:
-            raise ValueError("The maximum number of model samples must be prescribed as a numpy array of the same length as the number of models.")
-        if max_model_samples[0] < 1:
-            raise ValueError("The high-fidelity model must be sampled at least once.")
-        es, rhs = [], []
-        for i in range(self.N):
-            if np.isfinite(max_model_samples[i]):
-                es.append(self.ES[i])
-                rhs.append(int(np.round(max_model_samples[i])))
-        return es, rhs
+        """mosap.py:326-344."""
+        from .constraints import max_sample_constraints
+        return max_sample_constraints(self.ES, self.N, max_model_samples)
 
     def cleanup_solution(self, m, delta=0, tol=0):
-        """mosap.py:125-211: walk along null-space directions of the stacked cleanup matrices that do
-        not increase the cost, as far as positivity and the coverage constraints allow, while the
-        largest output variance does not get worse -- a sparser allocation of the same quality.
-        Like the reference it zeroes the entries of the caller's ``m`` that lie below ``tol``."""
-        from scipy.linalg import null_space
-        w = self.costs
-        E = self.output_indicators()
-        worst = lambda x: max(self.variances(x, delta=delta))
-        idx = np.argwhere(m > tol).flatten()
-        V0 = worst(m)
-        smax = 0
-        while len(idx) > self.N:
-            idx = np.argwhere(m > tol).flatten()
-            m[m < tol] = 0
-            wr, Er = w[idx], E[:, idx]
-            X = self.get_cleanup_matrices(m, delta=delta)[:, idx]
-            NN = null_space(X)
-            vals = wr @ NN
-            signs = np.sign(vals)
-            NN[:, signs > 0] *= -1                     # orient every direction so that it does not raise the cost
-            vals[signs > 0] *= -1
-            NN, vals = NN[:, abs(signs) > 0], vals[abs(signs) > 0]
-            order = np.argsort(abs(vals))[::-1]        # steepest cost decrease first
-            if len(vals) == 0:
-                break
-            em = Er @ m[idx]
-            for i in order:
-                t = NN[:, i]
-                evals = Er @ t
-                neg = np.argwhere(evals < 0).flatten()
-                s1 = np.inf if len(neg) == 0 else min(abs(em[neg] - 1) / abs(evals[neg]))
-                neg = np.argwhere(t < 0).flatten()
-                s2 = np.inf if len(neg) == 0 else min(m[idx][neg] / abs(t[neg]))
-                smax = max(min(s1, s2), 0)
-                if smax > 5 * tol:
-                    step = np.zeros_like(m); step[idx] = t
-                    mnew = m + smax * step
-                    V = worst(mnew)
-                    if V < V0 or abs(V - V0) / abs(V0) < 1.0e-4:
-                        m = mnew.copy()
-                        break
-                    smax = 0
-            if smax <= 5 * tol:
-                break
-        m[m < tol] = 0
-        return m
+        """mosap.py:125-211 (see bluest_b200/cleanup.py): a sparser allocation of the same quality and cost."""
+        from .cleanup import cleanup_solution
+        return cleanup_solution(self, m, delta=delta, tol=tol)
 
     def integer_projection(self, samples, budget=None, eps=None, max_model_samples=None):
         """mosap.py:213-292; the candidate variances of every output come from one batched device call each."""
@@ -195,25 +134,22 @@ class MOSAP(object):
         if solver != "scipy":
             raise ValueError("bluest_b200.MOSAP.solve provides solver='scipy'; for 'cvxopt'/'cvxpy'/'ipopt' hand the SAPS' "
                              "`psi` / closures to the reference's own drivers (INTEGRATION.md)")
-        samples = self.scipy_solve(budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, hess=hess,
-                                   sparse_constraints=sparse_constraints)
-        if samples is None:
-            self.samples = None
-            return None
-        if not continuous_relaxation:
+        allocation = self.scipy_solve(budget=budget, eps=eps, x0=x0, max_model_samples=max_model_samples, hess=hess,
+                                      sparse_constraints=sparse_constraints)
+        if allocation is not None and not continuous_relaxation:
             try:
-                samples = self.integer_projection(samples, budget=budget, eps=eps, max_model_samples=max_model_samples)
-            except AssertionError as ex:
+                allocation = self.integer_projection(allocation, budget=budget, eps=eps, max_model_samples=max_model_samples)
+            except AssertionError as ex:                   # the reference reports the failed assertion and gives up (mosap.py:313-317)
                 print(str(ex))
-                self.samples = None
-                return None
-        self.samples = samples
-        self.budget = budget
-        self.eps = eps
-        self.tot_cost = samples @ self.costs
-        for n in range(self.n_outputs):
-            self.SAPS[n].samples = samples[self.mappings[n]]
-        return samples
+                allocation = None
+        self.samples = allocation
+        if allocation is None:
+            return None
+        self.budget, self.eps = budget, eps
+        self.tot_cost = allocation @ self.costs
+        for sap, mp in zip(self.SAPS, self.mappings):
+            sap.samples = allocation[mp]
+        return allocation
 
     def scipy_solve(self, budget=None, eps=None, x0=None, max_model_samples=None, maxiter=5000, hess="dense", sparse_constraints=False,
                     reference_eps_bound=True):

@@ -309,18 +309,8 @@ class SAP(object):
 
     def get_max_sample_constraints(self, max_model_samples):
         """sap.py:222-240."""
-        if max_model_samples is None:
-            return [], []
-        if not isinstance(max_model_samples, np.ndarray) or len(max_model_samples) != self.N:
-            raise ValueError("The maximum number of model samples must be prescribed as a numpy array of the same length as the number of models.")
-        if max_model_samples[0] < 1:
-            raise ValueError("The high-fidelity model must be sampled at least once.")
-        es, rhs = [], []
-        for i in range(self.N):
-            if np.isfinite(max_model_samples[i]):
-                es.append(self.ES[i])
-                rhs.append(int(np.round(max_model_samples[i])))
-        return es, rhs
+        from .constraints import max_sample_constraints
+        return max_sample_constraints(self.ES, self.N, max_model_samples)
 
     def solve(self, budget=None, eps=None, solver="scipy", x0=None, continuous_relaxation=False, max_model_samples=None, solver_params=None, hess="dense", sparse_constraints=False):
         """Host-side driver kept from sap.py:189-220.  Only ``solver="scipy"`` (trust-constr
