@@ -366,3 +366,43 @@ def test_multi_output_scipy_driver_variants(mode):
         assert np.all(np.array(mos.variances(res.x)) <= kw["eps"][-1] ** 2 * (1 + 1e-6))
     with pytest.raises(ValueError):
         scipy_solve_multi(mos, x0=x0.copy(), hess="sparse", **kw)
+
+
+def test_mosap_constructor_and_solve_end_to_end_on_oracle_contexts(monkeypatch):
+    """The real ``bluest_b200.MOSAP`` class -- constructor, ``check_input``, ``solve(solver="scipy")`` with its
+    integer projection -- with the per-output device contexts replaced by oracle-backed stand-ins: the integer
+    allocation equals the one the REFERENCE's MOSAP produced from the same x0 (golden, mosap.npz)."""
+    import bluest_b200.mosap as mosap_mod
+    from bluest_b200 import intproj
+
+    class StubSAP(_OracleOutput):
+        def __init__(self, C, K, groups, costs, verbose=True, device=0):
+            super().__init__(C, K, [[list(g) for g in gk] for gk in groups])
+
+        def variance_GH(self, m, delta=0, nohess=False):
+            return self.o.variance_GH(m, delta, nohess=nohess, hess_mode="factored")
+
+    monkeypatch.setattr(mosap_mod, "SAP", StubSAP)
+    monkeypatch.setattr(intproj, "candidate_variances", _fake_candidates)
+    d = _load("mosap.npz")
+    tag = "solve_N5K3"
+    K = int(d[f"{tag}/K"]); Ks = d[f"{tag}/Ks"].tolist(); No = int(d[f"{tag}/n_outputs"])
+    groups = [d[f"{tag}/groups{k+1}"].tolist() for k in range(K)]
+    multi = [[d[f"{tag}/multi{n}_groups{k+1}"].tolist() for k in range(Ks[n])] for n in range(No)]
+    w = d[f"{tag}/w"]
+    mos = blu.MOSAP([d[f"{tag}/C{n}"] for n in range(No)], K, Ks, groups, multi, w, [w] * No, verbose=False)
+    monkeypatch.setattr(mos, "variances", lambda m, delta=0: [mos.SAPS[n].variance(np.asarray(m)[mos.mappings[n]], delta) for n in range(No)], raising=False)
+    assert isinstance(groups[0], np.ndarray) and groups[0].dtype == np.int64           # converted in place, mosap.py:34
+    assert mos.L == 25 and mos.flattened_groups[:3] == [[0], [1], [2]] and mos.samples is None
+    b, e = mos.check_input(None, 0.1)
+    assert b is None and np.array_equal(e, [0.1] * No)
+    with pytest.raises(ValueError):
+        mos.check_input(None, [0.1, 0.2])
+    with pytest.raises(ValueError):
+        mos.check_input(None, None)
+    np.random.seed(1234)
+    ints = mos.solve(budget=float(d[f"{tag}/budget"]), x0=d[f"{tag}/x0"].copy(), continuous_relaxation=False)
+    assert np.array_equal(ints, d[f"{tag}/integer_budget"])
+    assert mos.tot_cost == ints @ w and mos.budget == float(d[f"{tag}/budget"])
+    for n in range(No):
+        assert np.array_equal(mos.SAPS[n].samples, ints[mos.mappings[n]])
