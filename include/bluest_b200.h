@@ -51,7 +51,8 @@ extern "C" {
 #define BLU_BUF_PINV   2   /* (N,N)      pinv(Phi), symmetric */
 #define BLU_BUF_GRAD   3   /* (L)        gradient of the variance */
 #define BLU_BUF_U      4   /* (Lpad,NP)  row i = u_i = R_i^T Cinv_i R_i x, NP = 4*ceil(N/4) */
-#define BLU_BUF_V      5   /* (Lpad,NP)  row i = 2 pinv(Phi) u_i */
+#define BLU_BUF_V      5   /* (Lpad,NP)  row i = 2 pinv(Phi) u_i; written only by evaluations that need it
+                            * (dense Hessian, want_hess 1 or 2 / want_uv 1), not by the operator's (want_hess 3) */
 #define BLU_BUF_HESS   6   /* (L,ldH)    dense Hessian, row pitch ldH = 16*ceil(L/16) doubles */
 #define BLU_BUF_CINV   7   /* packed upper-triangular per-group inverses */
 #define BLU_BUF_SCAL   8   /* (8) doubles: [0]=variance, [1]=max|m|, [2]=sweeps, [3]=lambda_max */
