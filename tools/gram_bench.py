@@ -1,7 +1,7 @@
 """tools/gram_bench.py -- pilot-covariance Gram kernel (kernel 4) at BASELINE config 5:
 1e6 samples x 20 models, device-resident Y.  Prints kernel time, GB/s vs the measured HBM peak
 and the parity against the oracle on a 20000-sample prefix."""
-import os, sys, time
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np, torch

@@ -6,7 +6,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import bluest_b200 as blu, oracle as orc
-from bluest_b200 import intproj
 from bluest_b200.dist import GpuEngine
 
 def check(a, b, tol, what):
