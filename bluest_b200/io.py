@@ -43,20 +43,89 @@ def save_graph_data(filename, costs, adjacency, SG, dV=None):
     np.savez(filename, M=M, n_outputs=len(adjacency), costs=np.asarray(costs), **C_dict, SG=np.asarray(SG), dV=np.asarray(dV))
 
 
-def setup_mosap(graph, K=4, device=0, verbose=False):
-    """The group-enumeration half of ``BLUEProblem.setup_solver`` (blue_models.py:458-509) for a loaded
-    graph: cliques of size <= K per output inside model 0's component, union + sort, group costs, and
-    the device-backed MOSAP.  ``graph`` is what ``load_graph_data`` returns."""
+def is_subclique(adj, nodes):
+    """``is_subclique`` of blue_models.py:33-36 on an adjacency matrix: every pair of ``nodes`` -- a node with
+    itself included, the model graphs carry self-loops -- is joined by an edge (non-zero adjacency)."""
+    A = np.asarray(adj)
+    nodes = [int(v) for v in nodes]
+    return all(A[i, j] != 0 for a, i in enumerate(nodes) for j in nodes[a:])
+
+
+def prepare_groups(graph, K=4, groups=None, multi_groups=None):
+    """The group bookkeeping of ``BLUEProblem.setup_solver`` (blue_models.py:453-501) -> (K, Ks, groups, multi_groups).
+
+    Without user input: all cliques of size <= K of every output's model graph inside model 0's component.
+    With ``groups`` (used for every output) or ``multi_groups`` (one list per output): the user's groups are
+    sorted in place, those that are not cliques of the output's graph or leave model 0's component are dropped,
+    the rest are binned by size -- size classes may stay empty -- and ``Ks[n]`` is the largest size that survived.
+    Then the union over the outputs, each size class sorted lexicographically."""
     M, No = graph["M"], graph["n_outputs"]
-    K = min(K, M)
-    multi_groups, Ks = [], []
-    for n in range(No):
-        A = graph["adjacency"][n]
-        mg = enumerate_cliques(A, K, component_of=0)
-        multi_groups.append(mg)
-        Ks.append(min(K, len(mg)))
+    if multi_groups is not None and len(multi_groups) != No:
+        raise ValueError("multi_groups must be a list of groupings of the same length as the number of outputs.")
+    if groups is not None and multi_groups is None:
+        multi_groups = [groups for _ in range(No)]
+    if multi_groups is None:
+        K = min(K, M)
+        multi_groups, Ks = [], []
+        for n in range(No):
+            mg = enumerate_cliques(graph["adjacency"][n], K, component_of=0)
+            multi_groups.append(mg)
+            Ks.append(min(K, len(mg)))
+    else:
+        first_Ks = [min(max(len(g) for g in user), M) for user in multi_groups]
+        for n in range(No):
+            component = set(int(v) for v in graph["SG"][n])
+            binned = [[] for _ in range(first_Ks[n])]
+            for g in multi_groups[n]:
+                g.sort()                                                   # in place, like the reference
+                if is_subclique(graph["adjacency"][n], g) and all(int(v) in component for v in g):
+                    binned[len(g) - 1].append(g)
+            multi_groups[n] = binned
+        Ks = [min(max(len(g) for gk in mg for g in gk), M) for mg in multi_groups]
     Kmax = max(Ks)
-    groups = union_groups(multi_groups)
-    costs = group_costs(groups, graph["costs"])
+    union = [[] for _ in range(Kmax)]
+    seen = [set() for _ in range(Kmax)]
+    for n in range(No):
+        for k in range(Ks[n]):
+            for g in multi_groups[n][k]:
+                key = tuple(int(v) for v in g)
+                if key not in seen[k]:
+                    seen[k].add(key)
+                    union[k].append(g)
+    for k in range(Kmax):
+        union[k].sort()
+    return Kmax, Ks, union, multi_groups
+
+
+def setup_mosap(graph, K=4, device=0, verbose=False, groups=None, multi_groups=None):
+    """The construction half of ``BLUEProblem.setup_solver`` (blue_models.py:453-509) for a loaded graph: group
+    bookkeeping (``prepare_groups``), group costs, and the device-backed MOSAP.  ``graph`` is what
+    ``load_graph_data`` returns."""
+    Kmax, Ks, union, multi_groups = prepare_groups(graph, K=K, groups=groups, multi_groups=multi_groups)
+    costs = group_costs(union, graph["costs"])
     multi_costs = [group_costs(mg, graph["costs"]) for mg in multi_groups]
-    return MOSAP(graph["C"], Kmax, Ks, groups, multi_groups, costs, multi_costs, verbose=verbose, device=device)
+    return MOSAP(graph["C"], Kmax, Ks, union, multi_groups, costs, multi_costs, verbose=verbose, device=device)
+
+
+def setup_solver(graph, K=4, budget=None, eps=None, groups=None, multi_groups=None, solver="scipy", continuous_relaxation=False,
+                 max_model_samples=None, x0=None, device=0, verbose=False, **solve_kwargs):
+    """``BLUEProblem.setup_solver`` (blue_models.py:448-538) on a loaded graph: builds the MOSAP, solves the
+    allocation and returns ``(mosap, blue_data)`` with the reference's ``blue_data`` dictionary (``models``: the
+    groups that received samples, ``samples``, ``errors`` = sqrt of the output variances, ``total_cost``)."""
+    from .mosap import BLUESTError
+    if budget is None and eps is None:
+        raise ValueError("Need to specify either budget or RMSE tolerance")
+    if budget is not None and eps is not None:
+        eps = None                                                         # blue_models.py:450
+    if eps is not None and np.ndim(eps) == 0:
+        eps = [eps for _ in range(graph["n_outputs"])]
+    mosap = setup_mosap(graph, K=K, device=device, verbose=verbose, groups=groups, multi_groups=multi_groups)
+    mosap.solve(eps=eps, budget=budget, solver=solver, x0=x0, continuous_relaxation=continuous_relaxation,
+                max_model_samples=max_model_samples, **solve_kwargs)
+    if mosap.samples is None:
+        raise BLUESTError("MOSAP solution failed!")
+    Vs = mosap.variances(mosap.samples)
+    picked = np.argwhere(mosap.samples > 0).flatten()
+    blue_data = {"models": [mosap.flattened_groups[i] for i in picked], "samples": mosap.samples[mosap.samples > 0].copy(),
+                 "errors": np.sqrt(Vs), "total_cost": mosap.tot_cost}
+    return mosap, blue_data

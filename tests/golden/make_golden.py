@@ -23,6 +23,8 @@ Files written
   solve.npz       SAP.solve(solver="scipy") end to end: continuous solution and integer allocation
   mosap.npz       MOSAP cleanup matrices / cleanup_solution, multi-output integer projection (brute force and
                   randomised, misc.py:177-311), MOSAP.integer_projection, MOSAP.scipy_solve from a fixed x0
+  setup.npz       group bookkeeping of BLUEProblem.setup_solver (default enumeration, user groups / multi_groups)
+                  captured at the reference's MOSAP constructor call; setup_graph_data.npz is its input graph file
   pilot.npz       pilot-sample sums and C_hat computed with the reference's accumulation loop
 """
 import os
@@ -467,6 +469,76 @@ def make_mosap(ns):
     np.savez_compressed(os.path.join(OUT, "mosap.npz"), **out)
 
 
+def make_setup(ns):
+    """The group bookkeeping of BLUEProblem.setup_solver (blue_models.py:453-509): default clique enumeration,
+    user-supplied ``groups`` and per-output ``multi_groups`` (unsorted members, non-cliques, groups outside
+    model 0's component), captured at the MOSAP constructor call of the REAL reference class."""
+    import contextlib
+    import io
+    import networkx as nx
+    bm = ns.blue_models
+    M, No = 7, 2
+    rng = np.random.RandomState(91)
+    adjs = []
+    for n in range(No):
+        A = wishart(M, 92 + n)
+        A[1, 4] = A[4, 1] = 0.0                      # models 1 and 4 cannot be coupled
+        A[2, 5] = A[5, 2] = np.inf                   # uncorrelated, still an edge
+        if n == 1:
+            A[6, :] = 0.0; A[:, 6] = 0.0; A[6, 6] = 1.3     # model 6 is cut off from model 0's component in output 1
+            A[0, 3] = A[3, 0] = 0.0
+        adjs.append(A)
+    SG = []
+    for A in adjs:
+        comp = sorted(nx.node_connected_component(nx.from_numpy_array(A), 0))
+        SG.append(comp + [-1] * (M - len(comp)))     # rectangular for np.savez; -1 never matches a model id
+    costs = 2.0 ** (M - np.arange(M))
+    path = os.path.join(OUT, "setup_graph_data.npz")
+    np.savez(path, M=M, n_outputs=No, costs=costs, C0=adjs[0], C1=adjs[1], SG=np.array(SG), dV=np.nan * np.ones((No, M, M)))
+
+    captured = {}
+
+    class Capture(Exception):
+        pass
+
+    def fake_mosap(C, K, Ks, groups, multi_groups, costs, multi_costs, verbose=True):
+        captured.update(K=K, Ks=list(Ks), groups=[[list(g) for g in gk] for gk in groups],
+                        multi_groups=[[[list(g) for g in gk] for gk in mg] for mg in multi_groups],
+                        costs=np.array(costs), multi_costs=[np.array(c) for c in multi_costs])
+        raise Capture()
+
+    real = bm.MOSAP
+    bm.MOSAP = fake_mosap
+    out = {}
+    try:
+        user = [[3, 0], [0], [2, 1, 0], [1, 4], [4, 1, 0], [6], [0, 6], [5, 2, 0], [3], [0, 3, 2, 1], [2]]
+        multi = [[[0], [1, 0], [2, 0, 1], [4, 3]], [[0], [0, 3], [2, 0], [6, 0], [1, 2], [5]]]
+        cases = {"default_K3": dict(K=3), "default_K7": dict(K=7), "user_groups": dict(K=3, groups=user), "user_multi": dict(K=3, multi_groups=multi)}
+        for tag, kw in cases.items():
+            with contextlib.redirect_stdout(io.StringIO()):
+                prob = bm.BLUEProblem(M, datafile=path, n_outputs=No, verbose=False)
+            kw = {k: ([list(g) for g in v] if k == "groups" else [[list(g) for g in mg] for mg in v] if k == "multi_groups" else v) for k, v in kw.items()}
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    prob.setup_solver(eps=0.1, solver="scipy", **kw)
+            except Capture:
+                pass
+            out[f"{tag}/K"] = np.int64(captured["K"]); out[f"{tag}/Ks"] = np.array(captured["Ks"], dtype=np.int64)
+            out[f"{tag}/costs"] = captured["costs"]
+            for k, gk in enumerate(captured["groups"]):
+                out[f"{tag}/groups{k+1}"] = np.array(gk, dtype=np.int64).reshape(-1, k + 1)
+            for n, mg in enumerate(captured["multi_groups"]):
+                out[f"{tag}/n_classes{n}"] = np.int64(len(mg))
+                for k, gk in enumerate(mg):
+                    out[f"{tag}/multi{n}_groups{k+1}"] = np.array(gk, dtype=np.int64).reshape(-1, k + 1)
+                out[f"{tag}/multi_costs{n}"] = captured["multi_costs"][n]
+            print("setup", tag, captured["K"], captured["Ks"], [len(g) for g in captured["groups"]])
+    finally:
+        bm.MOSAP = real
+    out["user_groups_input"] = np.array([g + [-1] * (4 - len(g)) for g in user], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "setup.npz"), **out)
+
+
 def make_pilot():
     """The reference accumulates the pilot sums one sample at a time (blue_fn.py:159-167, N1=1)
     and then forms C_hat = sumsc/N - outer(sumse, sumse)/N^2 (blue_models.py:333)."""
@@ -497,5 +569,6 @@ if __name__ == "__main__":
     make_intproj(ns)
     make_solve(ns)
     make_mosap(ns)
+    make_setup(ns)
     make_pilot()
     print("done")

@@ -406,3 +406,81 @@ def test_mosap_constructor_and_solve_end_to_end_on_oracle_contexts(monkeypatch):
     assert mos.tot_cost == ints @ w and mos.budget == float(d[f"{tag}/budget"])
     for n in range(No):
         assert np.array_equal(mos.SAPS[n].samples, ints[mos.mappings[n]])
+
+
+@pytest.mark.parametrize("tag", ["default_K3", "default_K7", "user_groups", "user_multi"])
+def test_setup_solver_group_bookkeeping_equals_the_reference(tag):
+    """Row a1: io.prepare_groups against what the REAL ``BLUEProblem.setup_solver`` hands to the MOSAP
+    constructor (blue_models.py:453-509; golden captured there): default clique enumeration on non-complete
+    graphs with a cut-off model, user ``groups`` (unsorted members, non-cliques, groups outside model 0's
+    component -- dropped; size classes left empty) and per-output ``multi_groups``.  Integer work: bit-exact."""
+    from bluest_b200 import io
+    d = _load("setup.npz")
+    graph = io.load_graph_data(os.path.join(GOLDEN, "setup_graph_data.npz"))
+    assert graph["M"] == 7 and graph["n_outputs"] == 2
+    assert np.isnan(graph["C"][0][1, 4]) and graph["C"][0][2, 5] == 0.0                 # get_covariance view: 0 -> NaN, inf -> 0
+    kw = {"default_K3": dict(K=3), "default_K7": dict(K=7),
+          "user_groups": dict(K=3, groups=[[3, 0], [0], [2, 1, 0], [1, 4], [4, 1, 0], [6], [0, 6], [5, 2, 0], [3], [0, 3, 2, 1], [2]]),
+          "user_multi": dict(K=3, multi_groups=[[[0], [1, 0], [2, 0, 1], [4, 3]], [[0], [0, 3], [2, 0], [6, 0], [1, 2], [5]]])}[tag]
+    K, Ks, groups, multi = io.prepare_groups(graph, **kw)
+    assert K == int(d[f"{tag}/K"]) and list(Ks) == d[f"{tag}/Ks"].tolist()
+    assert len(groups) == K
+    for k in range(K):
+        assert np.array_equal(np.array(groups[k], dtype=np.int64).reshape(-1, k + 1), d[f"{tag}/groups{k+1}"])
+    for n in range(2):
+        assert len(multi[n]) == int(d[f"{tag}/n_classes{n}"])
+        for k in range(len(multi[n])):
+            assert np.array_equal(np.array(multi[n][k], dtype=np.int64).reshape(-1, k + 1), d[f"{tag}/multi{n}_groups{k+1}"])
+        assert np.array_equal(blu.group_costs(multi[n], graph["costs"]), d[f"{tag}/multi_costs{n}"])
+    assert np.array_equal(blu.group_costs(groups, graph["costs"]), d[f"{tag}/costs"])
+    if tag == "user_groups":
+        assert kw["groups"][0] == [0, 3]                                               # sorted in place, like the reference
+    assert io.is_subclique(graph["adjacency"][0], [0, 2, 5]) and not io.is_subclique(graph["adjacency"][0], [0, 1, 4])
+    with pytest.raises(ValueError):
+        io.prepare_groups(graph, multi_groups=[[[0]]])
+
+
+def test_setup_solver_front_end_on_oracle_contexts(monkeypatch):
+    """io.setup_solver (blue_models.py:448-538) end to end with user-supplied groups on a non-complete two-output
+    graph; the device contexts are oracle-backed stand-ins that speak the split begin/end evaluation protocol,
+    so the REAL MOSAP.variances / solve / integer projection run.  Checks the reference's ``blue_data`` contract."""
+    import bluest_b200.mosap as mosap_mod
+    from bluest_b200 import _lib, intproj, io
+
+    class StubSAP(_OracleOutput):
+        def __init__(self, C, K, groups, costs, verbose=True, device=0):
+            super().__init__(C, K, [[list(g) for g in gk] for gk in groups[:K]])
+
+        def variance_GH(self, m, delta=0, nohess=False):
+            return self.o.variance_GH(m, delta, nohess=nohess, hess_mode="factored")
+
+        def variance_GH_begin(self, m, delta=0, nohess=False, grad=True):
+            self._pending = (np.asarray(m, dtype=float), delta, nohess, grad)
+
+        def variance_GH_end(self):
+            m, delta, nohess, grad = self._pending
+            if np.abs(m).max() < 0.05:
+                return np.inf, None, None, _lib.FLAG_TINY
+            if not grad:
+                return self.o.variance(m, delta), None, None, 0
+            v, g, h = self.o.variance_GH(m, delta, nohess=nohess, hess_mode="factored")
+            return v, g, h, 0
+
+    monkeypatch.setattr(mosap_mod, "SAP", StubSAP)
+    monkeypatch.setattr(intproj, "candidate_variances", _fake_candidates)
+    graph = io.load_graph_data(os.path.join(GOLDEN, "setup_graph_data.npz"))
+    user = [[3, 0], [0], [2, 1, 0], [1, 4], [4, 1, 0], [6], [0, 6], [5, 2, 0], [3], [0, 3, 2, 1], [2], [1], [0, 1]]
+    eps = [0.25 * np.sqrt(graph["C"][n][0, 0]) for n in range(2)]
+    np.random.seed(5)
+    mosap, blue = io.setup_solver(graph, K=3, eps=eps, groups=[list(g) for g in user])
+    assert set(blue) == {"models", "samples", "errors", "total_cost"}
+    assert len(blue["models"]) == len(blue["samples"]) == int((mosap.samples > 0).sum())
+    assert all(s > 0 for s in blue["samples"]) and mosap.samples.dtype.kind == "i"
+    picked = [mosap.flattened_groups[i] for i in np.flatnonzero(mosap.samples)]
+    assert blue["models"] == picked
+    assert blue["total_cost"] == mosap.samples @ mosap.costs
+    assert np.all(blue["errors"] <= np.array(eps) * np.sqrt(1.0001) * (1 + 1e-9))          # projection accepts V <= 1.0001 eps^2
+    assert np.allclose(blue["errors"] ** 2, mosap.variances(mosap.samples))
+    # budget wins when both are given (blue_models.py:450); neither is an error
+    with pytest.raises(ValueError):
+        io.setup_solver(graph, K=3)
