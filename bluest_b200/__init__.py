@@ -9,7 +9,7 @@ from .groups import (balanced_slices, stream_cost, enumerate_cliques, enumerate_
                      indicator_ES, mappings, union_groups)
 from .sap import SAP                                    # noqa: F401
 from .mosap import MOSAP, BLUESTError                   # noqa: F401
-from .pilot import pilot_covariance                     # noqa: F401
+from .pilot import pilot_covariance, fill_missing_covariances, estimate_missing_covariances   # noqa: F401
 from . import cmisc, intproj, io                        # noqa: F401
 from .dist import ShardedEvaluator, GpuEngine          # noqa: F401
 from .install import install, uninstall                # noqa: F401

@@ -484,3 +484,30 @@ def test_setup_solver_front_end_on_oracle_contexts(monkeypatch):
     # budget wins when both are given (blue_models.py:450); neither is an error
     with pytest.raises(ValueError):
         io.setup_solver(graph, K=3)
+
+
+def test_fill_missing_covariances_matches_the_reference_rule():
+    """blue_models.py:340-346 restated with networkx exactly as the reference walks the graph edges."""
+    import networkx as nx
+    from bluest_b200.pilot import fill_missing_covariances
+    rng = np.random.RandomState(0)
+    N = 6
+    B = rng.randn(N, 3 * N); C_hat = B @ B.T / (3 * N)
+    C_hat[1, 4] = C_hat[4, 1] = 1e-9 * np.sqrt(C_hat[1, 1] * C_hat[4, 4])     # practically uncorrelated pair
+    A = np.full((N, N), np.nan)
+    A[0, 5] = A[5, 0] = 0.0                      # never coupled: no edge
+    A[2, 3] = A[3, 2] = 0.77                     # known already
+    A[2, 2] = 1.5
+    # the reference's loop
+    G = nx.from_numpy_array(A.copy())
+    for i, j, c in G.edges(data=True):
+        if np.isnan(c["weight"]):
+            if abs(C_hat[i, j] / np.sqrt(C_hat[i, i] * C_hat[j, j])) < 1.0e-7:
+                G[i][j]["weight"] = np.inf
+            else:
+                G[i][j]["weight"] = C_hat[i, j]
+    want = nx.adjacency_matrix(G).toarray()
+    got = fill_missing_covariances(A, C_hat)
+    assert np.array_equal(got, want)
+    assert np.isinf(got[1, 4]) and got[0, 5] == 0.0 and got[2, 3] == 0.77 and got[2, 2] == 1.5 and got[0, 0] == C_hat[0, 0]
+    assert np.isnan(A[0, 1])                       # the input is not modified
