@@ -606,7 +606,7 @@ def run_ours(args):
                "roofline": {"bound": "hbm", "kernel": "blu_hess_kernel<4,true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                             "avg_launch_ms": hess_ms, "peak_source": peak_src,
-                            "whole_eval_frac": (8.0 * L * L + 16.0 * N * L + 16.0 * 8 * N * (N + 1) * 2 ** (N - 2) + 24.0 * L)
+                            "whole_eval_frac": (8.0 * L * L + 16.0 * N * L + 16.0 * N * (N + 1) * 2 ** (N - 2) + 24.0 * L)
                                                / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak},
                "phases_ms": {"phi_pinv": float(np.mean(phases[:, 0])), "grad_uv": float(np.mean(phases[:, 1])),
                              "hessian": hess_ms, "eval_total": float(np.mean(phases[:, 3]))},

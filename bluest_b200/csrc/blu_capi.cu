@@ -104,7 +104,6 @@ struct blu_ctx {
     BluXchg *d_xchg = nullptr;         // this rank's exchange buffer (CUDA IPC shared)
     BluPeers peers{};                  // peers as mapped here; world == 0: not connected
     std::vector<void *> ipc_opened;
-    unsigned long long epoch = 0;
     double *d_Sop = nullptr;           // S = 2 pinv(Phi) of the evaluation the resident U factor belongs to (the operator's own copy)
     double *d_hvpart = nullptr, *d_hvp = nullptr, *d_hvout = nullptr;   // Hessian mat-vec: CTA partials of t, staged p and H p
     int hv_grid = 1;
@@ -215,11 +214,12 @@ static int build_chunks(blu_ctx *c)
     c->phi_warps = blu_stream_smem_bytes(c->sd, BLU_PHI_WARPS * c->N * c->N, (int)c->cls.size(), c->lutlen, BLU_PHI_WARPS) <= 200 * 1024 ? BLU_PHI_WARPS : 8;
     c->grid_phi = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + c->phi_warps * 3 - 1) / (c->phi_warps * 3)),
                                            (long long)c->nsm * (BLU_PHI_WARPS / c->phi_warps));
+    c->grid_phi = std::min(c->grid_phi, BLU_PHI_GROUP * BLU_PHI_MAXGROUPS);
     c->grid_grad = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS - 1) / BLU_STREAM_WARPS), (long long)c->nsm * 5);
     if (c->grid_phi > c->part_rows) {
         if (c->d_part) CUDA_TRY(cudaFree(c->d_part));
         c->d_part = nullptr;
-        CUDA_TRY(cudaMalloc(&c->d_part, sizeof(double) * (size_t)c->N * c->N * (c->grid_phi + 1)));   // + one row for the folded tile
+        CUDA_TRY(cudaMalloc(&c->d_part, sizeof(double) * (size_t)c->N * c->N * (c->grid_phi + BLU_PHI_MAXGROUPS + 1)));   // + the group sums of the in-kernel reduction
         c->part_rows = c->grid_phi;
     }
     return BLU_OK;
@@ -357,20 +357,22 @@ extern "C" int blu_ctx_set_covariance(blu_ctx *c, const double *C, double pivot_
     if (!(pivot_rtol >= 0.0)) pivot_rtol = 1e-10;
     const size_t NN = (size_t)c->N * c->N;
     CUDA_TRY(cudaMemcpyAsync(c->d_C, C, sizeof(double) * NN, cudaMemcpyHostToDevice, c->stream));
-    unsigned char *d_flag = nullptr;
-    CUDA_TRY(cudaMalloc(&d_flag, (size_t)c->L));
+    struct DevBuf {                                  // freed on every return path
+        void *p = nullptr;
+        ~DevBuf() { if (p) cudaFree(p); }
+    } flagbuf, todobuf;
+    CUDA_TRY(cudaMalloc(&flagbuf.p, (size_t)c->L));
+    unsigned char *d_flag = (unsigned char *)flagbuf.p;
     CUDA_TRY(cudaMemsetAsync(d_flag, 0, (size_t)c->L, c->stream));
     for (const BluClass &ci : c->cls) {
         blu_launch_invert_class(ci.k, c->nsm, c->stream, c->d_C, c->N, c->d_gidx + ci.ioff, ci.Lk, c->d_cinv + ci.coff, d_flag + ci.goff, pivot_rtol);
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { cudaFree(d_flag); return fail(BLU_ERR_CUDA, "invert kernel (k=%d): %s", ci.k, cudaGetErrorString(e)); }
+        if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "invert kernel (k=%d): %s", ci.k, cudaGetErrorString(e));
         c->launches++;
     }
     std::vector<unsigned char> flag((size_t)c->L);
-    cudaError_t e = cudaMemcpyAsync(flag.data(), d_flag, (size_t)c->L, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_flag);
-    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "group inversion failed: %s", cudaGetErrorString(e));
+    CUDA_TRY(cudaMemcpyAsync(flag.data(), d_flag, (size_t)c->L, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     // slow path for flagged groups
     long long nbad = 0;
     for (const BluClass &ci : c->cls) {
@@ -378,13 +380,13 @@ extern "C" int blu_ctx_set_covariance(blu_ctx *c, const double *C, double pivot_
         for (long long i = 0; i < ci.Lk; ++i) if (flag[(size_t)(ci.goff + i)]) todo.push_back(i);
         if (todo.empty()) continue;
         nbad += (long long)todo.size();
-        long long *d_todo = nullptr;
-        CUDA_TRY(cudaMalloc(&d_todo, sizeof(long long) * todo.size()));
+        if (todobuf.p) { cudaFree(todobuf.p); todobuf.p = nullptr; }
+        CUDA_TRY(cudaMalloc(&todobuf.p, sizeof(long long) * todo.size()));
+        long long *d_todo = (long long *)todobuf.p;
         CUDA_TRY(cudaMemcpyAsync(d_todo, todo.data(), sizeof(long long) * todo.size(), cudaMemcpyHostToDevice, c->stream));
         blu_launch_pinv_groups((unsigned)todo.size(), c->stream, c->d_C, c->N, ci.k, c->d_gidx + ci.ioff, d_todo, c->d_cinv + ci.coff, 1.0e-15);
-        e = cudaGetLastError();
+        cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        cudaFree(d_todo);
         if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "pinv kernel (k=%d): %s", ci.k, cudaGetErrorString(e));
         c->launches++;
     }
@@ -483,20 +485,15 @@ extern "C" int blu_ctx_assemble_psi(blu_ctx *c, double *psi)
 // --------------------------------------------------------------------------------------------
 static int launch_phi(blu_ctx *c, const double *d_m, double delta, int mode)
 {
+    // ONE launch: the streaming pass over the packed inverses, the in-kernel two-level reduction of the CTA
+    // tiles by the last CTAs to arrive, and the finish step (mode 0/1/2, or 3 = NVLink peer exchange) in that
+    // same last CTA (blu_phi.cuh).
     const int NN = c->N * c->N;
-    blu_phi_partial_kernel<<<c->grid_phi, c->phi_warps * 32, blu_stream_smem_bytes(c->sd, c->phi_warps * NN, (int)c->cls.size(), c->lutlen, c->phi_warps), c->stream>>>(
-        c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr);
-    KERNEL_CHECK(c);
-    const double *part = c->d_part;
-    int nparts = c->grid_phi;
-    if (nparts > 200) {                 // many partial tiles (N >= 17): fold them with NN/32 CTAs first (d_part has one spare row); below that the extra launch costs more than it saves
-        double *folded = c->d_part + (size_t)c->part_rows * NN;
-        blu_phi_fold_kernel<<<(NN + 31) / 32, BLU_FOLD_WARPS * 32, 0, c->stream>>>(c->d_part, nparts, NN, folded);
-        KERNEL_CHECK(c);
-        part = folded; nparts = 1;
-    }
-    blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
-        c->N, nparts, part, delta, mode, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr, c->peers, c->epoch);
+    const size_t smem = std::max(blu_stream_smem_bytes(c->sd, c->phi_warps * NN, (int)c->cls.size(), c->lutlen, c->phi_warps),
+                                 (size_t)BLU_FIN_SCRATCH_BYTES);
+    blu_phi_partial_kernel<<<c->grid_phi, c->phi_warps * 32, smem, c->stream>>>(
+        c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr,
+        mode, delta, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->peers);
     KERNEL_CHECK(c);
     return BLU_OK;
 }
@@ -863,6 +860,7 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
     for (int p = 0; p < npan; ++p) { ready[p].store(0); next[p].store(0); }
     const long long CW = 512;                                     // columns per work item
     auto worker = [&]() {
+        double *scratch = blu_host_mirror_scratch_alloc();           // owned by this worker for the whole download
         for (int p = 0; p < npan; ++p) {
             const long long r0 = p * PH, r1 = std::min<long long>(L, r0 + PH);
             const int nitems = (int)((L - r1 + CW - 1) / CW);
@@ -872,9 +870,10 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
                 const int it = next[p].fetch_add(1);
                 if (it >= nitems) break;
                 const long long c0 = r1 + it * CW, c1 = std::min<long long>(L, c0 + CW);
-                blu_host_mirror_block(hess, L, r0, r1, c0, c1);
+                blu_host_mirror_block(hess, L, r0, r1, c0, c1, scratch);
             }
         }
+        blu_host_mirror_scratch_free(scratch);
         blu_host_store_fence();                                     // streaming stores visible before join
     };
     const bool dbg = getenv("BLU_DEBUG_TIMING") != nullptr;
@@ -1224,7 +1223,7 @@ extern "C" int blu_shard_finish(blu_ctx *c, double delta, int want_grad, int wan
     const int NN = c->N * c->N;
     // BLU_BUF_PHI now holds the all-reduced upper-triangle sum; supp / max|m| were reduced by the host
     blu_phi_finish_kernel<<<1, BLU_FIN_THREADS, sizeof(double) * NN * BLU_FIN_SEG, c->stream>>>(
-        c->N, 0, c->d_part, delta, 1, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr, c->peers, c->epoch);
+        c->N, 0, c->d_part, delta, 1, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->d_hdr, c->peers);
     KERNEL_CHECK(c);
     if (want_grad || want_uv) return launch_grad(c, want_uv);
     return BLU_OK;
@@ -1246,16 +1245,19 @@ extern "C" int blu_ctx_peer_handle(blu_ctx *c, void *handle64)
     if (rc) return rc;
     if (!handle64) return fail(BLU_ERR_ARG, "null handle");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    if (!c->d_xchg) {
-        CUDA_TRY(cudaMalloc(&c->d_xchg, sizeof(BluXchg)));
-        CUDA_TRY(cudaMemset(c->d_xchg, 0, sizeof(BluXchg)));
-    }
+    if (!c->d_xchg) CUDA_TRY(cudaMalloc(&c->d_xchg, sizeof(BluXchg)));
+    // a fresh inbox for every connection: stale flags of an earlier one must never satisfy a wait
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemset(c->d_xchg, 0, sizeof(BluXchg)));
+    CUDA_TRY(cudaMemset(&c->d_hdr->epoch, 0, sizeof(unsigned long long)));
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, c->d_xchg));
     memcpy(handle64, &h, 64);
     return BLU_OK;
 }
 
+// Every rank calls blu_ctx_peer_handle, the handles are all-gathered on the host (that exchange is also the
+// barrier that orders every rank's inbox reset before anybody's first message), then blu_ctx_peer_connect.
 extern "C" int blu_ctx_peer_connect(blu_ctx *c, int world, int rank, const void *handles)
 {
     int rc = use(c);
@@ -1264,6 +1266,9 @@ extern "C" int blu_ctx_peer_connect(blu_ctx *c, int world, int rank, const void 
     if (!c->d_xchg) return fail(BLU_ERR_STATE, "call blu_ctx_peer_handle first");
     if (world > 1 && !handles) return fail(BLU_ERR_ARG, "null handles");
     if (c->N * c->N + 40 > BLU_XCHG_DOUBLES) return fail(BLU_ERR_ARG, "N too large for the exchange slot");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);      // mappings of an earlier connection
+    c->ipc_opened.clear();
     BluPeers p{};
     p.world = world; p.rank = rank;
     for (int r = 0; r < world; ++r) {
@@ -1276,7 +1281,6 @@ extern "C" int blu_ctx_peer_connect(blu_ctx *c, int world, int rank, const void 
         p.peer[r] = (BluXchg *)ptr;
     }
     c->peers = p;
-    c->epoch = 0;
     return BLU_OK;
 }
 
@@ -1287,8 +1291,7 @@ extern "C" int blu_shard_eval_fused(blu_ctx *c, const double *d_m, double delta,
     if (!c->have_inv) return fail(BLU_ERR_STATE, "inverses not set");
     if (c->peers.world < 1) return fail(BLU_ERR_STATE, "peers not connected: call blu_ctx_peer_connect first");
     if (!d_m) d_m = c->d_m;
-    c->launches = 0;
-    c->epoch += 1;                    // every rank counts its evaluations the same way
+    c->launches = 0;                  // the evaluation count (epoch) lives on the device: every rank's finish step increments its own
     rc = launch_phi(c, d_m, delta, 3);
     if (rc) return rc;
     if (want_grad || want_uv) return launch_grad(c, want_uv);

@@ -27,10 +27,18 @@ static inline void stream_run(double *dst, const double *src, int n)
     if (i < n) _mm_stream_si64((long long *)(dst + i), *(const long long *)(src + i));
 }
 
-void blu_host_mirror_block(double *H, long long L, long long r0, long long r1, long long c0, long long c1)
+double *blu_host_mirror_scratch_alloc() { return (double *)aligned_alloc(64, sizeof(double) * MIRROR_CW * MIRROR_MAXR); }
+void blu_host_mirror_scratch_free(double *buf) { free(buf); }
+
+// buf: the calling worker's transpose scratch (blu_host_mirror_scratch_alloc); NULL = no scratch could be
+// had: plain cached transpose, slower but correct.
+void blu_host_mirror_block(double *H, long long L, long long r0, long long r1, long long c0, long long c1, double *buf)
 {
-    static thread_local double *buf = nullptr;
-    if (!buf) buf = (double *)aligned_alloc(64, sizeof(double) * MIRROR_CW * MIRROR_MAXR);
+    if (!buf) {
+        for (long long r = r0; r < r1; ++r)
+            for (long long c = c0; c < c1; ++c) H[c * L + r] = H[r * L + c];
+        return;
+    }
     for (long long rb = r0; rb < r1; rb += MIRROR_MAXR) {
         const int nr = (int)std::min<long long>(MIRROR_MAXR, r1 - rb);
         for (long long cb = c0; cb < c1; cb += MIRROR_CW) {

@@ -23,5 +23,7 @@ cudaError_t blu_launch_v_from_u(int grid, cudaStream_t stream, const double *U, 
 
 // blu_hostmirror.cpp: H[c][r] = H[r][c] for r in [r0,r1), c in [c0,c1) of a dense row-major (L,L) host
 // matrix, written with streaming stores (no read-for-ownership of the destination lines).
-void blu_host_mirror_block(double *H, long long L, long long r0, long long r1, long long c0, long long c1);
+void blu_host_mirror_block(double *H, long long L, long long r0, long long r1, long long c0, long long c1, double *scratch);
+double *blu_host_mirror_scratch_alloc();          // one per worker thread, freed by the worker (NULL on failure: slow path)
+void blu_host_mirror_scratch_free(double *scratch);
 void blu_host_store_fence();

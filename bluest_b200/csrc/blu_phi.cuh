@@ -31,6 +31,8 @@ struct BluEvalHeader {          // small device-side status block of a context
     unsigned long long maxbits; // bit pattern of max|m|
     double scal[8];             // [0] variance [1] max|m| [2] sweeps [3] lambda_max [4] var (full pinv) [5] BLUE mean
     double xsup[32];            // first row of pinv(Phi[idx,idx]) scattered to model slots (PHIinvY0, misc.py:529-533)
+    unsigned long long epoch;   // evaluations of the fused multi-GPU path so far (device side: survives CUDA-graph replays)
+    unsigned tickets[40];       // arrival counters of the fused Phi reduction: [0] CTA groups, [1 + g] CTAs of group g (self-resetting)
 };
 
 // Explicit shared-space accesses with 32-bit addresses.  Through the generic pointers of the stream
@@ -106,12 +108,368 @@ __device__ __forceinline__ void blu_phi_chunk_any(const double *__restrict__ bas
     }
 }
 
+// Block-parallel in-place Gauss-Jordan inverse of the SPD n x n matrix in A (ld BLU_JLD), ping-pong
+// with B; one __syncthreads per pivot.  Returns (uniformly) false as soon as a pivot falls below
+// tol x its original diagonal entry (rank-deficient / indefinite): the caller then takes the
+// Jacobi pseudo-inverse.  On success the inverse is in the buffer returned through *out.
+__device__ __forceinline__ bool blu_block_gj(double *A, double *B, const double *diag0, int n, double tol,
+                                             double **out, int tid, int nthr)
+{
+    double *src = A, *dst = B;
+    for (int p = 0; p < n; ++p) {
+        const double piv = src[p * BLU_JLD + p];
+        if (!(piv > tol * diag0[p])) return false;            // same value in every thread
+        const double d = 1.0 / piv;
+        for (int t = tid; t < n * n; t += nthr) {
+            const int r = t / n, c = t - r * n;
+            const double arp = src[r * BLU_JLD + p], apc = src[p * BLU_JLD + c];
+            double v;
+            if (r == p) v = (c == p) ? d : apc * d;
+            else if (c == p) v = -(arp * d);
+            else v = fma(-(arp * d), apc, src[r * BLU_JLD + c]);
+            dst[r * BLU_JLD + c] = v;
+        }
+        __syncthreads();
+        double *tmp = src; src = dst; dst = tmp;
+    }
+    *out = src;
+    return true;
+}
+
+// pinv of the sub-block Phi[idx, idx] (idx: ns model ids) into P (ld BLU_JLD, ns x ns).
+// Fast path: Gauss-Jordan (the block is SPD and well conditioned in every regular evaluation);
+// fallback: Jacobi eigen pseudo-inverse with numpy's cutoff.  Returns the sweeps used (0 = fast path).
+__device__ __forceinline__ int blu_block_pinv(const double *phi, int N, const int *idx, int ns, double *A, double *V,
+                                              double *P, double *diag0, BluJacobiScratch *js, int tid, int nthr)
+{
+    for (int t = tid; t < ns * ns; t += nthr) {
+        const int r = t / ns, c = t - r * ns;
+        A[r * BLU_JLD + c] = phi[idx[r] * N + idx[c]];
+    }
+    if (tid < ns) diag0[tid] = phi[idx[tid] * N + idx[tid]];
+    __syncthreads();
+    double *res = nullptr;
+    if (blu_block_gj(A, V, diag0, ns, 1.0e-12, &res, tid, nthr)) {
+        for (int t = tid; t < ns * ns; t += nthr) {
+            const int r = t / ns, c = t - r * ns;
+            const int lo = r < c ? r : c, hi = r < c ? c : r;
+            P[r * BLU_JLD + c] = res[lo * BLU_JLD + hi];       // exactly symmetric
+        }
+        __syncthreads();
+        return 0;
+    }
+    __syncthreads();
+    const int n2 = ns + (ns & 1);
+    for (int t = tid; t < n2 * n2; t += nthr) {
+        const int r = t / n2, c = t - r * n2;
+        A[r * BLU_JLD + c] = (r < ns && c < ns) ? phi[idx[r] * N + idx[c]] : 0.0;
+    }
+    __syncthreads();
+    blu_sym_pinv(A, V, n2, js, P, BLU_JLD, ns, 1.0e-15, tid, nthr);
+    return js->sweeps;
+}
+
+#define BLU_FIN_THREADS 512
+#define BLU_MAX_PEERS 16
+#define BLU_XCHG_DOUBLES 1088                 // N*N + 40 <= 1064 doubles per message
+#define BLU_FIN_SEG 8
+#define BLU_PHI_GROUP 16                      // CTAs per group of the two-level in-kernel reduction of the partial tiles
+#define BLU_PHI_MAXGROUPS 39
+#define BLU_PEER_TIMEOUT_NS 4000000000ull     // a rank that never publishes: give up after 4 s instead of spinning forever
+
+// One rank's INBOX for the fused (peer-memory) all-reduce of the partial Phi.  Push model: at evaluation
+// number `epoch` every rank stores its partial sums (N*N raw upper-triangle sums + 33 SUM-reducible
+// indicators) into slot [epoch & 1][its own rank] of EVERY rank's inbox -- remote stores over NVLink into
+// cudaMalloc memory shared through CUDA IPC -- then, after a system-scope fence, the flag
+// ready[epoch & 1][its own rank] = epoch.  A rank only ever polls and reads its OWN memory.  Slot parity is
+// safe: a rank publishes epoch e+2 only after it has consumed epoch e+1, which every peer published
+// after it had finished reading epoch e.
+struct BluXchg {
+    double data[2][BLU_MAX_PEERS][BLU_XCHG_DOUBLES];
+    unsigned long long ready[2][BLU_MAX_PEERS];
+};
+struct BluPeers {
+    BluXchg *peer[BLU_MAX_PEERS];             // peer[r] = rank r's inbox as mapped in THIS process
+    int world, rank;
+};
+
+// Pre-reduction of the CTA partials for the stand-alone finish kernel (kept for the NCCL path and as the
+// reference point of the fused in-kernel reduction): CTA b owns entries [32b, 32b+32) of the N x N tile.
+#define BLU_FOLD_WARPS 8
+__global__ void __launch_bounds__(BLU_FOLD_WARPS * 32)
+blu_phi_fold_kernel(const double *__restrict__ part, int nparts, int NN, double *__restrict__ out)
+{
+    __shared__ double sh[BLU_FOLD_WARPS][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 32 + lane;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (e < NN) {
+        int p = w;
+        for (; p + 3 * BLU_FOLD_WARPS < nparts; p += 4 * BLU_FOLD_WARPS) {
+            a0 += part[(long long)p * NN + e];
+            a1 += part[(long long)(p + BLU_FOLD_WARPS) * NN + e];
+            a2 += part[(long long)(p + 2 * BLU_FOLD_WARPS) * NN + e];
+            a3 += part[(long long)(p + 3 * BLU_FOLD_WARPS) * NN + e];
+        }
+        for (; p < nparts; p += BLU_FOLD_WARPS) a0 += part[(long long)p * NN + e];
+    }
+    sh[w][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (w == 0 && e < NN) {
+        double s = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < BLU_FOLD_WARPS; ++ww) s += sh[ww][lane];
+        out[e] = s;
+    }
+}
+
+// Shared-memory scratch of the finish step (about 35 KB): carved from static arrays by the stand-alone
+// finish kernel and from the (by then idle) streaming ring by the fused Phi kernel.
+struct BluFinScratch {
+    double *A, *V, *Ph;       // BLU_JMAX x BLU_JLD each; Ph holds the un-mirrored upper-triangle sums on entry
+    double *Pm;               // BLU_JMAX x BLU_JMAX: the finished Phi
+    double *diag0;            // BLU_JMAX
+    BluJacobiScratch *js;
+    int *sidx;                // BLU_JMAX
+    int *ns;
+    unsigned *amask;
+};
+#define BLU_FIN_SCRATCH_BYTES (sizeof(double) * (3 * BLU_JMAX * BLU_JLD + BLU_JMAX * BLU_JMAX + BLU_JMAX) + sizeof(BluJacobiScratch) + sizeof(int) * (BLU_JMAX + 2) + 64)
+__device__ __forceinline__ BluFinScratch blu_fin_carve(unsigned char *raw)
+{
+    BluFinScratch f;
+    double *d = reinterpret_cast<double *>(raw);
+    f.A = d; d += BLU_JMAX * BLU_JLD;
+    f.V = d; d += BLU_JMAX * BLU_JLD;
+    f.Ph = d; d += BLU_JMAX * BLU_JLD;
+    f.Pm = d; d += BLU_JMAX * BLU_JMAX;
+    f.diag0 = d; d += BLU_JMAX;
+    f.js = reinterpret_cast<BluJacobiScratch *>(d);
+    int *ip = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(d) + ((sizeof(BluJacobiScratch) + 7) / 8) * 8);
+    f.sidx = ip; ip += BLU_JMAX;
+    f.ns = ip; ++ip;
+    f.amask = reinterpret_cast<unsigned *>(ip);
+    return f;
+}
+
+__device__ __forceinline__ unsigned long long blu_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Everything after the local reduction of the partial tiles, for one CTA (any block size):
+// f.Ph holds the raw upper-triangle sums of this rank.
+//   mode 0: mirror + delta only (get_phi).  mode 1: + pinv, x, S = 2 pinv, variance (misc.py:487-490).
+//   mode 2: hand the raw sums + SUM-reducible indicators out in `phi` (partial of a group slice, before an
+//           NCCL all-reduce).
+//   mode 3: fused multi-GPU path -- push the raw sums into every rank's inbox over NVLink, wait for every
+//           rank's message of this epoch, sum the inbox in rank order (bit-identical Phi on every rank),
+//           then continue exactly like mode 1.
+//   allreduced: the sums in f.Ph and the indicators in phi[NN..NN+32] come from an all-reduce (stand-alone
+//           finish kernel after NCCL).
+__device__ __forceinline__ void blu_finish_body(int N, double delta, int mode, bool allreduced,
+                                                double *__restrict__ phi, double *__restrict__ pinv, double *__restrict__ xrow,
+                                                double *__restrict__ S, BluEvalHeader *hdr, const BluPeers &peers,
+                                                const BluFinScratch &f, int tid, int nthr)
+{
+    const int NN = N * N;
+    double *Ph = f.Ph, *Pm = f.Pm;
+    if (mode == 3) {
+        const unsigned long long epoch = hdr->epoch + 1ull;              // same count on every rank
+        const int slot = (int)(epoch & 1ull);
+        const unsigned sp = hdr->supp;
+        const double mx = __longlong_as_double((long long)hdr->maxbits);
+        if (tid == 0) *f.ns = 0;
+        __syncthreads();
+        for (int r = 0; r < peers.world; ++r) {                          // remote stores: fire and forget
+            double *dst = peers.peer[r]->data[slot][peers.rank];
+            for (int e = tid; e < NN; e += nthr) dst[e] = Ph[(e / N) * BLU_JLD + (e % N)];
+            if (tid < 32) dst[NN + tid] = (sp >> tid) & 1u ? 1.0 : 0.0;
+            if (tid == 32) dst[NN + 32] = mx >= 0.05 ? 1.0 : 0.0;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < peers.world)                                           // publish: one flag per destination
+            *((volatile unsigned long long *)&peers.peer[tid]->ready[slot][peers.rank]) = epoch;
+        if (tid == 0) { hdr->supp = 0u; hdr->maxbits = 0ull; hdr->epoch = epoch; }
+        BluXchg *mine = peers.peer[peers.rank];
+        if (tid < peers.world) {                                         // wait for every rank's message (local polling)
+            volatile unsigned long long *flag = (volatile unsigned long long *)&mine->ready[slot][tid];
+            const unsigned long long t0 = blu_globaltimer();
+            unsigned spins = 0;
+            while (*flag < epoch) {
+                if ((++spins & 1023u) == 0u && blu_globaltimer() - t0 > BLU_PEER_TIMEOUT_NS) { *f.ns = -1; break; }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (*f.ns == -1) {                                               // a peer never arrived: report, do not hang
+            if (tid == 0) { hdr->flags = BLU_FLAG_PEER_TIMEOUT; hdr->scal[0] = nan(""); }
+            return;
+        }
+        for (int e = tid; e < NN + 33; e += nthr) {
+            double sum = 0.0;
+            for (int r = 0; r < peers.world; ++r) sum += __ldcv(&mine->data[slot][r][e]);     // rank order, uncached
+            phi[e] = sum;
+        }
+        __syncthreads();
+        for (int e = tid; e < NN; e += nthr) Ph[(e / N) * BLU_JLD + (e % N)] = phi[e];
+        __syncthreads();
+        allreduced = true;
+        mode = 1;
+    }
+    if (mode == 2) {
+        for (int e = tid; e < NN; e += nthr) phi[e] = Ph[(e / N) * BLU_JLD + (e % N)];
+        const unsigned sp = hdr->supp;
+        const double mx = __longlong_as_double((long long)hdr->maxbits);
+        __syncthreads();
+        if (tid < 32) phi[NN + tid] = (sp >> tid) & 1u ? 1.0 : 0.0;
+        if (tid == 32) phi[NN + 32] = mx >= 0.05 ? 1.0 : 0.0;
+        if (tid == 0) { hdr->supp = 0u; hdr->maxbits = 0ull; }
+        return;
+    }
+    // mirror the upper triangle, add delta on the diagonal
+    for (int e = tid; e < NN; e += nthr) {
+        const int r = e / N, c = e - r * N;
+        const int lo = r < c ? r : c, hi = r < c ? c : r;
+        double v = Ph[lo * BLU_JLD + hi];
+        if (r == c) v += delta;
+        phi[e] = v;
+        Pm[e] = v;
+    }
+    __syncthreads();
+    unsigned supp;
+    double maxabs;
+    if (!allreduced) {
+        supp = hdr->supp;
+        maxabs = __longlong_as_double((long long)hdr->maxbits);
+    } else {                              // SUM-reduced encodings
+        supp = 0u;
+        for (int a = 0; a < 32; ++a) if (phi[NN + a] > 0.0) supp |= 1u << a;
+        maxabs = phi[NN + 32] > 0.0 ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {                      // reset the reduction cells for the next evaluation
+        hdr->supp = 0u; hdr->maxbits = 0ull;
+        hdr->scal[1] = maxabs;
+    }
+    if (mode == 0) return;
+
+    unsigned flags = 0u;
+    if (maxabs < 0.05) {                 // misc.py:464,484
+        if (tid == 0) { hdr->flags = BLU_FLAG_TINY; hdr->scal[0] = INFINITY; }
+        return;
+    }
+    const unsigned all = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
+    if (!(supp & 1u)) flags |= BLU_FLAG_NO_MODEL0;
+    if ((supp & all) != all) flags |= BLU_FLAG_PARTIAL;
+
+    // ---- full pseudo-inverse (misc.py:487) ----
+    // Rows/columns of Phi that are entirely zero (models in no group with m_i != 0) split off as a
+    // zero block: pinv([[A,0],[0,0]]) = [[pinv(A),0],[0,0]].  The remaining "active" block is SPD
+    // in every regular evaluation and is inverted by Gauss-Jordan; Jacobi only if that fails.
+    if (tid < 32) {
+        bool nz = false;
+        if (tid < N) for (int c = 0; c < N; ++c) nz = nz || (Pm[tid * N + c] != 0.0);
+        const unsigned am = __ballot_sync(BLU_FULL, nz);
+        if (tid == 0) {
+            int cnt = 0;
+            for (int a = 0; a < N; ++a) if (am >> a & 1u) f.sidx[cnt++] = a;
+            *f.ns = cnt;
+            *f.amask = am;
+        }
+    }
+    __syncthreads();
+    const int na = *f.ns;
+    const unsigned active = *f.amask;
+    if (tid == 0) f.js->lmax = 0.0;
+    int sweeps = blu_block_pinv(Pm, N, f.sidx, na, f.A, f.V, Ph, f.diag0, f.js, tid, nthr);
+    for (int e = tid; e < NN; e += nthr) {
+        const int r = e / N, c = e - r * N;
+        double v = 0.0;
+        if ((active >> r & 1u) && (active >> c & 1u))
+            v = Ph[__popc(active & ((1u << r) - 1u)) * BLU_JLD + __popc(active & ((1u << c) - 1u))];
+        pinv[e] = v;
+        S[e] = 2.0 * v;
+        if (r == 0) xrow[c] = v;
+    }
+    __syncthreads();
+    if (tid == 0) { hdr->scal[2] = (double)sweeps; hdr->scal[3] = f.js->lmax; hdr->scal[4] = pinv[0]; }
+
+    // ---- variance on the support sub-block (misc.py:489-490) ----
+    const unsigned sup = supp & all;
+    if (sup == (active & all)) {
+        // pinv(Phi[idx,idx])[0,0] is the (first supported model) diagonal entry of the block above
+        const int s0 = sup ? __ffs(sup) - 1 : 0;
+        if (tid == 0) { hdr->scal[0] = sup ? pinv[s0 * N + s0] : INFINITY; hdr->flags = flags; }
+        if (tid < 32) hdr->xsup[tid] = (tid < N && (sup >> tid & 1u)) ? pinv[s0 * N + tid] : 0.0;
+        return;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cnt = 0;
+        for (int a = 0; a < N; ++a) if (sup >> a & 1u) f.sidx[cnt++] = a;
+        *f.ns = cnt;
+    }
+    __syncthreads();
+    const int nsub = *f.ns;
+    if (nsub > 0) blu_block_pinv(Pm, N, f.sidx, nsub, f.A, f.V, Ph, f.diag0, f.js, tid, nthr);
+    if (tid == 0) { hdr->scal[0] = nsub > 0 ? Ph[0] : INFINITY; hdr->flags = flags; }
+    if (tid < 32) hdr->xsup[tid] = 0.0;
+    __syncthreads();
+    if (tid < nsub) hdr->xsup[f.sidx[tid]] = Ph[tid];
+}
+
+// Stand-alone finish kernel (one CTA): fixed-order sum of `nparts` partial tiles (or, nparts == 0, the
+// all-reduced sums already sitting in `phi`), then blu_finish_body.
+__global__ void __launch_bounds__(BLU_FIN_THREADS)
+blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double delta, int mode,
+                      double *__restrict__ phi, double *__restrict__ pinv, double *__restrict__ xrow,
+                      double *__restrict__ S, BluEvalHeader *hdr, BluPeers peers)
+{
+    __shared__ __align__(16) unsigned char fraw[BLU_FIN_SCRATCH_BYTES];
+    extern __shared__ double red[];              // BLU_FIN_SEG x N*N staging for the partial sums
+    const BluFinScratch f = blu_fin_carve(fraw);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int NN = N * N;
+    if (tid == 0) *f.ns = 0;
+    if (nparts > 0) {
+        for (int t = tid; t < NN * BLU_FIN_SEG; t += nthr) {
+            const int seg = t / NN, e = t - seg * NN;
+            double s = 0.0;
+            int p = seg;
+            for (; p + 3 * BLU_FIN_SEG < nparts; p += 4 * BLU_FIN_SEG) {       // 4 loads in flight, same association every run
+                const double a0 = part[(long long)p * NN + e], a1 = part[(long long)(p + BLU_FIN_SEG) * NN + e];
+                const double a2 = part[(long long)(p + 2 * BLU_FIN_SEG) * NN + e], a3 = part[(long long)(p + 3 * BLU_FIN_SEG) * NN + e];
+                s += a0; s += a1; s += a2; s += a3;
+            }
+            for (; p < nparts; p += BLU_FIN_SEG) s += part[(long long)p * NN + e];
+            red[seg * NN + e] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < NN; e += nthr) {
+            double s = 0.0;
+#pragma unroll
+            for (int seg = 0; seg < BLU_FIN_SEG; ++seg) s += red[seg * NN + e];
+            f.Ph[(e / N) * BLU_JLD + (e % N)] = s;
+        }
+    } else {
+        for (int e = tid; e < NN; e += nthr) f.Ph[(e / N) * BLU_JLD + (e % N)] = phi[e];
+    }
+    __syncthreads();
+    blu_finish_body(N, delta, mode, nparts == 0, phi, pinv, xrow, S, hdr, peers, f, tid, nthr);
+}
+
 // `chunks` lists the work of this launch (whole context or the owned slice); see blu_stream.cuh.
 __global__ void __launch_bounds__(BLU_PHI_WARPS * 32)
 blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks, int sd,
                        const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
                        const unsigned *__restrict__ gmask, const double *__restrict__ m,
-                       double *__restrict__ part, BluEvalHeader *hdr)
+                       double *__restrict__ part, BluEvalHeader *hdr,
+                       int fin_mode, double delta, double *__restrict__ phi, double *__restrict__ pinv, double *__restrict__ xrow,
+                       double *__restrict__ S, BluPeers peers)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int NN = N * N;
@@ -177,298 +535,55 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
         for (int ww = 0; ww < nwarps; ++ww) sum += sm.extra[ww * NN + t];
         part[(long long)blockIdx.x * NN + t] = sum;
     }
-}
+    if (fin_mode < 0) return;                             // partial tiles only (stand-alone finish kernel follows)
 
-// Block-parallel in-place Gauss-Jordan inverse of the SPD n x n matrix in A (ld BLU_JLD), ping-pong
-// with B; one __syncthreads per pivot.  Returns (uniformly) false as soon as a pivot falls below
-// tol x its original diagonal entry (rank-deficient / indefinite): the caller then takes the
-// Jacobi pseudo-inverse.  On success the inverse is in the buffer returned through *out.
-__device__ __forceinline__ bool blu_block_gj(double *A, double *B, const double *diag0, int n, double tol,
-                                             double **out, int tid, int nthr)
-{
-    double *src = A, *dst = B;
-    for (int p = 0; p < n; ++p) {
-        const double piv = src[p * BLU_JLD + p];
-        if (!(piv > tol * diag0[p])) return false;            // same value in every thread
-        const double d = 1.0 / piv;
-        for (int t = tid; t < n * n; t += nthr) {
-            const int r = t / n, c = t - r * n;
-            const double arp = src[r * BLU_JLD + p], apc = src[p * BLU_JLD + c];
-            double v;
-            if (r == p) v = (c == p) ? d : apc * d;
-            else if (c == p) v = -(arp * d);
-            else v = fma(-(arp * d), apc, src[r * BLU_JLD + c]);
-            dst[r * BLU_JLD + c] = v;
-        }
-        __syncthreads();
-        double *tmp = src; src = dst; dst = tmp;
-    }
-    *out = src;
-    return true;
-}
-
-// pinv of the sub-block Phi[idx, idx] (idx: ns model ids) into P (ld BLU_JLD, ns x ns).
-// Fast path: Gauss-Jordan (the block is SPD and well conditioned in every regular evaluation);
-// fallback: Jacobi eigen pseudo-inverse with numpy's cutoff.  Returns the sweeps used (0 = fast path).
-__device__ __forceinline__ int blu_block_pinv(const double *phi, int N, const int *idx, int ns, double *A, double *V,
-                                              double *P, double *diag0, BluJacobiScratch *js, int tid, int nthr)
-{
-    for (int t = tid; t < ns * ns; t += nthr) {
-        const int r = t / ns, c = t - r * ns;
-        A[r * BLU_JLD + c] = phi[idx[r] * N + idx[c]];
-    }
-    if (tid < ns) diag0[tid] = phi[idx[tid] * N + idx[tid]];
-    __syncthreads();
-    double *res = nullptr;
-    if (blu_block_gj(A, V, diag0, ns, 1.0e-12, &res, tid, nthr)) {
-        for (int t = tid; t < ns * ns; t += nthr) {
-            const int r = t / ns, c = t - r * ns;
-            const int lo = r < c ? r : c, hi = r < c ? c : r;
-            P[r * BLU_JLD + c] = res[lo * BLU_JLD + hi];       // exactly symmetric
-        }
-        __syncthreads();
-        return 0;
-    }
-    __syncthreads();
-    const int n2 = ns + (ns & 1);
-    for (int t = tid; t < n2 * n2; t += nthr) {
-        const int r = t / n2, c = t - r * n2;
-        A[r * BLU_JLD + c] = (r < ns && c < ns) ? phi[idx[r] * N + idx[c]] : 0.0;
-    }
-    __syncthreads();
-    blu_sym_pinv(A, V, n2, js, P, BLU_JLD, ns, 1.0e-15, tid, nthr);
-    return js->sweeps;
-}
-
-#define BLU_FIN_THREADS 512
-#define BLU_MAX_PEERS 16
-#define BLU_XCHG_DOUBLES 1088                 // N*N + 40 <= 1064 doubles per slot
-
-// One rank's exchange buffer for the fused (peer-memory) all-reduce of the partial Phi:
-// two slots (epoch parity) of raw upper-triangle sums + SUM-reducible indicators, and the epoch
-// each slot was last published for.  Lives in cudaMalloc memory shared through CUDA IPC, so the
-// finish kernel of every rank reads every other rank's slot directly over NVLink.
-struct BluXchg {
-    double data[2][BLU_XCHG_DOUBLES];
-    unsigned long long ready[2];
-};
-struct BluPeers {
-    BluXchg *peer[BLU_MAX_PEERS];             // peer[r] = rank r's buffer as mapped in THIS process
-    int world, rank;
-};
-#define BLU_FIN_SEG 8
-
-// Pre-reduction of the CTA partials for the finish kernel: CTA b owns entries [32b, 32b+32) of the
-// N x N tile, its 8 warps sum interleaved subsets of the `nparts` partial tiles (coalesced rows, four
-// independent loads in flight per thread) and are combined in warp order -- a fixed association, so
-// the result is bit-reproducible.  One CTA doing this alone (the finish kernel) is latency-bound on
-// ~1 MB of partials; spread over NN/32 CTAs it takes a few microseconds.
-#define BLU_FOLD_WARPS 8
-__global__ void __launch_bounds__(BLU_FOLD_WARPS * 32)
-blu_phi_fold_kernel(const double *__restrict__ part, int nparts, int NN, double *__restrict__ out)
-{
-    __shared__ double sh[BLU_FOLD_WARPS][32];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * 32 + lane;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (e < NN) {
-        int p = w;
-        for (; p + 3 * BLU_FOLD_WARPS < nparts; p += 4 * BLU_FOLD_WARPS) {
-            a0 += part[(long long)p * NN + e];
-            a1 += part[(long long)(p + BLU_FOLD_WARPS) * NN + e];
-            a2 += part[(long long)(p + 2 * BLU_FOLD_WARPS) * NN + e];
-            a3 += part[(long long)(p + 3 * BLU_FOLD_WARPS) * NN + e];
-        }
-        for (; p < nparts; p += BLU_FOLD_WARPS) a0 += part[(long long)p * NN + e];
-    }
-    sh[w][lane] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (w == 0 && e < NN) {
-        double s = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < BLU_FOLD_WARPS; ++ww) s += sh[ww][lane];
-        out[e] = s;
-    }
-}
-
-// mode 0: reduce + mirror + delta only (get_phi).  mode 1: + pinv, x, S, variance.
-// mode 2: reduce only, no mirror/delta (partial Phi of a group slice, before the all-reduce).
-// nparts == 0: Phi already sits in `phi` as an un-mirrored upper-triangle sum (after all-reduce).
-// mode 3: fused multi-GPU path -- reduce the local CTA partials, publish them in this rank's exchange
-//         slot, wait for every peer's slot of the same epoch, sum all ranks in rank order (every rank
-//         gets the bit-identical Phi), then continue exactly like mode 1.  One kernel does the
-//         local reduction, the all-reduce over NVLink peer memory and the pseudo-inverse.
-__global__ void __launch_bounds__(BLU_FIN_THREADS)
-blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double delta, int mode,
-                      double *__restrict__ phi, double *__restrict__ pinv, double *__restrict__ xrow,
-                      double *__restrict__ S, BluEvalHeader *hdr, BluPeers peers, unsigned long long epoch)
-{
-    __shared__ double A[BLU_JMAX * BLU_JLD], V[BLU_JMAX * BLU_JLD], Ph[BLU_JMAX * BLU_JLD];
-    __shared__ double Pm[BLU_JMAX * BLU_JMAX];   // the finished Phi (mirrored, + delta), N x N dense: everything below reads this copy
-    extern __shared__ double red[];              // BLU_FIN_SEG x N*N staging for the partial sums
-    __shared__ BluJacobiScratch js;
-    __shared__ int sidx[BLU_JMAX];
-    __shared__ double diag0[BLU_JMAX];
-    __shared__ int ns;
-    __shared__ unsigned amask;
+    // ---- fused reduction + finish: the LAST CTA to arrive folds the partial tiles and carries on ----------
+    // Two levels so that no CTA reads more than BLU_PHI_GROUP + BLU_PHI_MAXGROUPS tiles: the last CTA of each
+    // group of BLU_PHI_GROUP consecutive CTAs folds the group's tiles (CTA order), the last group to finish folds
+    // the group sums (group order) -- a fixed association whichever CTA happens to do it, so the result is
+    // bit-reproducible.  Then the same CTA does the finish step (peer exchange, pinv, variance): one launch
+    // instead of partial -> fold -> finish.
+    __shared__ int s_last;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int NN = N * N;
-
-    if (nparts > 0) {
-        for (int t = tid; t < NN * BLU_FIN_SEG; t += nthr) {
-            const int seg = t / NN, e = t - seg * NN;
-            double s = 0.0;
-            int p = seg;
-            for (; p + 3 * BLU_FIN_SEG < nparts; p += 4 * BLU_FIN_SEG) {       // 4 loads in flight, same association every run
-                const double a0 = part[(long long)p * NN + e], a1 = part[(long long)(p + BLU_FIN_SEG) * NN + e];
-                const double a2 = part[(long long)(p + 2 * BLU_FIN_SEG) * NN + e], a3 = part[(long long)(p + 3 * BLU_FIN_SEG) * NN + e];
-                s += a0; s += a1; s += a2; s += a3;
-            }
-            for (; p < nparts; p += BLU_FIN_SEG) s += part[(long long)p * NN + e];
-            red[seg * NN + e] = s;
-        }
-        __syncthreads();
-        for (int e = tid; e < NN; e += nthr) {
-            double s = 0.0;
-#pragma unroll
-            for (int seg = 0; seg < BLU_FIN_SEG; ++seg) s += red[seg * NN + e];
-            Ph[(e / N) * BLU_JLD + (e % N)] = s;
-        }
-    } else {
-        for (int e = tid; e < NN; e += nthr) Ph[(e / N) * BLU_JLD + (e % N)] = phi[e];
-    }
-    __syncthreads();
-    if (mode == 3) {
-        const int slot = (int)(epoch & 1ull);
-        BluXchg *mine = peers.peer[peers.rank];
-        const unsigned sp = hdr->supp;
-        const double mx = __longlong_as_double((long long)hdr->maxbits);
-        for (int e = tid; e < NN; e += nthr) mine->data[slot][e] = Ph[(e / N) * BLU_JLD + (e % N)];
-        if (tid < 32) mine->data[slot][NN + tid] = (sp >> tid) & 1u ? 1.0 : 0.0;
-        if (tid == 32) mine->data[slot][NN + 32] = mx >= 0.05 ? 1.0 : 0.0;
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            hdr->supp = 0u; hdr->maxbits = 0ull;
-            *((volatile unsigned long long *)&mine->ready[slot]) = epoch;       // publish
-            __threadfence_system();
-        }
-        if (tid < peers.world) {                                                // wait for every rank
-            volatile unsigned long long *flag = (volatile unsigned long long *)&peers.peer[tid]->ready[slot];
-            while (*flag < epoch) { }
-        }
-        __syncthreads();
-        for (int e = tid; e < NN + 33; e += nthr) {
-            double sum = 0.0;
-            for (int r = 0; r < peers.world; ++r) sum += __ldcv(&peers.peer[r]->data[slot][e]);   // rank order, uncached
-            phi[e] = sum;
-        }
-        __syncthreads();
-        for (int e = tid; e < NN; e += nthr) Ph[(e / N) * BLU_JLD + (e % N)] = phi[e];
-        __syncthreads();
-        nparts = 0;                           // from here on: the all-reduced path of mode 1
-        mode = 1;
-    }
-    if (mode == 2) {
-        // partial of a group slice: raw upper-triangle sums, followed by SUM-reducible encodings
-        // of the support mask (32 indicators) and of "max|m| >= 0.05" (1 indicator)
-        for (int e = tid; e < NN; e += nthr) phi[e] = Ph[(e / N) * BLU_JLD + (e % N)];
-        const unsigned sp = hdr->supp;
-        const double mx = __longlong_as_double((long long)hdr->maxbits);
-        __syncthreads();
-        if (tid < 32) phi[NN + tid] = (sp >> tid) & 1u ? 1.0 : 0.0;
-        if (tid == 32) phi[NN + 32] = mx >= 0.05 ? 1.0 : 0.0;
-        if (tid == 0) { hdr->supp = 0u; hdr->maxbits = 0ull; }
-        return;
-    }
-    // mirror the upper triangle, add delta on the diagonal
-    for (int e = tid; e < NN; e += nthr) {
-        const int r = e / N, c = e - r * N;
-        const int lo = r < c ? r : c, hi = r < c ? c : r;
-        double v = Ph[lo * BLU_JLD + hi];
-        if (r == c) v += delta;
-        phi[e] = v;
-        Pm[e] = v;
-    }
-    __syncthreads();
-    unsigned supp;
-    double maxabs;
-    if (nparts > 0) {
-        supp = hdr->supp;
-        maxabs = __longlong_as_double((long long)hdr->maxbits);
-    } else {                              // all-reduced encodings written by mode 2
-        supp = 0u;
-        for (int a = 0; a < 32; ++a) if (phi[NN + a] > 0.0) supp |= 1u << a;
-        maxabs = phi[NN + 32] > 0.0 ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    if (tid == 0) {                      // reset the reduction cells for the next evaluation
-        hdr->supp = 0u; hdr->maxbits = 0ull;
-        hdr->scal[1] = maxabs;
-    }
-    if (mode == 0) return;
-
-    unsigned flags = 0u;
-    if (maxabs < 0.05) {                 // misc.py:464,484
-        if (tid == 0) { hdr->flags = BLU_FLAG_TINY; hdr->scal[0] = INFINITY; }
-        return;
-    }
-    const unsigned all = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
-    if (!(supp & 1u)) flags |= BLU_FLAG_NO_MODEL0;
-    if ((supp & all) != all) flags |= BLU_FLAG_PARTIAL;
-
-    // ---- full pseudo-inverse (misc.py:487) ----
-    // Rows/columns of Phi that are entirely zero (models in no group with m_i != 0) split off as a
-    // zero block: pinv([[A,0],[0,0]]) = [[pinv(A),0],[0,0]].  The remaining "active" block is SPD
-    // in every regular evaluation and is inverted by Gauss-Jordan; Jacobi only if that fails.
-    if (tid < 32) {
-        bool nz = false;
-        if (tid < N) for (int c = 0; c < N; ++c) nz = nz || (Pm[tid * N + c] != 0.0);
-        const unsigned am = __ballot_sync(BLU_FULL, nz);
-        if (tid == 0) {
-            int cnt = 0;
-            for (int a = 0; a < N; ++a) if (am >> a & 1u) sidx[cnt++] = a;
-            ns = cnt;
-            amask = am;
-        }
-    }
-    __syncthreads();
-    const int na = ns;
-    const unsigned active = amask;
-    if (tid == 0) js.lmax = 0.0;
-    int sweeps = blu_block_pinv(Pm, N, sidx, na, A, V, Ph, diag0, &js, tid, nthr);
-    for (int e = tid; e < NN; e += nthr) {
-        const int r = e / N, c = e - r * N;
-        double v = 0.0;
-        if ((active >> r & 1u) && (active >> c & 1u))
-            v = Ph[__popc(active & ((1u << r) - 1u)) * BLU_JLD + __popc(active & ((1u << c) - 1u))];
-        pinv[e] = v;
-        S[e] = 2.0 * v;
-        if (r == 0) xrow[c] = v;
-    }
-    __syncthreads();
-    if (tid == 0) { hdr->scal[2] = (double)sweeps; hdr->scal[3] = js.lmax; hdr->scal[4] = pinv[0]; }
-
-    // ---- variance on the support sub-block (misc.py:489-490) ----
-    const unsigned sup = supp & all;
-    if (sup == (active & all)) {
-        // pinv(Phi[idx,idx])[0,0] is the (first supported model) diagonal entry of the block above
-        const int s0 = sup ? __ffs(sup) - 1 : 0;
-        if (tid == 0) { hdr->scal[0] = sup ? pinv[s0 * N + s0] : INFINITY; hdr->flags = flags; }
-        if (tid < 32) hdr->xsup[tid] = (tid < N && (sup >> tid & 1u)) ? pinv[s0 * N + tid] : 0.0;
-        return;
-    }
+    const int grp = blockIdx.x / BLU_PHI_GROUP;
+    const int ngrp = (gridDim.x + BLU_PHI_GROUP - 1) / BLU_PHI_GROUP;
+    const int members = min(BLU_PHI_GROUP, (int)gridDim.x - grp * BLU_PHI_GROUP);
+    __threadfence();
     __syncthreads();
     if (tid == 0) {
-        int cnt = 0;
-        for (int a = 0; a < N; ++a) if (sup >> a & 1u) sidx[cnt++] = a;
-        ns = cnt;
+        const unsigned t = atomicAdd(&hdr->tickets[1 + grp], 1u);
+        s_last = (t == (unsigned)(members - 1));
+        if (s_last) hdr->tickets[1 + grp] = 0u;
     }
     __syncthreads();
-    const int nsub = ns;
-    if (nsub > 0) blu_block_pinv(Pm, N, sidx, nsub, A, V, Ph, diag0, &js, tid, nthr);
-    if (tid == 0) { hdr->scal[0] = nsub > 0 ? Ph[0] : INFINITY; hdr->flags = flags; }
-    if (tid < 32) hdr->xsup[tid] = 0.0;
+    if (!s_last) return;
+    __threadfence();
+    double *part2 = part + (size_t)gridDim.x * NN;        // group sums
+    for (int e = tid; e < NN; e += nthr) {
+        const double *pp = part + (size_t)grp * BLU_PHI_GROUP * NN + e;
+        double sum = 0.0;
+#pragma unroll 4
+        for (int cc = 0; cc < members; ++cc) sum += __ldcg(pp + (size_t)cc * NN);
+        part2[(size_t)grp * NN + e] = sum;
+    }
+    __threadfence();
     __syncthreads();
-    if (tid < nsub) hdr->xsup[sidx[tid]] = Ph[tid];
+    if (tid == 0) {
+        const unsigned t = atomicAdd(&hdr->tickets[0], 1u);
+        s_last = (t == (unsigned)(ngrp - 1));
+        if (s_last) hdr->tickets[0] = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const BluFinScratch f = blu_fin_carve(smraw);         // the ring and the accumulator tiles are idle now
+    for (int e = tid; e < NN; e += nthr) {
+        double sum = 0.0;
+#pragma unroll 4
+        for (int gg = 0; gg < ngrp; ++gg) sum += __ldcg(part2 + (size_t)gg * NN + e);
+        f.Ph[(e / N) * BLU_JLD + (e % N)] = sum;
+    }
+    __syncthreads();
+    blu_finish_body(N, delta, fin_mode, false, phi, pinv, xrow, S, hdr, peers, f, tid, nthr);
 }
+

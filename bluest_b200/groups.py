@@ -16,22 +16,26 @@ def enumerate_groups(N, K=None):
     return [[list(c) for c in combinations(range(N), k)] for k in range(1, K + 1)]
 
 
-def enumerate_cliques(adj, K, component_of=0):
+def enumerate_cliques(adj, K, component_of=0, nodes=None):
     """Cliques of size <= K of the coupling graph ``adj`` (non-zero = edge), restricted to the
-    connected component of model ``component_of`` (blue_models.py:462-474, :468).  Plain
-    breadth-first extension with increasing vertex ids, which reproduces networkx's
+    node set ``nodes`` -- the reference filters with its stored ``SG[n]`` (blue_models.py:462-474, :468) --
+    or, when ``nodes`` is None, to the connected component of model ``component_of`` computed from the
+    adjacency.  Plain breadth-first extension with increasing vertex ids, which reproduces networkx's
     size-major, lexicographic order."""
     adj = np.asarray(adj) != 0
     N = adj.shape[0]
-    comp = {component_of}
-    frontier = [component_of]
-    while frontier:
-        nxt = []
-        for u in frontier:
-            for v in range(N):
-                if v != u and adj[u, v] and v not in comp:
-                    comp.add(v); nxt.append(v)
-        frontier = nxt
+    if nodes is not None:
+        comp = set(int(v) for v in nodes)
+    else:
+        comp = {component_of}
+        frontier = [component_of]
+        while frontier:
+            nxt = []
+            for u in frontier:
+                for v in range(N):
+                    if v != u and adj[u, v] and v not in comp:
+                        comp.add(v); nxt.append(v)
+            frontier = nxt
     level = [[v] for v in range(N) if v in comp]
     out = []
     for k in range(1, min(K, N) + 1):

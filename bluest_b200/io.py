@@ -68,7 +68,8 @@ def prepare_groups(graph, K=4, groups=None, multi_groups=None):
         K = min(K, M)
         multi_groups, Ks = [], []
         for n in range(No):
-            mg = enumerate_cliques(graph["adjacency"][n], K, component_of=0)
+            SG = graph.get("SG") if hasattr(graph, "get") else None
+            mg = enumerate_cliques(graph["adjacency"][n], K, component_of=0, nodes=None if SG is None else SG[n])   # blue_models.py:468
             multi_groups.append(mg)
             Ks.append(min(K, len(mg)))
     else:

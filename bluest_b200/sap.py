@@ -326,7 +326,12 @@ class SAP(object):
             self.samples = None
             return None
         if not continuous_relaxation:
-            samples = self.integer_projection(samples, budget=budget, eps=eps, max_model_samples=max_model_samples)
+            try:
+                samples = self.integer_projection(samples, budget=budget, eps=eps, max_model_samples=max_model_samples)
+            except AssertionError as e:                    # sap.py:209-213
+                print(str(e))
+                self.samples = None
+                return None
         self.samples = samples
         self.budget = budget
         self.eps = eps

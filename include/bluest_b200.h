@@ -44,6 +44,7 @@ extern "C" {
 #define BLU_FLAG_TINY      1u /* max|m| < 0.05: reference returns inf (misc.py:464,484,510) */
 #define BLU_FLAG_NO_MODEL0 2u /* model 0 not in the support of m (misc.py:470 asserts) */
 #define BLU_FLAG_PARTIAL   4u /* support is a strict subset of the models (singular Phi) */
+#define BLU_FLAG_PEER_TIMEOUT 8u /* fused multi-GPU path: a peer rank never published its partial Phi (variance = NaN) */
 
 /* `which` for blu_ctx_device_ptr */
 #define BLU_BUF_M      0   /* (L)        sample vector of the last evaluation */

@@ -81,6 +81,33 @@ def enumerate_groups(N, K=None):
     return [[list(c) for c in combinations(range(N), k)] for k in range(1, K + 1)]
 
 
+def enumerate_group_arrays(N, K=None):
+    """``enumerate_groups`` as one (Lk,k) int64 array per size class -- same order, built without
+    a Python list per group, so 20 models (1 048 575 groups) take seconds."""
+    K = N if K is None else min(K, N)
+    out = []
+    for k in range(1, K + 1):
+        flat = np.fromiter((v for c in combinations(range(N), k) for v in c), dtype=np.int64)
+        out.append(flat.reshape(-1, k))
+    return out
+
+
+def batched_invcovs(C, group_arrays):
+    """Per-class flat inverse arrays of sap.py:72-79 for WELL-CONDITIONED SPD blocks: one batched
+    LAPACK inverse per size class instead of L calls of ``np.linalg.pinv`` (for such blocks pinv == inv
+    to rounding; tests/test_oracle.py pins this against the per-group pinv of ``SapOracle`` and the
+    golden reference inverses).  Lets the oracle cover 20 models (sap.py's own loop needs ~100 s there)."""
+    C = np.asarray(C, dtype=np.float64)
+    out = []
+    for gk in group_arrays:
+        if len(gk) == 0:
+            out.append(np.array([]))
+            continue
+        sub = C[gk[:, :, None], gk[:, None, :]]                  # (Lk,k,k) blocks C[g,g]
+        out.append(np.ascontiguousarray(np.linalg.inv(sub)).ravel())
+    return out
+
+
 def bin_user_groups(groups_list, N):
     """User-supplied flat list of groups -> sorted, binned by size (possibly empty
     classes), the way blue_models.py:476-491 does for a complete graph."""
@@ -143,7 +170,10 @@ def mosap_mappings(groups, multi_groups):
 class SapOracle:
     """CPU statement of ``SAP.__init__`` + ``get_variance_functions`` (sap.py:53-143)."""
 
-    def __init__(self, C, K, groups, costs=None, invcovs=None):
+    def __init__(self, C, K, groups, costs=None, invcovs=None, with_ES=True):
+        """``groups[k-1]``: lists of sorted model-index lists, or (Lk,k) int64 arrays.  ``invcovs``: use these
+        flat per-class inverses instead of the per-group pinv loop.  ``with_ES=False`` skips the O(L N)
+        indicator vectors (full-size checks that never read them)."""
         C = np.asarray(C, dtype=np.float64)
         self.C = C
         self.N = C.shape[0]
@@ -162,8 +192,8 @@ class SapOracle:
                 continue
             blocks = [np.linalg.pinv(C[np.ix_(g, g)]) for g in gk]      # sap.py:72-74
             self.invcovs.append(np.concatenate([b.ravel() for b in blocks]) if blocks else np.array([]))
-        self.ES = indicator_ES(groups, self.N)
-        self.e = self.ES[0]
+        self.ES = indicator_ES(groups, self.N) if with_ES else None
+        self.e = self.ES[0] if with_ES else None
         self._psi = None
 
     # psi: (N^2, L), hstack over non-empty classes (sap.py:129)

@@ -105,6 +105,39 @@ def test_hessian_operator_full_size(problem):
     assert maxrel((gp - gm) / (2 * h), op2 @ d) < 1e-5
 
 
+def test_phi_variance_gradient_20_models():
+    """20 models, all 1 048 575 groups (BASELINE config 5) against an INDEPENDENT value: the oracle with its
+    per-class batched LAPACK inverses (pinned against the reference's pinv blocks in tests/test_oracle.py) and the
+    restated native loops for Phi and the gradient.  Inverses, Phi, variance and gradient in full."""
+    import bluest_b200 as blu
+    N = 20
+    C = orc.wishart_cov(N, 0)
+    ga = orc.enumerate_group_arrays(N)
+    o = orc.SapOracle(C, N, ga, invcovs=orc.batched_invcovs(C, ga), with_ES=False)
+    L = o.L
+    assert L == 2 ** N - 1
+    groups = blu.enumerate_groups(N)
+    sap = blu.SAP(C, N, groups, np.ones(L), verbose=False)
+    assert sap.n_fallback == 0
+    for k in (1, 2, 7, 10, 13, 19, 20):                      # sampled size classes of the 881 MB of inverses
+        assert maxrel(sap.invcovs[k - 1], o.invcovs[k - 1]) < TOL
+    assert np.array_equal(np.asarray(sap.groups[9]), ga[9])  # bit-exact enumeration of the largest class
+    sap._invcovs = None
+    for seed in (0, 1):
+        m = orc.dense_m(L, seed)
+        assert maxrel(sap.get_phi(m), o.get_phi(m)) < TOL
+        vo, go, _ = o.variance_GH(m, nohess=True)
+        v, g, _ = sap.variance_GH(m, nohess=True)
+        assert abs(v - vo) <= TOL * vo
+        assert maxrel(g, go) < TOL
+        assert abs(sap.variance(m) - o.variance(m)) <= TOL * vo
+    ms = orc.sparse_m(L, N, 3)                               # an optimiser-like iterate: 2N non-zeros, singular Phi
+    vo, go, _ = o.variance_GH(ms, nohess=True)
+    v, g, _ = sap.variance_GH(ms, nohess=True)
+    assert abs(v - vo) <= TOL * vo and maxrel(g, go) < 1e-9
+    sap.close()
+
+
 def test_hessian_operator_20_models():
     """20 models, 1 048 575 groups: the dense Hessian (8.8 TB) cannot exist; the operator is checked
     against central differences of the gradient and against the oracle's factors on sampled rows."""

@@ -46,6 +46,27 @@ def test_setup_matches_reference(tag):
     assert np.array_equal(o2.psi, d[f"{tag}/psi"])
 
 
+@pytest.mark.parametrize("tag", ["N6K6", "N8K8"])
+def test_batched_inverses_match_reference(tag):
+    """The vectorised per-class inverse (one LAPACK batch per size class) that lets the oracle reach 20 models:
+    pinned against the reference's own per-group ``np.linalg.pinv`` blocks (golden) and the array enumeration
+    against the list one."""
+    d = _load("synthetic.npz")
+    C, K, groups, invcovs = _case(d, tag)
+    ga = [np.array(gk, dtype=np.int64).reshape(len(gk), k + 1) for k, gk in enumerate(groups)]
+    inv = orc.batched_invcovs(C, ga)
+    for k in range(K):
+        assert inv[k].shape == invcovs[k].shape
+        assert maxrel(inv[k], invcovs[k]) < TOL
+    N = C.shape[0]
+    for a, l in zip(orc.enumerate_group_arrays(N, K), orc.enumerate_groups(N, K)):
+        assert a.dtype == np.int64 and np.array_equal(a, np.array(l, dtype=np.int64))
+    o = orc.SapOracle(C, K, ga, invcovs=inv, with_ES=False)
+    for j in range(int(d[f"{tag}/n_m"])):
+        m = d[f"{tag}/m{j}"]; delta = float(d[f"{tag}/delta{j}"])
+        assert maxrel(o.get_phi(m, delta), d[f"{tag}/phi{j}"]) < TOL
+
+
 @pytest.mark.parametrize("tag", SYN_TAGS)
 def test_closures_match_reference(tag):
     """a5-a10 on dense / sparse / few-model / tiny / integer / threshold / delta / no-model-0 m."""

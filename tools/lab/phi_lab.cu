@@ -553,7 +553,10 @@ int main(int argc, char **argv)
         }
     }
     unsigned char *d_tgt; CK(cudaMalloc(&d_tgt, S)); CK(cudaMemcpy(d_tgt, htgt.data(), S, cudaMemcpyHostToDevice));
+    const int only = argc > 3 ? atoi(argv[3]) : -1;
+    int vidx = 0;
     auto run4 = [&](auto kern, int R, int warps, int cps, const char *tag) {
+        if (only >= 0 && vidx++ != only) return;
         const size_t smem = 8ull * warps * NT * R;
         if (smem * cps > 227 * 1024) { printf("%-44s skipped (smem %zu)\n", tag, smem); return; }
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
