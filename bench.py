@@ -483,6 +483,101 @@ def secondary_configs(device=0):
         sp.close()
     return out
 
+def shard_n20_benchmark(world, rank, local, dist, steps=200, N=20, pool=4):
+    """BASELINE config 5 / the north-star multi-GPU path under the driver's own launch: ONE problem with 20 models
+    (1 048 575 groups), the group enumeration cut into `world` contiguous work-balanced slices, one rank per slice.
+    Per evaluation and rank: one kernel streams the slice's packed inverses into partial Phi tiles, its last CTA folds
+    them, pushes the N^2+33 sums into every rank's inbox over NVLink peer memory, waits for the others, inverts Phi
+    and takes the variance; a second kernel streams the slice again for the gradient.  `pool` evaluations (different
+    sample vectors) are recorded into one CUDA graph and replayed.  Strong scaling: the work per evaluation is fixed.
+    Rank 0 checks variance and gradient of one evaluation against the CPU oracle (batched LAPACK inverses + the
+    restated native loops)."""
+    import torch
+    import bluest_b200 as blu
+    import oracle as orc
+    from bluest_b200.dist import GpuEngine, ShardedEvaluator
+    dev = "cuda:%d" % local
+    t0 = time.perf_counter()
+    C = orc.wishart_cov(N, 0)
+    ga = blu.enumerate_group_arrays(N)
+    sizes = [len(g) for g in ga]
+    L = int(sum(sizes))
+    sap = blu.SAP(C, N, ga, np.ones(L), verbose=False, device=local)
+    eng = GpuEngine(sap)
+    ev = ShardedEvaluator(eng, sizes, rank, world, dist=dist if world > 1 else None, fused=True)
+    setup_s = time.perf_counter() - t0
+    ms_host = [orc.dense_m(L, j) for j in range(pool)]
+    ms = [torch.from_numpy(m).to(dev) for m in ms_host]
+    var_out = torch.zeros(pool, dtype=torch.float64, device=dev)
+    flag_out = torch.zeros(pool, dtype=torch.int32, device=dev)
+    grad_out = torch.zeros((pool, L), dtype=torch.float64, device=dev)
+    ext = torch.cuda.ExternalStream(sap.stream(), device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def enqueue_pool():
+        for j in range(pool):
+            sap.set_grad_output(grad_out[j])
+            eng.shard_eval_fused(ms[j], 0.0, True, 0)
+            sap.save_result(var_out[j:j + 1], flag_out[j:j + 1])
+        sap.set_grad_output(None)
+
+    def timed(fn, reps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        fn(reps)
+        e1.record(ext)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) * 1e-3 / (reps * pool)
+
+    reps = max(2, steps // pool)
+    enqueue_pool()                                        # eager once: lazy allocations, first launches
+    sap.sync()
+    barrier()
+    t_eager = timed(lambda r: [enqueue_pool() for _ in range(r)], reps)
+    sap.graph_begin()
+    enqueue_pool()
+    gid = sap.graph_end()
+    sap.graph_launch(gid, 2)
+    sap.sync()
+    t_graph = timed(lambda r: sap.graph_launch(gid, r), reps)
+    # parity: every rank keeps its own slice of the gradient; sum the zero-padded slices onto every rank once
+    g0 = torch.zeros(L, dtype=torch.float64, device=dev)
+    g0[ev.lo:ev.hi] = grad_out[0, ev.lo:ev.hi]
+    if world > 1:
+        dist.all_reduce(g0, op=dist.ReduceOp.SUM)
+    flags = int(flag_out.max().item())
+    v_dev = float(var_out[0].item())
+    out = None
+    if rank == 0:
+        t1 = time.perf_counter()
+        o = orc.SapOracle(C, N, orc.enumerate_group_arrays(N), invcovs=orc.batched_invcovs(C, orc.enumerate_group_arrays(N)), with_ES=False)
+        vo, go, _ = o.variance_GH(ms_host[0], nohess=True)
+        oracle_s = time.perf_counter() - t1
+        gd = g0.cpu().numpy()
+        S_inv = N * (N + 1) * 2 ** (N - 2)
+        algo = 16.0 * S_inv + 24.0 * L
+        peak, peak_src = peaks()
+        t = min(t_graph, t_eager)
+        out = {"models": N, "groups": L, "n_gpus": world, "scaling": "strong", "evaluations_timed": reps * pool,
+               "us_per_eval": t * 1e6, "evals_per_s": 1.0 / t, "us_per_eval_cuda_graph": t_graph * 1e6, "us_per_eval_eager": t_eager * 1e6,
+               "algorithmic_GBps": algo / t / 1e9, "frac_of_n_gpus_x_hbm_peak": algo / t / 1e9 / (peak * world), "peak_source": peak_src + " x n_gpus",
+               "parity_maxrel": {"variance": abs(v_dev - vo) / abs(vo), "gradient": float(np.max(np.abs(gd - go)) / np.max(np.abs(go))),
+                                 "against": "CPU oracle (per-class batched LAPACK inverses, restated native loops), sample vector 0, %.1f s on rank 0" % oracle_s},
+               "flags": flags, "slices": [list(sl) for sl in ev.slices], "setup_s": setup_s,
+               "exchange": "in-kernel push of N^2+33 doubles into every rank's inbox over NVLink peer memory (CUDA IPC), no NCCL on the data path",
+               "launches_per_eval": 2}
+    sap.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -586,7 +681,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
 
+    # ---- the group-sharded 20-model evaluation (north-star multi-GPU path), every rank takes part ----
+    shard20 = None
+    if args.shard20:
+        try:
+            shard20 = shard_n20_benchmark(world, rank, local, dist, steps=max(40, args.steps))
+        except Exception as ex:
+            shard20 = {"failed": repr(ex)}
+
     if rank == 0:
+        # the variance of the last warm-up evaluation against the CPU oracle (batched LAPACK inverses + native loops)
+        try:
+            ga = orc.enumerate_group_arrays(N)
+            oc = orc.SapOracle(C, N, ga, invcovs=orc.batched_invcovs(C, ga), with_ES=False)
+            v_or = oc.variance(ms_host[(args.warmup - 1) % npool])
+            var_check = {"variance": var0, "oracle": float(v_or), "rel_err": float(abs(var0 - v_or) / abs(v_or)), "flags": int(flags0)}
+        except Exception as ex:
+            var_check = {"variance": var0, "failed": repr(ex)}
         peak, peak_src = peaks()
         hess_ms = float(np.mean(phases[:, 2]))
         algo_bytes = 8.0 * L * L
@@ -604,7 +715,9 @@ def run_ours(args):
                "dtype": "f64", "data": "synthetic", "impl": "ours",
                "config": workload_config(N, L),
                "roofline": {"bound": "hbm", "kernel": "blu_hess_kernel<4,true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                            "frac": achieved / peak, "traffic": traffic,
+                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch of this kernel (profiles/hess_kernel_traffic.json), not re-measured by this run",
+                            "algorithmic_bytes_per_launch": algo_bytes,
                             "avg_launch_ms": hess_ms, "peak_source": peak_src,
                             "whole_eval_frac": (8.0 * L * L + 16.0 * N * L + 16.0 * N * (N + 1) * 2 ** (N - 2) + 24.0 * L)
                                                / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak},
@@ -622,7 +735,8 @@ def run_ours(args):
                                        "(rank 0's rate x ranks; not the headline: the reference API returns the dense array)"},
                "gpu_launches": launches_per_eval * args.steps,
                "launches_per_eval": launches_per_eval,
-               "clocks": clocks, "setup_s": setup_s, "variance_check": var0}
+               "clocks": clocks, "setup_s": setup_s, "variance_check": var_check,
+               "shard_n20": shard20}
         if world == 1 and not args.no_cpu:
             try:
                 ref = CpuReference(N, seed=0)
@@ -755,6 +869,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-solve", dest="solve", action="store_false", help="skip the end-to-end SAP solve comparison")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the brief measurements of the other BASELINE configs")
+    ap.add_argument("--no-shard20", dest="shard20", action="store_false", help="skip the group-sharded 20-model evaluation")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "shard"], help="sweep: independent instances per GPU (default); shard: one problem, groups sharded")
     ap.add_argument("--nohess", action="store_true", help="shard mode: Phi + variance + gradient only (e.g. --models 20)")
     ap.add_argument("--gather-grad", action="store_true", help="shard mode: all-gather the gradient slices")

@@ -5,7 +5,7 @@ native routines; everything numerical runs in hand-written CUDA behind libbluest
 (include/bluest_b200.h).  No CPU fallback: importing works anywhere, calling needs a GPU.
 """
 from ._lib import BluError, device_count, lib          # noqa: F401
-from .groups import (balanced_slices, stream_cost, enumerate_cliques, enumerate_groups, group_costs,     # noqa: F401
+from .groups import (balanced_slices, stream_cost, enumerate_cliques, enumerate_groups, enumerate_group_arrays, group_costs,     # noqa: F401
                      indicator_ES, mappings, union_groups)
 from .sap import SAP                                    # noqa: F401
 from .mosap import MOSAP, BLUESTError                   # noqa: F401
@@ -15,6 +15,6 @@ from .dist import ShardedEvaluator, GpuEngine          # noqa: F401
 from .install import install, uninstall                # noqa: F401
 from .sweep import solve_sweep, split_instances        # noqa: F401
 
-__all__ = ["SAP", "MOSAP", "BLUESTError", "BluError", "pilot_covariance", "cmisc", "enumerate_groups",
+__all__ = ["SAP", "MOSAP", "BLUESTError", "BluError", "pilot_covariance", "cmisc", "enumerate_groups", "enumerate_group_arrays",
            "enumerate_cliques", "union_groups", "group_costs", "indicator_ES", "mappings", "balanced_slices",
            "device_count", "lib", "ShardedEvaluator", "GpuEngine", "install", "uninstall", "solve_sweep", "split_instances"]

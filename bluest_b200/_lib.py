@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbluest_b200.so")
 
 BLU_OK, BLU_ERR_ARG, BLU_ERR_CUDA, BLU_ERR_STATE, BLU_ERR_NOMEM, BLU_ERR_NODEVICE = range(6)
-FLAG_TINY, FLAG_NO_MODEL0, FLAG_PARTIAL = 1, 2, 4
+FLAG_TINY, FLAG_NO_MODEL0, FLAG_PARTIAL, FLAG_PEER_TIMEOUT = 1, 2, 4, 8
 BUF_M, BUF_PHI, BUF_PINV, BUF_GRAD, BUF_U, BUF_V, BUF_HESS, BUF_CINV, BUF_SCAL = range(9)
 
 c_int, c_i64, c_dbl, c_uint = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_uint
@@ -48,6 +48,11 @@ SIGNATURES = {
     "blu_ctx_set_option": (c_int, [p_void, ctypes.c_char_p, c_int]),
     "blu_ctx_timing_log": (c_int, [p_void, c_int]),
     "blu_ctx_timing_read": (c_int, [p_void, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(c_int)]),
+    "blu_ctx_graph_begin": (c_int, [p_void]),
+    "blu_ctx_graph_end": (c_int, [p_void, ctypes.POINTER(c_int)]),
+    "blu_ctx_graph_launch": (c_int, [p_void, c_int, c_int]),
+    "blu_ctx_save_result": (c_int, [p_void, p_void, p_void]),
+    "blu_ctx_set_grad_output": (c_int, [p_void, p_void]),
     "blu_ctx_set_slice": (c_int, [p_void, c_i64, c_i64]),
     "blu_ctx_peer_handle": (c_int, [p_void, p_void]),
     "blu_ctx_peer_connect": (c_int, [p_void, c_int, c_int, p_void]),

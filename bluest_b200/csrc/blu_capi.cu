@@ -110,6 +110,9 @@ struct blu_ctx {
     bool uv_ready = false, v_ready = false;   // U (and V) hold the factors of the last want_hess evaluation
     std::vector<cudaEvent_t> evlog;    // optional per-evaluation event log (4 events per evaluation)
     int evlog_n = 0;
+    bool capturing = false;            // between blu_ctx_graph_begin and _end: the stream records instead of running
+    std::vector<cudaGraphExec_t> graphs;
+    double *d_grad_out = nullptr;      // where the gradient kernels write (default: d_grad)
 };
 
 static int use(blu_ctx *c)
@@ -164,6 +167,7 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     cudaFree(c->d_x); cudaFree(c->d_S); cudaFree(c->d_grad); cudaFree(c->d_U); cudaFree(c->d_V); cudaFree(c->d_H);
     cudaFree(c->d_hdr); cudaFree(c->d_chunks); cudaFree(c->d_soa); cudaFree(c->d_soff); cudaFree(c->d_tiles);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
     cudaFree(c->d_xchg);
     cudaFree(c->d_hvpart); cudaFree(c->d_hvp); cudaFree(c->d_hvout); cudaFree(c->d_Sop);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
@@ -571,6 +575,7 @@ static int launch_v_from_u(blu_ctx *c)
 static int launch_grad(blu_ctx *c, int uv)
 {
     const bool want_uv = uv != 0;
+    double *gout = c->d_grad_out ? c->d_grad_out : c->d_grad;
     if (want_uv) {
         int rc0 = ensure_uv(c);
         if (rc0) return rc0;
@@ -586,13 +591,13 @@ static int launch_grad(blu_ctx *c, int uv)
         if (rc) return rc;
         if (want_uv && (rc = ensure_uv(c))) return rc;
         CUDA_TRY(blu_launch_grad_soa(want_uv, c->grid_soa, c->stream, c->d_cls, (int)c->cls.size(), c->N, c->NP, c->K, c->d_tiles, c->ntiles,
-                                     c->d_soa, c->d_soff, c->d_gmask, c->d_x, c->lo, c->hi, c->d_grad, want_uv ? c->d_U : nullptr));
+                                     c->d_soa, c->d_soff, c->d_gmask, c->d_x, c->lo, c->hi, gout, want_uv ? c->d_U : nullptr));
         c->launches++;
         return uv == 1 ? launch_v_from_u(c) : BLU_OK;
     }
     if (!want_uv) {
         blu_grad_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->sd, 0, (int)c->cls.size(), c->lutlen), c->stream>>>(
-            c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_grad);
+            c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, gout);
         KERNEL_CHECK(c);
         return BLU_OK;
     }
@@ -601,7 +606,7 @@ static int launch_grad(blu_ctx *c, int uv)
     c->v_ready = true;                  // the entry-per-lane kernel writes both factors
     blu_gradu_kernel<<<c->grid_grad, BLU_STREAM_WARPS * 32, blu_stream_smem_bytes(c->sd, c->N * c->N, (int)c->cls.size(), c->lutlen), c->stream>>>(
         c->d_cls, (int)c->cls.size(), c->N, c->NP, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, c->d_x, c->d_S,
-        c->d_grad, c->d_U, c->d_V);
+        gout, c->d_U, c->d_V);
     KERNEL_CHECK(c);
     return BLU_OK;
 }
@@ -662,6 +667,12 @@ extern "C" int blu_eval_device(blu_ctx *c, const double *d_m, double delta, int 
     if (c->lo != 0 || c->hi != c->L) return fail(BLU_ERR_STATE, "context owns a slice: use the blu_shard_* calls");
     if (!d_m) d_m = c->d_m;
     c->launches = 0;
+    if (c->capturing) {                 // inside a graph: kernels only (phase events belong to eager runs)
+        if ((rc = launch_phi(c, d_m, delta, 1))) return rc;
+        if (want_grad || want_hess) { if ((rc = launch_grad(c, want_hess == 0 ? 0 : (want_hess == 3 ? 2 : 1)))) return rc; }
+        if (want_hess == 1) { if ((rc = launch_hess(c, true))) return rc; }
+        return BLU_OK;
+    }
     cudaEvent_t *ev = c->ev;
     if ((size_t)(c->evlog_n + 1) * 4 <= c->evlog.size()) { ev = c->evlog.data() + (size_t)c->evlog_n * 4; c->evlog_n++; }
     CUDA_TRY(cudaEventRecord(ev[0], c->stream));
@@ -795,6 +806,69 @@ extern "C" int blu_ctx_device_ptr(blu_ctx *c, int which, void **ptr, int64_t *nb
     }
     *ptr = p;
     if (nbytes) *nbytes = n;
+    return BLU_OK;
+}
+
+// ---- CUDA graphs ---------------------------------------------------------------------------
+// Everything the device-resident calls (blu_eval_device, blu_shard_eval_fused, blu_hess_matvec_device,
+// blu_ctx_save_result) enqueue between _begin and _end is recorded into a graph instead of running; replaying
+// it costs one launch for the whole chain (small problems and sharded evaluations are launch-latency bound).
+// Buffers must exist already: run the same calls once eagerly first (lazy allocations cannot be captured).
+extern "C" int blu_ctx_graph_begin(blu_ctx *c)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (c->capturing) return fail(BLU_ERR_STATE, "a graph is already being recorded on this context");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    c->capturing = true;
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_graph_end(blu_ctx *c, int *graph_id)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->capturing) return fail(BLU_ERR_STATE, "no graph is being recorded");
+    c->capturing = false;
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(cudaStreamEndCapture(c->stream, &g));
+    cudaGraphExec_t ge = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    c->graphs.push_back(ge);
+    if (graph_id) *graph_id = (int)c->graphs.size() - 1;
+    return BLU_OK;
+}
+
+extern "C" int blu_ctx_graph_launch(blu_ctx *c, int graph_id, int times)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (graph_id < 0 || graph_id >= (int)c->graphs.size()) return fail(BLU_ERR_ARG, "unknown graph %d", graph_id);
+    if (c->capturing) return fail(BLU_ERR_STATE, "cannot launch while recording");
+    for (int t = 0; t < times; ++t) CUDA_TRY(cudaGraphLaunch(c->graphs[graph_id], c->stream));
+    return BLU_OK;
+}
+
+// Keep the scalar results of the evaluation just enqueued (stream ordered, capturable): *d_var = variance,
+// *d_flags = BLU_FLAG_* -- the context's own status block is overwritten by the next evaluation.
+extern "C" int blu_ctx_save_result(blu_ctx *c, double *d_var, unsigned *d_flags)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (d_var) CUDA_TRY(cudaMemcpyAsync(d_var, &c->d_hdr->scal[0], sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (d_flags) CUDA_TRY(cudaMemcpyAsync(d_flags, &c->d_hdr->flags, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+    return BLU_OK;
+}
+
+// Redirect the gradient of the following evaluations to d_grad (L doubles on the context's device; NULL: back to
+// the context's own buffer): a batch of evaluations keeps every gradient without a copy.
+extern "C" int blu_ctx_set_grad_output(blu_ctx *c, double *d_grad)
+{
+    if (!c) return fail(BLU_ERR_ARG, "null context");
+    c->d_grad_out = d_grad;
     return BLU_OK;
 }
 

@@ -22,7 +22,8 @@ _saved = {}
 _L1 = ("assemble_psi_c", "objectiveK_c", "gradK_c", "hessKQ_c", "cleanupK_c")
 _L2_METHODS = ("__init__", "get_variance_functions", "_m", "eval_device", "upload_m", "sync", "last_result", "last_timing",
                "timing_log", "timing_read", "last_launches", "device_ptr", "device_buffer", "stream", "close", "__del__", "compute_BLUE_estimator", "integer_projection",
-               "variance_GH_begin", "variance_GH_end", "hess_matvec", "hess_operator", "hess_matvec_device", "set_option")
+               "variance_GH_begin", "variance_GH_end", "hess_matvec", "hess_operator", "hess_matvec_device", "set_option",
+               "graph_begin", "graph_end", "graph_launch", "save_result", "set_grad_output")
 
 
 def make_hybrid(ref_sap_cls):
@@ -30,6 +31,8 @@ def make_hybrid(ref_sap_cls):
     ns = {name: getattr(B200SAP, name) for name in _L2_METHODS}
     ns["psi"] = B200SAP.psi
     ns["invcovs"] = B200SAP.invcovs
+    for lazy in ("ES", "e", "flattened_groups"):             # built on first use (sap.py:66-71, 89-95)
+        ns[lazy] = getattr(B200SAP, lazy)
     ns["__doc__"] = "bluest.sap.SAP with the sample-allocation hot path on the B200 (bluest_b200)."
     return type("SAP", (ref_sap_cls,), ns)
 

@@ -35,19 +35,20 @@ class SAP(object):
         self.tot_cost = None
         self.device = device
 
-        flattened_groups = []
         sizes = [0] + [len(groupsk) for groupsk in groups]
         flat = []
         for k in range(1, K + 1):
             gk = groups[k - 1]
-            flattened_groups.extend(list(g) for g in gk)
-            arr = np.array(gk, dtype=np.int64).reshape(len(gk), k) if len(gk) else np.array(gk, dtype=np.int64)
+            if isinstance(gk, np.ndarray):                       # already an (Lk,k) index array: taken as it is
+                arr = np.ascontiguousarray(gk, dtype=np.int64).reshape(len(gk), k) if len(gk) else np.array([], dtype=np.int64)
+            else:
+                arr = np.array(gk, dtype=np.int64).reshape(len(gk), k) if len(gk) else np.array(gk, dtype=np.int64)
             groups[k - 1] = arr                                  # sap.py:77 mutates the caller's list too
             if len(gk):
                 flat.append(arr.ravel())
         self.sizes = sizes
         self.groups = groups
-        self.flattened_groups = flattened_groups
+        self._flattened_groups = None                            # sap.py:66-71: built on first use (a Python list per group)
         self.cumsizes = np.cumsum(sizes)
         self.L = self.cumsizes[-1]
 
@@ -69,11 +70,28 @@ class SAP(object):
         self._invcovs = None
         self._psi = None
 
-        self.ES = indicator_ES([g for g in groups], self.N)
-        self.e = self.ES[0]
+        self._ES = None                                          # sap.py:89-95: N vectors of length L, built on first use
         self.get_variance_functions()
 
     # ---- lazily materialised host views ------------------------------------------------------
+    @property
+    def flattened_groups(self):
+        """sap.py:66-71: every group as a Python list, flat (size-major) order."""
+        if self._flattened_groups is None:
+            self._flattened_groups = [g.tolist() for gk in self.groups for g in np.asarray(gk).reshape(len(gk), -1)]
+        return self._flattened_groups
+
+    @property
+    def ES(self):
+        """sap.py:89-95: ES[i][g] = int(model i is in group g)."""
+        if self._ES is None:
+            self._ES = indicator_ES([g for g in self.groups], self.N)
+        return self._ES
+
+    @property
+    def e(self):
+        return self.ES[0]
+
     @property
     def invcovs(self):
         """``invcovs[k-1]``: flat (Lk*k*k) float64, row-major [i][j][l] (sap.py:78-79)."""
@@ -208,6 +226,32 @@ class SAP(object):
         if d_m is not None:
             ptr = ctypes.c_void_p(int(d_m.data_ptr()) if hasattr(d_m, "data_ptr") else int(d_m))
         check(lib().blu_eval_device(self._ctx, ptr, float(delta), int(bool(grad)), int(bool(hess))))
+
+    # ---- CUDA graphs over the device-resident calls --------------------------------------------
+    def graph_begin(self):
+        """Start recording the device-resident calls of this SAP (``eval_device``, ``save_result``,
+        ``hess_matvec_device``, the sharded engine's calls) into a CUDA graph instead of running them."""
+        check(lib().blu_ctx_graph_begin(self._ctx))
+
+    def graph_end(self):
+        """Stop recording; returns the graph id for ``graph_launch``."""
+        gid = ctypes.c_int(-1)
+        check(lib().blu_ctx_graph_end(self._ctx, ctypes.byref(gid)))
+        return gid.value
+
+    def graph_launch(self, graph_id, times=1):
+        check(lib().blu_ctx_graph_launch(self._ctx, int(graph_id), int(times)))
+
+    def save_result(self, d_var=None, d_flags=None):
+        """Stream-ordered copy of the last enqueued evaluation's variance / flags into device memory
+        (torch tensors or raw pointers)."""
+        ptr = lambda t: None if t is None else ctypes.c_void_p(int(t.data_ptr()) if hasattr(t, "data_ptr") else int(t))
+        check(lib().blu_ctx_save_result(self._ctx, ptr(d_var), ptr(d_flags)))
+
+    def set_grad_output(self, d_grad=None):
+        """Gradient destination of the following device evaluations (None: the context's own buffer)."""
+        ptr = None if d_grad is None else ctypes.c_void_p(int(d_grad.data_ptr()) if hasattr(d_grad, "data_ptr") else int(d_grad))
+        check(lib().blu_ctx_set_grad_output(self._ctx, ptr))
 
     def upload_m(self, m):
         """Copy a host m into the context's device buffer (BLU_BUF_M)."""

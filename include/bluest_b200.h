@@ -176,6 +176,21 @@ int blu_ctx_set_option(blu_ctx *ctx, const char *name, int value);
 /* Number of kernels the last evaluation launched. */
 int blu_ctx_last_launches(blu_ctx *ctx);
 
+/* CUDA graphs: everything the device-resident calls (blu_eval_device, blu_shard_eval_fused,
+ * blu_hess_matvec_device, blu_ctx_save_result) enqueue between _begin and _end is recorded instead of run;
+ * blu_ctx_graph_launch replays it `times` times on the context's stream (asynchronous).  Run the same calls
+ * once eagerly first: lazily allocated buffers cannot be created while recording.  The reference has no
+ * analogue; this is the device-side form of the solver loops of sap.py:410-416 / mosap.py:595-607, where
+ * small problems are pure launch latency. */
+int blu_ctx_graph_begin(blu_ctx *ctx);
+int blu_ctx_graph_end(blu_ctx *ctx, int *graph_id);
+int blu_ctx_graph_launch(blu_ctx *ctx, int graph_id, int times);
+/* Stream-ordered copy of the last enqueued evaluation's variance / status flags to device memory of the
+ * caller (either may be NULL): keeps the scalars of every evaluation of a batch or a graph. */
+int blu_ctx_save_result(blu_ctx *ctx, double *d_var, unsigned *d_flags);
+/* Gradient destination of the following evaluations (L doubles in HBM; NULL = BLU_BUF_GRAD). */
+int blu_ctx_set_grad_output(blu_ctx *ctx, double *d_grad);
+
 /* Group-sharded evaluation: a context may own a contiguous slice
  * [lo,hi) of the flat group enumeration.  The three phases are exposed separately so the host
  * can put the NCCL exchange between them:
