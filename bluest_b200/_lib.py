@@ -26,6 +26,7 @@ SIGNATURES = {
     "blu_version": (ctypes.c_char_p, []),
     "blu_ctx_create": (c_int, [c_int, c_int, c_int, p_i64, p_i64, ctypes.POINTER(p_void)]),
     "blu_ctx_destroy": (c_int, [p_void]),
+    "blu_ctx_clone": (c_int, [p_void, ctypes.POINTER(p_void)]),
     "blu_ctx_set_covariance": (c_int, [p_void, p_dbl, c_dbl, p_i64]),
     "blu_ctx_set_invcovs": (c_int, [p_void, c_int, p_dbl]),
     "blu_ctx_get_invcovs": (c_int, [p_void, c_int, p_dbl]),
@@ -48,6 +49,7 @@ SIGNATURES = {
     "blu_ctx_set_option": (c_int, [p_void, ctypes.c_char_p, c_int]),
     "blu_ctx_timing_log": (c_int, [p_void, c_int]),
     "blu_ctx_timing_read": (c_int, [p_void, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(c_int)]),
+    "blu_ctx_last_stamps": (c_int, [p_void, ctypes.POINTER(ctypes.c_uint64)]),
     "blu_ctx_graph_begin": (c_int, [p_void]),
     "blu_ctx_graph_end": (c_int, [p_void, ctypes.POINTER(c_int)]),
     "blu_ctx_graph_launch": (c_int, [p_void, c_int, c_int]),

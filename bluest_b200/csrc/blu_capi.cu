@@ -113,6 +113,7 @@ struct blu_ctx {
     bool capturing = false;            // between blu_ctx_graph_begin and _end: the stream records instead of running
     std::vector<cudaGraphExec_t> graphs;
     double *d_grad_out = nullptr;      // where the gradient kernels write (default: d_grad)
+    bool is_clone = false;             // shares the read-only tables / inverses / work lists of another context (blu_ctx_clone)
 };
 
 static int use(blu_ctx *c)
@@ -162,10 +163,13 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     if (!c) return BLU_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_cls); cudaFree(c->d_gidx); cudaFree(c->d_gmask); cudaFree(c->d_lut); cudaFree(c->d_cinv);
-    cudaFree(c->d_C); cudaFree(c->d_m); cudaFree(c->d_part); cudaFree(c->d_phi); cudaFree(c->d_pinv);
+    if (!c->is_clone) {                // a clone borrows these from its parent
+        cudaFree(c->d_cls); cudaFree(c->d_gidx); cudaFree(c->d_gmask); cudaFree(c->d_lut); cudaFree(c->d_cinv);
+        cudaFree(c->d_C); cudaFree(c->d_chunks); cudaFree(c->d_soa); cudaFree(c->d_soff); cudaFree(c->d_tiles);
+    }
+    cudaFree(c->d_m); cudaFree(c->d_part); cudaFree(c->d_phi); cudaFree(c->d_pinv);
     cudaFree(c->d_x); cudaFree(c->d_S); cudaFree(c->d_grad); cudaFree(c->d_U); cudaFree(c->d_V); cudaFree(c->d_H);
-    cudaFree(c->d_hdr); cudaFree(c->d_chunks); cudaFree(c->d_soa); cudaFree(c->d_soff); cudaFree(c->d_tiles);
+    cudaFree(c->d_hdr);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
     cudaFree(c->d_xchg);
@@ -350,6 +354,54 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
     return BLU_OK;
 }
 
+static int ensure_soa(blu_ctx *c);
+
+// A second evaluation LANE on the same problem: the clone shares the parent's read-only data (group tables,
+// packed inverses in both layouts, work lists of the current slice) and owns only the small per-evaluation state
+// (stream, partial tiles, Phi, pinv, x, gradient, status block, exchange inbox).  Two lanes on two streams let the
+// serial tail of one evaluation (fold, peer exchange, N x N inverse: one CTA) overlap the streaming kernels of the
+// next -- independent evaluations of a sweep, or of a solver that evaluates several trial points.
+// The parent must have its inverses set; it must outlive the clone and keep its slice while the clone lives.
+extern "C" int blu_ctx_clone(blu_ctx *p, blu_ctx **out)
+{
+    if (!out) return fail(BLU_ERR_ARG, "null out");
+    *out = nullptr;
+    int rc = use(p);
+    if (rc) return rc;
+    if (!p->have_inv) return fail(BLU_ERR_STATE, "clone: the parent's inverses are not set");
+    if (p->hi - p->lo >= (long long)p->nsm * 2 * 32 && p->use_soa) { if ((rc = ensure_soa(p))) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    blu_ctx *c = new (std::nothrow) blu_ctx(*p);      // scalars, host tables and the shared device pointers
+    if (!c) return fail(BLU_ERR_NOMEM, "host allocation failed");
+    c->is_clone = true;
+    c->stream = nullptr;
+    for (auto &e : c->ev) e = nullptr;
+    c->evlog.clear(); c->evlog_n = 0; c->panel_ev.clear(); c->graphs.clear(); c->ipc_opened.clear();
+    c->d_m = c->d_part = c->d_phi = c->d_pinv = c->d_x = c->d_S = c->d_grad = c->d_U = c->d_V = c->d_H = nullptr;
+    c->d_hdr = nullptr; c->h_hdr = nullptr; c->h_m = c->h_grad = nullptr; c->pend_hess = nullptr; c->pending = false;
+    c->d_xchg = nullptr; c->peers = BluPeers{}; c->d_Sop = c->d_hvpart = c->d_hvp = c->d_hvout = nullptr;
+    c->H_rows = 0; c->uv_ready = c->v_ready = false; c->capturing = false; c->d_grad_out = nullptr; c->timed = false;
+#define CL_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int code_ = fail(e_ == cudaErrorMemoryAllocation ? BLU_ERR_NOMEM : BLU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); blu_ctx_destroy(c); return code_; } } while (0)
+    const size_t NN = (size_t)c->N * c->N;
+    CL_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CL_TRY(cudaEventCreate(&e));
+    CL_TRY(cudaMalloc(&c->d_m, sizeof(double) * c->L));
+    CL_TRY(cudaMalloc(&c->d_part, sizeof(double) * NN * (c->part_rows + BLU_PHI_MAXGROUPS + 1)));
+    CL_TRY(cudaMalloc(&c->d_phi, sizeof(double) * (NN + 40)));
+    CL_TRY(cudaMalloc(&c->d_pinv, sizeof(double) * NN));
+    CL_TRY(cudaMalloc(&c->d_x, sizeof(double) * BLU_MAX_MODELS));
+    CL_TRY(cudaMalloc(&c->d_S, sizeof(double) * NN));
+    CL_TRY(cudaMalloc(&c->d_grad, sizeof(double) * c->L));
+    CL_TRY(cudaMalloc(&c->d_hdr, sizeof(BluEvalHeader)));
+    CL_TRY(cudaMemsetAsync(c->d_hdr, 0, sizeof(BluEvalHeader), c->stream));
+    CL_TRY(cudaHostAlloc(&c->h_hdr, sizeof(BluEvalHeader), cudaHostAllocDefault));
+    memset(c->h_hdr, 0, sizeof(BluEvalHeader));
+    CL_TRY(cudaStreamSynchronize(c->stream));
+#undef CL_TRY
+    *out = c;
+    return BLU_OK;
+}
+
 // --------------------------------------------------------------------------------------------
 // kernel (1): inverses
 // --------------------------------------------------------------------------------------------
@@ -358,6 +410,7 @@ extern "C" int blu_ctx_set_covariance(blu_ctx *c, const double *C, double pivot_
     int rc = use(c);
     if (rc) return rc;
     if (!C) return fail(BLU_ERR_ARG, "null covariance");
+    if (c->is_clone) return fail(BLU_ERR_STATE, "a clone shares its parent's inverses: set them on the parent");
     if (!(pivot_rtol >= 0.0)) pivot_rtol = 1e-10;
     const size_t NN = (size_t)c->N * c->N;
     CUDA_TRY(cudaMemcpyAsync(c->d_C, C, sizeof(double) * NN, cudaMemcpyHostToDevice, c->stream));
@@ -406,6 +459,7 @@ extern "C" int blu_ctx_set_invcovs(blu_ctx *c, int k, const double *invcovs_k)
     int rc = use(c);
     if (rc) return rc;
     if (k < 1 || k > c->K) return fail(BLU_ERR_ARG, "class k=%d outside [1,%d]", k, c->K);
+    if (c->is_clone) return fail(BLU_ERR_STATE, "a clone shares its parent's inverses: set them on the parent");
     const int idx = c->cls_of_k[k];
     if (idx < 0) return BLU_OK;                       // empty class: nothing to ingest (sap.py:79)
     if (!invcovs_k) return fail(BLU_ERR_ARG, "null invcovs");
@@ -768,6 +822,20 @@ extern "C" int blu_ctx_last_timing(blu_ctx *c, float *ms)
 }
 
 extern "C" int blu_ctx_last_launches(blu_ctx *c) { return c ? c->launches : 0; }
+
+// Profiling aid: %globaltimer stamps (ns) the last CTA of the fused Phi kernel left at its milestones
+// ([1] own stream done, [2] last of its group, [3] final fold starts, [4] rank sums complete, [5] peer exchange
+// complete, [6] Phi ready, [7] pinv written, [9] done).  Synchronises.
+extern "C" int blu_ctx_last_stamps(blu_ctx *c, unsigned long long *stamps16)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!stamps16) return fail(BLU_ERR_ARG, "null stamps");
+    rc = fetch_header(c);
+    if (rc) return rc;
+    memcpy(stamps16, c->h_hdr->stamp, sizeof(unsigned long long) * 16);
+    return BLU_OK;
+}
 
 // Options: "soa" (default 1) -- gradient / U,V kernels on the group-interleaved copy of the inverses
 // (blu_soa.cuh); 0 selects the entry-per-lane kernels of blu_grad.cuh on the group-major copy.
@@ -1274,6 +1342,7 @@ extern "C" int blu_ctx_set_slice(blu_ctx *c, int64_t lo, int64_t hi)
     if (lo < 0 || hi > c->L || lo > hi) return fail(BLU_ERR_ARG, "slice [%lld,%lld) outside [0,%lld]", (long long)lo, (long long)hi, c->L);
     int rc = use(c);
     if (rc) return rc;
+    if (c->is_clone) return fail(BLU_ERR_STATE, "a clone keeps its parent's slice: set the slice on the parent, then clone");
     c->lo = lo; c->hi = hi;
     c->tiles_valid = false;
     c->uv_ready = false; c->v_ready = false;      // factors of another slice are not this slice's factors

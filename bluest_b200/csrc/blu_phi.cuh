@@ -25,6 +25,13 @@
 
 #define BLU_PHI_WARPS 16            // one CTA per SM: half as many partial tiles for the finish kernel
 
+__device__ __forceinline__ unsigned long long blu_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct BluEvalHeader {          // small device-side status block of a context
     unsigned supp;              // support mask (OR)
     unsigned flags;             // BLU_FLAG_* of the last evaluation
@@ -33,7 +40,9 @@ struct BluEvalHeader {          // small device-side status block of a context
     double xsup[32];            // first row of pinv(Phi[idx,idx]) scattered to model slots (PHIinvY0, misc.py:529-533)
     unsigned long long epoch;   // evaluations of the fused multi-GPU path so far (device side: survives CUDA-graph replays)
     unsigned tickets[40];       // arrival counters of the fused Phi reduction: [0] CTA groups, [1 + g] CTAs of group g (self-resetting)
+    unsigned long long stamp[16]; // %globaltimer (ns) at the milestones of the last CTA of the fused Phi kernel (profiling aid, see BLU_STAMP)
 };
+#define BLU_STAMP(hdr, i) do { if (threadIdx.x == 0) (hdr)->stamp[i] = blu_globaltimer(); } while (0)
 
 // Explicit shared-space accesses with 32-bit addresses.  Through the generic pointers of the stream
 // structs the compiler emitted generic LD.E.64 for the staged values and rebuilt the shared window base
@@ -116,18 +125,23 @@ __device__ __forceinline__ bool blu_block_gj(double *A, double *B, const double 
                                              double **out, int tid, int nthr)
 {
     double *src = A, *dst = B;
+    // thread <-> (column c = tid & 31, rows r0, r0 + nthr/32, ...): no integer division in the pivot loop, the
+    // pivot-row element is the same for all of a thread's rows, the pivot-column elements are warp broadcasts
+    const int c = tid & 31, r0 = tid >> 5, rstep = nthr >> 5;
     for (int p = 0; p < n; ++p) {
         const double piv = src[p * BLU_JLD + p];
         if (!(piv > tol * diag0[p])) return false;            // same value in every thread
-        const double d = 1.0 / piv;
-        for (int t = tid; t < n * n; t += nthr) {
-            const int r = t / n, c = t - r * n;
-            const double arp = src[r * BLU_JLD + p], apc = src[p * BLU_JLD + c];
-            double v;
-            if (r == p) v = (c == p) ? d : apc * d;
-            else if (c == p) v = -(arp * d);
-            else v = fma(-(arp * d), apc, src[r * BLU_JLD + c]);
-            dst[r * BLU_JLD + c] = v;
+        const double d = __drcp_rn(piv);                      // correctly rounded reciprocal without the slow division path
+        if (c < n) {
+            const double apc = src[p * BLU_JLD + c];
+            for (int r = r0; r < n; r += rstep) {
+                const double arp = src[r * BLU_JLD + p];
+                double v;
+                if (r == p) v = (c == p) ? d : apc * d;
+                else if (c == p) v = -(arp * d);
+                else v = fma(-(arp * d), apc, src[r * BLU_JLD + c]);
+                dst[r * BLU_JLD + c] = v;
+            }
         }
         __syncthreads();
         double *tmp = src; src = dst; dst = tmp;
@@ -252,13 +266,6 @@ __device__ __forceinline__ BluFinScratch blu_fin_carve(unsigned char *raw)
     return f;
 }
 
-__device__ __forceinline__ unsigned long long blu_globaltimer()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 // Everything after the local reduction of the partial tiles, for one CTA (any block size):
 // f.Ph holds the raw upper-triangle sums of this rank.
 //   mode 0: mirror + delta only (get_phi).  mode 1: + pinv, x, S = 2 pinv, variance (misc.py:487-490).
@@ -289,36 +296,44 @@ __device__ __forceinline__ void blu_finish_body(int N, double delta, int mode, b
             if (tid < 32) dst[NN + tid] = (sp >> tid) & 1u ? 1.0 : 0.0;
             if (tid == 32) dst[NN + 32] = mx >= 0.05 ? 1.0 : 0.0;
         }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < peers.world)                                           // publish: one flag per destination
-            *((volatile unsigned long long *)&peers.peer[tid]->ready[slot][peers.rank]) = epoch;
-        if (tid == 0) { hdr->supp = 0u; hdr->maxbits = 0ull; hdr->epoch = epoch; }
+        __syncthreads();                                                 // every thread's stores are issued ...
         BluXchg *mine = peers.peer[peers.rank];
-        if (tid < peers.world) {                                         // wait for every rank's message (local polling)
-            volatile unsigned long long *flag = (volatile unsigned long long *)&mine->ready[slot][tid];
+        if (tid < peers.world) {
+            // ... and ordered before the flag by a system-scope release of the publishing thread (cumulative over the barrier)
+            unsigned long long *fl = &peers.peer[tid]->ready[slot][peers.rank];
+            asm volatile("fence.acq_rel.sys;\n\tst.relaxed.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(epoch) : "memory");
+            // wait for rank tid's message in OUR inbox (local polling), bounded
+            const unsigned long long *flag = &mine->ready[slot][tid];
             const unsigned long long t0 = blu_globaltimer();
             unsigned spins = 0;
-            while (*flag < epoch) {
+            for (;;) {
+                unsigned long long seen;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+                if (seen >= epoch) break;
                 if ((++spins & 1023u) == 0u && blu_globaltimer() - t0 > BLU_PEER_TIMEOUT_NS) { *f.ns = -1; break; }
             }
         }
-        __threadfence_system();
+        if (tid == 0) { hdr->supp = 0u; hdr->maxbits = 0ull; hdr->epoch = epoch; }
         __syncthreads();
         if (*f.ns == -1) {                                               // a peer never arrived: report, do not hang
             if (tid == 0) { hdr->flags = BLU_FLAG_PEER_TIMEOUT; hdr->scal[0] = nan(""); }
             return;
         }
         for (int e = tid; e < NN + 33; e += nthr) {
+            double v[BLU_MAX_PEERS];
+#pragma unroll
+            for (int r = 0; r < BLU_MAX_PEERS; ++r) v[r] = r < peers.world ? __ldcv(&mine->data[slot][r][e]) : 0.0;   // uncached, all in flight
             double sum = 0.0;
-            for (int r = 0; r < peers.world; ++r) sum += __ldcv(&mine->data[slot][r][e]);     // rank order, uncached
-            phi[e] = sum;
+#pragma unroll
+            for (int r = 0; r < BLU_MAX_PEERS; ++r) sum += v[r];          // rank order: bit-identical Phi on every rank
+            if (e < NN) Ph[(e / N) * BLU_JLD + (e % N)] = sum;
+            if (e >= NN) phi[e] = sum;                                   // reduced indicators (read back below)
         }
-        __syncthreads();
-        for (int e = tid; e < NN; e += nthr) Ph[(e / N) * BLU_JLD + (e % N)] = phi[e];
+        __threadfence_block();
         __syncthreads();
         allreduced = true;
         mode = 1;
+        BLU_STAMP(hdr, 5);                                               // [5] peer exchange complete
     }
     if (mode == 2) {
         for (int e = tid; e < NN; e += nthr) phi[e] = Ph[(e / N) * BLU_JLD + (e % N)];
@@ -384,6 +399,7 @@ __device__ __forceinline__ void blu_finish_body(int N, double delta, int mode, b
     __syncthreads();
     const int na = *f.ns;
     const unsigned active = *f.amask;
+    BLU_STAMP(hdr, 6);                                                   // [6] Phi mirrored, support known
     if (tid == 0) f.js->lmax = 0.0;
     int sweeps = blu_block_pinv(Pm, N, f.sidx, na, f.A, f.V, Ph, f.diag0, f.js, tid, nthr);
     for (int e = tid; e < NN; e += nthr) {
@@ -396,6 +412,7 @@ __device__ __forceinline__ void blu_finish_body(int N, double delta, int mode, b
         if (r == 0) xrow[c] = v;
     }
     __syncthreads();
+    BLU_STAMP(hdr, 7);                                                   // [7] pseudo-inverse written
     if (tid == 0) { hdr->scal[2] = (double)sweeps; hdr->scal[3] = f.js->lmax; hdr->scal[4] = pinv[0]; }
 
     // ---- variance on the support sub-block (misc.py:489-490) ----
@@ -544,7 +561,9 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
     // bit-reproducible.  Then the same CTA does the finish step (peer exchange, pinv, variance): one launch
     // instead of partial -> fold -> finish.
     __shared__ int s_last;
+    __shared__ unsigned long long s_t0;
     const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) s_t0 = blu_globaltimer();
     const int grp = blockIdx.x / BLU_PHI_GROUP;
     const int ngrp = (gridDim.x + BLU_PHI_GROUP - 1) / BLU_PHI_GROUP;
     const int members = min(BLU_PHI_GROUP, (int)gridDim.x - grp * BLU_PHI_GROUP);
@@ -558,12 +577,17 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    const unsigned long long t_g0 = blu_globaltimer();
     double *part2 = part + (size_t)gridDim.x * NN;        // group sums
     for (int e = tid; e < NN; e += nthr) {
         const double *pp = part + (size_t)grp * BLU_PHI_GROUP * NN + e;
+        double v[BLU_PHI_GROUP];
+        const bool upper = (e / N) <= (e % N);                // the tiles hold the upper triangle only
+#pragma unroll
+        for (int cc = 0; cc < BLU_PHI_GROUP; ++cc) v[cc] = (upper && cc < members) ? __ldcg(pp + (size_t)cc * NN) : 0.0;   // all in flight at once
         double sum = 0.0;
-#pragma unroll 4
-        for (int cc = 0; cc < members; ++cc) sum += __ldcg(pp + (size_t)cc * NN);
+#pragma unroll
+        for (int cc = 0; cc < BLU_PHI_GROUP; ++cc) sum += v[cc];    // CTA order
         part2[(size_t)grp * NN + e] = sum;
     }
     __threadfence();
@@ -576,14 +600,26 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (tid == 0) { hdr->stamp[1] = s_t0; hdr->stamp[2] = t_g0; }   // [1] this CTA's stream done, [2] it was the last of its group
+    BLU_STAMP(hdr, 3);                                    // [3] last group: final fold starts
     const BluFinScratch f = blu_fin_carve(smraw);         // the ring and the accumulator tiles are idle now
     for (int e = tid; e < NN; e += nthr) {
+        const int r = e / N, cc0 = e - r * N;
         double sum = 0.0;
-#pragma unroll 4
-        for (int gg = 0; gg < ngrp; ++gg) sum += __ldcg(part2 + (size_t)gg * NN + e);
-        f.Ph[(e / N) * BLU_JLD + (e % N)] = sum;
+        if (r <= cc0) {
+            for (int g0 = 0; g0 < ngrp; g0 += 8) {              // 8 loads in flight, group order
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (g0 + u < ngrp) ? __ldcg(part2 + (size_t)(g0 + u) * NN + e) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum += v[u];
+            }
+        }
+        f.Ph[r * BLU_JLD + cc0] = sum;
     }
     __syncthreads();
+    BLU_STAMP(hdr, 4);                                    // [4] sums of this rank complete
     blu_finish_body(N, delta, fin_mode, false, phi, pinv, xrow, S, hdr, peers, f, tid, nthr);
+    BLU_STAMP(hdr, 9);                                    // [9] finish step done
 }
 

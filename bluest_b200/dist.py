@@ -29,10 +29,13 @@ from .groups import balanced_slices, stream_cost
 
 
 class ShardedEvaluator:
-    def __init__(self, engine, sizes, rank, world, dist=None, group=None, fused=False, replicate_front=False, weight=stream_cost):
+    def __init__(self, engine, sizes, rank, world, dist=None, group=None, fused=False, replicate_front=False, weight=stream_cost,
+                 set_slice=True):
         """engine: object with shard_phi / shard_finish / shard_hess / buffers (see GpuEngine).
         sizes = [L1..LK].  fused=True: the Phi all-reduce runs inside the finish kernel over NVLink
-        peer memory (engine.connect_peers) instead of a separate NCCL call."""
+        peer memory (engine.connect_peers) instead of a separate NCCL call.
+        set_slice=False: the engine is a second evaluation lane (``SAP.clone()``) that already carries its
+        parent's slice; only the peer connection of the lane is made."""
         self.engine = engine
         self.fused = bool(fused)
         # replicate_front: every rank evaluates Phi, pinv, gradient and U,V for ALL groups (tens of
@@ -53,7 +56,8 @@ class ShardedEvaluator:
             self.slices = [(0, self.L)] * world
             self.lo, self.hi = 0, self.L
         else:
-            engine.set_slice(self.lo, self.hi)
+            if set_slice:
+                engine.set_slice(self.lo, self.hi)
             if self.fused:
                 engine.connect_peers(rank, world, dist, group)
 

@@ -227,6 +227,19 @@ class SAP(object):
             ptr = ctypes.c_void_p(int(d_m.data_ptr()) if hasattr(d_m, "data_ptr") else int(d_m))
         check(lib().blu_eval_device(self._ctx, ptr, float(delta), int(bool(grad)), int(bool(hess))))
 
+    def clone(self):
+        """A second evaluation lane on the same problem (``blu_ctx_clone``): shares this SAP's inverses and tables in
+        HBM, owns its stream and per-evaluation buffers, so evaluations on the two overlap on the device.  Only the
+        device-resident interface and the closures are meaningful on the clone; close it before this SAP."""
+        import copy
+        other = copy.copy(self)
+        other._ctx = ctypes.c_void_p()
+        check(lib().blu_ctx_clone(self._ctx, ctypes.byref(other._ctx)))
+        other._parent = self                                     # keeps the owner of the shared buffers alive
+        other._pending = None
+        other.get_variance_functions()
+        return other
+
     # ---- CUDA graphs over the device-resident calls --------------------------------------------
     def graph_begin(self):
         """Start recording the device-resident calls of this SAP (``eval_device``, ``save_result``,

@@ -76,6 +76,12 @@ const char *blu_version(void);
 int blu_ctx_create(int device, int N, int K, const int64_t *sizes, const int64_t *groups_flat,
                    blu_ctx **out);
 int blu_ctx_destroy(blu_ctx *ctx);
+/* A second evaluation lane on the same problem: shares the parent's read-only HBM data (group tables, packed
+ * inverses, work lists of the parent's current slice), owns its stream and the small per-evaluation buffers.
+ * Evaluations on parent and clone run concurrently (the one-CTA serial tail of one overlaps the streaming kernels
+ * of the other).  The parent must outlive the clone and keep its slice; set_covariance / set_invcovs / set_slice
+ * on a clone fail with BLU_ERR_STATE. */
+int blu_ctx_clone(blu_ctx *parent, blu_ctx **out);
 
 /* Kernel (1): batched inversion of C[g_i,g_i] for every group (replaces the L calls of
  * np.linalg.pinv at sap.py:72-74).  One warp-slice per group, shuffle-based Gauss-Jordan; groups
@@ -175,6 +181,11 @@ int blu_ctx_timing_read(blu_ctx *ctx, float *ms, int *n);
 int blu_ctx_set_option(blu_ctx *ctx, const char *name, int value);
 /* Number of kernels the last evaluation launched. */
 int blu_ctx_last_launches(blu_ctx *ctx);
+
+/* Profiling aid: 16 %globaltimer stamps (ns) left by the last CTA of the fused Phi kernel at its milestones
+ * ([1] own stream done, [2] last of its group, [3] final fold starts, [4] rank sums complete, [5] peer exchange
+ * complete, [6] Phi ready, [7] pinv written, [9] finish done).  Synchronises. */
+int blu_ctx_last_stamps(blu_ctx *ctx, unsigned long long *stamps16);
 
 /* CUDA graphs: everything the device-resident calls (blu_eval_device, blu_shard_eval_fused,
  * blu_hess_matvec_device, blu_ctx_save_result) enqueue between _begin and _end is recorded instead of run;

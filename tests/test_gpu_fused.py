@@ -79,6 +79,58 @@ def _worker(rank, world, port, N, ret):
         dist.destroy_process_group()
 
 
+def test_clone_lane_and_graph_replay():
+    """A clone (second evaluation lane) shares the parent's inverses and must reproduce its results bit for bit,
+    also when parent and clone evaluate concurrently on their own streams and when the evaluations are replayed
+    from a CUDA graph (the device-side epoch of the fused exchange keeps counting across replays)."""
+    import torch
+    import bluest_b200 as blu
+    from bluest_b200 import _lib
+    from bluest_b200.dist import GpuEngine, ShardedEvaluator
+    N = 12
+    C = orc.wishart_cov(N, 4)
+    ga = blu.enumerate_group_arrays(N)
+    sizes = [len(g) for g in ga]
+    L = sum(sizes)
+    sap = blu.SAP(C, N, ga, np.ones(L), verbose=False)
+    o = orc.SapOracle(C, N, orc.enumerate_group_arrays(N), invcovs=orc.batched_invcovs(C, orc.enumerate_group_arrays(N)), with_ES=False)
+    ev = ShardedEvaluator(GpuEngine(sap), sizes, 0, 1, fused=True)
+    lane2 = sap.clone()
+    eng2 = GpuEngine(lane2)
+    ShardedEvaluator(eng2, sizes, 0, 1, fused=True, set_slice=False)
+    with pytest.raises(blu.BluError):
+        _lib.check(_lib.lib().blu_ctx_set_slice(lane2._ctx, 0, 10))          # a clone keeps its parent's slice
+    ms = [orc.dense_m(L, s) for s in range(4)]
+    dms = [torch.from_numpy(m).cuda() for m in ms]
+    var = torch.zeros(8, dtype=torch.float64, device="cuda"); grads = torch.zeros((8, L), dtype=torch.float64, device="cuda")
+    lanes = [(sap, ev.engine), (lane2, eng2)]
+
+    def enqueue(slot, j, lane):
+        s_, e_ = lanes[lane]
+        s_.set_grad_output(grads[slot]); e_.shard_eval_fused(dms[j], 0.0, True, 0); s_.save_result(var[slot:slot + 1]); s_.set_grad_output(None)
+    for j in range(4):
+        enqueue(j, j, 0); enqueue(4 + j, j, 1)                  # both lanes at once, eager
+    sap.sync(); lane2.sync()
+    for j in range(4):
+        vo, go, _ = o.variance_GH(ms[j], nohess=True)
+        assert abs(var[j].item() - vo) <= 1e-12 * vo and maxrel(grads[j].cpu().numpy(), go) < 1e-12
+        assert var[j].item() == var[4 + j].item() and torch.equal(grads[j], grads[4 + j])     # lanes agree bit for bit
+    keep_v, keep_g = var.clone(), grads.clone()
+    var.zero_(); grads.zero_()
+    gids = []
+    for lane, (s_, _) in enumerate(lanes):
+        s_.graph_begin()
+        for j in range(4):
+            enqueue(4 * lane + j, j, lane)
+        gids.append(s_.graph_end())
+    for rep in range(3):
+        sap.graph_launch(gids[0]); lane2.graph_launch(gids[1])
+    sap.sync(); lane2.sync()
+    assert torch.equal(var, keep_v) and torch.equal(grads, keep_g)
+    assert sap.last_result()[1] == 0 and lane2.last_result()[1] == 0
+    lane2.close(); sap.close()
+
+
 def test_fused_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:

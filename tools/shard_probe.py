@@ -57,4 +57,26 @@ for world in (1, 2, 4, 8):
             rows.append((hi - lo, t_phi, t_fin))
         print("world=%d weight=%-11s max phi %.1f  max fin+grad %.1f  sum-of-max %.1f | " % (world, wname, max(r[1] for r in rows), max(r[2] for r in rows),
               max(r[1] for r in rows) + max(r[2] for r in rows)) + " ".join("[%d: %.0f+%.0f]" % r for r in rows), flush=True)
+# fixed costs: a slice of a few groups in the middle of the enumeration
+sap2 = sap
+for (lo, hi) in ((500000, 500032), (500000, 504096), (500000, 532768)):
+    _lib.check(lib.blu_ctx_set_slice(sap._ctx, lo, hi))
+    t_phi = timed(lambda: _lib.check(lib.blu_shard_phi(sap._ctx, mp)), 50)
+    t_fin = timed(lambda: _lib.check(lib.blu_shard_finish(sap._ctx, 0.0, 0, 0)), 50)
+    t_fg = timed(lambda: _lib.check(lib.blu_shard_finish(sap._ctx, 0.0, 1, 0)), 50)
+    print("slice of %d groups: phi %.1f us, finish alone %.1f us, finish+grad %.1f us" % (hi - lo, t_phi, t_fin, t_fg), flush=True)
+# where the serial tail of the fused Phi kernel goes: globaltimer stamps of its last CTA (world = 1: self push)
+_lib.check(lib.blu_ctx_set_slice(sap._ctx, 0, L))
+from bluest_b200.dist import GpuEngine
+eng = GpuEngine(sap)
+eng.connect_peers(0, 1)
+for (lo, hi) in ((0, L), (500000, 532768), (0, 130000)):
+    _lib.check(lib.blu_ctx_set_slice(sap._ctx, lo, hi))
+    for _ in range(3):
+        _lib.check(lib.blu_shard_eval_fused(sap._ctx, mp, 0.0, 1, 0))
+    st = (ctypes.c_uint64 * 16)()
+    _lib.check(lib.blu_ctx_last_stamps(sap._ctx, st))
+    s = [int(v) for v in st]
+    names = {2: "group-last", 3: "final fold starts", 4: "rank sums", 5: "exchange", 6: "Phi ready", 7: "pinv", 9: "done"}
+    print("slice [%d,%d): " % (lo, hi) + ", ".join("%s +%.1f us" % (names[i], (s[i] - s[1]) / 1e3) for i in (2, 3, 4, 5, 6, 7, 9)), flush=True)
 sap.close()
