@@ -483,7 +483,7 @@ def secondary_configs(device=0):
         sp.close()
     return out
 
-def shard_n20_benchmark(world, rank, local, dist, steps=200, N=20, pool=4):
+def shard_n20_benchmark(world, rank, local, dist, steps=200, N=20, pool=4, nlanes=2, lane_sweep=()):
     """BASELINE config 5 / the north-star multi-GPU path under the driver's own launch: ONE problem with 20 models
     (1 048 575 groups), the group enumeration cut into `world` contiguous work-balanced slices, one rank per slice.
     Per evaluation and rank: one kernel streams the slice's packed inverses into partial Phi tiles, its last CTA folds
@@ -505,11 +505,15 @@ def shard_n20_benchmark(world, rank, local, dist, steps=200, N=20, pool=4):
     sap = blu.SAP(C, N, ga, np.ones(L), verbose=False, device=local)
     eng = GpuEngine(sap)
     ev = ShardedEvaluator(eng, sizes, rank, world, dist=dist if world > 1 else None, fused=True)
-    # second evaluation lane: same inverses in HBM, own stream / status / inbox (blu_ctx_clone)
-    sap2 = sap.clone()
-    eng2 = GpuEngine(sap2)
-    ev2 = ShardedEvaluator(eng2, sizes, rank, world, dist=dist if world > 1 else None, fused=True, set_slice=False)
-    lanes = [(sap, eng), (sap2, eng2)]
+    # further evaluation lanes: same inverses in HBM, own stream / status / inbox each (blu_ctx_clone)
+    max_lanes = max([nlanes] + list(lane_sweep))
+    pool = max(pool, max_lanes)
+    lanes = [(sap, eng)]
+    for _ in range(1, max_lanes):
+        s_k = sap.clone()
+        e_k = GpuEngine(s_k)
+        ShardedEvaluator(e_k, sizes, rank, world, dist=dist if world > 1 else None, fused=True, set_slice=False)
+        lanes.append((s_k, e_k))
     setup_s = time.perf_counter() - t0
     ms_host = [orc.dense_m(L, j) for j in range(pool)]
     ms = [torch.from_numpy(m).to(dev) for m in ms_host]
@@ -549,9 +553,14 @@ def shard_n20_benchmark(world, rank, local, dist, steps=200, N=20, pool=4):
         return float(t[0]) * 1e-3 / (reps * pool)
 
     reps = max(2, steps // pool)
-    for j in range(pool):                                 # eager once on both lanes: lazy allocations, first launches
-        enqueue(j, 0); enqueue(j, 1)
-    sap.sync(); sap2.sync()
+    def sync_all():
+        for s_, _ in lanes:
+            s_.sync()
+
+    for j in range(pool):                                 # eager once on every lane: lazy allocations, first launches
+        for lane in range(max_lanes):
+            enqueue(j, lane)
+    sync_all()
     barrier()
     # (a) one lane, eager launches and as a CUDA graph: evaluation after evaluation (the latency of a sequential solver)
     t_eager = timed(lambda r: [enqueue(j, 0) for _ in range(r) for j in range(pool)], reps, 1)
@@ -562,24 +571,29 @@ def shard_n20_benchmark(world, rank, local, dist, steps=200, N=20, pool=4):
     sap.graph_launch(gid, 2)
     sap.sync()
     t_graph = timed(lambda r: sap.graph_launch(gid, r), reps, 1)
-    # (b) two lanes: independent evaluations alternate between two streams, the one-CTA tail of one (fold, peer
-    #     exchange, N x N inverse) overlaps the streaming kernels of the other (the throughput of a sweep)
-    gids = []
-    for lane, (s_, _) in enumerate(lanes):
-        s_.graph_begin()
-        for j in range(lane, pool, 2):
-            enqueue(j, lane)
-        gids.append(s_.graph_end())
-    for lane, (s_, _) in enumerate(lanes):
-        s_.graph_launch(gids[lane], 2)
-    sap.sync(); sap2.sync()
+    # (b) several lanes: independent evaluations alternate between the lanes' streams, the one-CTA tail of one
+    #     (fold, peer exchange, N x N inverse) overlaps the streaming kernels of the others (the throughput of a sweep)
+    def lanes_time(nl):
+        gids = []
+        for lane in range(nl):
+            s_ = lanes[lane][0]
+            s_.graph_begin()
+            for j in range(lane, pool, nl):
+                enqueue(j, lane)
+            gids.append(s_.graph_end())
+        for lane in range(nl):
+            lanes[lane][0].graph_launch(gids[lane], 2)
+        sync_all()
 
-    def two_lanes(r):
-        for _ in range(r):
-            sap.graph_launch(gids[0], 1)
-            sap2.graph_launch(gids[1], 1)
-    t_two = timed(two_lanes, reps, 2)
-    sap.sync(); sap2.sync()
+        def go(r):
+            for _ in range(r):
+                for lane in range(nl):
+                    lanes[lane][0].graph_launch(gids[lane], 1)
+        t = timed(go, reps, nl)
+        sync_all()
+        return t
+    t_two = lanes_time(nlanes)
+    sweep = {str(nl): lanes_time(nl) * 1e6 for nl in lane_sweep}
     # parity: every rank keeps its own slice of the gradient; sum the zero-padded slices onto every rank once
     g0 = torch.zeros(L, dtype=torch.float64, device=dev)
     g0[ev.lo:ev.hi] = grad_out[0, ev.lo:ev.hi]
@@ -599,16 +613,17 @@ def shard_n20_benchmark(world, rank, local, dist, steps=200, N=20, pool=4):
         peak, peak_src = peaks()
         t = min(t_graph, t_eager, t_two)
         out = {"models": N, "groups": L, "n_gpus": world, "scaling": "strong", "evaluations_timed": reps * pool,
-               "us_per_eval": t * 1e6, "evals_per_s": 1.0 / t, "us_per_eval_two_lanes": t_two * 1e6,
+               "us_per_eval": t * 1e6, "evals_per_s": 1.0 / t, "lanes": nlanes, "us_per_eval_lanes": t_two * 1e6, "us_per_eval_by_lanes": sweep,
                "us_per_eval_one_lane_cuda_graph": t_graph * 1e6, "us_per_eval_one_lane_eager": t_eager * 1e6,
-               "mode": "independent evaluations alternate between two evaluation lanes (two streams on the same inverses); one lane = strictly one evaluation after the other",
+               "mode": "independent evaluations alternate between the evaluation lanes (one stream each, all on the same inverses in HBM); one lane = strictly one evaluation after the other",
                "algorithmic_GBps": algo / t / 1e9, "frac_of_n_gpus_x_hbm_peak": algo / t / 1e9 / (peak * world), "peak_source": peak_src + " x n_gpus",
                "parity_maxrel": {"variance": abs(v_dev - vo) / abs(vo), "gradient": float(np.max(np.abs(gd - go)) / np.max(np.abs(go))),
                                  "against": "CPU oracle (per-class batched LAPACK inverses, restated native loops), sample vector 0, %.1f s on rank 0" % oracle_s},
                "flags": flags, "slices": [list(sl) for sl in ev.slices], "setup_s": setup_s,
                "exchange": "in-kernel push of N^2+33 doubles into every rank's inbox over NVLink peer memory (CUDA IPC), no NCCL on the data path",
                "launches_per_eval": 2}
-    sap2.close()
+    for s_, _ in lanes[1:]:
+        s_.close()
     sap.close()
     return out
 
@@ -720,7 +735,7 @@ def run_ours(args):
     shard20 = None
     if args.shard20:
         try:
-            shard20 = shard_n20_benchmark(world, rank, local, dist, steps=max(40, args.steps))
+            shard20 = shard_n20_benchmark(world, rank, local, dist, steps=max(40, args.steps), nlanes=args.lanes)
         except Exception as ex:
             shard20 = {"failed": repr(ex)}
 
@@ -870,6 +885,24 @@ def run_shard(args):
         dist.destroy_process_group()
 
 
+def run_shard20_only(args):
+    """Development aid: only the group-sharded 20-model benchmark, with a sweep over the number of lanes."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = shard_n20_benchmark(world, rank, local, dist, steps=max(40, args.steps), nlanes=args.lanes, lane_sweep=(1, 2, 3, 4, 6))
+    if rank == 0:
+        emit(out)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -905,7 +938,8 @@ def main():
     ap.add_argument("--no-solve", dest="solve", action="store_false", help="skip the end-to-end SAP solve comparison")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the brief measurements of the other BASELINE configs")
     ap.add_argument("--no-shard20", dest="shard20", action="store_false", help="skip the group-sharded 20-model evaluation")
-    ap.add_argument("--mode", default="sweep", choices=["sweep", "shard"], help="sweep: independent instances per GPU (default); shard: one problem, groups sharded")
+    ap.add_argument("--lanes", type=int, default=2, help="evaluation lanes of the group-sharded 20-model benchmark")
+    ap.add_argument("--mode", default="sweep", choices=["sweep", "shard", "shard20"], help="sweep: independent instances per GPU (default); shard: one problem, groups sharded")
     ap.add_argument("--nohess", action="store_true", help="shard mode: Phi + variance + gradient only (e.g. --models 20)")
     ap.add_argument("--gather-grad", action="store_true", help="shard mode: all-gather the gradient slices")
     ap.add_argument("--shard-front", action="store_true", help="shard mode with Hessian: also shard Phi/grad/U,V by groups and exchange U,V (default: replicate the cheap front end, shard only the Hessian rows)")
@@ -914,6 +948,8 @@ def main():
     if args.impl == "reference":
         args.steps = min(args.steps, 5)
         run_reference(args)
+    elif args.mode == "shard20":
+        run_shard20_only(args)
     elif args.mode == "shard":
         args.warmup = max(args.warmup, 3)
         run_shard(args)

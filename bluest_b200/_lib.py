@@ -68,6 +68,8 @@ SIGNATURES = {
     "blu_hess_matvec": (c_int, [p_void, p_dbl, c_int, p_dbl]),
     "blu_hess_matvec_device": (c_int, [p_void, p_void, p_void]),
     "blu_pilot_covariance": (c_int, [c_int, p_void, c_i64, c_int, c_int, p_dbl, p_dbl, p_dbl, ctypes.POINTER(ctypes.c_float)]),
+    "blu_pilot_sums": (c_int, [c_int, p_void, c_i64, c_int, c_int, c_i64, c_int, c_int, p_void, p_void, c_int, ctypes.POINTER(ctypes.c_float)]),
+    "blu_pilot_finalize": (c_int, [p_dbl, c_i64, c_int, c_int, p_dbl, p_dbl, p_dbl, p_dbl, p_dbl, p_dbl]),
     "blu_assemble_psi_c": (c_int, [p_dbl, c_int, c_int, c_int, p_i64, p_dbl]),
     "blu_objectiveK_c": (c_int, [p_dbl, c_int, c_int, c_int, p_dbl, p_i64, p_dbl]),
     "blu_objectiveK_c_i64": (c_int, [p_dbl, c_int, c_int, c_int, p_i64, p_i64, p_dbl]),

@@ -1453,6 +1453,24 @@ extern "C" int blu_pilot_covariance(int device, const double *Y, int64_t n, int 
     return blu_gram_run(Y, n, N, y_on_device, s1, S2, C_hat, kernel_ms, g_err);
 }
 
+extern "C" int blu_pilot_sums(int device, const double *Y, int64_t n, int N, int n_out, int64_t ystride, int y_on_device,
+                              int telescoped, void *producer_stream, double *sums, int sums_on_device, float *kernel_ms)
+{
+    int rc = need_device(device);
+    if (rc) return rc;
+    if (!Y || !sums || n < 1 || N < 1 || N > BLU_MAX_MODELS || n_out < 1) return fail(BLU_ERR_ARG, "bad pilot-sample arguments");
+    if (ystride != 0 && ystride < n * N) return fail(BLU_ERR_ARG, "output stride smaller than one sample matrix");
+    return blu_gram_sums(Y, n, N, n_out, ystride, y_on_device, telescoped, (cudaStream_t)producer_stream, sums, sums_on_device, kernel_ms, g_err);
+}
+
+extern "C" int blu_pilot_finalize(const double *sums, int64_t n_total, int N, int telescoped, double *s1, double *S2, double *C_hat,
+                                  double *d1, double *d2, double *dV)
+{
+    if (!sums || n_total < 1 || N < 1 || N > BLU_MAX_MODELS) return fail(BLU_ERR_ARG, "bad pilot-sum arguments");
+    blu_gram_finalize(sums, n_total, N, telescoped, s1, S2, C_hat, d1, d2, dV);
+    return BLU_OK;
+}
+
 // --------------------------------------------------------------------------------------------
 // Level 1
 // --------------------------------------------------------------------------------------------

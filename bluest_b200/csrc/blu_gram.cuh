@@ -1,45 +1,63 @@
-// blu_gram.cuh -- kernel (4): pilot-sample covariance as an FP64 tensor-core Gram contraction.
+// blu_gram.cuh -- kernel (4): the pilot-sample sums as an FP64 tensor-core Gram contraction.
 //
-// Replaces the per-sample Python accumulation of blue_fn.py:159-167 (sumse[i] += P_i,
-// sumsc[j,i] += P_i P_j) and the formula of blue_models.py:333,
-//     C_hat = sumsc / n - outer(sumse, sumse) / n^2      (biased, one pass).
-// Y is the (n, N) row-major sample matrix.  The model axis is padded to NT tiles of 8 columns with
+// Replaces the per-sample Python accumulation of blue_fn.py:147-167:
+//     sumse[n][i] += P_i,   sumsc[n][j,i] += P_i P_j,
+//     sumsd1[n][i][j] += P_i - P_j,   sumsd2[n][i][j] += (P_i - P_j)^2     (compute_mlmc_differences)
+// for n_out outputs in one launch (grid.y = output), and feeds the formulas of blue_models.py:333,339
+//     C_hat = sumsc / n - outer(sumse, sumse) / n^2,      dV = sumsd2 / n - (sumsd1 / n)^2
+// (evaluated on the host from the (N^2 + N) sums per output: blu_pilot_finalize).
+//
+// Y[o] is the (n, N) row-major sample matrix of output o.  The model axis is padded to NT tiles of 8 columns with
 // one extra column of ones at index N, so the column sums come out of the same contraction:
-// G = [Y 1]^T [Y 1]  =>  S2 = G[:N,:N], s1 = G[:N, N].
-// A warp walks its contiguous slab of samples (bulk-async staged through shared memory) 4 at a time: the fragment of tile t held by a lane
-// (sample lane&3, column 8t + lane>>2) is at once the A operand (row = column index, k = sample)
-// and the B operand (k = sample, col = column index) of mma.m8n8k4.f64, so every loaded double is
-// used NT times.  Only tile pairs ti <= tj are accumulated.  Reduction: warps -> CTA in shared
-// memory in warp order, CTAs -> result in block order by a second kernel: no atomics,
-// bit-reproducible.  The kernel is an HBM stream of 8 n N bytes.
+//     G = [X 1]^T [X 1]   =>   sumsc = G[:N,:N], sumse = G[:N, N].
+// TELE = false: X = Y.  TELE = true: X = Z, the TELESCOPED samples Z_0 = Y_0, Z_j = Y_j - Y_{j-1}, formed in
+// registers.  Y_i - Y_j is then a sum of consecutive Z columns, so the difference sums of the MLMC pairs are sums
+// of Gram entries OF DIFFERENCES: sumsd2[i][j] = sum_{l,l' in (i,j]} G^Z[l,l'] has no cancellation against the
+// (much larger) variances of the models themselves, which sumsc[i,i] - 2 sumsc[i,j] + sumsc[j,j] would have for the
+// strongly coupled models a multilevel hierarchy consists of; sumse and sumsc are prefix sums of the same G^Z.
+//
+// A warp walks its contiguous slab of samples (bulk-async staged through a private 3-stage ring) 4 at a time: the
+// fragment of tile t held by a lane (sample lane&3, column 8t + lane>>2) is at once the A operand (row = column
+// index, k = sample) and the B operand (k = sample, col = column index) of mma.m8n8k4.f64, so every loaded double
+// is used NT times.  Only tile pairs ti <= tj are accumulated.  Reduction: warps -> CTA in shared memory in warp
+// order; CTAs -> result by the last CTAs to arrive (two levels, fixed order, as in blu_phi.cuh): no atomics on
+// data, no second launch, bit-reproducible.  The kernel is an HBM stream of 8 n N bytes per output.
 #pragma once
 #include <string>
+#include <vector>
 #include "blu_common.cuh"
 #include "blu_hess.cuh"
 #include "blu_stream.cuh"
 
 #define BLU_GRAM_WARPS 8
-
+#define BLU_GRAM_NS 3                        // ring depth per warp
 #define BLU_GRAM_STAGE_DOUBLES 544           // >= 16 samples x 32 models + skew/round-up slack
+#define BLU_GRAM_GROUP 16                    // CTAs per group of the in-kernel reduction
+#define BLU_GRAM_MAXGROUPS 40
 
-// Each warp owns a contiguous slab of samples and streams it through a private two-stage
-// shared-memory ring with bulk asynchronous copies (cp.async.bulk + mbarrier, as blu_stream.cuh):
-// a stage holds `spc` samples (spc*N doubles, one contiguous span of Y).  Fragments are read
-// from shared memory; nothing in the MMA loop waits on a global load.
-template <int NT>
+template <int NT, bool TELE>
 __global__ void __launch_bounds__(BLU_GRAM_WARPS * 32)
-blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab, int spc, double *__restrict__ part)
+blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n, int N, long long slab, int spc,
+                double *__restrict__ part_all, double *__restrict__ G_all, unsigned *__restrict__ tickets_all)
 {
     constexpr int NPG = 8 * NT;
+    constexpr int E = NPG * NPG;
     constexpr int NPAIR = NT * (NT + 1) / 2;
-    extern __shared__ __align__(16) double gsm_raw[];   // [WARPS][2][STAGE] stages | [WARPS][NPG*NPG] reduction | barriers
+    extern __shared__ __align__(16) double gsm_raw[];   // [WARPS][NS][STAGE] stages | [WARPS][E] reduction | barriers
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *stage0 = gsm_raw + (size_t)(2 * w) * BLU_GRAM_STAGE_DOUBLES;
-    double *stage1 = stage0 + BLU_GRAM_STAGE_DOUBLES;
-    double *sred = gsm_raw + (size_t)2 * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES + (size_t)w * NPG * NPG;
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(gsm_raw + (size_t)2 * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES
-                                                                      + (size_t)BLU_GRAM_WARPS * NPG * NPG) + 2 * w;
-    if (lane == 0) { blu_mbar_init(&bars[0], 1); blu_mbar_init(&bars[1], 1); blu_mbar_fence_init(); }
+    const int o = blockIdx.y;
+    const double *__restrict__ Y = Yall + (long long)o * ystride;
+    double *__restrict__ part = part_all + (size_t)o * (gridDim.x + BLU_GRAM_MAXGROUPS) * E;
+    double *__restrict__ G = G_all + (size_t)o * E;
+    unsigned *tickets = tickets_all + (size_t)o * (BLU_GRAM_MAXGROUPS + 1);
+    double *stages = gsm_raw + (size_t)(BLU_GRAM_NS * w) * BLU_GRAM_STAGE_DOUBLES;
+    double *sall = gsm_raw + (size_t)BLU_GRAM_NS * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES;
+    double *sred = sall + (size_t)w * E;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sall + (size_t)BLU_GRAM_WARPS * E) + BLU_GRAM_NS * w;
+    if (lane == 0) {
+        for (int s = 0; s < BLU_GRAM_NS; ++s) blu_mbar_init(&bars[s], 1);
+        blu_mbar_fence_init();
+    }
     __syncwarp();
     const int ks = lane & 3, cq = lane >> 2;
     const long long gw = (long long)blockIdx.x * BLU_GRAM_WARPS + w;
@@ -57,18 +75,24 @@ blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab
         if (lane == 0) {
             const unsigned bytes = (unsigned)(((skew + cnt * N) * 8 + 15) & ~15ll);
             blu_mbar_expect_tx(&bars[st], bytes);
-            blu_bulk_g2s(st ? stage1 : stage0, (const void *)(addr & ~15ull), bytes, &bars[st]);
+            blu_bulk_g2s(stages + (size_t)st * BLU_GRAM_STAGE_DOUBLES, (const void *)(addr & ~15ull), bytes, &bars[st]);
         }
         return skew;
     };
-    int skew_cur = 0, skew_nxt = 0;
-    if (s0 < s1) skew_cur = issue(s0, 0);
+    int skew[BLU_GRAM_NS];
+    long long sissue = s0;                                // next chunk to issue
+    int nissued = 0;
+    for (; nissued < BLU_GRAM_NS - 1 && sissue < s1; ++nissued, sissue += spc) skew[nissued] = issue(sissue, nissued);
     int it = 0;
     for (long long sb = s0; sb < s1; sb += spc, ++it) {
-        const int st = it & 1;
-        if (sb + spc < s1) skew_nxt = issue(sb + spc, st ^ 1);
-        blu_mbar_wait(&bars[st], (unsigned)((it >> 1) & 1));
-        const double *base = (st ? stage1 : stage0) + skew_cur;
+        const int st = it % BLU_GRAM_NS;
+        if (sissue < s1) {                                // refill the stage consumed one step ago
+            const int sn = (it + BLU_GRAM_NS - 1) % BLU_GRAM_NS;
+            skew[sn] = issue(sissue, sn);
+            sissue += spc;
+        }
+        blu_mbar_wait(&bars[st], (unsigned)((it / BLU_GRAM_NS) & 1));
+        const double *base = stages + (size_t)st * BLU_GRAM_STAGE_DOUBLES + skew[st];
         const int cnt = (int)((s1 - sb) < spc ? (s1 - sb) : spc);
         for (int r0 = 0; r0 < cnt; r0 += 4) {
             const int row = r0 + ks;
@@ -77,7 +101,14 @@ blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const int col = 8 * t + cq;
-                f[t] = rok ? ((col < N) ? base[row * N + col] : (col == N ? 1.0 : 0.0)) : 0.0;
+                double v = 0.0;
+                if (rok) {
+                    if (col < N) {
+                        v = base[row * N + col];
+                        if (TELE && col > 0) v -= base[row * N + col - 1];        // Z_j = Y_j - Y_{j-1}
+                    } else if (col == N) v = 1.0;
+                }
+                f[t] = v;
             }
             int p = 0;
 #pragma unroll
@@ -86,7 +117,6 @@ blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab
                 for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[p][0], acc[p][1], f[ti], f[tj]); ++p; }
         }
         __syncwarp();                                   // stage consumed before it is refilled
-        skew_cur = skew_nxt;
     }
     // warp tile -> shared (C fragment: row lane>>2, cols 2*(lane&3)+{0,1})
     {
@@ -102,146 +132,235 @@ blu_gram_kernel(const double *__restrict__ Y, long long n, int N, long long slab
             }
     }
     __syncthreads();
-    const double *sall = gsm_raw + (size_t)2 * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES;
-    for (int t = threadIdx.x; t < NPG * NPG; t += blockDim.x) {
+    for (int t = threadIdx.x; t < E; t += blockDim.x) {
         const int r = t / NPG, c = t - r * NPG;
-        if ((r >> 3) > (c >> 3)) continue;                  // lower tiles are never produced
+        double sum = 0.0;
+        if ((r >> 3) <= (c >> 3)) {                           // lower tiles are never produced
+#pragma unroll
+            for (int ww = 0; ww < BLU_GRAM_WARPS; ++ww) sum += sall[(size_t)ww * E + t];
+        }
+        part[(size_t)blockIdx.x * E + t] = sum;
+    }
+
+    // ---- fused reduction over CTAs: last CTA of a group folds the group (CTA order), last group folds the groups ----
+    __shared__ int s_last;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int grp = blockIdx.x / BLU_GRAM_GROUP;
+    const int ngrp = (gridDim.x + BLU_GRAM_GROUP - 1) / BLU_GRAM_GROUP;
+    const int members = min(BLU_GRAM_GROUP, (int)gridDim.x - grp * BLU_GRAM_GROUP);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(&tickets[1 + grp], 1u);
+        s_last = (t == (unsigned)(members - 1));
+        if (s_last) tickets[1 + grp] = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double *part2 = part + (size_t)gridDim.x * E;
+    for (int e = tid; e < E; e += nthr) {
+        const int r = e / NPG, c = e - r * NPG;
+        double v[BLU_GRAM_GROUP];
+        const bool up = (r >> 3) <= (c >> 3);
+        const double *pp = part + (size_t)grp * BLU_GRAM_GROUP * E + e;
+#pragma unroll
+        for (int cc = 0; cc < BLU_GRAM_GROUP; ++cc) v[cc] = (up && cc < members) ? __ldcg(pp + (size_t)cc * E) : 0.0;
         double sum = 0.0;
 #pragma unroll
-        for (int ww = 0; ww < BLU_GRAM_WARPS; ++ww) sum += sall[(size_t)ww * NPG * NPG + t];
-        part[(long long)blockIdx.x * NPG * NPG + t] = sum;
+        for (int cc = 0; cc < BLU_GRAM_GROUP; ++cc) sum += v[cc];
+        part2[(size_t)grp * E + e] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(&tickets[0], 1u);
+        s_last = (t == (unsigned)(ngrp - 1));
+        if (s_last) tickets[0] = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = tid; e < E; e += nthr) {
+        const int r = e / NPG, c = e - r * NPG;
+        double sum = 0.0;
+        if ((r >> 3) <= (c >> 3)) {
+            for (int g0 = 0; g0 < ngrp; g0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (g0 + u < ngrp) ? __ldcg(part2 + (size_t)(g0 + u) * E + e) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum += v[u];
+            }
+        }
+        G[e] = sum;
     }
 }
 
-// Fixed-order reduction over CTAs + covariance formula, spread over E/32 CTAs: CTA b owns the 32
-// entries [32b, 32b+32) of the Gram tile; its 8 warps sum interleaved subsets of the partial tiles
-// (coalesced 256-byte rows, independent loads in flight) and are combined in warp order, so the
-// association is fixed.  The CTA that finishes last (a ticket counter: control flow only, no
-// arithmetic through atomics) turns G into s1, S2 and C_hat.  A single-CTA version of this reduction
-// took as long as the streaming kernel itself (1.4 MB of partials behind one SM's load queue).
-#define BLU_GRAM_FIN_WARPS 8
-__global__ void __launch_bounds__(BLU_GRAM_FIN_WARPS * 32)
-blu_gram_finish_kernel(const double *__restrict__ part, int nparts, int NPG, int N, long long n,
-                       double *__restrict__ G, unsigned *__restrict__ ticket,
-                       double *__restrict__ s1, double *__restrict__ S2, double *__restrict__ Chat)
+// G tiles (upper tile pairs) of every output -> packed sums: per output N*N Gram entries (full, symmetric) then the
+// N column sums.  One small CTA per output.
+__global__ void blu_gram_pack_kernel(const double *__restrict__ G_all, int NPG, int N, double *__restrict__ sums)
 {
-    __shared__ double sh[BLU_GRAM_FIN_WARPS][32];
-    __shared__ bool last;
-    const int E = NPG * NPG;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * 32 + lane;
-    double sum = 0.0;
-    if (e < E) {
-        const int r = e / NPG, c = e - r * NPG;
-        if ((r >> 3) <= (c >> 3)) {                              // lower tiles are never produced
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int p = w;
-            for (; p + 3 * BLU_GRAM_FIN_WARPS < nparts; p += 4 * BLU_GRAM_FIN_WARPS) {
-                a0 += part[(long long)p * E + e];
-                a1 += part[(long long)(p + BLU_GRAM_FIN_WARPS) * E + e];
-                a2 += part[(long long)(p + 2 * BLU_GRAM_FIN_WARPS) * E + e];
-                a3 += part[(long long)(p + 3 * BLU_GRAM_FIN_WARPS) * E + e];
-            }
-            for (; p < nparts; p += BLU_GRAM_FIN_WARPS) a0 += part[(long long)p * E + e];
-            sum = (a0 + a1) + (a2 + a3);
-        }
-    }
-    sh[w][lane] = sum;
-    __syncthreads();
-    if (w == 0 && e < E) {
-        double g = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < BLU_GRAM_FIN_WARPS; ++ww) g += sh[ww][lane];
-        G[e] = g;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    if (threadIdx.x == 0) *ticket = 0u;                          // ready for the next call on this buffer
-    const double dn = (double)n;
+    const double *G = G_all + (size_t)blockIdx.x * NPG * NPG;
+    double *out = sums + (size_t)blockIdx.x * (N * N + N);
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
         const int r = t / N, c = t - r * N;
         const int lo = r < c ? r : c, hi = r < c ? c : r;
-        const double g = __ldcg(G + lo * NPG + hi);              // upper triangle holds the sums
-        const double a = __ldcg(G + r * NPG + N), b = __ldcg(G + c * NPG + N);
-        S2[t] = g;
-        Chat[t] = g / dn - (a * b) / (dn * dn);
+        out[t] = G[lo * NPG + hi];
     }
-    for (int t = threadIdx.x; t < N; t += blockDim.x) s1[t] = __ldcg(G + t * NPG + N);
+    for (int t = threadIdx.x; t < N; t += blockDim.x) out[N * N + t] = G[t * NPG + N];
 }
 
 template <int NT>
-static cudaError_t blu_gram_launch(const double *dY, long long n, int N, int grid, long long slab, double *d_part, cudaStream_t st)
+static cudaError_t blu_gram_launch(bool tele, const double *dY, long long ystride, long long n, int N, int n_out, int grid, long long slab,
+                                   double *d_part, double *d_G, unsigned *d_tickets, cudaStream_t st)
 {
     const int spc = (512 / N) & ~3;                      // samples per stage: multiple of 4, <= 512 doubles
-    const size_t smem = sizeof(double) * ((size_t)2 * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES + (size_t)BLU_GRAM_WARPS * (8 * NT) * (8 * NT))
-                        + sizeof(unsigned long long) * 2 * BLU_GRAM_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(blu_gram_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    blu_gram_kernel<NT><<<grid, BLU_GRAM_WARPS * 32, smem, st>>>(dY, n, N, slab, spc, d_part);
+    const size_t smem = sizeof(double) * ((size_t)BLU_GRAM_NS * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES + (size_t)BLU_GRAM_WARPS * (8 * NT) * (8 * NT))
+                        + sizeof(unsigned long long) * BLU_GRAM_NS * BLU_GRAM_WARPS;
+    cudaError_t e;
+    dim3 g((unsigned)grid, (unsigned)n_out);
+    if (tele) {
+        if ((e = cudaFuncSetAttribute(blu_gram_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        blu_gram_kernel<NT, true><<<g, BLU_GRAM_WARPS * 32, smem, st>>>(dY, ystride, n, N, slab, spc, d_part, d_G, d_tickets);
+    } else {
+        if ((e = cudaFuncSetAttribute(blu_gram_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        blu_gram_kernel<NT, false><<<g, BLU_GRAM_WARPS * 32, smem, st>>>(dY, ystride, n, N, slab, spc, d_part, d_G, d_tickets);
+    }
     return cudaGetLastError();
 }
 
-static int blu_gram_run(const double *Y, long long n, int N, int y_on_device, double *s1, double *S2, double *C_hat,
-                        float *kernel_ms, std::string &err)
+// Sums of n_out sample matrices.  Y: (n_out blocks of (n, N) row-major, `ystride` doubles apart; host or device.
+// sums: n_out x (N*N + N) doubles, host or device.  producer: CUDA stream that wrote a device-resident Y (the
+// kernel waits for the work queued on it so far), or NULL.
+static int blu_gram_sums(const double *Y, long long n, int N, int n_out, long long ystride, int y_on_device, int telescoped,
+                         cudaStream_t producer, double *sums, int sums_on_device, float *kernel_ms, std::string &err)
 {
-    const int NT = (N + 1 + 7) / 8, NPG = 8 * NT;
+    const int NT = (N + 1 + 7) / 8, NPG = 8 * NT, E = NPG * NPG;
+    if (ystride <= 0) ystride = n * N;
     cudaDeviceProp prop; int dev = 0;
     cudaGetDevice(&dev);
     cudaGetDeviceProperties(&prop, dev);
     const long long warps_wanted = (n + 255) / 256;                       // >= 256 samples per warp
+    const int ctas_per_sm = 1;                                            // 3-stage rings: one CTA of 8 warps per SM
     int grid = (int)std::max<long long>(1, std::min<long long>((warps_wanted + BLU_GRAM_WARPS - 1) / BLU_GRAM_WARPS,
-                                                                  (long long)prop.multiProcessorCount * 2));
+                                                                  std::max<long long>(1, (long long)prop.multiProcessorCount * ctas_per_sm / n_out)));
+    grid = std::min(grid, BLU_GRAM_GROUP * BLU_GRAM_MAXGROUPS);
     const long long nwarps = (long long)grid * BLU_GRAM_WARPS;
     long long slab = (n + nwarps - 1) / nwarps;
     slab = ((slab + 15) / 16) * 16;
-    double *dY = nullptr, *d_part = nullptr, *d_out = nullptr;
+    double *dY = nullptr, *d_part = nullptr, *d_G = nullptr, *d_sums = nullptr;
+    unsigned *d_tickets = nullptr;
     cudaStream_t st = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, ep = nullptr;
     cudaError_t e = cudaSuccess;
+    const size_t nsums = (size_t)n_out * (N * N + N);
     auto done = [&](int code) {
         if (!y_on_device) cudaFree(dY);
-        cudaFree(d_part); cudaFree(d_out);
+        cudaFree(d_part); cudaFree(d_G); cudaFree(d_tickets);
+        if (!sums_on_device) cudaFree(d_sums);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
+        if (ep) cudaEventDestroy(ep);
         if (st) cudaStreamDestroy(st);
-        if (code) err = std::string("pilot covariance: ") + cudaGetErrorString(e);
+        if (code) err = std::string("pilot sums: ") + cudaGetErrorString(e);
         return code;
     };
     if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return done(BLU_ERR_CUDA);
-    if (y_on_device) dY = const_cast<double *>(Y);
-    else {
-        if ((e = cudaMalloc(&dY, sizeof(double) * n * N)) != cudaSuccess) return done(BLU_ERR_NOMEM);
-        if ((e = cudaMemcpyAsync(dY, Y, sizeof(double) * n * N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return done(BLU_ERR_CUDA);
+    if (y_on_device) {
+        dY = const_cast<double *>(Y);
+        if (producer) {                                   // order behind the stream that produced Y
+            if ((e = cudaEventCreateWithFlags(&ep, cudaEventDisableTiming)) != cudaSuccess) return done(BLU_ERR_CUDA);
+            if ((e = cudaEventRecord(ep, producer)) != cudaSuccess) return done(BLU_ERR_CUDA);
+            if ((e = cudaStreamWaitEvent(st, ep, 0)) != cudaSuccess) return done(BLU_ERR_CUDA);
+        }
+    } else {
+        const size_t tot = (size_t)((n_out - 1) * ystride + n * N);
+        if ((e = cudaMalloc(&dY, sizeof(double) * tot)) != cudaSuccess) return done(BLU_ERR_NOMEM);
+        if ((e = cudaMemcpyAsync(dY, Y, sizeof(double) * tot, cudaMemcpyHostToDevice, st)) != cudaSuccess) return done(BLU_ERR_CUDA);
     }
-    if ((e = cudaMalloc(&d_part, sizeof(double) * NPG * NPG * grid)) != cudaSuccess) return done(BLU_ERR_NOMEM);
-    if ((e = cudaMalloc(&d_out, sizeof(double) * (2 * N * N + N + NPG * NPG + 2))) != cudaSuccess) return done(BLU_ERR_NOMEM);
-    double *d_G = d_out + 2 * N * N + N;                          // reduced Gram tile, then the ticket counter
-    unsigned *d_ticket = reinterpret_cast<unsigned *>(d_G + NPG * NPG);
-    if ((e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), st)) != cudaSuccess) return done(BLU_ERR_CUDA);
+    if ((e = cudaMalloc(&d_part, sizeof(double) * E * (size_t)(grid + BLU_GRAM_MAXGROUPS) * n_out)) != cudaSuccess) return done(BLU_ERR_NOMEM);
+    if ((e = cudaMalloc(&d_G, sizeof(double) * E * (size_t)n_out)) != cudaSuccess) return done(BLU_ERR_NOMEM);
+    if ((e = cudaMalloc(&d_tickets, sizeof(unsigned) * (BLU_GRAM_MAXGROUPS + 1) * (size_t)n_out)) != cudaSuccess) return done(BLU_ERR_NOMEM);
+    if (sums_on_device) d_sums = sums;
+    else if ((e = cudaMalloc(&d_sums, sizeof(double) * nsums)) != cudaSuccess) return done(BLU_ERR_NOMEM);
+    if ((e = cudaMemsetAsync(d_tickets, 0, sizeof(unsigned) * (BLU_GRAM_MAXGROUPS + 1) * (size_t)n_out, st)) != cudaSuccess) return done(BLU_ERR_CUDA);
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
+    const bool tele = telescoped != 0;
     switch (NT) {
-        case 1: e = blu_gram_launch<1>(dY, n, N, grid, slab, d_part, st); break;
-        case 2: e = blu_gram_launch<2>(dY, n, N, grid, slab, d_part, st); break;
-        case 3: e = blu_gram_launch<3>(dY, n, N, grid, slab, d_part, st); break;
-        case 4: e = blu_gram_launch<4>(dY, n, N, grid, slab, d_part, st); break;
-        default: e = blu_gram_launch<5>(dY, n, N, grid, slab, d_part, st); break;
+        case 1: e = blu_gram_launch<1>(tele, dY, ystride, n, N, n_out, grid, slab, d_part, d_G, d_tickets, st); break;
+        case 2: e = blu_gram_launch<2>(tele, dY, ystride, n, N, n_out, grid, slab, d_part, d_G, d_tickets, st); break;
+        case 3: e = blu_gram_launch<3>(tele, dY, ystride, n, N, n_out, grid, slab, d_part, d_G, d_tickets, st); break;
+        case 4: e = blu_gram_launch<4>(tele, dY, ystride, n, N, n_out, grid, slab, d_part, d_G, d_tickets, st); break;
+        default: e = blu_gram_launch<5>(tele, dY, ystride, n, N, n_out, grid, slab, d_part, d_G, d_tickets, st); break;
     }
     if (e != cudaSuccess) return done(BLU_ERR_CUDA);
-    blu_gram_finish_kernel<<<(NPG * NPG + 31) / 32, BLU_GRAM_FIN_WARPS * 32, 0, st>>>(d_part, grid, NPG, N, n, d_G, d_ticket,
-                                                                                     d_out, d_out + N, d_out + N + N * N);
-    if ((e = cudaGetLastError()) != cudaSuccess) return done(BLU_ERR_CUDA);
     cudaEventRecord(e1, st);
-    std::vector<double> h((size_t)(2 * N * N + N));
-    if ((e = cudaMemcpyAsync(h.data(), d_out, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(BLU_ERR_CUDA);
+    blu_gram_pack_kernel<<<n_out, 256, 0, st>>>(d_G, NPG, N, d_sums);
+    if ((e = cudaGetLastError()) != cudaSuccess) return done(BLU_ERR_CUDA);
+    if (!sums_on_device && (e = cudaMemcpyAsync(sums, d_sums, sizeof(double) * nsums, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(BLU_ERR_CUDA);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(BLU_ERR_CUDA);
     if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
-    if (s1) memcpy(s1, h.data(), sizeof(double) * N);
-    if (S2) memcpy(S2, h.data() + N, sizeof(double) * N * N);
-    if (C_hat) memcpy(C_hat, h.data() + N + N * N, sizeof(double) * N * N);
     return done(BLU_OK);
+}
+
+// Host arithmetic on the (all-reduced) sums of ONE output: the reference's outputs from either form.
+//   sums = [N*N Gram | N column sums] of Y (telescoped = 0) or of Z (telescoped = 1), n = total number of samples.
+// Outputs (each may be NULL): s1 (N) = sumse, S2 (N,N) = sumsc, C_hat (N,N) (blue_models.py:333),
+// d1, d2 (N,N): sumsd1[i][j], sumsd2[i][j] for i < j, zero elsewhere (blue_fn.py:147-157),
+// dV (N,N): sumsd2/n - (sumsd1/n)^2 for i < j, NaN elsewhere (blue_models.py:339).
+static void blu_gram_finalize(const double *sums, long long n, int N, int telescoped, double *s1, double *S2, double *C_hat,
+                              double *d1, double *d2, double *dV)
+{
+    const double *G = sums, *cs = sums + (size_t)N * N;
+    std::vector<double> a1(N), A2((size_t)N * N), D1((size_t)N * N, 0.0), D2((size_t)N * N, 0.0);
+    if (!telescoped) {
+        for (int i = 0; i < N; ++i) a1[i] = cs[i];
+        for (int t = 0; t < N * N; ++t) A2[t] = G[t];
+        for (int i = 0; i < N; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                D1[(size_t)i * N + j] = a1[i] - a1[j];
+                D2[(size_t)i * N + j] = (G[(size_t)i * N + i] - 2.0 * G[(size_t)i * N + j]) + G[(size_t)j * N + j];
+            }
+    } else {
+        // Y_j = Z_0 + ... + Z_j: prefix sums of the column sums, two-dimensional prefix sums of the Gram matrix
+        double run = 0.0;
+        for (int i = 0; i < N; ++i) { run += cs[i]; a1[i] = run; }
+        std::vector<double> R((size_t)N * N);              // R[l][j] = sum_{l' <= j} G[l][l']
+        for (int l = 0; l < N; ++l) { double r = 0.0; for (int j = 0; j < N; ++j) { r += G[(size_t)l * N + j]; R[(size_t)l * N + j] = r; } }
+        for (int j = 0; j < N; ++j) { double r = 0.0; for (int i = 0; i < N; ++i) { r += R[(size_t)i * N + j]; A2[(size_t)i * N + j] = r; } }
+        for (int i = 0; i < N; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                double t1 = 0.0, t2 = 0.0;                  // Y_i - Y_j = -(Z_{i+1} + ... + Z_j)
+                for (int l = i + 1; l <= j; ++l) {
+                    t1 += cs[l];
+                    for (int lp = i + 1; lp <= j; ++lp) t2 += G[(size_t)l * N + lp];
+                }
+                D1[(size_t)i * N + j] = -t1;
+                D2[(size_t)i * N + j] = t2;
+            }
+    }
+    const double dn = (double)n;
+    for (int i = 0; i < N; ++i) if (s1) s1[i] = a1[i];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            const size_t t = (size_t)i * N + j;
+            if (S2) S2[t] = A2[t];
+            if (C_hat) C_hat[t] = A2[t] / dn - (a1[i] * a1[j]) / (dn * dn);
+            if (d1) d1[t] = D1[t];
+            if (d2) d2[t] = D2[t];
+            if (dV) dV[t] = (j > i) ? D2[t] / dn - (D1[t] / dn) * (D1[t] / dn) : nan("");
+        }
+}
+
+// blu_pilot_covariance (include/bluest_b200.h): one output, plain Gram, host results.
+static int blu_gram_run(const double *Y, long long n, int N, int y_on_device, double *s1, double *S2, double *C_hat,
+                        float *kernel_ms, std::string &err)
+{
+    std::vector<double> sums((size_t)N * N + N);
+    int rc = blu_gram_sums(Y, n, N, 1, 0, y_on_device, 0, nullptr, sums.data(), 0, kernel_ms, err);
+    if (rc) return rc;
+    blu_gram_finalize(sums.data(), n, N, 0, s1, S2, C_hat, nullptr, nullptr, nullptr);
+    return BLU_OK;
 }

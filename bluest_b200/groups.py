@@ -152,10 +152,12 @@ def mappings(groups, multi_groups):
 
 
 def stream_cost(k):
-    """Relative cost of one group of size k in the streaming kernels (Phi, gradient): a fixed
-    per-group part plus one 32-entry step per 32 packed entries (T_k = k(k+1)/2).  Much flatter than
-    the k^2 of the reference's loops: the kernels are instruction-bound, not byte-bound, on small groups."""
-    return 2.0 + (k * (k + 1) // 2 + 31) // 32
+    """Relative cost of one group of size k in the two streaming kernels (Phi: one lane per packed entry, gradient:
+    one lane per group): the packed entries T_k = k(k+1)/2 plus a fixed per-group part.  Measured on B200 at 20
+    models (tools/shard_probe.py): for 2 / 4 / 8 slices this weight gives the smallest sum of the slowest Phi and the
+    slowest gradient slice (8 slices: 41 + 30 us against 43 + 35 us for a per-32-entry step count and 45 + 31 us for
+    the reference's k^2)."""
+    return k * (k + 1) / 2.0 + 4.0
 
 
 def balanced_slices(sizes, world, weight=None):

@@ -7,26 +7,88 @@ import numpy as np
 from ._lib import check, dptr, lib
 
 
+def _producer_stream(Y):
+    """The torch stream a device-resident Y was (possibly still is being) written on: the Gram kernel runs on its
+    own stream and is ordered behind it (stream contract of the *_device entry points: work queued on the CURRENT
+    torch stream of Y's device before the call is waited for)."""
+    import torch
+    return ctypes.c_void_p(int(torch.cuda.current_stream(Y.device).cuda_stream))
+
+
+def pilot_sums(Y, device=0, telescoped=False, dist=None, group=None, return_ms=False):
+    """Y: (n, N) or (n_out, n, N) samples -- numpy, or a contiguous CUDA float64 torch tensor.  One launch for all
+    outputs.  Returns ``sums`` (n_out, N*N + N): per output the Gram matrix then the column sums (of Y, or of the
+    telescoped differences Z_0 = Y_0, Z_j = Y_j - Y_{j-1} when ``telescoped``), and the total sample count.
+
+    ``dist`` (torch.distributed, optional): every rank passes ITS rows of the sample matrix; the per-rank sums are
+    added with one all-reduce of (N*N + N) n_out doubles over NCCL (the reduction of blue_fn.py:177-187)."""
+    on_device = hasattr(Y, "data_ptr")
+    if on_device:
+        assert Y.is_cuda and Y.is_contiguous() and Y.dim() in (2, 3) and str(Y.dtype) == "torch.float64"
+        shape = tuple(Y.shape)
+        ptr = ctypes.c_void_p(int(Y.data_ptr()))
+        device = Y.device.index or 0
+        producer = _producer_stream(Y)
+    else:
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        shape = Y.shape
+        ptr = ctypes.c_void_p(Y.ctypes.data)
+        producer = None
+    n_out = 1 if len(shape) == 2 else int(shape[0])
+    n, N = int(shape[-2]), int(shape[-1])
+    ms = ctypes.c_float(0.0)
+    world = dist.get_world_size(group) if dist is not None else 1
+    if world > 1:
+        import torch
+        dsums = torch.empty((n_out, N * N + N), dtype=torch.float64, device="cuda:%d" % device)
+        check(lib().blu_pilot_sums(device, ptr, n, N, n_out, 0, int(on_device), int(bool(telescoped)), producer,
+                                   ctypes.c_void_p(int(dsums.data_ptr())), 1, ctypes.byref(ms)))
+        cnt = torch.tensor([float(n)], dtype=torch.float64, device=dsums.device)
+        dist.all_reduce(dsums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+        sums = dsums.cpu().numpy()
+        n_total = int(round(float(cnt.item())))
+    else:
+        sums = np.empty((n_out, N * N + N))
+        check(lib().blu_pilot_sums(device, ptr, n, N, n_out, 0, int(on_device), int(bool(telescoped)), producer,
+                                   ctypes.c_void_p(sums.ctypes.data), 0, ctypes.byref(ms)))
+        n_total = n
+    if return_ms:
+        return sums, n_total, ms.value
+    return sums, n_total
+
+
+def finalize_sums(sums, n_total, N, telescoped=False):
+    """The reference's quantities from the (reduced) sums, per output: dict of arrays with a leading output axis --
+    ``sumse`` (N), ``sumsc`` (N,N), ``C_hat`` (N,N) (blue_models.py:333), ``sumsd1`` / ``sumsd2`` (N,N; entries
+    i < j, blue_fn.py:147-157) and ``dV`` (N,N; i < j, NaN elsewhere; blue_models.py:339)."""
+    sums = np.ascontiguousarray(sums, dtype=np.float64).reshape(-1, N * N + N)
+    No = sums.shape[0]
+    out = {k: np.empty((No, N) if k == "sumse" else (No, N, N)) for k in ("sumse", "sumsc", "C_hat", "sumsd1", "sumsd2", "dV")}
+    for o in range(No):
+        check(lib().blu_pilot_finalize(dptr(sums[o]), int(n_total), int(N), int(bool(telescoped)), dptr(out["sumse"][o]), dptr(out["sumsc"][o]),
+                                       dptr(out["C_hat"][o]), dptr(out["sumsd1"][o]), dptr(out["sumsd2"][o]), dptr(out["dV"][o])))
+    return out
+
+
+def pilot_statistics(Y, device=0, dist=None, group=None, telescoped=True):
+    """Everything ``estimate_missing_covariances`` takes from ``blue_fn(..., compute_mlmc_differences=True)``
+    (blue_models.py:331-339) for all outputs in one pass over the samples: see ``finalize_sums``."""
+    sums, n_total = pilot_sums(Y, device=device, telescoped=telescoped, dist=dist, group=group)
+    N = int(Y.shape[-1])
+    return finalize_sums(sums, n_total, N, telescoped=telescoped)
+
+
 def pilot_covariance(Y, device=0, return_ms=False):
     """Y: (n, N) samples (numpy array, or a CUDA float64 torch tensor for a device-resident
     matrix).  Returns (sumse (N,), sumsc (N,N), C_hat (N,N)) with
     C_hat = sumsc/n - outer(sumse, sumse)/n^2   (blue_models.py:333, biased one-pass formula)."""
-    on_device = hasattr(Y, "data_ptr")
-    if on_device:
-        assert Y.is_cuda and Y.is_contiguous() and Y.dim() == 2 and str(Y.dtype) == "torch.float64"
-        n, N = Y.shape
-        ptr = ctypes.c_void_p(int(Y.data_ptr()))
-        device = Y.device.index or 0
-    else:
-        Y = np.ascontiguousarray(Y, dtype=np.float64)
-        n, N = Y.shape
-        ptr = ctypes.c_void_p(Y.ctypes.data)
-    s1 = np.empty(N); S2 = np.empty((N, N)); Ch = np.empty((N, N))
-    ms = ctypes.c_float(0.0)
-    check(lib().blu_pilot_covariance(device, ptr, int(n), int(N), int(on_device), dptr(s1), dptr(S2), dptr(Ch), ctypes.byref(ms)))
+    sums, n_total, ms = pilot_sums(Y, device=device, telescoped=False, return_ms=True)
+    N = int(Y.shape[-1])
+    r = finalize_sums(sums, n_total, N, telescoped=False)
     if return_ms:
-        return s1, S2, Ch, ms.value
-    return s1, S2, Ch
+        return r["sumse"][0], r["sumsc"][0], r["C_hat"][0], ms
+    return r["sumse"][0], r["sumsc"][0], r["C_hat"][0]
 
 
 def fill_missing_covariances(adjacency, C_hat, rtol=1.0e-7):

@@ -252,6 +252,25 @@ int blu_host_free(void *p);
 int blu_pilot_covariance(int device, const double *Y, int64_t n, int N, int y_on_device,
                          double *s1, double *S2, double *C_hat, float *kernel_ms);
 
+/* The sums behind it, for n_out outputs at once and for a row split across devices (blue_fn.py:147-167 incl. the
+ * MLMC difference sums, blue_fn.py:177-187 is the reduction between ranks):
+ *   Y            n_out sample matrices (n, N) row-major, `ystride` doubles apart (0 = n*N); host or device
+ *   telescoped   0: sums of Y.  1: sums of Z, Z_0 = Y_0, Z_j = Y_j - Y_{j-1} -- the difference sums of the MLMC
+ *                pairs then come from Gram entries of differences and do not cancel against the model variances
+ *   producer_stream  (cudaStream_t) stream that wrote a device-resident Y, or NULL: the kernel is ordered behind it
+ *   sums         n_out x (N*N + N) doubles: per output the (symmetric) Gram matrix, then the N column sums; host
+ *                memory, or device memory (sums_on_device) so that ranks holding different sample rows can add
+ *                their sums with one all-reduce of (N*N + N) n_out doubles before blu_pilot_finalize.
+ * (one extra tile column carries the ones that produce the column sums: N <= 32 means at most 5 tiles of 8). */
+int blu_pilot_sums(int device, const double *Y, int64_t n, int N, int n_out, int64_t ystride, int y_on_device,
+                   int telescoped, void *producer_stream, double *sums, int sums_on_device, float *kernel_ms);
+/* Host arithmetic on the (all-reduced) sums of ONE output (n_total = samples over all ranks).  Outputs, each may
+ * be NULL: s1 (N) = sumse, S2 (N,N) = sumsc, C_hat (N,N) = S2/n - s1 s1^T/n^2 (blue_models.py:333), d1 / d2 (N,N)
+ * = sumsd1[i][j] / sumsd2[i][j] for i < j, 0 elsewhere (blue_fn.py:147-157), dV (N,N) = d2/n - (d1/n)^2 for i < j,
+ * NaN elsewhere (blue_models.py:339). */
+int blu_pilot_finalize(const double *sums, int64_t n_total, int N, int telescoped, double *s1, double *S2, double *C_hat,
+                       double *d1, double *d2, double *dV);
+
 /* ------------------------------------------------------------------------------------------
  * Level 1: drop-ins for `_cmisc_bluest` (bluest/cmisc.cpp).  Host pointers, in-place "+=".
  * ------------------------------------------------------------------------------------------ */

@@ -26,6 +26,7 @@ Files written
   setup.npz       group bookkeeping of BLUEProblem.setup_solver (default enumeration, user groups / multi_groups)
                   captured at the reference's MOSAP constructor call; setup_graph_data.npz is its input graph file
   pilot.npz       pilot-sample sums and C_hat computed with the reference's accumulation loop
+  pilot_mlmc.npz  the reference's blue_fn with MLMC differences, two outputs (sums, difference sums, C_hat, dV)
 """
 import os
 import sys
@@ -558,6 +559,57 @@ def make_pilot():
     np.savez_compressed(os.path.join(OUT, "pilot.npz"), Y=Y, sumse=sumse, sumsc=sumsc, C_hat=C_hat)
 
 
+def make_pilot_mlmc():
+    """The reference's own sampling loop ``bluest.blue_fn.blue_fn`` (blue_fn.py:36-227) with
+    ``compute_mlmc_differences=True`` on two outputs: column sums, Gram sums and the MLMC difference sums, followed
+    by the formulas of ``estimate_missing_covariances`` (blue_models.py:333, :339).  One case sample by sample
+    (N1 = 1), one in batches (N1 = 16), a strongly coupled (multilevel-like) model hierarchy in both."""
+    import importlib
+    bf = importlib.import_module("bluest.blue_fn")
+    rng = np.random.RandomState(33)
+    M, n, No = 6, 400, 2
+    base = rng.standard_normal((n, 1))
+    Ys = []
+    for o in range(No):                                     # model j = common signal + a perturbation that shrinks with j
+        pert = rng.standard_normal((n, M)) * (0.5 ** np.arange(M))[None, :] * (1.0 + o)
+        Ys.append((1.0 + 0.2 * o) * base + pert + 0.25 * (o + 1))
+    Ys = np.array(Ys)                                       # (No, n, M)
+
+    class Problem:
+        def __init__(self):
+            self.at = 0
+
+        def evaluate(self, ls, samples):
+            if np.ndim(samples[0]) == 0:                    # one sample
+                k = self.at; self.at += 1
+                return [[Ys[o][k, l] for l in ls] for o in range(No)]
+            cnt = len(samples[0])
+            k = self.at; self.at += cnt
+            return [[Ys[o][k:k + cnt, l] for l in ls] for o in range(No)]
+
+    ls = list(range(M))
+    out = {"Y": Ys}
+    for tag, N1 in (("one", 1), ("batch", 16)):
+        prob = Problem()
+        if N1 == 1:
+            sampler = lambda ls_: [0.0 for _ in ls_]
+        else:
+            sampler = lambda ls_, N=1: [np.zeros(N) for _ in ls_]
+        sumse, sumsc, cost, sd1, sd2 = bf.blue_fn(ls, n, prob, sampler=sampler, N1=N1, No=No, verbose=False, compute_mlmc_differences=True)
+        sumse = np.array([[float(v) for v in row] for row in sumse])
+        sd1 = np.array([[[float(sd1[o][i][j]) for j in range(M)] for i in range(M)] for o in range(No)])
+        sd2 = np.array([[[float(sd2[o][i][j]) for j in range(M)] for i in range(M)] for o in range(No)])
+        C_hat = np.array([sumsc[o] / n - np.outer(sumse[o], sumse[o]) / n ** 2 for o in range(No)])      # blue_models.py:333
+        dV = np.full((No, M, M), np.nan)
+        for o in range(No):
+            for i in range(M):
+                for j in range(i + 1, M):
+                    dV[o, i, j] = sd2[o, i, j] / n - (sd1[o, i, j] / n) * (sd1[o, i, j] / n)             # blue_models.py:339
+        out.update({tag + "/sumse": sumse, tag + "/sumsc": np.array(sumsc), tag + "/sumsd1": sd1, tag + "/sumsd2": sd2,
+                    tag + "/C_hat": C_hat, tag + "/dV": dV})
+    np.savez_compressed(os.path.join(OUT, "pilot_mlmc.npz"), **out)
+
+
 if __name__ == "__main__":
     ns = ref_shim.load(with_models=True)
     make_synthetic(ns)
@@ -571,4 +623,5 @@ if __name__ == "__main__":
     make_mosap(ns)
     make_setup(ns)
     make_pilot()
+    make_pilot_mlmc()
     print("done")

@@ -159,3 +159,41 @@ def test_fused_two_gpus():
     a, b = ret[0][3], ret[1][3]
     assert np.array_equal(a["hp"], b["hp"]) and maxrel(a["hp"], Hp) < 1e-12
     assert a["hi"] == b["lo"] and maxrel(np.concatenate([a["own"], b["own"]]), Hp) < 1e-12
+
+
+def _pilot_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    import bluest_b200 as blu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    d = np.load(os.path.join(ROOT, "tests", "golden", "pilot_mlmc.npz"))
+    Y = d["Y"]                                             # (No, n, M): every rank takes its rows of every output
+    n = Y.shape[1]
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    mine = torch.from_numpy(np.ascontiguousarray(Y[:, lo:hi, :])).to("cuda:%d" % rank)
+    r = blu.pilot_statistics(mine, dist=dist, telescoped=True)
+    ret[rank] = {k: v.copy() for k, v in r.items()}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pilot_row_split_two_gpus():
+    """The sample rows split over two ranks (blue_fn.py:108-110 splits the samples over the MPI ranks, :177-187 adds the
+    sums): per-rank Gram kernels, ONE NCCL all-reduce of (N^2+N) n_out doubles, same statistics on every rank."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_pilot_worker, args=(2, 29900 + os.getpid() % 90, ret), nprocs=2, join=True)
+    d = np.load(os.path.join(ROOT, "tests", "golden", "pilot_mlmc.npz"))
+    M = d["Y"].shape[2]
+    iu = np.triu_indices(M, 1)
+    for k in ("sumse", "sumsc", "C_hat"):
+        assert np.array_equal(ret[0][k], ret[1][k])
+        assert maxrel(ret[0][k], d["one/" + k]) < 1e-12
+    for o in range(d["Y"].shape[0]):
+        assert maxrel(ret[0]["dV"][o][iu], d["one/dV"][o][iu]) < 1e-12
+        assert maxrel(ret[0]["sumsd1"][o][iu], d["one/sumsd1"][o][iu]) < 1e-12

@@ -7,7 +7,7 @@ import pytest
 
 import bluest_b200 as blu
 import oracle as orc
-from conftest import GOLDEN
+from conftest import GOLDEN, maxrel
 
 
 def _load(name):
@@ -511,3 +511,35 @@ def test_fill_missing_covariances_matches_the_reference_rule():
     assert np.array_equal(got, want)
     assert np.isinf(got[1, 4]) and got[0, 5] == 0.0 and got[2, 3] == 0.77 and got[2, 2] == 1.5 and got[0, 0] == C_hat[0, 0]
     assert np.isnan(A[0, 1])                       # the input is not modified
+
+
+def _np_sums(Y, telescoped):
+    """(N*N + N) sums of one (n, N) sample matrix, plain or telescoped, in numpy."""
+    X = Y.copy()
+    if telescoped:
+        X[:, 1:] = Y[:, 1:] - Y[:, :-1]
+    return np.concatenate([(X.T @ X).ravel(), X.sum(axis=0)])
+
+
+@pytest.mark.parametrize("telescoped", [False, True])
+def test_pilot_finalize_reproduces_reference_blue_fn(telescoped):
+    """``blu_pilot_finalize`` (host arithmetic of the C ABI, no GPU needed) on sums formed in numpy reproduces what the
+    REAL reference ``blue_fn(compute_mlmc_differences=True)`` + blue_models.py:333,339 produced (tests/golden/pilot_mlmc.npz):
+    sumse, sumsc, C_hat, the MLMC difference sums and dV, for both outputs, from the plain and from the telescoped form."""
+    from bluest_b200.pilot import finalize_sums
+    d = np.load(os.path.join(GOLDEN, "pilot_mlmc.npz"))
+    Y = d["Y"]
+    No, n, M = Y.shape
+    sums = np.array([_np_sums(Y[o], telescoped) for o in range(No)])
+    r = finalize_sums(sums, n, M, telescoped=telescoped)
+    iu = np.triu_indices(M, 1)
+    for tag in ("one", "batch"):
+        assert maxrel(r["sumse"], d[tag + "/sumse"]) < 1e-13
+        assert maxrel(r["sumsc"], d[tag + "/sumsc"]) < 1e-13
+        assert maxrel(r["C_hat"], d[tag + "/C_hat"]) < 1e-12
+        for o in range(No):
+            assert maxrel(r["sumsd1"][o][iu], d[tag + "/sumsd1"][o][iu]) < 1e-12
+            assert maxrel(r["sumsd2"][o][iu], d[tag + "/sumsd2"][o][iu]) < 1e-12
+            rel = np.abs(r["dV"][o][iu] - d[tag + "/dV"][o][iu]) / np.abs(d[tag + "/dV"][o][iu])
+            assert rel.max() < (1e-13 if telescoped else 1e-11)          # element-wise: the telescoped form has no cancellation
+            assert np.all(np.isnan(r["dV"][o][np.tril_indices(M)]))
