@@ -938,7 +938,7 @@ def main():
     ap.add_argument("--no-solve", dest="solve", action="store_false", help="skip the end-to-end SAP solve comparison")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the brief measurements of the other BASELINE configs")
     ap.add_argument("--no-shard20", dest="shard20", action="store_false", help="skip the group-sharded 20-model evaluation")
-    ap.add_argument("--lanes", type=int, default=2, help="evaluation lanes of the group-sharded 20-model benchmark")
+    ap.add_argument("--lanes", type=int, default=6, help="evaluation lanes of the group-sharded 20-model benchmark")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "shard", "shard20"], help="sweep: independent instances per GPU (default); shard: one problem, groups sharded")
     ap.add_argument("--nohess", action="store_true", help="shard mode: Phi + variance + gradient only (e.g. --models 20)")
     ap.add_argument("--gather-grad", action="store_true", help="shard mode: all-gather the gradient slices")

@@ -27,6 +27,7 @@
 #include "blu_gram.cuh"
 #include "blu_intproj.cuh"
 #include "blu_level1.cuh"
+#include "blu_kkt.cuh"
 
 // --------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -1332,6 +1333,132 @@ extern "C" int blu_candidate_variances(blu_ctx *c, const double *basephi, int LL
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_base); cudaFree(d_psis); cudaFree(d_V); cudaFree(d_idx); cudaFree(d_ms);
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? BLU_ERR_NOMEM : BLU_ERR_CUDA, "candidate_variances: %s", cudaGetErrorString(e));
+    return BLU_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Row f1: structure-exploiting KKT solve of the SDP of sap.py:242-307 (blu_kkt.cuh)
+// --------------------------------------------------------------------------------------------
+static bool small_inverse(const double *A, int M, double *inv)       // Gauss-Jordan with partial pivoting, M <= 33
+{
+    std::vector<double> a(A, A + (size_t)M * M);
+    for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) inv[i * M + j] = (i == j) ? 1.0 : 0.0;
+    for (int p = 0; p < M; ++p) {
+        int piv = p;
+        for (int r = p + 1; r < M; ++r) if (fabs(a[r * M + p]) > fabs(a[piv * M + p])) piv = r;
+        if (a[piv * M + p] == 0.0) return false;
+        if (piv != p) for (int c = 0; c < M; ++c) { std::swap(a[p * M + c], a[piv * M + c]); std::swap(inv[p * M + c], inv[piv * M + c]); }
+        const double dinv = 1.0 / a[p * M + p];
+        for (int c = 0; c < M; ++c) { a[p * M + c] *= dinv; inv[p * M + c] *= dinv; }
+        for (int r = 0; r < M; ++r) {
+            if (r == p) continue;
+            const double f = a[r * M + p];
+            if (f == 0.0) continue;
+            for (int c = 0; c < M; ++c) { a[r * M + c] -= f * a[p * M + c]; inv[r * M + c] -= f * inv[p * M + c]; }
+        }
+    }
+    return true;
+}
+
+extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, const double *Gx, const double *d, const double *r,
+                             const double *bx, const double *bz, double *ux, double *uz, float *device_ms)
+{
+    int rc = use(c);
+    if (rc) return rc;
+    if (!c->have_inv) return fail(BLU_ERR_STATE, "inverses not set");
+    if (c->lo != 0 || c->hi != c->L) return fail(BLU_ERR_STATE, "context owns a slice");
+    if (!d || !r || !bx || !bz || !ux || !uz || (nlin > 0 && !Gx)) return fail(BLU_ERR_ARG, "null argument");
+    if (has_t != 0 && has_t != 1) return fail(BLU_ERR_ARG, "has_t must be 0 or 1");
+    const int N = c->N, M = N + 1, MM = M * M;
+    const long long L = c->L, n = L + has_t;
+    const int Qs = M * (M + 1) / 2, Q = Qs + nlin, QP = ((Q + 1 + 7) / 8) * 8;      // + the right-hand-side column
+    if (nlin < 0 || Q > 255) return fail(BLU_ERR_ARG, "capacitance matrix of order %d exceeds 255 (N=%d, %d dense rows)", Q, N, nlin);
+    for (long long t = 0; t < n + nlin; ++t) if (!(d[t] > 0.0)) return fail(BLU_ERR_ARG, "scaling d[%lld] is not positive", t);
+    // host: r^-1, Lam = r^-T r^-1, Wm = Lam Z Lam  (Z = the 's' part of bz, a symmetric matrix)
+    std::vector<double> rinv(MM), Lam(MM), tmp(MM), Wm(MM);
+    if (!small_inverse(r, M, rinv.data())) return fail(BLU_ERR_ARG, "the scaling matrix r is singular");
+    for (int a = 0; a < M; ++a) for (int b = 0; b < M; ++b) { double s = 0.0; for (int q = 0; q < M; ++q) s += rinv[q * M + a] * rinv[q * M + b]; Lam[a * M + b] = s; }
+    const double *Z = bz + n + nlin;
+    auto sandwich = [&](const double *X, double *out) {            // out = Lam X Lam
+        for (int a = 0; a < M; ++a) for (int b = 0; b < M; ++b) { double s = 0.0; for (int q = 0; q < M; ++q) s += Lam[a * M + q] * X[q * M + b]; tmp[a * M + b] = s; }
+        for (int a = 0; a < M; ++a) for (int b = 0; b < M; ++b) { double s = 0.0; for (int q = 0; q < M; ++q) s += tmp[a * M + q] * Lam[q * M + b]; out[a * M + b] = s; }
+    };
+    sandwich(Z, Wm.data());
+    // device buffers
+    struct DevBuf { void *p = nullptr; ~DevBuf() { if (p) cudaFree(p); } };
+    DevBuf bBs, bsmall, bvec;
+    const size_t nsmall = (size_t)2 * MM + (size_t)Q * Q + 2 * 256 + 8;           // rinv | Wm | cap | v | y | info
+    const size_t nvec = (size_t)(n + nlin) + (size_t)nlin * n + 5 * (size_t)n + nlin;   // d | Gx | bx | bz0 | g1tw | rhs | ux
+    CUDA_TRY(cudaMalloc(&bBs.p, sizeof(double) * (size_t)n * QP));
+    CUDA_TRY(cudaMalloc(&bsmall.p, sizeof(double) * nsmall));
+    CUDA_TRY(cudaMalloc(&bvec.p, sizeof(double) * nvec));
+    double *d_Bs = (double *)bBs.p;
+    double *d_rinv = (double *)bsmall.p, *d_Wm = d_rinv + MM, *d_cap = d_Wm + MM, *d_v = d_cap + (size_t)Q * Q, *d_y = d_v + 256;
+    int *d_info = (int *)(d_y + 256);
+    double *d_d = (double *)bvec.p, *d_Gx = d_d + (n + nlin), *d_bx = d_Gx + (size_t)nlin * n, *d_bz0 = d_bx + n;
+    double *d_g1tw = d_bz0 + (n + nlin), *d_rhs = d_g1tw + n, *d_ux = d_rhs + n;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(d_rinv, rinv.data(), sizeof(double) * MM, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_Wm, Wm.data(), sizeof(double) * MM, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_d, d, sizeof(double) * (n + nlin), cudaMemcpyHostToDevice, st));
+    if (nlin) CUDA_TRY(cudaMemcpyAsync(d_Gx, Gx, sizeof(double) * (size_t)nlin * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_bx, bx, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_bz0, bz, sizeof(double) * (n + nlin), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_info, 0xff, sizeof(int), st));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    c->launches = 0;
+    {
+        const size_t smem = sizeof(double) * ((size_t)2 * MM + (size_t)BLU_KKT_WARPS * M * N);
+        CUDA_TRY(cudaFuncSetAttribute(blu_kkt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)std::max<long long>(1, std::min<long long>((n + BLU_KKT_WARPS - 1) / BLU_KKT_WARPS, (long long)c->nsm * 4));
+        blu_kkt_rows_kernel<<<grid, BLU_KKT_WARPS * 32, smem, st>>>(c->d_cls, (int)c->cls.size(), N, L, has_t, scales, c->d_gidx, c->d_cinv, d_rinv, d_Wm,
+                                                                    d_d, nlin, d_Gx, d_d + n, Q, QP, d_Bs, d_g1tw);
+        KERNEL_CHECK(c);
+        blu_kkt_rhs_kernel<<<(int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)c->nsm * 8)), 256, 0, st>>>(
+            n, nlin, d_bx, d_bz0, d_d, d_Gx, d_d + n, d_g1tw, Q, QP, d_rhs, d_Bs);
+        KERNEL_CHECK(c);
+        const int NTQ = QP / 8;
+        blu_kkt_syrk_kernel<<<NTQ * (NTQ + 1) / 2, BLU_KKT_WARPS * 32, 0, st>>>(d_Bs, n, Q, QP, d_cap, d_v);
+        KERNEL_CHECK(c);
+        const size_t csm = sizeof(double) * (size_t)Q * (Q + 1);
+        CUDA_TRY(cudaFuncSetAttribute(blu_kkt_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        blu_kkt_chol_kernel<<<1, 512, csm, st>>>(d_cap, Q, d_v, d_y, d_info);
+        KERNEL_CHECK(c);
+        blu_kkt_apply_kernel<<<(int)std::max<long long>(1, std::min<long long>((n + BLU_KKT_WARPS - 1) / BLU_KKT_WARPS, (long long)c->nsm * 4)), BLU_KKT_WARPS * 32, 0, st>>>(
+            d_Bs, n, Q, QP, d_y, d_d, d_rhs, d_ux);
+        KERNEL_CHECK(c);
+    }
+    // G1 ux needs Phi(ux_m): the ordinary Phi kernel on the solution's group part
+    int rcp = launch_phi(c, d_ux + has_t, 0.0, 0);
+    cudaEventRecord(e1, st);
+    std::vector<double> phi((size_t)N * N);
+    int info = -1;
+    cudaError_t e = (rcp == BLU_OK) ? cudaSuccess : cudaErrorUnknown;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ux, d_ux, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(phi.data(), c->d_phi, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (device_ms && e == cudaSuccess) cudaEventElapsedTime(device_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rcp != BLU_OK) return rcp;
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "kkt_solve: %s", cudaGetErrorString(e));
+    if (info != 0) return fail(BLU_ERR_ARG, "kkt_solve: the capacitance matrix is not positive definite (Cholesky stopped at column %d)", info);
+    // uz0 = d^-2 (G0 ux - bz0),  G0 = [-I; Gx]
+    for (long long t = 0; t < n; ++t) uz[t] = (-ux[t] - bz[t]) / (d[t] * d[t]);
+    for (int q = 0; q < nlin; ++q) {
+        double s = 0.0;
+        for (long long t = 0; t < n; ++t) s += Gx[(size_t)q * n + t] * ux[t];
+        uz[n + q] = (s - bz[n + q]) / (d[n + q] * d[n + q]);
+    }
+    // uz1 = vec(Lam (G1 ux - Z) Lam),  G1 ux = -scales pad(Phi(ux_m)) - ux_t E_NN
+    std::vector<double> X(MM, 0.0), out(MM);
+    for (int a = 0; a < N; ++a) for (int b = 0; b < N; ++b) X[a * M + b] = -scales * phi[(size_t)a * N + b];
+    if (has_t) X[N * M + N] -= ux[0];
+    for (int t = 0; t < MM; ++t) X[t] -= Z[t];
+    sandwich(X.data(), out.data());
+    memcpy(uz + n + nlin, out.data(), sizeof(double) * MM);
     return BLU_OK;
 }
 

@@ -227,6 +227,37 @@ class SAP(object):
             ptr = ctypes.c_void_p(int(d_m.data_ptr()) if hasattr(d_m, "data_ptr") else int(d_m))
         check(lib().blu_eval_device(self._ctx, ptr, float(delta), int(bool(grad)), int(bool(hess))))
 
+    # ---- structure-exploiting KKT solve for the SDP solvers (row f1) ----------------------------
+    def sdp_linear_rows(self, budget_mode=True, max_model_samples=None):
+        """The dense rows of the SDP's linear cone as sap.py:259-287 builds them (without the -I block) and the scale
+        factor of sap.py:258: ``(Gx (nlin, n), scales, has_t)``, n = L + has_t."""
+        L = int(self.L)
+        w = np.asarray(self.costs, dtype=np.float64)
+        e = np.asarray(self.e, dtype=np.float64)
+        es, _ = self.get_max_sample_constraints(max_model_samples)
+        scales = 1.0 / np.abs(self.psi).sum(axis=0).mean()
+        if budget_mode:
+            rows = [np.concatenate([[0.0], w]), -np.concatenate([[0.0], e])] + [-np.concatenate([[0.0], -np.asarray(ee, dtype=np.float64)]) for ee in es]
+        else:
+            rows = [-e] + [np.asarray(ee, dtype=np.float64) for ee in es]
+        n = L + (1 if budget_mode else 0)
+        return np.ascontiguousarray(np.array(rows, dtype=np.float64).reshape(len(rows), n)), float(scales), (1 if budget_mode else 0)
+
+    def kkt_solve(self, has_t, scales, Gx, d, r, bx, bz, return_ms=False):
+        """One KKT solve of the SDP's interior-point iteration on the device (``blu_kkt_solve``): the system
+        [0 G^T; G -W^T W][ux; uz] = [bx; bz] with G = [-I; Gx; G1], W from the Nesterov-Todd scalings ``d`` (linear
+        cone, length n + nlin) and ``r`` ((N+1, N+1), semidefinite block).  Returns (ux, uz)."""
+        L, M = int(self.L), self.N + 1
+        n = L + int(has_t)
+        Gx = np.ascontiguousarray(Gx, dtype=np.float64).reshape(-1, n) if np.size(Gx) else np.zeros((0, n))
+        nlin = Gx.shape[0]
+        d = f64(d, n + nlin, "d"); r = f64(r, M * M, "r"); bx = f64(bx, n, "bx"); bz = f64(bz, n + nlin + M * M, "bz")
+        ux = np.empty(n); uz = np.empty(n + nlin + M * M)
+        ms = ctypes.c_float(0.0)
+        check(lib().blu_kkt_solve(self._ctx, int(has_t), float(scales), int(nlin), dptr(Gx) if nlin else None, dptr(d), dptr(r), dptr(bx), dptr(bz),
+                                  dptr(ux), dptr(uz), ctypes.byref(ms)))
+        return (ux, uz, ms.value) if return_ms else (ux, uz)
+
     def clone(self):
         """A second evaluation lane on the same problem (``blu_ctx_clone``): shares this SAP's inverses and tables in
         HBM, owns its stream and per-evaluation buffers, so evaluations on the two overlap on the device.  Only the

@@ -153,6 +153,21 @@ int blu_blue_estimator(blu_ctx *ctx, const double *samples, const double *sums_f
 int blu_candidate_variances(blu_ctx *ctx, const double *basephi, int LL, const int64_t *idx,
                             const int64_t *ms, int64_t ncand, double rcond, double *Vs);
 
+/* Structure-exploiting KKT solve ("next" row f1) for the semidefinite programme SAP.cvxopt_solve builds
+ * (sap.py:242-307) -- what a `kktsolver` callback handed to cvxopt.solvers.sdp (sap.py:289 passes none, so cvxopt
+ * factorises the dense KKT matrix) would call once per interior-point iteration and right-hand side.
+ *   variables   x in R^n, n = L + has_t (has_t = 1: budget mode, x = [t, m/budget], sap.py:259-275; 0: tolerance mode)
+ *   G0 = [-I_n; Gx]  Gx (nlin, n) row-major: the dense rows of the linear cone (cost, coverage, sample caps)
+ *   G1          column of group i = -scales * vec(pad(Psi_i)) ((N+1) x (N+1), last row/column zero), t column = -E_NN
+ *   d (n+nlin)  Nesterov-Todd scaling of the linear cone (W['d']), r ((N+1)^2) of the semidefinite block (W['r'][0])
+ *   bx (n), bz (n + nlin + (N+1)^2)   right-hand side;  ux, uz: same shapes, the solution of
+ *        [0 G^T; G -W^T W] [ux; uz] = [bx; bz]     (uz UNSCALED: a cvxopt kktsolver returns W uz)
+ * Diagonal + rank (N+1)(N+2)/2 + nlin: one weighted Gram contraction over the packed inverses (FP64 tensor cores)
+ * and a Cholesky of that order, instead of the dense (L+1)^3/3.  device_ms (optional): CUDA-event time of the
+ * device part. */
+int blu_kkt_solve(blu_ctx *ctx, int has_t, double scales, int nlin, const double *Gx, const double *d, const double *r,
+                  const double *bx, const double *bz, double *ux, double *uz, float *device_ms);
+
 /* Device-resident evaluation: d_m lives on the context's device (or NULL to reuse BLU_BUF_M).
  * want_grad / want_hess select the work (want_hess == 2: the U,V factors only, no Hessian -- the
  * caller then asks for row panels with blu_shard_hess; want_hess == 3: the U factor only, all the
