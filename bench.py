@@ -478,7 +478,23 @@ def secondary_configs(device=0):
         for _ in range(30):
             fn()
         res[name + "_us"] = (time.perf_counter() - t0) / 30 * 1e6
+    res["path"] = "all outputs in ONE kernel launch (blu_batch_eval: a CTA per output) for variances / variance_GH(nohess); dense Hessians per context"
     out["mosap_4x10_host_api"] = res
+    # config 2 x sweep: 64 sample vectors (budgets) of one 10-model problem in one launch vs one evaluation at a time
+    sp0 = mos.SAPS[0]
+    M64 = np.array([orc.dense_m(L, j) for j in range(64)])
+    for _ in range(3):
+        blu.evaluate_many(sp0, M64)
+    t0 = time.perf_counter()
+    for _ in range(30):
+        blu.evaluate_many(sp0, M64)
+    t_b = (time.perf_counter() - t0) / 30
+    t0 = time.perf_counter()
+    for j in range(64):
+        sp0.variance_GH(M64[j], nohess=True)
+    t_1 = time.perf_counter() - t0
+    out["sweep64_n10_host_api"] = {"one_launch_us_per_batch": t_b * 1e6, "one_launch_us_per_evaluation": t_b * 1e6 / 64,
+                                   "one_by_one_us_per_batch": t_1 * 1e6, "api": "bluest_b200.evaluate_many(sap, M (64, L)) -> variances (64,), gradients (64, L)"}
     for sp in mos.SAPS:
         sp.close()
     return out

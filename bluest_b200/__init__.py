@@ -15,7 +15,8 @@ from . import cmisc, intproj, io                        # noqa: F401
 from .dist import ShardedEvaluator, GpuEngine          # noqa: F401
 from .install import install, uninstall                # noqa: F401
 from .sweep import solve_sweep, split_instances        # noqa: F401
+from .batch import Batch, evaluate_many                 # noqa: F401
 
 __all__ = ["SAP", "MOSAP", "BLUESTError", "BluError", "pilot_covariance", "pilot_sums", "pilot_statistics", "finalize_sums", "cmisc", "enumerate_groups", "enumerate_group_arrays",
            "enumerate_cliques", "union_groups", "group_costs", "indicator_ES", "mappings", "balanced_slices",
-           "device_count", "lib", "ShardedEvaluator", "GpuEngine", "install", "uninstall", "solve_sweep", "split_instances"]
+           "device_count", "lib", "ShardedEvaluator", "GpuEngine", "install", "uninstall", "solve_sweep", "split_instances", "Batch", "evaluate_many"]

@@ -39,6 +39,9 @@ SIGNATURES = {
     "blu_cleanup_matrix": (c_int, [p_void, p_dbl, c_dbl, c_int, p_dbl, ctypes.POINTER(c_uint)]),
     "blu_blue_estimator": (c_int, [p_void, p_dbl, p_dbl, p_dbl, p_dbl, p_dbl, ctypes.POINTER(c_uint)]),
     "blu_candidate_variances": (c_int, [p_void, p_dbl, c_int, p_i64, p_i64, c_i64, c_dbl, p_dbl]),
+    "blu_batch_create": (c_int, [ctypes.POINTER(p_void), c_int, ctypes.POINTER(p_i64), c_i64, ctypes.POINTER(p_void)]),
+    "blu_batch_eval": (c_int, [p_void, p_dbl, c_int, c_dbl, p_dbl, ctypes.POINTER(c_uint), p_dbl]),
+    "blu_batch_destroy": (c_int, [p_void]),
     "blu_kkt_solve": (c_int, [p_void, c_int, c_dbl, c_int, p_dbl, p_dbl, p_dbl, p_dbl, p_dbl, p_dbl, p_dbl, ctypes.POINTER(ctypes.c_float)]),
     "blu_eval_device": (c_int, [p_void, p_void, c_dbl, c_int, c_int]),
     "blu_ctx_sync": (c_int, [p_void]),

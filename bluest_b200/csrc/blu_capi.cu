@@ -28,6 +28,7 @@
 #include "blu_intproj.cuh"
 #include "blu_level1.cuh"
 #include "blu_kkt.cuh"
+#include "blu_batch.cuh"
 
 // --------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -1459,6 +1460,191 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     for (int t = 0; t < MM; ++t) X[t] -= Z[t];
     sandwich(X.data(), out.data());
     memcpy(uz + n + nlin, out.data(), sizeof(double) * MM);
+    return BLU_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Batched evaluation of small problems: P problems x B sample vectors in one launch (blu_batch.cuh)
+// --------------------------------------------------------------------------------------------
+struct blu_batch {
+    int device = 0, P = 0, Nmax = 0, capB = 0;
+    long long Lm = 0, gtot = 0, Lmax = 0, capC = 0, capG = 0;
+    bool mapped = false, resident = false;
+    std::vector<blu_ctx *> ctxs;
+    std::vector<BluBatchProb> probs;
+    std::vector<long long> pre;                 // prefix sums of the problems' group counts
+    std::vector<long long *> d_maps;
+    BluBatchProb *d_probs = nullptr;
+    BluEvalHeader *d_hdrs = nullptr;
+    double *d_scratch = nullptr, *d_m = nullptr, *d_var = nullptr, *d_grad = nullptr;
+    unsigned *d_flags = nullptr;
+    double *h_m = nullptr, *h_var = nullptr, *h_grad = nullptr;
+    unsigned *h_flags = nullptr;
+    cudaStream_t stream = nullptr;
+    size_t smem = 0;
+};
+
+static void batch_free_buffers(blu_batch *b)
+{
+    cudaFree(b->d_hdrs); cudaFree(b->d_scratch); cudaFree(b->d_m); cudaFree(b->d_var); cudaFree(b->d_grad); cudaFree(b->d_flags);
+    if (b->h_m) cudaFreeHost(b->h_m);
+    if (b->h_var) cudaFreeHost(b->h_var);
+    if (b->h_grad) cudaFreeHost(b->h_grad);
+    if (b->h_flags) cudaFreeHost(b->h_flags);
+    b->d_hdrs = nullptr; b->d_scratch = b->d_m = b->d_var = b->d_grad = nullptr; b->d_flags = nullptr;
+    b->h_m = b->h_var = b->h_grad = nullptr; b->h_flags = nullptr;
+    b->capB = 0;
+}
+
+extern "C" int blu_batch_destroy(blu_batch *b)
+{
+    if (!b) return BLU_OK;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    batch_free_buffers(b);
+    for (auto p : b->d_maps) cudaFree(p);
+    cudaFree(b->d_probs);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return BLU_OK;
+}
+
+// ctxs: P contexts on one device with their inverses set.  maps == NULL: a sample vector is the concatenation of the
+// problems' own vectors (Lm = sum of their L is implied).  maps != NULL: all problems read ONE shared vector of length
+// Lm through maps[p] (L_p indices), the `m[mappings[n]]` of mosap.py:88,95.
+extern "C" int blu_batch_create(blu_ctx **ctxs, int P, const int64_t *const *maps, int64_t Lm, blu_batch **out)
+{
+    if (!out) return fail(BLU_ERR_ARG, "null out");
+    *out = nullptr;
+    if (!ctxs || P < 1) return fail(BLU_ERR_ARG, "no problems");
+    for (int p = 0; p < P; ++p) {
+        if (!ctxs[p]) return fail(BLU_ERR_ARG, "null context %d", p);
+        if (ctxs[p]->device != ctxs[0]->device) return fail(BLU_ERR_ARG, "all problems of a batch must live on one device");
+        if (!ctxs[p]->have_inv) return fail(BLU_ERR_STATE, "inverses of problem %d not set", p);
+        if (ctxs[p]->lo != 0 || ctxs[p]->hi != ctxs[p]->L) return fail(BLU_ERR_STATE, "problem %d owns a slice", p);
+        if (maps && !maps[p]) return fail(BLU_ERR_ARG, "null map %d", p);
+    }
+    int rc = use(ctxs[0]);
+    if (rc) return rc;
+    blu_batch *b = new (std::nothrow) blu_batch();
+    if (!b) return fail(BLU_ERR_NOMEM, "host allocation failed");
+    b->device = ctxs[0]->device; b->P = P; b->mapped = maps != nullptr;
+    b->ctxs.assign(ctxs, ctxs + P);
+    b->pre.assign(P + 1, 0);
+    for (int p = 0; p < P; ++p) { b->pre[p + 1] = b->pre[p] + ctxs[p]->L; b->Nmax = std::max(b->Nmax, ctxs[p]->N); }
+    b->gtot = b->pre[P];
+    b->Lm = maps ? Lm : b->gtot;
+    if (b->Lm < 1) { delete b; return fail(BLU_ERR_ARG, "empty sample vector"); }
+#define BT_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int code_ = fail(e_ == cudaErrorMemoryAllocation ? BLU_ERR_NOMEM : BLU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); blu_batch_destroy(b); return code_; } } while (0)
+    BT_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    b->probs.resize(P);
+    for (int p = 0; p < P; ++p) {
+        blu_ctx *c = ctxs[p];
+        BluBatchProb &q = b->probs[p];
+        q.cls = c->d_cls; q.gidx = c->d_gidx; q.cinv = c->d_cinv; q.gmask = c->d_gmask; q.lut = c->d_lut; q.map = nullptr;
+        q.cinv_len = c->cinv_len; q.gidx_len = c->gidx_len; q.lutlen = c->lutlen; q.pad = 0;
+        q.L = c->L; q.moff = b->pre[p]; q.goff = b->pre[p]; q.ncls = (int)c->cls.size(); q.N = c->N;
+        if (maps) {
+            for (long long i = 0; i < c->L; ++i)
+                if (maps[p][i] < 0 || maps[p][i] >= Lm) { blu_batch_destroy(b); return fail(BLU_ERR_ARG, "map %d entry %lld outside [0,%lld)", p, i, (long long)Lm); }
+            long long *dm = nullptr;
+            BT_TRY(cudaMalloc(&dm, sizeof(long long) * c->L));
+            b->d_maps.push_back(dm);
+            BT_TRY(cudaMemcpyAsync(dm, maps[p], sizeof(long long) * c->L, cudaMemcpyHostToDevice, b->stream));
+            q.map = dm;
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));       // the contexts' setup work (inversion) is complete
+    }
+    BT_TRY(cudaMalloc(&b->d_probs, sizeof(BluBatchProb) * P));
+    BT_TRY(cudaMemcpyAsync(b->d_probs, b->probs.data(), sizeof(BluBatchProb) * P, cudaMemcpyHostToDevice, b->stream));
+    long long Lmax = 0, cmax = 0, gmax = 0; int lutmax = 0;
+    for (int p = 0; p < P; ++p) {
+        Lmax = std::max(Lmax, ctxs[p]->L); cmax = std::max(cmax, ctxs[p]->cinv_len); gmax = std::max(gmax, ctxs[p]->gidx_len);
+        lutmax = std::max(lutmax, ctxs[p]->lutlen);
+    }
+    b->Lmax = Lmax;
+    const size_t fixed = sizeof(double) * ((size_t)BLU_BATCH_WARPS * b->Nmax * b->Nmax + 32 + (size_t)Lmax) + BLU_FIN_SCRATCH_BYTES
+                         + sizeof(unsigned short) * (size_t)((lutmax + 7) / 8 * 8);
+    // resident mode: the whole problem (inverses + ids) in shared memory next to the fixed part; else 32 KB chunks
+    const size_t res_bytes = sizeof(double) * (size_t)cmax + (size_t)((gmax + 15) / 16 * 16);
+    b->resident = fixed + res_bytes <= 220 * 1024;
+    b->capC = b->resident ? cmax : BLU_BATCH_CHUNK;
+    b->capG = b->resident ? (gmax + 15) / 16 * 16 : BLU_BATCH_CHUNK;
+    b->smem = fixed + sizeof(double) * (size_t)b->capC + (size_t)b->capG;
+    if (b->smem > 220 * 1024) { blu_batch_destroy(b); return fail(BLU_ERR_ARG, "problems too large for the one-CTA-per-evaluation batch (%lld groups): use the per-context calls", Lmax); }
+    BT_TRY(cudaFuncSetAttribute(blu_batch_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    BT_TRY(cudaStreamSynchronize(b->stream));
+#undef BT_TRY
+    *out = b;
+    return BLU_OK;
+}
+
+static int batch_reserve(blu_batch *b, int B)
+{
+    if (B <= b->capB) return BLU_OK;
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    batch_free_buffers(b);
+    const size_t PB = (size_t)b->P * B, NN = (size_t)b->Nmax * b->Nmax;
+    CUDA_TRY(cudaMalloc(&b->d_hdrs, sizeof(BluEvalHeader) * PB));
+    CUDA_TRY(cudaMemsetAsync(b->d_hdrs, 0, sizeof(BluEvalHeader) * PB, b->stream));
+    CUDA_TRY(cudaMalloc(&b->d_scratch, sizeof(double) * PB * (3 * NN + 40 + 32)));
+    CUDA_TRY(cudaMalloc(&b->d_m, sizeof(double) * (size_t)B * b->Lm));
+    CUDA_TRY(cudaMalloc(&b->d_var, sizeof(double) * PB));
+    CUDA_TRY(cudaMalloc(&b->d_flags, sizeof(unsigned) * PB));
+    CUDA_TRY(cudaMalloc(&b->d_grad, sizeof(double) * (size_t)B * b->gtot));
+    CUDA_TRY(cudaHostAlloc(&b->h_m, sizeof(double) * (size_t)B * b->Lm, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&b->h_var, sizeof(double) * PB, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&b->h_flags, sizeof(unsigned) * PB, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&b->h_grad, sizeof(double) * (size_t)B * b->gtot, cudaHostAllocDefault));
+    b->capB = B;
+    return BLU_OK;
+}
+
+// m: (B, Lm) host, row-major.  var, flags: (P, B).  grad (optional): for problem p a (B, L_p) block at offset
+// B * (L_0 + ... + L_{p-1}); rows of evaluations with BLU_FLAG_TINY are filled with inf (misc.py:484).
+extern "C" int blu_batch_eval(blu_batch *b, const double *m, int B, double delta, double *var, unsigned *flags, double *grad)
+{
+    if (!b) return fail(BLU_ERR_ARG, "null batch");
+    if (!m || !var || B < 1) return fail(BLU_ERR_ARG, "bad batch arguments");
+    CUDA_TRY(cudaSetDevice(b->device));
+    int rc = batch_reserve(b, B);
+    if (rc) return rc;
+    const size_t PB = (size_t)b->P * B;
+    memcpy(b->h_m, m, sizeof(double) * (size_t)B * b->Lm);
+    CUDA_TRY(cudaMemcpyAsync(b->d_m, b->h_m, sizeof(double) * (size_t)B * b->Lm, cudaMemcpyHostToDevice, b->stream));
+    const bool dbg = getenv("BLU_DEBUG_TIMING") != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, b->stream); }
+    dim3 grid((unsigned)b->P, (unsigned)B);
+    blu_batch_eval_kernel<<<grid, BLU_BATCH_WARPS * 32, b->smem, b->stream>>>(b->d_probs, b->d_m, b->Lm, delta, grad ? 1 : 0, b->Lmax, b->capC, b->capG, b->resident ? 1 : 0, b->d_hdrs, b->d_scratch,
+                                                                             b->d_var, b->d_flags, b->d_grad);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "batch kernel launch failed: %s", cudaGetErrorString(e));
+    if (dbg) cudaEventRecord(e1, b->stream);
+    CUDA_TRY(cudaMemcpyAsync(b->h_var, b->d_var, sizeof(double) * PB, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->h_flags, b->d_flags, sizeof(unsigned) * PB, cudaMemcpyDeviceToHost, b->stream));
+    if (grad) CUDA_TRY(cudaMemcpyAsync(b->h_grad, b->d_grad, sizeof(double) * (size_t)B * b->gtot, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (dbg) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        BluEvalHeader h0;
+        cudaMemcpy(&h0, b->d_hdrs, sizeof(BluEvalHeader), cudaMemcpyDeviceToHost);
+        auto us = [&](int i) { return (double)(h0.stamp[i] - h0.stamp[0]) * 1e-3; };
+        fprintf(stderr, "[blu] batch kernel %d x %d: %.1f us | CTA 0: staged +%.1f, Phi summed +%.1f, Phi ready +%.1f, pinv +%.1f, finish +%.1f, grad +%.1f us\n",
+                b->P, B, ms * 1e3f, us(1), us(4), us(6), us(7), us(8), grad ? us(9) : 0.0);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    memcpy(var, b->h_var, sizeof(double) * PB);
+    if (flags) memcpy(flags, b->h_flags, sizeof(unsigned) * PB);
+    if (grad) {
+        memcpy(grad, b->h_grad, sizeof(double) * (size_t)B * b->gtot);
+        for (int p = 0; p < b->P; ++p)
+            for (int v = 0; v < B; ++v)
+                if (b->h_flags[(size_t)p * B + v] & BLU_FLAG_TINY) {
+                    double *row = grad + b->pre[p] * B + (long long)v * b->ctxs[p]->L;
+                    for (long long i = 0; i < b->ctxs[p]->L; ++i) row[i] = std::numeric_limits<double>::infinity();
+                }
+    }
     return BLU_OK;
 }
 

@@ -54,9 +54,31 @@ class MOSAP(object):
             raise ValueError("eps must be a scalar or an array of tolerances")
         return budget, np.array(eps)
 
+    def _small_batch(self):
+        """One-launch evaluation of all outputs (bluest_b200/batch.py) when every output's problem is small enough
+        that an evaluation is launch latency, not streaming (a CTA per output handles at most ~8k groups well)."""
+        if not hasattr(self, "_batch"):
+            self._batch = None
+            if max(int(s.L) for s in self.SAPS) <= 8192:
+                from .batch import Batch
+                self._batch = Batch(self.SAPS, maps=self.mappings, Lm=int(self.L))
+        return self._batch
+
     def variances(self, m, delta=0):
-        """mosap.py:86-89; the outputs are evaluated concurrently (one stream per context)."""
+        """mosap.py:86-89; all outputs in one kernel launch when they are small, else concurrently (one stream per
+        context)."""
         from . import _lib
+        bt = self._small_batch()
+        if bt is not None:
+            var, flags, _ = bt.eval(m, delta=delta, grad=False)
+            out = []
+            for n in range(self.n_outputs):
+                if flags[n, 0] & _lib.FLAG_TINY:
+                    out.append(np.inf)
+                    continue
+                assert not (flags[n, 0] & _lib.FLAG_NO_MODEL0)             # misc.py:470
+                out.append(float(var[n, 0]))
+            return out
         for n in range(self.n_outputs):
             self.SAPS[n].variance_GH_begin(m[self.mappings[n]], delta=delta, nohess=True, grad=False)
         out = []
@@ -70,8 +92,15 @@ class MOSAP(object):
         return out
 
     def variance_GH(self, m, nohess=False, delta=0):
-        """mosap.py:91-100; all outputs in flight at once, results collected in output order."""
+        """mosap.py:91-100; without Hessians all outputs are one kernel launch (small problems), else all outputs in
+        flight at once, results collected in output order."""
         from . import _lib
+        bt = self._small_batch() if nohess else None
+        if bt is not None:
+            var, flags, grads = bt.eval(m, delta=delta, grad=True)
+            if np.any(flags[:, 0] & _lib.FLAG_TINY):
+                raise IndexError("tuple index out of range (max|m| < 0.05: misc.py:484 returns a 2-tuple)")
+            return [float(v) for v in var[:, 0]], [np.array(g[0]) for g in grads], [None] * self.n_outputs
         for n in range(self.n_outputs):
             self.SAPS[n].variance_GH_begin(m[self.mappings[n]], delta=delta, nohess=nohess)
         variances, gradients, hessians = [], [], []

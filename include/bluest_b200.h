@@ -153,6 +153,18 @@ int blu_blue_estimator(blu_ctx *ctx, const double *samples, const double *sums_f
 int blu_candidate_variances(blu_ctx *ctx, const double *basephi, int LL, const int64_t *idx,
                             const int64_t *ms, int64_t ncand, double rcond, double *Vs);
 
+/* Batched evaluation of SMALL problems: P problems x B sample vectors in ONE kernel launch, one CTA per pair --
+ * the device form of the loop over outputs of mosap.py:86-100 (`SAPS[n].variance_GH(m[mappings[n]])`) and of the
+ * instances of a budget / tolerance sweep, which are pure launch latency one at a time.
+ *   ctxs   P contexts on one device, inverses set.  maps == NULL: one input vector is the concatenation of the
+ *          problems' own sample vectors.  maps[p] (L_p indices into a shared vector of length Lm): mosap's mappings.
+ *   blu_batch_eval: m (B, Lm) host row-major -> var, flags (P, B); grad (optional): for problem p a (B, L_p) block at
+ *          offset B * (L_0 + ... + L_{p-1}), filled with inf where BLU_FLAG_TINY (misc.py:484).  No Hessian. */
+typedef struct blu_batch blu_batch;
+int blu_batch_create(blu_ctx **ctxs, int P, const int64_t *const *maps, int64_t Lm, blu_batch **out);
+int blu_batch_eval(blu_batch *batch, const double *m, int B, double delta, double *var, unsigned *flags, double *grad);
+int blu_batch_destroy(blu_batch *batch);
+
 /* Structure-exploiting KKT solve ("next" row f1) for the semidefinite programme SAP.cvxopt_solve builds
  * (sap.py:242-307) -- what a `kktsolver` callback handed to cvxopt.solvers.sdp (sap.py:289 passes none, so cvxopt
  * factorises the dense KKT matrix) would call once per interior-point iteration and right-hand side.
