@@ -103,6 +103,7 @@ struct blu_ctx {
     std::vector<cudaEvent_t> panel_ev; // one event per Hessian row panel (symmetric download)
     int mirror_threads = 0;            // 0: automatic (see download_hessian_symmetric)
     bool sym_download = true;          // dense Hessian to the host: upper block-triangle over PCIe, lower mirrored by host threads
+    int sym_full_rows_pct = 10;        // share (%) of the lower triangle that still travels by DMA (the bottom rows, in full)
     BluXchg *d_xchg = nullptr;         // this rank's exchange buffer (CUDA IPC shared)
     BluPeers peers{};                  // peers as mapped here; world == 0: not connected
     std::vector<void *> ipc_opened;
@@ -853,6 +854,7 @@ extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
     if (!strcmp(name, "sym_download")) { c->sym_download = value != 0; return BLU_OK; }
     if (!strcmp(name, "soa")) { c->use_soa = value != 0; return BLU_OK; }
     if (!strcmp(name, "mirror_threads")) { c->mirror_threads = value; return BLU_OK; }
+    if (!strcmp(name, "sym_full_rows_pct")) { c->sym_full_rows_pct = value; return BLU_OK; }
     if (!strcmp(name, "hess_onebuf")) { c->hess_onebuf = value != 0; return BLU_OK; }
     return fail(BLU_ERR_ARG, "unknown option %s", name);
 }
@@ -986,10 +988,18 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
     const long long PH = 1024;                                   // panel height (rows)
     const int npan = (int)((L + PH - 1) / PH);
     while ((int)c->panel_ev.size() < npan) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->panel_ev.push_back(e); }
+    // The host mirror (4.3 GB of reads + 4.3 GB of streaming stores next to the DMA's own 4.3 GB of writes) is the
+    // slower of the two parties: the bottom panels -- whose lower-triangle part is the longest -- cross PCIe as FULL
+    // rows, so the host mirrors only into the rows above them.  With the measured rates (DMA 57 GB/s, mirror ~39 GB/s
+    // while the DMA runs) on the pool's hosts the optimum is flat between 0 and ~19 % (host memory bandwidth is shared by both): 10 % by default.
+    const double dma_share = std::min(100, std::max(0, c->sym_full_rows_pct)) / 100.0;
+    long long cs = (long long)std::floor((double)L * std::sqrt(1.0 - dma_share));
+    cs = std::min<long long>(L, ((cs + PH - 1) / PH) * PH);       // first fully transferred row, panel aligned
     for (int p = 0; p < npan; ++p) {
         const long long r0 = p * PH, r1 = std::min<long long>(L, r0 + PH);
-        CUDA_TRY(cudaMemcpy2DAsync(hess + r0 * L + r0, sizeof(double) * L, c->d_H + r0 * c->ldH + r0, sizeof(double) * c->ldH,
-                                   sizeof(double) * (L - r0), (size_t)(r1 - r0), cudaMemcpyDeviceToHost, c->stream));
+        const long long c0 = r0 >= cs ? 0 : r0;                   // full rows below the split, columns >= r0 above it
+        CUDA_TRY(cudaMemcpy2DAsync(hess + r0 * L + c0, sizeof(double) * L, c->d_H + r0 * c->ldH + c0, sizeof(double) * c->ldH,
+                                   sizeof(double) * (L - c0), (size_t)(r1 - r0), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaEventRecord(c->panel_ev[p], c->stream));
     }
     // host threads for the mirroring: all cores (at most 16), shared fairly when torchrun runs one rank per GPU
@@ -1007,13 +1017,14 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
         double *scratch = blu_host_mirror_scratch_alloc();           // owned by this worker for the whole download
         for (int p = 0; p < npan; ++p) {
             const long long r0 = p * PH, r1 = std::min<long long>(L, r0 + PH);
-            const int nitems = (int)((L - r1 + CW - 1) / CW);
+            const long long cend = std::min(L, cs);                   // rows >= cs arrive whole
+            const int nitems = cend > r1 ? (int)((cend - r1 + CW - 1) / CW) : 0;
             if (nitems <= 0) continue;
             while (ready[p].load(std::memory_order_acquire) == 0) std::this_thread::yield();
             for (;;) {
                 const int it = next[p].fetch_add(1);
                 if (it >= nitems) break;
-                const long long c0 = r1 + it * CW, c1 = std::min<long long>(L, c0 + CW);
+                const long long c0 = r1 + it * CW, c1 = std::min<long long>(cend, c0 + CW);
                 blu_host_mirror_block(hess, L, r0, r1, c0, c1, scratch);
             }
         }

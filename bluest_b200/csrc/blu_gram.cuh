@@ -30,7 +30,8 @@
 #include "blu_stream.cuh"
 
 #define BLU_GRAM_WARPS 8
-#define BLU_GRAM_NS 3                        // ring depth per warp
+#define BLU_GRAM_NS 2                        // ring depth per warp: two CTAs (16 warps) per SM keep the FP64 tensor pipe fed --
+                                             // with 3 stages and one CTA per SM the DMMA pipe was 57 % busy, waiting on its own accumulators
 #define BLU_GRAM_STAGE_DOUBLES 544           // >= 16 samples x 32 models + skew/round-up slack
 #define BLU_GRAM_GROUP 16                    // CTAs per group of the in-kernel reduction
 #define BLU_GRAM_MAXGROUPS 40
@@ -64,9 +65,13 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
     const long long s0 = gw * slab;
     long long s1 = s0 + slab;
     if (s1 > n) s1 = n;
-    double acc[NPAIR][2];
+    // two accumulator sets, alternating between consecutive blocks of 4 samples: a DMMA depends on the one two blocks
+    // back, not on the previous one (the FP64 tensor pipe stalled on that dependency)
+    double acc[2][NPAIR][2];
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) { acc[p][0] = 0.0; acc[p][1] = 0.0; }
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) { acc[h][p][0] = 0.0; acc[h][p][1] = 0.0; }
 
     auto issue = [&](long long sb, int st) -> int {       // copy samples [sb, sb+cnt) into stage st; returns the skew
         const long long cnt = (s1 - sb) < spc ? (s1 - sb) : spc;
@@ -94,27 +99,30 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
         blu_mbar_wait(&bars[st], (unsigned)((it / BLU_GRAM_NS) & 1));
         const double *base = stages + (size_t)st * BLU_GRAM_STAGE_DOUBLES + skew[st];
         const int cnt = (int)((s1 - sb) < spc ? (s1 - sb) : spc);
-        for (int r0 = 0; r0 < cnt; r0 += 4) {
-            const int row = r0 + ks;
-            const bool rok = row < cnt;
-            double f[NT];
+        for (int r0 = 0; r0 < cnt; r0 += 8) {
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                const int col = 8 * t + cq;
-                double v = 0.0;
-                if (rok) {
-                    if (col < N) {
-                        v = base[row * N + col];
-                        if (TELE && col > 0) v -= base[row * N + col - 1];        // Z_j = Y_j - Y_{j-1}
-                    } else if (col == N) v = 1.0;
+            for (int h = 0; h < 2; ++h) {
+                const int row = r0 + 4 * h + ks;
+                const bool rok = row < cnt;
+                double f[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const int col = 8 * t + cq;
+                    double v = 0.0;
+                    if (rok) {
+                        if (col < N) {
+                            v = base[row * N + col];
+                            if (TELE && col > 0) v -= base[row * N + col - 1];        // Z_j = Y_j - Y_{j-1}
+                        } else if (col == N) v = 1.0;
+                    }
+                    f[t] = v;
                 }
-                f[t] = v;
+                int p = 0;
+#pragma unroll
+                for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+                    for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[h][p][0], acc[h][p][1], f[ti], f[tj]); ++p; }
             }
-            int p = 0;
-#pragma unroll
-            for (int ti = 0; ti < NT; ++ti)
-#pragma unroll
-                for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[p][0], acc[p][1], f[ti], f[tj]); ++p; }
         }
         __syncwarp();                                   // stage consumed before it is refilled
     }
@@ -126,8 +134,8 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
 #pragma unroll
             for (int tj = ti; tj < NT; ++tj) {
                 const int r = 8 * ti + cq, c = 8 * tj + 2 * ks;
-                sred[r * NPG + c] = acc[p][0];
-                sred[r * NPG + c + 1] = acc[p][1];
+                sred[r * NPG + c] = acc[0][p][0] + acc[1][p][0];
+                sred[r * NPG + c + 1] = acc[0][p][1] + acc[1][p][1];
                 ++p;
             }
     }
@@ -242,7 +250,7 @@ static int blu_gram_sums(const double *Y, long long n, int N, int n_out, long lo
     cudaGetDevice(&dev);
     cudaGetDeviceProperties(&prop, dev);
     const long long warps_wanted = (n + 255) / 256;                       // >= 256 samples per warp
-    const int ctas_per_sm = 1;                                            // 3-stage rings: one CTA of 8 warps per SM
+    const int ctas_per_sm = 2;                                            // 2-stage rings: two CTAs of 8 warps per SM
     int grid = (int)std::max<long long>(1, std::min<long long>((warps_wanted + BLU_GRAM_WARPS - 1) / BLU_GRAM_WARPS,
                                                                   std::max<long long>(1, (long long)prop.multiProcessorCount * ctas_per_sm / n_out)));
     grid = std::min(grid, BLU_GRAM_GROUP * BLU_GRAM_MAXGROUPS);

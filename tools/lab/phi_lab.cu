@@ -419,6 +419,114 @@ phi_kernel5(const Cls *__restrict__ cls, int N, const Tile *__restrict__ tiles, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sixth form: precomputed byte targets (as the fourth/fifth), but the rows are STAGED by the bulk copy engine into a
+// deep per-warp ring (bytes in flight independent of registers and warps), few warps with R = 16 private slots.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect(unsigned long long *bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{ asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nW6:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D6;\nbra W6;\nD6:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int R, int UB, int WARPS, int NS>
+__global__ void __launch_bounds__(WARPS * 32)
+phi_kernel6(const Cls *__restrict__ cls, int N, const Tile *__restrict__ tiles, int ntiles, const double *__restrict__ soa,
+            const unsigned char *__restrict__ tgt, const double *__restrict__ m, double *__restrict__ part)
+{
+    constexpr int P = 32 / R;
+    constexpr int STAGE = UB * 288;                       // UB rows: 256 B of values + 32 B of targets each
+    extern __shared__ __align__(128) unsigned char s6[];
+    const int NT = N * (N + 1) / 2;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *acc = reinterpret_cast<double *>(s6) + (size_t)w * NT * R;
+    unsigned char *ring = s6 + sizeof(double) * (size_t)WARPS * NT * R + (size_t)w * NS * STAGE;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(s6 + sizeof(double) * (size_t)WARPS * NT * R + (size_t)WARPS * NS * STAGE) + w * NS;
+    for (int t = lane; t < NT * R; t += 32) acc[t] = 0.0;
+    if (lane == 0) { for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+    const int slot = lane % R, phase = lane / R;
+    const unsigned acc_s = smem_u32(acc) + 8u * slot;
+    const int gw = blockIdx.x * WARPS + w, nw = gridDim.x * WARPS;
+    // producer cursor over (tile, sub-chunk of UB rows)
+    int pq = gw, ps = 0;                                  // tile list index, sub-chunk
+    Tile pt = pq < ntiles ? tiles[pq] : Tile{0, 0, 0};
+    int pT = pq < ntiles ? cls[pt.cls].T : 0;
+    long long prow0 = pq < ntiles ? cls[pt.cls].soff / 32 + pt.t * pT : 0;
+    auto issue = [&](int st) {
+        const int e0 = ps * UB;
+        const int cnt = (pT - e0) < UB ? (pT - e0) : UB;
+        if (lane == 0) {
+            mbar_expect(&bars[st], (unsigned)(cnt * 288));
+            bulk_g2s(ring + (size_t)st * STAGE, soa + (prow0 + e0) * 32, (unsigned)(cnt * 256), &bars[st]);
+            bulk_g2s(ring + (size_t)st * STAGE + UB * 256, tgt + (prow0 + e0) * 32, (unsigned)(cnt * 32), &bars[st]);
+        }
+        if ((ps + 1) * UB >= pT) {
+            ps = 0; pq += nw;
+            if (pq < ntiles) { pt = tiles[pq]; pT = cls[pt.cls].T; prow0 = cls[pt.cls].soff / 32 + pt.t * pT; }
+        } else ++ps;
+    };
+    int nissued = 0;
+    for (; nissued < NS - 1 && pq < ntiles; ++nissued) issue(nissued);
+    int it = 0;
+    for (int q = gw; q < ntiles; q += nw) {
+        const Tile tl = tiles[q];
+        const Cls ci = cls[tl.cls];
+        const long long gi = tl.t * 32 + lane;
+        const double mv = gi < ci.Lk ? m[ci.goff + gi] : 0.0;
+        const int T = ci.T;
+        for (int e0 = 0; e0 < T; e0 += UB, ++it) {
+            const int st = it % NS;
+            if (pq < ntiles) issue((it + NS - 1) % NS);
+            mbar_wait(&bars[st], (unsigned)((it / NS) & 1));
+            const int cnt = (T - e0) < UB ? (T - e0) : UB;
+            const unsigned vs = smem_u32(ring + (size_t)st * STAGE) + 8u * lane;
+            const unsigned ts = smem_u32(ring + (size_t)st * STAGE + UB * 256) + lane;
+            unsigned at[UB]; double v[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                unsigned tg;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(tg) : "r"(ts + 32u * u) : "memory");
+                v[u] = lds64(vs + 256u * u);
+                at[u] = acc_s + 8u * R * tg;
+            }
+#pragma unroll
+            for (int ph = 0; ph < P; ++ph) {
+                if (P == 1 || phase == ph) {
+                    double o[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) if (u < cnt) o[u] = lds64(at[u]);
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) if (u < cnt) o[u] = fma(mv, v[u], o[u]);
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) if (u < cnt) sts64(at[u], o[u]);
+                }
+                if (P > 1) __syncwarp();
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    __syncthreads();
+    const double *sacc6 = reinterpret_cast<const double *>(s6);
+    for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+        double s = 0.0;
+        for (int ww = 0; ww < WARPS; ++ww) {
+            const double *aw = sacc6 + (size_t)ww * NT * R + (size_t)t * R;
+            double sw = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) sw += aw[r];
+            s += sw;
+        }
+        part[(long long)blockIdx.x * NT + t] = s;
+    }
+}
+
 __global__ void ref_kernel(const Cls *cls, int ncls, int N, const double *soa, const unsigned *gmask, const double *m, double *phi)
 {
     for (int ic = 0; ic < ncls; ++ic) {
@@ -570,16 +678,28 @@ int main(int argc, char **argv)
         char nm[160]; snprintf(nm, sizeof nm, "%s R=%d warps=%d ctas/sm=%d (err %.1e)", tag, R, warps, cps, err / refmax);
         report(nm, us);
     };
-    run4(phi_kernel5<16, 8, 8>, 16, 8, 1, "phi5 UB=8");
-    run4(phi_kernel5<16, 16, 8>, 16, 8, 1, "phi5 UB=16");
-    run4(phi_kernel5<8, 8, 16>, 8, 16, 1, "phi5 UB=8");
-    run4(phi_kernel5<8, 4, 16>, 8, 16, 1, "phi5 UB=4");
     run4(phi_kernel5<8, 8, 8>, 8, 8, 2, "phi5 UB=8");
-    run4(phi_kernel5<4, 8, 16>, 4, 16, 2, "phi5 UB=8");
-    run4(phi_kernel5<4, 4, 32>, 4, 32, 1, "phi5 UB=4");
-    run4(phi_kernel5<4, 8, 8>, 4, 8, 4, "phi5 UB=8");
-    run4(phi_kernel5<32, 16, 4>, 32, 4, 1, "phi5 UB=16");
-    run4(phi_kernel5<2, 8, 8>, 2, 8, 8, "phi5 UB=8");
-    run4(phi_kernel5<1, 8, 8>, 1, 8, 8, "phi5 UB=8");
+    auto run6 = [&](auto kern, int R, int warps, int UB, int NS, const char *tag) {
+        const size_t smem = 8ull * warps * NT * R + (size_t)warps * NS * UB * 288 + 8ull * warps * NS;
+        if (smem > 227 * 1024) { printf("%-44s skipped (smem %zu)\n", tag, smem); return; }
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = nsm;
+        auto go = [&] { kern<<<grid, warps * 32, smem>>>(d_cls, N, d_tiles, ntiles, d_soa, d_tgt, d_m, d_part); };
+        const float us = timeit(go, 20);
+        CK(cudaGetLastError());
+        fold_kernel<<<(NT + 127) / 128, 128>>>(d_part, grid, NT, d_phi);
+        CK(cudaMemcpy(hphi.data(), d_phi, 8 * NT, cudaMemcpyDeviceToHost));
+        double err = 0; for (int t = 0; t < NT; ++t) err = std::max(err, fabs(hphi[t] - href[t]));
+        char nm[160]; snprintf(nm, sizeof nm, "%s R=%d warps=%d UB=%d NS=%d smem=%zuK (err %.1e)", tag, R, warps, UB, NS, smem >> 10, err / refmax);
+        report(nm, us);
+    };
+    run6(phi_kernel6<16, 16, 4, 6>, 16, 4, 16, 6, "phi6");
+    run6(phi_kernel6<16, 8, 4, 12>, 16, 4, 8, 12, "phi6");
+    run6(phi_kernel6<16, 16, 5, 3>, 16, 5, 16, 3, "phi6");
+    run6(phi_kernel6<8, 16, 8, 3>, 8, 8, 16, 3, "phi6");
+    run6(phi_kernel6<8, 8, 8, 6>, 8, 8, 8, 6, "phi6");
+    run6(phi_kernel6<8, 16, 6, 5>, 8, 6, 16, 5, "phi6");
+    run6(phi_kernel6<32, 16, 2, 8>, 32, 2, 16, 8, "phi6");
+    run6(phi_kernel6<4, 8, 16, 3>, 4, 16, 8, 3, "phi6");
     return 0;
 }
