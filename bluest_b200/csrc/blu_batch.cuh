@@ -89,7 +89,7 @@ blu_batch_eval_kernel(const BluBatchProb *__restrict__ probs, const double *__re
     unsigned char *fraw = braw + sizeof(double) * (size_t)BLU_BATCH_WARPS * NN;
     double *sx = reinterpret_cast<double *>(fraw + BLU_FIN_SCRATCH_BYTES);
     double *sm = sx + 32;                                 // the problem's sample vector
-    double *sC = sm + Lmax;
+    double *sC = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sm + Lmax) + 15) & ~static_cast<uintptr_t>(15));   // bulk copies need 16-byte aligned destinations
     uint8_t *sG = reinterpret_cast<uint8_t *>(sC + capC);
     unsigned short *sjl = reinterpret_cast<unsigned short *>(sG + capG);
     __shared__ unsigned s_supp;

@@ -1575,7 +1575,7 @@ extern "C" int blu_batch_create(blu_ctx **ctxs, int P, const int64_t *const *map
     }
     b->Lmax = Lmax;
     const size_t fixed = sizeof(double) * ((size_t)BLU_BATCH_WARPS * b->Nmax * b->Nmax + 32 + (size_t)Lmax) + BLU_FIN_SCRATCH_BYTES
-                         + sizeof(unsigned short) * (size_t)((lutmax + 7) / 8 * 8);
+                         + sizeof(unsigned short) * (size_t)((lutmax + 7) / 8 * 8) + 16;      // + alignment slack of the staged inverses
     // resident mode: the whole problem (inverses + ids) in shared memory next to the fixed part; else 32 KB chunks
     const size_t res_bytes = sizeof(double) * (size_t)cmax + (size_t)((gmax + 15) / 16 * 16);
     b->resident = fixed + res_bytes <= 220 * 1024;

@@ -43,6 +43,75 @@ def save_graph_data(filename, costs, adjacency, SG, dV=None):
     np.savez(filename, M=M, n_outputs=len(adjacency), costs=np.asarray(costs), **C_dict, SG=np.asarray(SG), dV=np.asarray(dV))
 
 
+def sample_file_name(filename, ls):
+    """blue_fn.py:97-100: the sample file of the coupled models ``ls`` is ``<base><l0><l1>...<ext>``."""
+    ext = "." + filename.split(".")[-1]
+    base = ".".join(filename.split(".")[:-1]) + "".join(str(l) for l in ls)
+    return base + ext
+
+
+def save_sample_file(filename, ls, values, inputs, outputs_to_save=None):
+    """The sample snapshot ``blue_fn`` keeps when it is given ``filename`` (blue_fn.py:97-104, 132-145, 189-222), same
+    keys and same append semantics, for model outputs that were evaluated in batches:
+
+      values   (n_outputs, n, len(ls)) array (device tensors are copied to the host): ``values[o, s, i]`` = output o of
+               model ``ls[i]`` for sample s -> keys ``values_<o>_<i>`` (only the outputs in ``outputs_to_save``)
+      inputs   (n, len(ls)) or list of per-model arrays: the samples the models were evaluated on -> ``inputs_<i>``
+      plus ``models``, ``n_samples``, ``n_outputs``.
+
+    If the file exists its lists are extended and ``n_samples`` is increased (blue_fn.py:205-218); the models and the
+    number of outputs must match.  Returns the path written."""
+    import os
+    if hasattr(values, "cpu"):
+        values = values.cpu().numpy()
+    values = np.asarray(values)
+    No, n, Lm = values.shape
+    if Lm != len(ls):
+        raise ValueError("values has %d model columns, expected %d" % (Lm, len(ls)))
+    if outputs_to_save is None:
+        outputs_to_save = list(range(No))
+    path = sample_file_name(filename, ls)
+    out = {"values_%d_%d" % (o, i): [values[o, s, i] for s in range(n)] if o in outputs_to_save else [] for o in range(No) for i in range(Lm)}
+    for i in range(Lm):
+        col = inputs[i] if isinstance(inputs, (list, tuple)) else np.asarray(inputs)[:, i]
+        # the reference appends a sample's input once per SAVED OUTPUT (the append sits inside its loop over the
+        # outputs, blue_fn.py:135-140): reproduced, so that files written here and there can extend one another
+        out["inputs_%d" % i] = [col[s] for s in range(n) for _ in outputs_to_save]
+    out["models"] = np.array([ls])
+    out["n_samples"] = np.array([n])
+    out["n_outputs"] = np.array([No])
+    if os.path.isfile(path):
+        old = dict(np.load(path, allow_pickle=True))
+        if [int(v) for v in np.ravel(old["models"])] != [int(v) for v in ls]:
+            raise AssertionError("sample file %s holds other models" % path)
+        if int(np.ravel(old["n_outputs"])[0]) != No:
+            raise AssertionError("sample file %s holds another number of outputs" % path)
+        for key in list(old.keys()):
+            if "values" in key or "inputs" in key:
+                out[key] = [item for item in old[key]] + out[key]
+        out["n_samples"] = np.array([int(np.ravel(old["n_samples"])[0]) + n])
+    np.savez_compressed(path, **out)
+    return path
+
+
+def load_sample_file(filename, ls=None):
+    """Read a sample snapshot back: ``(values (n_outputs, n, len(ls)) with NaN for outputs that were not saved, inputs
+    (n, len(ls)), n_samples)``.  ``ls`` given: ``filename`` is the base name handed to ``blue_fn``; None: the full path."""
+    path = sample_file_name(filename, ls) if ls is not None else filename
+    d = np.load(path, allow_pickle=True)
+    models = [int(v) for v in np.ravel(d["models"])]
+    No = int(np.ravel(d["n_outputs"])[0]); n = int(np.ravel(d["n_samples"])[0])
+    vals = np.full((No, n, len(models)), np.nan)
+    for o in range(No):
+        for i in range(len(models)):
+            a = np.asarray(d["values_%d_%d" % (o, i)], dtype=np.float64)
+            if a.size:
+                vals[o, :, i] = a
+    ins = np.array([np.asarray(d["inputs_%d" % i], dtype=np.float64) for i in range(len(models))]).T
+    rep = ins.shape[0] // n if n else 1                    # one copy of every input per saved output (see save_sample_file)
+    return vals, ins[::max(rep, 1)], n
+
+
 def is_subclique(adj, nodes):
     """``is_subclique`` of blue_models.py:33-36 on an adjacency matrix: every pair of ``nodes`` -- a node with
     itself included, the model graphs carry self-loops -- is joined by an edge (non-zero adjacency)."""

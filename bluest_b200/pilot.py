@@ -79,6 +79,54 @@ def pilot_statistics(Y, device=0, dist=None, group=None, telescoped=True):
     return finalize_sums(sums, n_total, N, telescoped=telescoped)
 
 
+class PilotAccumulator:
+    """The accumulation loop of ``blue_fn`` (blue_fn.py:115-167) for model outputs that are produced in batches of N1
+    samples and stay on the GPU: every ``add`` runs the Gram kernel on one batch and adds its (N*N + N) n_out sums to a
+    device-resident running total -- nothing but those sums ever leaves HBM.  ``finalize`` all-reduces the totals over
+    the ranks (blue_fn.py:177-187) and returns what ``finalize_sums`` returns.
+
+        acc = PilotAccumulator(N, n_outputs)
+        for it in range(0, n, N1):
+            Ps = model(samples[it:it + N1])          # (n_outputs, N1, N) CUDA float64 tensor
+            acc.add(Ps)
+        stats = acc.finalize(dist)                   # sumse, sumsc, C_hat, sumsd1, sumsd2, dV
+    """
+
+    def __init__(self, N, n_outputs=1, device=0, telescoped=True):
+        import torch
+        self.N, self.n_out, self.device, self.telescoped = int(N), int(n_outputs), int(device), bool(telescoped)
+        self.sums = torch.zeros((self.n_out, self.N * self.N + self.N), dtype=torch.float64, device="cuda:%d" % self.device)
+        self._tmp = torch.empty_like(self.sums)
+        self.n = 0
+
+    def add(self, Y):
+        """Y: (n_out, n_batch, N) or (n_batch, N) contiguous CUDA float64 tensor (host arrays are uploaded)."""
+        import torch
+        if not hasattr(Y, "data_ptr"):
+            Y = torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float64)).to(self.sums.device)
+        assert Y.is_cuda and Y.is_contiguous() and str(Y.dtype) == "torch.float64"
+        shape = tuple(Y.shape)
+        n_out = 1 if len(shape) == 2 else int(shape[0])
+        if n_out != self.n_out or int(shape[-1]) != self.N:
+            raise ValueError("batch of shape %s does not match %d outputs x %d models" % (shape, self.n_out, self.N))
+        nb = int(shape[-2])
+        check(lib().blu_pilot_sums(self.device, ctypes.c_void_p(int(Y.data_ptr())), nb, self.N, self.n_out, 0, 1, int(self.telescoped),
+                                   _producer_stream(Y), ctypes.c_void_p(int(self._tmp.data_ptr())), 1, None))
+        self.sums += self._tmp                     # the call above returned after its own stream finished
+        self.n += nb
+
+    def finalize(self, dist=None, group=None):
+        import torch
+        sums, n = self.sums, self.n
+        if dist is not None and dist.get_world_size(group) > 1:
+            sums = sums.clone()
+            cnt = torch.tensor([float(n)], dtype=torch.float64, device=sums.device)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+            n = int(round(float(cnt.item())))
+        return finalize_sums(sums.cpu().numpy(), n, self.N, telescoped=self.telescoped)
+
+
 def pilot_covariance(Y, device=0, return_ms=False):
     """Y: (n, N) samples (numpy array, or a CUDA float64 torch tensor for a device-resident
     matrix).  Returns (sumse (N,), sumsc (N,N), C_hat (N,N)) with

@@ -316,6 +316,24 @@ def test_pilot_statistics_mlmc_two_outputs(blu):
     assert maxrel(r["C_hat"], rp["C_hat"]) < 1e-12
 
 
+def test_pilot_accumulator_batches(blu):
+    """blue_fn.py:115-167 on the device: sums accumulated over batches of N1 samples that live in HBM equal the golden
+    statistics of the reference's sample-by-sample loop."""
+    import torch
+    d = _load("pilot_mlmc.npz")
+    Y = torch.from_numpy(d["Y"]).cuda()
+    No, n, M = Y.shape
+    acc = blu.PilotAccumulator(M, No, telescoped=True)
+    for it in range(0, n, 64):
+        acc.add(Y[:, it:it + 64, :].contiguous())
+    r = acc.finalize()
+    iu = np.triu_indices(M, 1)
+    assert acc.n == n
+    assert maxrel(r["sumse"], d["batch/sumse"]) < TOL and maxrel(r["sumsc"], d["batch/sumsc"]) < TOL and maxrel(r["C_hat"], d["batch/C_hat"]) < TOL
+    for o in range(No):
+        assert maxrel(r["dV"][o][iu], d["batch/dV"][o][iu]) < TOL
+
+
 def test_pilot_covariance(blu):
     d = _load("pilot.npz")
     s1, S2, C = blu.pilot_covariance(d["Y"])
@@ -464,6 +482,13 @@ def test_end_to_end_scipy_solve_matches_reference(blu, tag):
     assert maxrel(cont, d[f"{tag}/continuous"]) < 5e-3
     vr = orc.SapOracle(C, K, groups).variance(d[f"{tag}/continuous"])
     assert abs(sap.variance(cont) - vr) <= 1e-4 * vr
+    # (1) the north-star claim, sharp: from the SAME continuous iterate (the reference's own) the integer allocation,
+    #     its variance and its cost are the reference's, exactly / to 1e-12
+    same = sap.integer_projection(d[f"{tag}/continuous"].copy(), budget=float(d[f"{tag}/budget"]))
+    assert np.array_equal(same, d[f"{tag}/integer"])
+    assert abs(sap.variance(same) - float(d[f"{tag}/variance"])) <= 1e-12 * float(d[f"{tag}/variance"])
+    assert float(same @ sap.costs) == float(d[f"{tag}/cost"])
+    # (2) the whole solve, where the solver's own stopping noise enters
     ints = sap.solve(budget=float(d[f"{tag}/budget"]), solver="scipy", x0=d[f"{tag}/x0"].copy(), continuous_relaxation=False)
     # The stopping iterate of trust-constr is only defined to ~1e-3 (see above), so a rounding
     # candidate can flip; the projection itself is exact given the same input (test_integer_projection).
