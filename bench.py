@@ -468,6 +468,29 @@ def secondary_configs(device=0):
     best = min(blu.pilot_covariance(Y, return_ms=True)[3] for _ in range(5))
     out["pilot_gram_1e6x20"] = {"kernel_us": best * 1e3, "GBps": 8.0 * 1e6 * 20 / (best * 1e-3) / 1e9, "roofline_frac": 8.0 * 1e6 * 20 / (best * 1e-3) / 1e9 / peak}
     del Y
+    # row f1: one KKT solve of the SDP's interior-point iteration at 15 models (the dense KKT matrix would have 65 796 rows)
+    try:
+        N = 15
+        ga15 = blu.enumerate_group_arrays(N)
+        L15 = sum(len(g) for g in ga15)
+        c15 = blu.group_costs(ga15, 2.0 ** (N - np.arange(N))); c15 = c15 / c15.max()
+        s15 = blu.SAP(orc.wishart_cov(N, 0), N, ga15, c15, verbose=False, device=device)
+        Gx, scales, has_t = s15.sdp_linear_rows(budget_mode=True)
+        rng = np.random.RandomState(9)
+        n15, nlin, M15 = L15 + 1, Gx.shape[0], N + 1
+        Z = rng.randn(M15, M15); Z = Z + Z.T
+        argsk = (has_t, scales, Gx, 0.5 + 1.5 * rng.rand(n15 + nlin), np.eye(M15) + 0.1 * rng.randn(M15, M15), rng.randn(n15),
+                 np.concatenate([rng.randn(n15 + nlin), Z.ravel()]))
+        s15.kkt_solve(*argsk)
+        t0 = time.perf_counter()
+        ux, uz, ms = s15.kkt_solve(*argsk, return_ms=True)
+        out["kkt_solve_n15"] = {"device_ms": ms, "host_api_ms": (time.perf_counter() - t0) * 1e3, "unknowns": n15,
+                                "capacitance_order": (M15 * (M15 + 1)) // 2 + nlin,
+                                "dense_equivalent": "(L+1)^3/3 = %.1e flops per factorisation in the reference's call (sap.py:289, no kktsolver)" % ((n15 ** 3) / 3.0)}
+        s15.close()
+        del ga15
+    except Exception as ex:
+        out["kkt_solve_n15"] = {"failed": repr(ex)}
     # config 4: MOSAP, 4 outputs x 10 models (1023 groups each), host API, outputs evaluated concurrently
     N, No = 10, 4
     groups = blu.enumerate_groups(N)
