@@ -59,7 +59,7 @@ class MOSAP(object):
         that an evaluation is launch latency, not streaming (a CTA per output handles at most ~8k groups well)."""
         if not hasattr(self, "_batch"):
             self._batch = None
-            if max(int(s.L) for s in self.SAPS) <= 8192:
+            if all(getattr(s, "_ctx", None) for s in self.SAPS) and max(int(s.L) for s in self.SAPS) <= 8192:
                 from .batch import Batch
                 self._batch = Batch(self.SAPS, maps=self.mappings, Lm=int(self.L))
         return self._batch
