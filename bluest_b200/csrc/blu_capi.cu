@@ -1149,7 +1149,7 @@ static int launch_hv_apply(blu_ctx *c, const double *d_t, double *d_out)
     const long long rows = c->hi - c->lo;
     const int grid = (int)std::max<long long>(1, std::min<long long>((rows + BLU_HVA_THREADS - 1) / BLU_HVA_THREADS, (long long)c->nsm * 8));
     switch (c->NP) {
-#define HV_CASE(P) case P: blu_hv_apply_kernel<P><<<grid, BLU_HVA_THREADS, 0, c->stream>>>(c->d_U, c->d_Sop, c->N, d_t, c->lo, c->hi, d_out); break;
+#define HV_CASE(P) case P: blu_hv_apply_kernel<P><<<grid, BLU_HVA_THREADS, 0, c->stream>>>(c->d_U, c->d_Sop, c->N, d_t, c->lo, c->hi, d_out, 1); break;
         HV_CASE(4) HV_CASE(8) HV_CASE(12) HV_CASE(16) HV_CASE(20) HV_CASE(24) HV_CASE(28) HV_CASE(32)
 #undef HV_CASE
     }
@@ -1398,12 +1398,14 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     sandwich(Z, Wm.data());
     // device buffers
     struct DevBuf { void *p = nullptr; ~DevBuf() { if (p) cudaFree(p); } };
-    DevBuf bBs, bsmall, bvec;
+    DevBuf bBs, bsmall, bvec, bpart;
     const size_t nsmall = (size_t)2 * MM + (size_t)Q * Q + 2 * 256 + 8;           // rinv | Wm | cap | v | y | info
     const size_t nvec = (size_t)(n + nlin) + (size_t)nlin * n + 5 * (size_t)n + nlin;   // d | Gx | bx | bz0 | g1tw | rhs | ux
     CUDA_TRY(cudaMalloc(&bBs.p, sizeof(double) * (size_t)n * QP));
     CUDA_TRY(cudaMalloc(&bsmall.p, sizeof(double) * nsmall));
     CUDA_TRY(cudaMalloc(&bvec.p, sizeof(double) * nvec));
+    CUDA_TRY(cudaMalloc(&bpart.p, sizeof(double) * 64 * 16 * (size_t)((QP / 8) * (QP / 8 + 1) / 2)));      // partial tiles: 16 row splits at most
+    double *d_part = (double *)bpart.p;
     double *d_Bs = (double *)bBs.p;
     double *d_rinv = (double *)bsmall.p, *d_Wm = d_rinv + MM, *d_cap = d_Wm + MM, *d_v = d_cap + (size_t)Q * Q, *d_y = d_v + 256;
     int *d_info = (int *)(d_y + 256);
@@ -1422,7 +1424,7 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     cudaEventRecord(e0, st);
     c->launches = 0;
     {
-        const size_t smem = sizeof(double) * ((size_t)2 * MM + (size_t)BLU_KKT_WARPS * M * N);
+        const size_t smem = sizeof(double) * ((size_t)2 * M * (M | 1) + (size_t)BLU_KKT_WARPS * M * (N | 1));
         CUDA_TRY(cudaFuncSetAttribute(blu_kkt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = (int)std::max<long long>(1, std::min<long long>((n + BLU_KKT_WARPS - 1) / BLU_KKT_WARPS, (long long)c->nsm * 4));
         blu_kkt_rows_kernel<<<grid, BLU_KKT_WARPS * 32, smem, st>>>(c->d_cls, (int)c->cls.size(), N, L, has_t, scales, c->d_gidx, c->d_cinv, d_rinv, d_Wm,
@@ -1431,8 +1433,11 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
         blu_kkt_rhs_kernel<<<(int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)c->nsm * 8)), 256, 0, st>>>(
             n, nlin, d_bx, d_bz0, d_d, d_Gx, d_d + n, d_g1tw, Q, QP, d_rhs, d_Bs);
         KERNEL_CHECK(c);
-        const int NTQ = QP / 8;
-        blu_kkt_syrk_kernel<<<NTQ * (NTQ + 1) / 2, BLU_KKT_WARPS * 32, 0, st>>>(d_Bs, n, Q, QP, d_cap, d_v);
+        const int NTQ = QP / 8, npairs = NTQ * (NTQ + 1) / 2;
+        const int nsplit = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, n / 2048), ((long long)c->nsm * 6 + npairs - 1) / npairs));
+        blu_kkt_syrk_kernel<<<dim3((unsigned)npairs, (unsigned)nsplit), BLU_KKT_WARPS * 32, 0, st>>>(d_Bs, n, QP, d_part);
+        KERNEL_CHECK(c);
+        blu_kkt_capfold_kernel<<<(npairs * 64 + 255) / 256, 256, 0, st>>>(d_part, npairs, nsplit, Q, QP, d_cap, d_v);
         KERNEL_CHECK(c);
         const size_t csm = sizeof(double) * (size_t)Q * (Q + 1);
         CUDA_TRY(cudaFuncSetAttribute(blu_kkt_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));

@@ -46,10 +46,11 @@ blu_kkt_rows_kernel(const BluClass *__restrict__ cls, int ncls, int N, long long
                     const double *__restrict__ dlin, int Q, int QP, double *__restrict__ Bs, double *__restrict__ g1tw)
 {
     const int M = N + 1, Qs = M * (M + 1) / 2;
-    extern __shared__ double kraw[];                      // [M*M r^-1][M*M Wm][WARPS x M*N Tt]
-    double *sR = kraw, *sW = kraw + M * M;
+    const int MP = M | 1;                                 // odd leading dimensions: rows of r^-1 / Tt land in different banks
+    extern __shared__ double kraw[];                      // [M*MP r^-1][M*MP Wm][WARPS x M*(N|1) Tt]
+    double *sR = kraw, *sW = kraw + M * MP;
     __shared__ BluClass scls[BLU_MAX_MODELS_C];
-    for (int t = threadIdx.x; t < M * M; t += blockDim.x) { sR[t] = rinv[t]; sW[t] = Wm[t]; }
+    for (int t = threadIdx.x; t < M * M; t += blockDim.x) { sR[(t / M) * MP + (t % M)] = rinv[t]; sW[(t / M) * MP + (t % M)] = Wm[t]; }
     for (int t = threadIdx.x; t < ncls; t += blockDim.x) scls[t] = cls[t];
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,10 +66,10 @@ blu_kkt_rows_kernel(const BluClass *__restrict__ cls, int ncls, int N, long long
                 int a = 0, rem = q;
                 while (rem >= M - a) { rem -= M - a; ++a; }
                 const int b = a + rem;
-                const double v = -(sR[a * M + N] * sR[b * M + N]);
+                const double v = -(sR[a * MP + N] * sR[b * MP + N]);
                 row[q] = dc * (a == b ? v : rt2 * v);
             }
-            if (lane == 0) dotw = -sW[N * M + N];
+            if (lane == 0) dotw = -sW[N * MP + N];
         } else {
             const long long i = col - has_t;
             int ic = 0;
@@ -78,16 +79,17 @@ blu_kkt_rows_kernel(const BluClass *__restrict__ cls, int ncls, int N, long long
             const int k = ci.k;
             const uint8_t *g = gidx + ci.ioff + il * k;
             const double *C = cinv + ci.coff + il * ci.T;
-            double *Tt = kraw + 2 * M * M + (size_t)w * M * N;    // Tt[a][l] = sum_j r^-1[a][g_j] C[j][l]
+            const int KP = k | 1;
+            double *Tt = kraw + 2 * M * MP + (size_t)w * M * (N | 1);    // Tt[a][l] = sum_j r^-1[a][g_j] C[j][l], leading dimension KP
             // Tt[a][l] = sum_j r^-1[a][g_j] C[j][l]
             for (int t = lane; t < M * k; t += 32) {
                 const int a = t / k, l = t - a * k;
                 double s = 0.0;
                 for (int j = 0; j < k; ++j) {
                     const int lo = j < l ? j : l, hi = j < l ? l : j;
-                    s = fma(sR[a * M + g[j]], C[blu_pk(k, lo, hi)], s);
+                    s = fma(sR[a * MP + g[j]], C[blu_pk(k, lo, hi)], s);
                 }
-                Tt[a * k + l] = s;
+                Tt[a * KP + l] = s;
             }
             __syncwarp();
             for (int q = lane; q < Qs; q += 32) {
@@ -95,7 +97,7 @@ blu_kkt_rows_kernel(const BluClass *__restrict__ cls, int ncls, int N, long long
                 while (rem >= M - a) { rem -= M - a; ++a; }
                 const int b = a + rem;
                 double s = 0.0;
-                for (int l = 0; l < k; ++l) s = fma(Tt[a * k + l], sR[b * M + g[l]], s);
+                for (int l = 0; l < k; ++l) s = fma(Tt[a * KP + l], sR[b * MP + g[l]], s);
                 s *= -scales;
                 row[q] = dc * (a == b ? s : rt2 * s);
             }
@@ -104,7 +106,7 @@ blu_kkt_rows_kernel(const BluClass *__restrict__ cls, int ncls, int N, long long
                 int j = 0, rem = e;
                 while (rem >= k - j) { rem -= k - j; ++j; }
                 const int l = j + rem;
-                const double wv = (j == l) ? sW[g[j] * M + g[j]] : (sW[g[j] * M + g[l]] + sW[g[l] * M + g[j]]);
+                const double wv = (j == l) ? sW[g[j] * MP + g[j]] : (sW[g[j] * MP + g[l]] + sW[g[l] * MP + g[j]]);
                 dotw = fma(C[e], wv, dotw);
             }
             dotw *= -scales;
@@ -140,8 +142,10 @@ __global__ void blu_kkt_rhs_kernel(long long n, int nlin, const double *__restri
 // warp hide the DMMA latency.  Bs (n x QP doubles, tens of MB) is L2 resident, so re-reading two tile columns per
 // pair costs L2 bandwidth only.  Warps are combined in warp order: no partial tiles in HBM, no atomics, bit-reproducible.
 __global__ void __launch_bounds__(BLU_KKT_WARPS * 32)
-blu_kkt_syrk_kernel(const double *__restrict__ Bs, long long n, int Q, int QP, double *__restrict__ cap, double *__restrict__ v)
+blu_kkt_syrk_kernel(const double *__restrict__ Bs, long long n, int QP, double *__restrict__ part)
 {
+    // grid (tile pairs, row splits): more CTAs per SM = more strided L2 reads in flight (one split was latency bound:
+    // long_scoreboard 59 warps per issue, tensor pipe 4 %); partial 8 x 8 tiles, folded in split order by the next kernel
     __shared__ double red[BLU_KKT_WARPS][64];
     const int NTQ = QP >> 3;
     int ti = 0, rem = blockIdx.x;
@@ -149,19 +153,23 @@ blu_kkt_syrk_kernel(const double *__restrict__ Bs, long long n, int Q, int QP, d
     const int tj = ti + rem;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ks = lane & 3, cq = lane >> 2;
+    const long long rows_per = (((n + gridDim.y - 1) / gridDim.y) + 15) / 16 * 16;
+    const long long r0 = (long long)blockIdx.y * rows_per;
+    long long r1 = r0 + rows_per;
+    if (r1 > n) r1 = n;
     double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
     const double *pi = Bs + 8 * ti + cq, *pj = Bs + 8 * tj + cq;
-    for (long long base = (long long)w * 16; base < n; base += (long long)BLU_KKT_WARPS * 16) {
-        double fi[4], fj[4];
+    for (long long base = r0 + (long long)w * 32; base < r1; base += (long long)BLU_KKT_WARPS * 32) {
+        double fi[8], fj[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const long long row = base + 4 * u + ks;
-            const bool ok = row < n;
+            const bool ok = row < r1;
             fi[u] = ok ? __ldg(pi + row * QP) : 0.0;
             fj[u] = ok ? __ldg(pj + row * QP) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) blu_dmma(acc[u][0], acc[u][1], fi[u], fj[u]);
+        for (int u = 0; u < 8; ++u) blu_dmma(acc[u & 3][0], acc[u & 3][1], fi[u], fj[u]);
     }
     const double c0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
     const double c1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
@@ -172,7 +180,23 @@ blu_kkt_syrk_kernel(const double *__restrict__ Bs, long long n, int Q, int QP, d
         double s = 0.0;
 #pragma unroll
         for (int ww = 0; ww < BLU_KKT_WARPS; ++ww) s += red[ww][threadIdx.x];
-        const int r = 8 * ti + (threadIdx.x >> 3), c = 8 * tj + (threadIdx.x & 7);
+        part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + threadIdx.x] = s;
+    }
+}
+
+// cap = I + sum over the row splits (split order) of the partial tiles, mirrored; v = column Q.
+__global__ void blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, int Q, int QP,
+                                       double *__restrict__ cap, double *__restrict__ v)
+{
+    const int NTQ = QP >> 3;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npairs * 64; t += gridDim.x * blockDim.x) {
+        const int p = t >> 6, e = t & 63;
+        int ti = 0, rem = p;
+        while (rem >= NTQ - ti) { rem -= NTQ - ti; ++ti; }
+        const int tj = ti + rem;
+        double s = 0.0;
+        for (int sp = 0; sp < nsplit; ++sp) s += part[((size_t)sp * npairs + p) * 64 + e];
+        const int r = 8 * ti + (e >> 3), c = 8 * tj + (e & 7);
         if (r < Q && c < Q) {
             if (ti != tj || r <= c) {
                 const double val = s + (r == c ? 1.0 : 0.0);
@@ -191,19 +215,32 @@ blu_kkt_chol_kernel(double *__restrict__ cap, int Q, const double *__restrict__ 
     const int ld = Q + 1, tid = threadIdx.x, nthr = blockDim.x;
     for (int t = tid; t < Q * Q; t += nthr) cs[(t / Q) * ld + (t % Q)] = cap[t];
     __syncthreads();
+    // left-looking: column j = (A[j:, j] - L[j:, :j] L[j, :j]^T) / l_jj, thread i owns row i -- two barriers per column,
+    // row reads are conflict free (odd leading dimension), the pivot row is a broadcast
+    __shared__ double s_piv;
     for (int j = 0; j < Q; ++j) {
-        const double djj = cs[j * ld + j];
+        double sv[1];
+        const int i = j + tid;
+        sv[0] = 0.0;
+        if (i < Q) {
+            double acc0 = cs[i * ld + j], acc1 = 0.0;
+            const double *ri = cs + i * ld, *rj = cs + j * ld;
+            int c = 0;
+#pragma unroll 4
+            for (; c + 1 < j; c += 2) {                       // independent loads batched: the plain loop waited ~35 cycles per term
+                acc0 = fma(-ri[c], rj[c], acc0);
+                acc1 = fma(-ri[c + 1], rj[c + 1], acc1);
+            }
+            if (c < j) acc0 = fma(-ri[c], rj[c], acc0);
+            acc0 += acc1;
+            sv[0] = acc0;
+            if (i == j) s_piv = acc0;
+        }
+        __syncthreads();
+        const double djj = s_piv;
         if (!(djj > 0.0)) { if (tid == 0) *info = j + 1; return; }          // same value in every thread
         const double sj = sqrt(djj);
-        __syncthreads();
-        for (int i = j + tid; i < Q; i += nthr) cs[i * ld + j] = (i == j) ? sj : cs[i * ld + j] / sj;
-        __syncthreads();
-        // trailing update of the lower triangle: cs[i][c] -= l_ij l_cj for j < c <= i
-        const int rem = Q - j - 1;
-        for (int t = tid; t < rem * rem; t += nthr) {
-            const int i = j + 1 + t / rem, c = j + 1 + t % rem;
-            if (c <= i) cs[i * ld + c] = fma(-cs[i * ld + j], cs[c * ld + j], cs[i * ld + c]);
-        }
+        if (i < Q) cs[i * ld + j] = (i == j) ? sj : sv[0] / sj;
         __syncthreads();
     }
     // forward and backward substitution by one warp (Q <= 240): lane-strided dot products, shuffle reduction

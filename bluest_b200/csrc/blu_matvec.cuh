@@ -108,7 +108,7 @@ blu_hv_reduce_kernel(const double *__restrict__ U, const double *__restrict__ p,
 template <int NP>
 __global__ void __launch_bounds__(BLU_HVA_THREADS)
 blu_hv_apply_kernel(const double *__restrict__ U, const double *__restrict__ S, int N, const double *__restrict__ t_in,
-                    long long lo, long long hi, double *__restrict__ out)
+                    long long lo, long long hi, double *__restrict__ out, int reverse)
 {
     __shared__ double t[32];
     __shared__ double prod[BLU_HVA_THREADS / 32][32 * (NP + 1)];
@@ -123,7 +123,13 @@ blu_hv_apply_kernel(const double *__restrict__ U, const double *__restrict__ S, 
     const int w = tid >> 5, lane = tid & 31;
     constexpr int NWARP = BLU_HVA_THREADS / 32;
     double *pw = prod[w];
-    for (long long r0 = lo + ((long long)blockIdx.x * NWARP + w) * 32; r0 < hi; r0 += (long long)gridDim.x * NWARP * 32) {
+    // reverse: walk the 32-row blocks from the END of the range.  The reduce pass that precedes this kernel streamed U
+    // front to back, so the last ~100 MB of it are still in the 126 MB L2: reading backwards turns most of this
+    // pass's DRAM traffic into L2 hits when U (168 MB at 20 models) does not fit -- and leaves the FRONT of U in L2
+    // for the next product's reduce pass.
+    const long long nblk = (hi - lo + 31) / 32;
+    for (long long blk = (long long)blockIdx.x * NWARP + w; blk < nblk; blk += (long long)gridDim.x * NWARP) {
+        const long long r0 = lo + (reverse ? (nblk - 1 - blk) : blk) * 32;
         const int nrow = (int)((hi - r0) < 32 ? (hi - r0) : 32);
         const double *ub = U + r0 * NP;
         if (nrow == 32) {
