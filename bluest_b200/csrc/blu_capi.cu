@@ -71,6 +71,10 @@ struct blu_ctx {
     uint8_t *d_gidx = nullptr;
     unsigned *d_gmask = nullptr;
     uint16_t *d_lut = nullptr;
+    unsigned *d_plut = nullptr;          // bank-aware run table of the Phi kernel (blu_phi.cuh)
+    BluChunk *d_wchunks = nullptr;       // Phi kernel: its chunk list laid out warp by warp ...
+    int *d_wstart = nullptr;             // ... and the first chunk of every warp (+ end sentinel)
+    int phi_stages = 2, phi_ns = 2, phi_sd = 0, idsd = 64;
     double *d_cinv = nullptr;
     long long cinv_len = 0, gidx_len = 0;
     double *d_C = nullptr, *d_m = nullptr, *d_part = nullptr, *d_phi = nullptr, *d_pinv = nullptr;
@@ -86,7 +90,7 @@ struct blu_ctx {
     BluTile *d_tiles = nullptr;
     int ntiles = 0, grid_soa = 1;
     BluChunk *d_chunks = nullptr;      // work list of the owned slice (blu_stream.cuh)
-    int nchunks = 0, lutlen = 0, part_rows = 0, phi_warps = BLU_PHI_WARPS;
+    int nchunks = 0, lutlen = 0, plutlen = 0, part_rows = 0, phi_warps = BLU_PHI_WARPS;
     int sd = BLU_CHUNK_DOUBLES + 4;    // stage size (doubles) of the streaming kernels
     bool have_inv = false;
     bool hess_attr_done[3] = {false, false, false};
@@ -167,8 +171,8 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (!c->is_clone) {                // a clone borrows these from its parent
-        cudaFree(c->d_cls); cudaFree(c->d_gidx); cudaFree(c->d_gmask); cudaFree(c->d_lut); cudaFree(c->d_cinv);
-        cudaFree(c->d_C); cudaFree(c->d_chunks); cudaFree(c->d_soa); cudaFree(c->d_soff); cudaFree(c->d_tiles);
+        cudaFree(c->d_cls); cudaFree(c->d_gidx); cudaFree(c->d_gmask); cudaFree(c->d_lut); cudaFree(c->d_plut); cudaFree(c->d_cinv);
+        cudaFree(c->d_C); cudaFree(c->d_chunks); cudaFree(c->d_wchunks); cudaFree(c->d_wstart); cudaFree(c->d_soa); cudaFree(c->d_soff); cudaFree(c->d_tiles);
     }
     cudaFree(c->d_m); cudaFree(c->d_part); cudaFree(c->d_phi); cudaFree(c->d_pinv);
     cudaFree(c->d_x); cudaFree(c->d_S); cudaFree(c->d_grad); cudaFree(c->d_U); cudaFree(c->d_V); cudaFree(c->d_H);
@@ -221,12 +225,68 @@ static int build_chunks(blu_ctx *c)
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     // launch geometry: ~4 chunks per warp, at most two CTAs per SM for the Phi kernel (its partial
     // tiles are reduced by one CTA afterwards), a few more for the gradient kernels
-    const long long want = std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS * 3 - 1) / (BLU_STREAM_WARPS * 3));
-    c->phi_warps = blu_stream_smem_bytes(c->sd, BLU_PHI_WARPS * c->N * c->N, (int)c->cls.size(), c->lutlen, BLU_PHI_WARPS) <= 200 * 1024 ? BLU_PHI_WARPS : 8;
-    c->grid_phi = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + c->phi_warps * 3 - 1) / (c->phi_warps * 3)),
-                                           (long long)c->nsm * (BLU_PHI_WARPS / c->phi_warps));
-    c->grid_phi = std::min(c->grid_phi, BLU_PHI_GROUP * BLU_PHI_MAXGROUPS);
     c->grid_grad = (int)std::min<long long>(std::max<long long>(1, ((long long)c->nchunks + BLU_STREAM_WARPS - 1) / BLU_STREAM_WARPS), (long long)c->nsm * 5);
+    {   // Phi kernel (blu_phi.cuh): its own chunk list (chunk payload and ring depth differ from the gradient kernels'),
+        // laid out warp by warp -- every warp walks a few CONTIGUOUS runs of the list (the register run-length
+        // accumulation carries on across chunks), the runs cut at equal cost and dealt round-robin.
+        const int ns = c->phi_stages == 4 ? 4 : 2;
+        const long long paycap = ns == 4 ? 272 : BLU_CHUNK_DOUBLES;
+        const long long pmaxpay = std::max<long long>(((long long)c->Tmax + 15) / 16 * 16, std::min<long long>(paycap, std::max<long long>(272, share)));
+        const long long pcap = std::max<long long>(std::max<long long>(96, c->Tmax), std::min<long long>(pmaxpay, total / ((long long)c->nsm * BLU_PHI_WARPS * 3)));
+        std::vector<BluChunk> pch;
+        long long idmax = 16;
+        for (size_t ic = 0; ic < c->cls.size(); ++ic) {
+            const BluClass &ci = c->cls[ic];
+            const long long i0 = std::max<long long>(c->lo - ci.goff, 0), i1 = std::min<long long>(c->hi - ci.goff, ci.Lk);
+            if (i1 <= i0) continue;
+            const int G = (int)std::max<long long>(1, std::min<long long>(32, pcap / ci.T));
+            idmax = std::max<long long>(idmax, (long long)G * ci.k);
+            for (long long i = i0; i < i1; i += G) {
+                BluChunk b; b.cls = (int)ic; b.g = (int)std::min<long long>(G, i1 - i); b.i0 = i;
+                pch.push_back(b);
+            }
+        }
+        c->phi_ns = ns;
+        c->phi_sd = (int)(((pmaxpay + 4) + 1) / 2 * 2);
+        c->idsd = (int)((idmax + 15) / 16 * 16 + 48);            // G*k bytes + 16-byte skew, rounded; slack for idle lanes
+        c->phi_warps = blu_phi_smem_bytes(ns, c->phi_sd, c->idsd, c->N, (int)c->cls.size(), BLU_PHI_WARPS) <= 200 * 1024 ? BLU_PHI_WARPS : 8;
+        c->grid_phi = (int)std::min<long long>(std::max<long long>(1, ((long long)pch.size() + c->phi_warps * 3 - 1) / (c->phi_warps * 3)),
+                                               (long long)c->nsm * (BLU_PHI_WARPS / c->phi_warps));
+        c->grid_phi = std::min(c->grid_phi, BLU_PHI_GROUP * BLU_PHI_MAXGROUPS);
+        const int nW = c->grid_phi * c->phi_warps;
+        const int R = pch.size() >= (size_t)nW * 36 ? 12 : (pch.size() >= (size_t)nW * 12 ? 4 : 1);      // runs per warp
+        const size_t nRuns = (size_t)nW * R;
+        std::vector<long long> pre(pch.size() + 1, 0);
+        for (size_t i = 0; i < pch.size(); ++i) pre[i + 1] = pre[i] + (long long)pch[i].g * (c->cls[(size_t)pch[i].cls].psteps + 1) + 6;
+        std::vector<size_t> rs(nRuns + 1, pch.size());
+        rs[0] = 0;
+        {
+            size_t pos = 0;
+            for (size_t j = 1; j < nRuns; ++j) {
+                const long long want_cost = (long long)((__int128)pre[pch.size()] * (long long)j / (long long)nRuns);
+                while (pos < pch.size() && pre[pos] < want_cost) ++pos;
+                rs[j] = pos;
+            }
+        }
+        std::vector<BluChunk> wch;
+        wch.reserve(pch.size());
+        std::vector<int> wst((size_t)nW + 1, 0);
+        for (int w = 0; w < nW; ++w) {
+            wst[(size_t)w] = (int)wch.size();
+            for (int r = 0; r < R; ++r) {
+                const size_t j = (size_t)r * nW + w;
+                for (size_t q = rs[j]; q < rs[j + 1]; ++q) wch.push_back(pch[q]);
+            }
+        }
+        wst[(size_t)nW] = (int)wch.size();
+        if (c->d_wchunks) CUDA_TRY(cudaFree(c->d_wchunks));
+        if (c->d_wstart) CUDA_TRY(cudaFree(c->d_wstart));
+        c->d_wchunks = nullptr; c->d_wstart = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_wchunks, sizeof(BluChunk) * std::max<size_t>(wch.size(), 1)));
+        CUDA_TRY(cudaMalloc(&c->d_wstart, sizeof(int) * wst.size()));
+        if (!wch.empty()) CUDA_TRY(cudaMemcpy(c->d_wchunks, wch.data(), sizeof(BluChunk) * wch.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c->d_wstart, wst.data(), sizeof(int) * wst.size(), cudaMemcpyHostToDevice));
+    }
     if (c->grid_phi > c->part_rows) {
         if (c->d_part) CUDA_TRY(cudaFree(c->d_part));
         c->d_part = nullptr;
@@ -301,6 +361,36 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
                 for (int l = j; l < ci.k; ++l) lut[(size_t)(ci.lutoff + e++)] = (uint16_t)((j << 8) | l);
         }
     }
+    // Run table of the Phi kernel (blu_phi_chunk_run): the packed entries of a class sorted by l DESCENDING (entries
+    // whose target moves most often first) and first-fit packed into half-warps of 16 entries with 16 DIFFERENT
+    // shared-memory banks (packed position mod 16), so a half-warp's staged loads are conflict-free.  Two half-warps
+    // = one 32-lane step.  Word: position | j << 10 | l << 15 | valid << 20.
+    std::vector<unsigned> plut;
+    for (BluClass &ci : c->cls) {
+        struct Ent { int l, j, pos; };
+        std::vector<Ent> ents;
+        for (int j = 0; j < ci.k; ++j)
+            for (int l = j; l < ci.k; ++l) ents.push_back({l, j, blu_pk(ci.k, j, l)});
+        std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.l > b.l; });
+        std::vector<std::vector<Ent>> halves;
+        std::vector<unsigned> used;
+        for (const Ent &en : ents) {
+            const unsigned bit = 1u << (en.pos & 15);
+            size_t h = 0;
+            while (h < halves.size() && (used[h] & bit)) ++h;
+            if (h == halves.size()) { halves.emplace_back(); used.push_back(0u); }
+            halves[h].push_back(en); used[h] |= bit;
+        }
+        ci.plutoff = (int)plut.size();
+        ci.psteps = (int)(halves.size() + 1) / 2;
+        plut.resize(plut.size() + (size_t)ci.psteps * 32, 0u);
+        for (size_t h = 0; h < halves.size(); ++h)
+            for (size_t q = 0; q < halves[h].size(); ++q) {
+                const Ent &en = halves[h][q];
+                plut[(size_t)ci.plutoff + (h / 2) * 32 + (h & 1) * 16 + q] = (unsigned)en.pos | ((unsigned)en.j << 10) | ((unsigned)en.l << 15) | (1u << 20);
+            }
+    }
+    if (plut.empty()) plut.push_back(0u);
     c->inv_set.assign(c->cls.size(), 0);
 
     cudaDeviceProp prop;
@@ -309,9 +399,10 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
     CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CTX_TRY(cudaEventCreate(&e));
     CTX_TRY(cudaMalloc(&c->d_cls, sizeof(BluClass) * c->cls.size()));
-    CTX_TRY(cudaMalloc(&c->d_gidx, std::max<long long>(ioff, 1)));
+    CTX_TRY(cudaMalloc(&c->d_gidx, std::max<long long>(ioff, 1) + 32));                 // + slack for 16-byte rounded bulk copies
     CTX_TRY(cudaMalloc(&c->d_gmask, sizeof(unsigned) * L));
     CTX_TRY(cudaMalloc(&c->d_lut, sizeof(uint16_t) * lut.size()));
+    CTX_TRY(cudaMalloc(&c->d_plut, sizeof(unsigned) * plut.size()));
     CTX_TRY(cudaMalloc(&c->d_cinv, sizeof(double) * (std::max<long long>(coff, 1) + 16)));   // + slack for 16-byte rounded bulk copies
     CTX_TRY(cudaMemsetAsync(c->d_cinv, 0, sizeof(double) * (std::max<long long>(coff, 1) + 16), c->stream));
     CTX_TRY(cudaMemcpyAsync(c->d_cls, c->cls.data(), sizeof(BluClass) * c->cls.size(), cudaMemcpyHostToDevice, c->stream));
@@ -319,7 +410,9 @@ extern "C" int blu_ctx_create(int device, int N, int K, const int64_t *sizes, co
     CTX_TRY(cudaMemcpyAsync(c->d_gmask, gmask.data(), sizeof(unsigned) * L, cudaMemcpyHostToDevice, c->stream));
     CTX_TRY(cudaMemcpyAsync(c->d_lut, lut.data(), sizeof(uint16_t) * lut.size(), cudaMemcpyHostToDevice, c->stream));
 
+    CTX_TRY(cudaMemcpyAsync(c->d_plut, plut.data(), sizeof(unsigned) * plut.size(), cudaMemcpyHostToDevice, c->stream));
     c->lutlen = (int)lut.size();
+    c->plutlen = (int)plut.size();
 
     const size_t NN = (size_t)N * N;
     CTX_TRY(cudaMalloc(&c->d_C, sizeof(double) * NN));
@@ -549,11 +642,10 @@ static int launch_phi(blu_ctx *c, const double *d_m, double delta, int mode)
     // ONE launch: the streaming pass over the packed inverses, the in-kernel two-level reduction of the CTA
     // tiles by the last CTAs to arrive, and the finish step (mode 0/1/2, or 3 = NVLink peer exchange) in that
     // same last CTA (blu_phi.cuh).
-    const int NN = c->N * c->N;
-    const size_t smem = std::max(blu_stream_smem_bytes(c->sd, c->phi_warps * NN, (int)c->cls.size(), c->lutlen, c->phi_warps),
-                                 (size_t)BLU_FIN_SCRATCH_BYTES);
+    const size_t smem = std::max(blu_phi_smem_bytes(c->phi_ns, c->phi_sd, c->idsd, c->N, (int)c->cls.size(), c->phi_warps), (size_t)BLU_FIN_SCRATCH_BYTES);
     blu_phi_partial_kernel<<<c->grid_phi, c->phi_warps * 32, smem, c->stream>>>(
-        c->d_cls, (int)c->cls.size(), c->N, c->d_chunks, c->nchunks, c->sd, c->d_cinv, c->d_lut, c->lutlen, c->d_gmask, d_m, c->d_part, c->d_hdr,
+        c->d_cls, (int)c->cls.size(), c->N, c->d_wchunks, c->d_wstart, c->phi_ns, c->phi_sd, c->idsd, c->d_cinv, c->d_gidx, c->d_lut, c->d_plut,
+        c->d_gmask, d_m, c->d_part, c->d_hdr,
         mode, delta, c->d_phi, c->d_pinv, c->d_x, c->d_S, c->peers);
     KERNEL_CHECK(c);
     return BLU_OK;
@@ -856,6 +948,14 @@ extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
     if (!strcmp(name, "mirror_threads")) { c->mirror_threads = value; return BLU_OK; }
     if (!strcmp(name, "sym_full_rows_pct")) { c->sym_full_rows_pct = value; return BLU_OK; }
     if (!strcmp(name, "hess_onebuf")) { c->hess_onebuf = value != 0; return BLU_OK; }
+    if (!strcmp(name, "phi_stages")) {          // ring depth of the Phi kernel: 2 (4 KB chunks) or 4 (2 KB chunks)
+        if (value != 2 && value != 4) return fail(BLU_ERR_ARG, "phi_stages must be 2 or 4");
+        if (c->is_clone) return fail(BLU_ERR_STATE, "set phi_stages on the parent context");
+        int rc = use(c);
+        if (rc) return rc;
+        c->phi_stages = value;
+        return build_chunks(c);
+    }
     return fail(BLU_ERR_ARG, "unknown option %s", name);
 }
 

@@ -30,6 +30,8 @@ struct BluClass {
     long long ioff;   // offset of the class in gidx (bytes)
     long long coff;   // offset of the class in cinv (doubles)
     int lutoff;       // offset of the class's (j,l) table in the LUT
+    int plutoff;      // offset (32-bit words) of the class's bank-aware run table (Phi kernel, blu_phi.cuh)
+    int psteps;       // 32-lane steps per group in that table
     int pad;
 };
 

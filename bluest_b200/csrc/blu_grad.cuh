@@ -35,7 +35,7 @@ __device__ __forceinline__ double blu_grad_chunk(const double *__restrict__ base
     }
     double mine = 0.0;
     for (int g = 0; g < ng; ++g) {
-        const int gv = ids[g * 32 + lane];
+        const int gv = ids[g * BLU_IDS_LD + lane];
         const double xg = blu_shfl(xv, gv);
         const double *cp = base + g * T;
         double sum = 0.0;
@@ -56,7 +56,7 @@ __device__ __forceinline__ double blu_grad_chunk_any(const double *__restrict__ 
 {
     double mine = 0.0;
     for (int g = 0; g < ng; ++g) {
-        const int gv = ids[g * 32 + lane];
+        const int gv = ids[g * BLU_IDS_LD + lane];
         const double xg = blu_shfl(xv, gv);
         const double *cp = base + g * T;
         double sum = 0.0;
@@ -85,7 +85,7 @@ blu_grad_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChun
     const BluStreamSmem sm = blu_stream_carve(smraw, sd, 0, ncls, lutlen);
     const BluWarpStream ws = blu_stream_begin(sm, sd, cls, ncls, lut, lutlen);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *ids = sm.ids + w * 32 * 32;
+    unsigned char *ids = sm.ids + w * BLU_IDS_BYTES;
     const double xv = lane < N ? xrow[lane] : 0.0;
     const int gw = blockIdx.x * BLU_STREAM_WARPS + w;
     const int nw = gridDim.x * BLU_STREAM_WARPS;
@@ -136,7 +136,7 @@ blu_gradu_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, cons
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) sS[t] = S[t];
     const BluWarpStream ws = blu_stream_begin(sm, sd, cls, ncls, lut, lutlen);       // ends with __syncthreads
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *ids = sm.ids + w * 32 * 32;
+    unsigned char *ids = sm.ids + w * BLU_IDS_BYTES;
     const double xv = lane < N ? xrow[lane] : 0.0;
     const int gw = blockIdx.x * BLU_STREAM_WARPS + w;
     const int nw = gridDim.x * BLU_STREAM_WARPS;
@@ -158,7 +158,7 @@ blu_gradu_kernel(const BluClass *__restrict__ cls, int ncls, int N, int NP, cons
         double mine = 0.0;
         for (int g = 0; g < cur.g; ++g) {
             const unsigned mask = __shfl_sync(BLU_FULL, cur.mask, g);
-            const int gv = ids[g * 32 + lane];
+            const int gv = ids[g * BLU_IDS_LD + lane];
             const double xg = blu_shfl(xv, gv);
             const double *st = base + g * T;
             // lane j < k: row j of Cinv_i x[g_i]
@@ -267,7 +267,7 @@ blu_ysum_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChun
     const BluStreamSmem sm = blu_stream_carve(smraw, sd, BLU_STREAM_WARPS * 32, ncls, lutlen);
     const BluWarpStream ws = blu_stream_begin(sm, sd, cls, ncls, lut, lutlen);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *ids = sm.ids + w * 32 * 32;
+    unsigned char *ids = sm.ids + w * BLU_IDS_BYTES;
     double *yacc = sm.extra + w * 32;
     yacc[lane] = 0.0;
     __syncwarp();
@@ -288,7 +288,7 @@ blu_ysum_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChun
         const double *base = ws.stage[s] + cur.skew;
         blu_expand_ids(cur.mask, k, ids, lane);
         for (int g = 0; g < cur.g; ++g) {
-            const int gv = ids[g * 32 + lane];
+            const int gv = ids[g * BLU_IDS_LD + lane];
             const double sv = lane < k ? sums[ci.ioff + (cur.i0 + g) * k + lane] : 0.0;
             const double *st = base + g * T;
             const int j = lane < k ? lane : k - 1;

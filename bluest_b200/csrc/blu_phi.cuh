@@ -3,17 +3,19 @@
 // N x N pseudo-inverse and the variance (misc.py:463-477, 487-490).
 //
 // blu_phi_partial_kernel: each warp streams chunks of consecutive groups of the packed inverse
-// array through its shared-memory ring (bulk async copies, blu_stream.cuh); lane e of a
-// 32-entry step owns packed entry (j,l) of the group and adds m_i * Cinv_i[j,l] into the warp's
-// PRIVATE N x N accumulator tile in shared memory at (g[j], g[l]).  Inside one group all targets
-// are distinct, so the read-modify-write needs no atomics; groups are separated by __syncwarp().
-// Only the upper triangle is ever touched (groups are sorted, j <= l).  Warps are combined in a
-// fixed order into one partial tile per CTA -- atomic-free and run-to-run deterministic.
-// Groups with m_i == 0 are skipped (they contribute exact zeros): an optimiser iterate with 2N
-// non-zeros reads 2N groups, not 2^N.
+// array through its shared-memory ring (bulk async copies completing on mbarriers).  A lane owns packed
+// entry (j,l) of every group of a class and sums m_i * Cinv_i[j,l] in a REGISTER for as long as the
+// entry's target (g[j], g[l]) stays the same -- in the reference's enumeration order that is a run of
+// many groups -- then adds the run into the warp's PRIVATE N x N accumulator tile in shared memory
+// ("the streaming pass" below).  Inside one flush all targets are distinct, so the read-modify-write
+// needs no atomics.  Only the upper triangle is ever touched (groups are sorted, j <= l).  Warps are
+// combined in a fixed order into one partial tile per CTA -- atomic-free and run-to-run deterministic.
+// Groups with m_i == 0 are skipped (they contribute exact zeros).
 // Also reduced here: the support mask (models touched by groups with |m_i| > 1e-6,
 // misc.py:453-457) and max|m| (early-out of misc.py:464,484) -- both by order-independent
 // integer atomics (OR, MAX on the IEEE bit pattern), hence deterministic.
+// The last CTAs to arrive fold the partial tiles (two levels, fixed order) and the very last one does
+// the finish step in the same launch.
 //
 // blu_phi_finish_kernel (one CTA): fixed-order sum of the CTA partials, mirror, + delta I, then
 // pinv(Phi) by parallel Jacobi, x = first row, S = 2 pinv(Phi), and the variance from the support
@@ -23,7 +25,13 @@
 #include "blu_jacobi.cuh"
 #include "blu_stream.cuh"
 
-#define BLU_PHI_WARPS 16            // one CTA per SM: half as many partial tiles for the finish kernel
+#define BLU_PHI_WARPS 16            // most warps per CTA of the streaming pass (8 when the tiles are large)
+// dynamic shared memory of blu_phi_partial_kernel (layout: see the kernel)
+__host__ __device__ __forceinline__ size_t blu_phi_smem_bytes(int ns, int sd, int idsd, int N, int ncls, int warps)
+{
+    return sizeof(double) * ((size_t)warps * ns * sd + (size_t)warps * N * N) + sizeof(BluClass) * ncls
+           + sizeof(unsigned long long) * warps * 4 + 16 + (size_t)warps * 512 + (size_t)warps * ns * idsd;
+}
 
 __device__ __forceinline__ unsigned long long blu_globaltimer()
 {
@@ -53,61 +61,279 @@ __device__ __forceinline__ double blu_lds_f64(unsigned addr)
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
     return v;
 }
+// staged values: read-only while a chunk is consumed -- no memory clobber, so the loads of the next group may be
+// issued ahead of the tile updates of the current one (volatile keeps them behind the mbarrier wait)
+__device__ __forceinline__ double blu_lds_f64_ro(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void blu_sts_f64(unsigned addr, double v)
 {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-// Consume one staged chunk for the Phi accumulation.  S = ceil(T/32) steps per group, fully
-// unrolled; the lane's (j,l) pairs are fixed for the whole chunk and live in registers.
-template <int S>
-__device__ __forceinline__ void blu_phi_chunk(const double *__restrict__ base, const unsigned short *__restrict__ lt, int T, int ng,
-                                              unsigned live, double mreg, const unsigned char *__restrict__ ids,
-                                              double *__restrict__ acc, int N, int lane)
+// ---- the streaming pass -------------------------------------------------------------------------------------
+// Run-length accumulation in registers over a per-warp bulk-copy ring.
+//
+// In the enumeration order of sap.py:73 (itertools.combinations: last member fastest) consecutive groups of a class
+// share their leading members, so packed entry (j,l) -- target Phi[ids[j], ids[l]] -- keeps its target over a RUN of
+// groups as long as members 0..l stay put.  A lane therefore sums m_i Cinv_i[j,l] in a REGISTER and touches the
+// warp's shared tile only when its target changes (or the warp leaves the class): most of the read-modify-write
+// traffic, whose bank conflicts were 41 % of the round-1 kernel's shared-memory wavefronts, is gone.  The lane <->
+// entry table (plut, built by the host) sorts the entries by l descending, so only the first step(s) of a group ever
+// change target, and packs them into half-warps whose 16 staged values sit in 16 different banks (the staged loads
+// stay conflict-free although the lanes no longer read consecutive entries).
+//
+// A warp walks its own list of chunks (wchunks, laid out per warp by the host: several CONTIGUOUS, cost-balanced
+// runs of the chunk list, so the register runs carry on across chunk boundaries) through an NS-stage ring: a stage
+// holds the packed inverses of one chunk (bulk copy 1) and the member ids of its groups (bulk copy 2: k bytes per
+// group straight from gidx, no mask expansion), both completing on the stage's mbarrier; copies are issued NS-1
+// chunks ahead.  Per chunk the warp works out eff_i = leading members shared with the previous SAMPLED group from
+// the masks (one group per lane) and leaves 16-byte records {m_i, eff_i} in shared memory for the group loop.
+// The order of the additions is fixed by the chunk lists alone: bit-reproducible.  Any group order is handled (a
+// target change is detected from the masks, not assumed); orders without shared prefixes just flush every group.
+//   plut word: bits 0-9 packed position, 10-14 j, 15-19 l, 20 valid
+#define BLU_PHI_RUN_MAXSTEPS 9
+#define BLU_PHI_MAXSTAGES 4
+
+struct BluPhiStream {
+    unsigned val_s, ids_s, bar_s;   // shared addresses of stage 0 (values, ids) and mbarrier 0 of this warp
+    unsigned sdb, idsd;             // stage pitch in bytes (values, ids)
+    unsigned rec_s;                 // the 32 records
+};
+struct BluPhiChunkRegs {
+    int cls, g, skew, skewb;        // skew: bytes to skip in the value stage, skewb: bytes to skip in the id stage
+    double m;                       // m of group (i0 + lane), 0 beyond g
+    unsigned mask;                  // membership mask of group (i0 + lane)
+};
+
+__device__ __forceinline__ void blu_mbar_expect_tx_s(unsigned bar_s, unsigned bytes)
 {
-    int ja[S], la[S];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void blu_bulk_g2s_s(unsigned dst_s, const void *src, unsigned bytes, unsigned bar_s)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
+}
+__device__ __forceinline__ void blu_mbar_wait_s(unsigned bar_s, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BLU_WAIT_S:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BLU_DONE_S;\n"
+        "bra BLU_WAIT_S;\n"
+        "BLU_DONE_S:\n"
+        "}\n" ::"r"(bar_s), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ BluPhiChunkRegs blu_phi_prefetch(const BluChunk ch, const BluClass *__restrict__ scls,
+                                                            const double *__restrict__ cinv, const unsigned char *__restrict__ gidx,
+                                                            const double *__restrict__ m, const unsigned *__restrict__ gmask,
+                                                            const BluPhiStream &ps, const int st, const int lane)
+{
+    BluPhiChunkRegs r;
+    const BluClass ci = scls[ch.cls];
+    const unsigned long long addr = (unsigned long long)(cinv + ci.coff + ch.i0 * ci.T);
+    const unsigned long long addrb = (unsigned long long)(gidx + ci.ioff + ch.i0 * ci.k);
+    r.skew = (int)(addr & 15ull);
+    r.skewb = (int)(addrb & 15ull);
+    r.cls = ch.cls; r.g = ch.g;
+    if (lane == 0) {
+        const unsigned bytes = (unsigned)((r.skew + ch.g * ci.T * 8 + 15) & ~15);
+        const unsigned bytesb = (unsigned)((r.skewb + ch.g * ci.k + 15) & ~15);
+        const unsigned bar = ps.bar_s + 8u * st;
+        blu_mbar_expect_tx_s(bar, bytes + bytesb);
+        blu_bulk_g2s_s(ps.val_s + ps.sdb * st, (const void *)(addr & ~15ull), bytes, bar);
+        blu_bulk_g2s_s(ps.ids_s + ps.idsd * st, (const void *)(addrb & ~15ull), bytesb, bar);
+    }
+    const long long gi = ci.goff + ch.i0 + lane;
+    const bool ok = lane < ch.g;
+    r.m = ok ? m[gi] : 0.0;
+    r.mask = ok ? gmask[gi] : 0u;
+    return r;
+}
+
+__device__ __forceinline__ unsigned blu_lds_u8(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// The groups of one landed chunk.  DENSE: every group of the chunk is sampled (no per-group test).
+template <int S, bool DENSE>
+__device__ __forceinline__ void blu_phi_groups(const int ng, const unsigned live, unsigned cp_s, unsigned idp_s, unsigned rp_s,
+                                               const int T, const int k, const int N, const int pmin, const unsigned acc_s,
+                                               const unsigned (&off)[S], const int (&js)[S], const int (&ls)[S],
+                                               unsigned (&pt)[S], double (&ar)[S])
+{
+#ifdef BLU_PHI_NOCOMPUTE
+    return;                                                       // lab switch: the ring alone (wrong results)
+#endif
+    for (int g = 0; g < ng; ++g, cp_s += 8u * T, idp_s += k, rp_s += 16u) {
+        if (!DENSE && !((live >> g) & 1u)) continue;              // m_i == 0 contributes exact zeros
+        // every shared load of the group is issued up front (one latency per group, not a chain of them): the
+        // record, the staged values, and for step 0 -- whose lanes change target with almost every group -- the
+        // candidate member ids and the pending tile entry
+        unsigned lo, hi, e, pad;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(e), "=r"(pad) : "r"(rp_s) : "memory");
+        double v[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) v[s] = blu_lds_f64_ro(cp_s + off[s]);
+        unsigned a0 = 0u, b0 = 0u;
+        double old0 = 0.0;
+        if (ls[0] >= pmin) {                                      // pmin: smallest eff of the chunk -- lanes below it never move here
+            a0 = blu_lds_u8(idp_s + js[0]); b0 = blu_lds_u8(idp_s + ls[0]);
+            old0 = blu_lds_f64_ro(pt[0]);
+        }
+        const double mi = __hiloint2double((int)hi, (int)lo);
+        const int pend = (int)e;
+        if (ls[0] >= pend) {                                      // this lane's target moves with this group
+            blu_sts_f64(pt[0], old0 + ar[0]);
+            ar[0] = 0.0;
+            pt[0] = acc_s + 8u * (a0 * N + b0);
+        }
+        ar[0] = fma(mi, v[0], ar[0]);
+#pragma unroll
+        for (int s = 1; s < S; ++s) {
+            const bool p = ls[s] >= pend;
+            if (__any_sync(BLU_FULL, p)) {                        // steps > 0 hold low-l entries: they rarely move
+                if (p) {
+                    const unsigned a = blu_lds_u8(idp_s + js[s]), b = blu_lds_u8(idp_s + ls[s]);
+                    blu_sts_f64(pt[s], blu_lds_f64(pt[s]) + ar[s]);
+                    ar[s] = 0.0;
+                    pt[s] = acc_s + 8u * (a * N + b);
+                }
+            }
+            ar[s] = fma(mi, v[s], ar[s]);
+        }
+        __syncwarp();                                             // tile updates of different groups stay ordered
+    }
+}
+
+// Loop state of a warp's walk over its chunk list.
+template <int NS>
+struct BluPhiWalk {
+    int c, c1, it;                  // next chunk to consume, end of the list, chunks consumed so far (ring position)
+    BluPhiChunkRegs q[NS - 1];      // registers of chunks c .. c+NS-2 (copies in flight or landed)
+    BluChunk dnext;                 // descriptor of chunk c + NS - 1, fetched one chunk early
+    unsigned supp;
+    double mymax;
+#ifdef BLU_PHI_PROFILE
+    long long tpre, texp, twait, tloop;
+#endif
+};
+
+// Consume chunks c, c+1, ... of the walk for as long as they belong to class `mycls` (S steps per group).
+template <int S, int NS>
+__device__ __forceinline__ void blu_phi_class_run(BluPhiWalk<NS> &wk, const int mycls, const BluClass ci, const unsigned *__restrict__ plt,
+                                                  const BluChunk *__restrict__ chunks, const BluClass *__restrict__ scls,
+                                                  const double *__restrict__ cinv, const unsigned char *__restrict__ gidx,
+                                                  const double *__restrict__ m, const unsigned *__restrict__ gmask,
+                                                  const BluPhiStream &ps, double *__restrict__ acc, const int N, const int lane)
+{
+    constexpr int D = NS - 1;
+    unsigned off[S], pt[S];
+    int js[S], ls[S];
+    double ar[S];
+    const unsigned acc_s = blu_smem_u32(acc);
+    const int T = ci.T, k = ci.k;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const int e = s * 32 + lane;
-        const unsigned jl = e < T ? lt[e] : 0u;
-        ja[s] = jl >> 8; la[s] = jl & 255u;
+        const unsigned wd = __ldg(plt + s * 32 + lane);          // global (L1-resident): one coalesced line per step
+        const bool valid = (wd >> 20) & 1u;
+        off[s] = 8u * (wd & 1023u);
+        js[s] = (int)((wd >> 10) & 31u);
+        ls[s] = valid ? (int)((wd >> 15) & 31u) : -1;            // -1: idle lane of a partly filled step, never flushes
+        ar[s] = 0.0;
+        pt[s] = acc_s;                                           // nothing pending: the first flush adds 0.0 to acc[0]
     }
-    const unsigned acc_s = blu_smem_u32(acc);
-    const unsigned ids_s = blu_smem_u32(ids) + lane;
-    unsigned cp_s = blu_smem_u32(base) + 8u * lane;       // staged entry `lane` of the current group
-    for (int g = 0; g < ng; ++g, cp_s += 8u * T) {
-        if (!((live >> g) & 1u)) continue;                // m_i == 0 contributes exact zeros
-        const double mi = blu_shfl(mreg, g);
-        unsigned gv;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(gv) : "r"(ids_s + 32u * g) : "memory");
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const bool ok = s * 32 + lane < T;
-            const double v = ok ? blu_lds_f64(cp_s + 256u * s) : 0.0;
-            const int a = __shfl_sync(BLU_FULL, (int)gv, ja[s]);
-            const int b = __shfl_sync(BLU_FULL, (int)gv, la[s]);
-            if (ok) {
-                const unsigned at = acc_s + 8u * (unsigned)(a * N + b);
-                blu_sts_f64(at, fma(mi, v, blu_lds_f64(at)));
-            }
+    unsigned lastmask = 0u;
+    bool havelast = false;
+    do {
+        const int st = wk.it & (NS - 1);
+        BluPhiChunkRegs nxt;
+#ifdef BLU_PHI_PROFILE
+        const long long tp0 = clock64();
+#endif
+        if (wk.c + D < wk.c1) nxt = blu_phi_prefetch(wk.dnext, scls, cinv, gidx, m, gmask, ps, (wk.it + D) & (NS - 1), lane);
+#ifdef BLU_PHI_PROFILE
+        const long long tp1 = clock64(); wk.tpre += tp1 - tp0;
+#endif
+        if (wk.c + D + 1 < wk.c1) wk.dnext = chunks[wk.c + D + 1];
+        const BluPhiChunkRegs cur = wk.q[0];
+        const double am = fabs(cur.m);
+        wk.mymax = fmax(wk.mymax, am);
+        if (am > 1.0e-6) wk.supp |= cur.mask;
+        const unsigned live = __ballot_sync(BLU_FULL, cur.m != 0.0);
+        const unsigned bar = ps.bar_s + 8u * st;
+        const unsigned parity = (unsigned)((wk.it / NS) & 1);
+        if (live) {
+            // members shared with the previous SAMPLED group (lane g: group g): entries with l below that keep their target
+            const unsigned below = live & ((1u << lane) - 1u);
+            const int pl = 31 - __clz(below);                     // -1: none in this chunk -> the last sampled group before it
+            unsigned pm = __shfl_sync(BLU_FULL, cur.mask, pl < 0 ? 0 : pl);
+            if (pl < 0) pm = lastmask;
+            const unsigned x = cur.mask ^ pm;
+            int eff = x ? __popc(cur.mask & ((1u << (__ffs(x) - 1)) - 1u)) : k;
+            if (pl < 0 && !havelast) eff = 0;
+            lastmask = __shfl_sync(BLU_FULL, cur.mask, 31 - __clz(live));
+            havelast = true;
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ps.rec_s + 16u * lane), "r"((unsigned)__double2loint(cur.m)),
+                         "r"((unsigned)__double2hiint(cur.m)), "r"((unsigned)eff), "r"(0u) : "memory");
+            __syncwarp();
+            const int pmin = __reduce_min_sync(BLU_FULL, ((live >> lane) & 1u) ? eff : 32);
+#ifdef BLU_PHI_PROFILE
+            const long long tw0 = clock64(); wk.texp += tw0 - tp1;
+#endif
+            blu_mbar_wait_s(bar, parity);                         // everything above overlapped the copies
+#ifdef BLU_PHI_PROFILE
+            const long long tw1 = clock64(); wk.twait += tw1 - tw0;
+#endif
+            const unsigned cp_s = ps.val_s + ps.sdb * st + (unsigned)cur.skew;
+            const unsigned idp_s = ps.ids_s + ps.idsd * st + (unsigned)cur.skewb;
+            if (live == (cur.g >= 32 ? BLU_FULL : (1u << cur.g) - 1u))
+                blu_phi_groups<S, true>(cur.g, live, cp_s, idp_s, ps.rec_s, T, k, N, pmin, acc_s, off, js, ls, pt, ar);
+            else
+                blu_phi_groups<S, false>(cur.g, live, cp_s, idp_s, ps.rec_s, T, k, N, pmin, acc_s, off, js, ls, pt, ar);
+#ifdef BLU_PHI_PROFILE
+            wk.tloop += clock64() - tw1;
+#endif
+        } else {
+            blu_mbar_wait_s(bar, parity);                         // the stage must have landed before it is reused
         }
+        __syncwarp();                                             // stage and records consumed before they are rewritten
+#pragma unroll
+        for (int d = 0; d + 1 < D; ++d) wk.q[d] = wk.q[d + 1];
+        wk.q[D - 1] = nxt;
+        ++wk.c; ++wk.it;
+    } while (wk.c < wk.c1 && wk.q[0].cls == mycls);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {                                 // leaving the class: everything still in registers
+        if (ls[s] >= 0) blu_sts_f64(pt[s], blu_lds_f64(pt[s]) + ar[s]);
         __syncwarp();
     }
 }
-// generic step count (k > 22)
-__device__ __forceinline__ void blu_phi_chunk_any(const double *__restrict__ base, const unsigned short *__restrict__ lt, int T, int ng,
+
+// generic step count (groups of more than 23 members): classic walk, lane = packed entry, tile update per entry
+__device__ __forceinline__ void blu_phi_chunk_any(const double *__restrict__ base, const unsigned short *__restrict__ lt, int T, int k, int ng,
                                                   unsigned live, double mreg, const unsigned char *__restrict__ ids,
                                                   double *__restrict__ acc, int N, int lane)
 {
     for (int g = 0; g < ng; ++g) {
         if (!((live >> g) & 1u)) continue;
         const double mi = blu_shfl(mreg, g);
-        const int gv = ids[g * 32 + lane];
+        const int gv = lane < k ? ids[g * k + lane] : 0;
         const double *cp = base + g * T;
         for (int e0 = 0; e0 < T; e0 += 32) {
             const int e = e0 + lane;
             const bool ok = e < T;
-            const unsigned jl = ok ? lt[e] : 0u;
+            const unsigned jl = ok ? __ldg(lt + e) : 0u;
             const double v = ok ? cp[e] : 0.0;
             const int a = __shfl_sync(BLU_FULL, gv, jl >> 8);
             const int b = __shfl_sync(BLU_FULL, gv, jl & 255u);
@@ -115,6 +341,67 @@ __device__ __forceinline__ void blu_phi_chunk_any(const double *__restrict__ bas
         }
         __syncwarp();
     }
+}
+
+// The whole streaming pass of one warp: chunks wstart[gw] .. wstart[gw+1]-1 of wchunks.
+template <int NS>
+__device__ __forceinline__ void blu_phi_walk(const int c0, const int c1, const BluChunk *__restrict__ chunks, const BluClass *__restrict__ scls,
+                                             const double *__restrict__ cinv, const unsigned char *__restrict__ gidx,
+                                             const unsigned short *__restrict__ lut, const unsigned *__restrict__ plut,
+                                             const double *__restrict__ m, const unsigned *__restrict__ gmask,
+                                             const BluPhiStream &ps, double *__restrict__ acc, const int N, const int lane,
+                                             unsigned &supp_out, double &max_out, BluEvalHeader *blu_prof_hdr)
+{
+    constexpr int D = NS - 1;
+    BluPhiWalk<NS> wk;
+    wk.c = c0; wk.c1 = c1; wk.it = 0; wk.supp = 0u; wk.mymax = 0.0;
+#ifdef BLU_PHI_PROFILE
+    wk.tpre = wk.texp = wk.twait = wk.tloop = 0;
+#endif
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        if (c0 + d < c1) wk.q[d] = blu_phi_prefetch(chunks[c0 + d], scls, cinv, gidx, m, gmask, ps, d, lane);
+    if (c0 + D < c1) wk.dnext = chunks[c0 + D];
+    while (wk.c < wk.c1) {
+        const int mycls = wk.q[0].cls;
+        const BluClass ci = scls[mycls];
+        const unsigned *plt = plut + ci.plutoff;
+#define BLU_PHI_RUN_CASE(S_) case S_: blu_phi_class_run<S_, NS>(wk, mycls, ci, plt, chunks, scls, cinv, gidx, m, gmask, ps, acc, N, lane); break;
+        switch (ci.psteps) {
+            BLU_PHI_RUN_CASE(1) BLU_PHI_RUN_CASE(2) BLU_PHI_RUN_CASE(3) BLU_PHI_RUN_CASE(4) BLU_PHI_RUN_CASE(5)
+            BLU_PHI_RUN_CASE(6) BLU_PHI_RUN_CASE(7) BLU_PHI_RUN_CASE(8) BLU_PHI_RUN_CASE(9)
+            default: {                                    // very large groups: one chunk at a time, classic walk
+                const int st = wk.it & (NS - 1);
+                BluPhiChunkRegs nxt;
+                if (wk.c + D < wk.c1) nxt = blu_phi_prefetch(wk.dnext, scls, cinv, gidx, m, gmask, ps, (wk.it + D) & (NS - 1), lane);
+                if (wk.c + D + 1 < wk.c1) wk.dnext = chunks[wk.c + D + 1];
+                const BluPhiChunkRegs cur = wk.q[0];
+                const double am = fabs(cur.m);
+                wk.mymax = fmax(wk.mymax, am);
+                if (am > 1.0e-6) wk.supp |= cur.mask;
+                const unsigned live = __ballot_sync(BLU_FULL, cur.m != 0.0);
+                blu_mbar_wait_s(ps.bar_s + 8u * st, (unsigned)((wk.it / NS) & 1));
+                if (live) {
+                    const double *base = reinterpret_cast<const double *>(__cvta_shared_to_generic(ps.val_s + ps.sdb * st + (unsigned)cur.skew));
+                    const unsigned char *idb = reinterpret_cast<const unsigned char *>(__cvta_shared_to_generic(ps.ids_s + ps.idsd * st + (unsigned)cur.skewb));
+                    blu_phi_chunk_any(base, lut + ci.lutoff, ci.T, ci.k, cur.g, live, cur.m, idb, acc, N, lane);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d + 1 < D; ++d) wk.q[d] = wk.q[d + 1];
+                wk.q[D - 1] = nxt;
+                ++wk.c; ++wk.it;
+            } break;
+        }
+#undef BLU_PHI_RUN_CASE
+    }
+    supp_out = wk.supp; max_out = wk.mymax;
+#ifdef BLU_PHI_PROFILE
+    if (lane == 0) {
+        atomicAdd(&blu_prof_hdr->stamp[13], (unsigned long long)wk.tpre); atomicAdd(&blu_prof_hdr->stamp[14], (unsigned long long)wk.texp);
+        atomicAdd(&blu_prof_hdr->stamp[10], (unsigned long long)wk.twait); atomicAdd(&blu_prof_hdr->stamp[15], (unsigned long long)wk.tloop);
+    }
+#endif
 }
 
 // Block-parallel in-place Gauss-Jordan inverse of the SPD n x n matrix in A (ld BLU_JLD), ping-pong
@@ -479,10 +766,12 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
     blu_finish_body(N, delta, mode, nparts == 0, phi, pinv, xrow, S, hdr, peers, f, tid, nthr);
 }
 
-// `chunks` lists the work of this launch (whole context or the owned slice); see blu_stream.cuh.
+// `wchunks` lists the work of this launch (whole context or the owned slice) warp by warp: warp w of the grid walks
+// wchunks[wstart[w] .. wstart[w+1]).  ns: ring stages (2 or 4).  Dynamic shared memory: blu_phi_smem_bytes.
 __global__ void __launch_bounds__(BLU_PHI_WARPS * 32)
-blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ chunks, int nchunks, int sd,
-                       const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
+blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ wchunks, const int *__restrict__ wstart,
+                       int ns, int sd, int idsd, const double *__restrict__ cinv, const unsigned char *__restrict__ gidx,
+                       const unsigned short *__restrict__ lut, const unsigned *__restrict__ plut,
                        const unsigned *__restrict__ gmask, const double *__restrict__ m,
                        double *__restrict__ part, BluEvalHeader *hdr,
                        int fin_mode, double delta, double *__restrict__ phi, double *__restrict__ pinv, double *__restrict__ xrow,
@@ -491,55 +780,49 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
     extern __shared__ __align__(16) unsigned char smraw[];
     const int NN = N * N;
     const int nwarps = blockDim.x >> 5;                  // 16 normally, 8 when N is large (shared-memory budget)
-    const BluStreamSmem sm = blu_stream_carve(smraw, sd, nwarps * NN, ncls, lutlen, nwarps);
-    const BluWarpStream ws = blu_stream_begin(sm, sd, cls, ncls, lut, lutlen);
+    // shared memory: [value stages warps x ns x sd doubles][tiles warps x N*N][class table][mbarriers warps x 4]
+    //                [records warps x 32 x 16 B][id stages warps x ns x idsd bytes]      (blu_phi_smem_bytes)
+    // The run table (plut) and, for the generic fallback of very large groups, the classic (j,l) table are read from
+    // global memory: shared memory decides how many CTAs fit on an SM.
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *acc = sm.extra + w * NN;                     // this warp's private N x N tile
-    unsigned char *ids = sm.ids + w * 32 * 32;
-    for (int t = lane; t < NN; t += 32) acc[t] = 0.0;
-    __syncwarp();
-
-    unsigned supp = 0u;
-    double mymax = 0.0;
-    const int gw = blockIdx.x * nwarps + w;
-    const int nw = gridDim.x * nwarps;
-
-    int c = gw;
-    BluChunkRegs cur, nxt;
-    BluChunk dnext;                                       // descriptor of chunk c + nw, fetched one round early
-    if (c < nchunks) cur = blu_prefetch_chunk(chunks[c], sm.cls, cinv, m, gmask, ws, 0, lane);
-    if (c + nw < nchunks) dnext = chunks[c + nw];
-    for (int it = 0; c < nchunks; c += nw, ++it) {
-        const int s = it & 1;
-        if (c + nw < nchunks) nxt = blu_prefetch_chunk(dnext, sm.cls, cinv, m, gmask, ws, s ^ 1, lane);
-        if (c + 2 * nw < nchunks) dnext = chunks[c + 2 * nw];
-        const BluClass ci = sm.cls[cur.cls];
-        const int T = ci.T;
-        const unsigned short *lt = sm.lut + ci.lutoff;
-        const double am = fabs(cur.m);
-        mymax = fmax(mymax, am);
-        if (am > 1.0e-6) supp |= cur.mask;
-        const unsigned live = __ballot_sync(BLU_FULL, cur.m != 0.0);
-        blu_mbar_wait(ws.bar[s], (unsigned)((it >> 1) & 1));
-        const double *base = ws.stage[s] + cur.skew;
-        if (live) {
-            blu_expand_ids(cur.mask, ci.k, ids, lane);
-            switch ((T + 31) >> 5) {
-                case 1: blu_phi_chunk<1>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-                case 2: blu_phi_chunk<2>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-                case 3: blu_phi_chunk<3>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-                case 4: blu_phi_chunk<4>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-                case 5: blu_phi_chunk<5>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-                case 6: blu_phi_chunk<6>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-                case 7: blu_phi_chunk<7>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-                case 8: blu_phi_chunk<8>(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-                default: blu_phi_chunk_any(base, lt, T, cur.g, live, cur.m, ids, acc, N, lane); break;
-            }
-        }
-        __syncwarp();                                     // stage s fully consumed before it is refilled
-        cur = nxt;
+    double *stages = reinterpret_cast<double *>(smraw);
+    double *tiles = stages + (size_t)nwarps * ns * sd;
+    BluClass *scls = reinterpret_cast<BluClass *>(tiles + (size_t)nwarps * NN);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(scls + ncls);
+    unsigned char *recs = reinterpret_cast<unsigned char *>(bars + nwarps * BLU_PHI_MAXSTAGES);
+    recs += (16 - (blu_smem_u32(recs) & 15u)) & 15u;
+    unsigned char *idst = recs + (size_t)nwarps * 512;
+    for (int t = threadIdx.x; t < ncls; t += blockDim.x) scls[t] = cls[t];
+    BluPhiStream ps;
+    ps.sdb = 8u * (unsigned)sd; ps.idsd = (unsigned)idsd;
+    ps.val_s = blu_smem_u32(stages + (size_t)w * ns * sd);
+    ps.ids_s = blu_smem_u32(idst + (size_t)w * ns * idsd);
+    ps.bar_s = blu_smem_u32(bars + w * BLU_PHI_MAXSTAGES);
+    ps.rec_s = blu_smem_u32(recs + (size_t)w * 512);
+    if (lane == 0) {
+        for (int q = 0; q < ns; ++q) blu_mbar_init(bars + w * BLU_PHI_MAXSTAGES + q, 1);
+        blu_mbar_fence_init();
     }
-    supp = __reduce_or_sync(BLU_FULL, supp);
+    double *acc = tiles + w * NN;                        // this warp's private N x N tile
+    for (int t = lane; t < NN; t += 32) acc[t] = 0.0;
+    __syncthreads();
+
+    const int gw = blockIdx.x * nwarps + w;
+    unsigned wsupp = 0u;
+    double mymax = 0.0;
+#ifdef BLU_PHI_PROFILE
+    const long long prof_t0 = clock64();
+#endif
+    if (ns == 4) blu_phi_walk<4>(wstart[gw], wstart[gw + 1], wchunks, scls, cinv, gidx, lut, plut, m, gmask, ps, acc, N, lane, wsupp, mymax, hdr);
+    else         blu_phi_walk<2>(wstart[gw], wstart[gw + 1], wchunks, scls, cinv, gidx, lut, plut, m, gmask, ps, acc, N, lane, wsupp, mymax, hdr);
+#ifdef BLU_PHI_PROFILE
+    if (lane == 0) {
+        atomicAdd(&hdr->stamp[11], (unsigned long long)(clock64() - prof_t0));
+        atomicAdd(&hdr->stamp[12], 1ull);
+        atomicMax(&hdr->stamp[8], (unsigned long long)(clock64() - prof_t0));
+    }
+#endif
+    unsigned supp = __reduce_or_sync(BLU_FULL, wsupp);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mymax = fmax(mymax, __shfl_xor_sync(BLU_FULL, mymax, o));
     if (lane == 0) {
@@ -549,7 +832,7 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
     __syncthreads();
     for (int t = threadIdx.x; t < NN; t += blockDim.x) {
         double sum = 0.0;
-        for (int ww = 0; ww < nwarps; ++ww) sum += sm.extra[ww * NN + t];
+        for (int ww = 0; ww < nwarps; ++ww) sum += tiles[ww * NN + t];
         part[(long long)blockIdx.x * NN + t] = sum;
     }
     if (fin_mode < 0) return;                             // partial tiles only (stand-alone finish kernel follows)

@@ -98,6 +98,10 @@ __device__ __forceinline__ BluChunkRegs blu_prefetch_chunk(const BluChunk ch, co
 //   [stages  WARPS x 2 x sd doubles][extra doubles (kernel specific)]
 //   [class table][(j,l) LUT u16][mbarriers WARPS x 2][member-id scratch WARPS x 32 groups x 32 bytes]
 #define BLU_STREAM_WARPS 8
+// member-id scratch of one warp: 32 groups x BLU_IDS_LD bytes.  Row pitch 33 (not 32): lane g writes byte j of ITS row
+// when the masks are expanded, and with a pitch of 32 the 32 lanes hit 4 banks (8-way conflict per store).
+#define BLU_IDS_LD 33
+#define BLU_IDS_BYTES 1088                          // 32 * 33 rounded up to 64
 
 struct BluStreamSmem {
     double *stages;
@@ -114,7 +118,7 @@ __host__ __device__ __forceinline__ size_t blu_stream_smem_bytes(int sd, int ext
     b += sizeof(BluClass) * ncls;
     b += ((sizeof(unsigned short) * lutlen + 7) / 8) * 8;
     b += sizeof(unsigned long long) * warps * 2;
-    b += warps * 32 * 32;
+    b += (size_t)warps * BLU_IDS_BYTES;
     return b;
 }
 
@@ -154,7 +158,7 @@ __device__ __forceinline__ void blu_expand_ids(unsigned mask, int k, unsigned ch
     unsigned mk = mask;
     for (int j = 0; j < k; ++j) {
         const int b = __ffs(mk) - 1;
-        ids[lane * 32 + j] = (unsigned char)(b < 0 ? 0 : b);
+        ids[lane * BLU_IDS_LD + j] = (unsigned char)(b < 0 ? 0 : b);
         mk &= mk - 1u;
     }
     __syncwarp();

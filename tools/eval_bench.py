@@ -14,6 +14,8 @@ groups = blu.enumerate_groups(N, K)
 L = sum(len(g) for g in groups)
 t0 = time.perf_counter()
 sap = blu.SAP(C, K, groups, np.ones(L), verbose=False)
+if os.environ.get("BLU_PHI_STAGES"):
+    sap.set_option("phi_stages", int(os.environ["BLU_PHI_STAGES"]))
 sap.sync()
 print("N=%d K=%d L=%d setup %.3f s (n_fallback=%d)" % (N, K, L, time.perf_counter() - t0, sap.n_fallback))
 m = torch.from_numpy(orc.dense_m(L, 0)).cuda()
