@@ -274,7 +274,7 @@ static int build_chunks(blu_ctx *c)
         for (int w = 0; w < nW; ++w) {
             wst[(size_t)w] = (int)wch.size();
             for (int r = 0; r < R; ++r) {
-                const size_t j = (size_t)r * nW + w;
+                const size_t j = (size_t)r * nW + ((r & 1) ? nW - 1 - w : w);   // serpentine: errors of the cost model that grow along the list cancel
                 for (size_t q = rs[j]; q < rs[j + 1]; ++q) wch.push_back(pch[q]);
             }
         }
@@ -931,6 +931,13 @@ extern "C" int blu_ctx_last_stamps(blu_ctx *c, unsigned long long *stamps16)
     memcpy(stamps16, c->h_hdr->stamp, sizeof(unsigned long long) * 16);
     return BLU_OK;
 }
+
+#ifdef BLU_PHI_PROFILE
+extern "C" int blu_prof_warp_read(long long *out, int nwarps)
+{
+    return cudaMemcpyFromSymbol(out, blu_prof_warp, sizeof(long long) * 4 * (size_t)nwarps) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // Options: "soa" (default 1) -- gradient / U,V kernels on the group-interleaved copy of the inverses
 // (blu_soa.cuh); 0 selects the entry-per-lane kernels of blu_grad.cuh on the group-major copy.

@@ -97,6 +97,9 @@ __device__ __forceinline__ void blu_sts_f64(unsigned addr, double v)
 //   plut word: bits 0-9 packed position, 10-14 j, 15-19 l, 20 valid
 #define BLU_PHI_RUN_MAXSTEPS 9
 #define BLU_PHI_MAXSTAGES 4
+#ifdef BLU_PHI_PROFILE
+__device__ long long blu_prof_warp[8192][4];     // per warp of the grid: total cycles, group-loop cycles, chunks, groups
+#endif
 
 struct BluPhiStream {
     unsigned val_s, ids_s, bar_s;   // shared addresses of stage 0 (values, ids) and mbarrier 0 of this warp
@@ -165,16 +168,31 @@ __device__ __forceinline__ unsigned blu_lds_u8(unsigned addr)
     return v;
 }
 
+// predicated shared loads that leave the destination untouched when the predicate is off (no per-iteration zeroing)
+__device__ __forceinline__ void blu_lds_u8_if(unsigned &dst, unsigned addr, int on)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %2, 0;\n@p ld.shared.u8 %0, [%1];\n}\n" : "+r"(dst) : "r"(addr), "r"(on));
+}
+__device__ __forceinline__ void blu_lds_f64_if(double &dst, unsigned addr, int on)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %2, 0;\n@p ld.shared.f64 %0, [%1];\n}\n" : "+d"(dst) : "r"(addr), "r"(on));
+}
+
 // The groups of one landed chunk.  DENSE: every group of the chunk is sampled (no per-group test).
+// lrest: largest l among the entries of steps 1..S-1 (warp-uniform): those steps are looked at only when a group
+// moves a member that low.  n8 = 8 N.
 template <int S, bool DENSE>
 __device__ __forceinline__ void blu_phi_groups(const int ng, const unsigned live, unsigned cp_s, unsigned idp_s, unsigned rp_s,
-                                               const int T, const int k, const int N, const int pmin, const unsigned acc_s,
+                                               const int T, const int k, const unsigned n8, const int pmin, const int lrest, const unsigned acc_s,
                                                const unsigned (&off)[S], const int (&js)[S], const int (&ls)[S],
                                                unsigned (&pt)[S], double (&ar)[S])
 {
 #ifdef BLU_PHI_NOCOMPUTE
     return;                                                       // lab switch: the ring alone (wrong results)
 #endif
+    const int early = ls[0] >= pmin;                              // pmin: smallest eff of the chunk -- lanes below it never move here
+    unsigned a0 = 0u, b0 = 0u;
+    double old0 = 0.0;
     for (int g = 0; g < ng; ++g, cp_s += 8u * T, idp_s += k, rp_s += 16u) {
         if (!DENSE && !((live >> g) & 1u)) continue;              // m_i == 0 contributes exact zeros
         // every shared load of the group is issued up front (one latency per group, not a chain of them): the
@@ -185,33 +203,30 @@ __device__ __forceinline__ void blu_phi_groups(const int ng, const unsigned live
         double v[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) v[s] = blu_lds_f64_ro(cp_s + off[s]);
-        unsigned a0 = 0u, b0 = 0u;
-        double old0 = 0.0;
-        if (ls[0] >= pmin) {                                      // pmin: smallest eff of the chunk -- lanes below it never move here
-            a0 = blu_lds_u8(idp_s + js[0]); b0 = blu_lds_u8(idp_s + ls[0]);
-            old0 = blu_lds_f64_ro(pt[0]);
-        }
+        blu_lds_u8_if(a0, idp_s + js[0], early);
+        blu_lds_u8_if(b0, idp_s + ls[0], early);
+        blu_lds_f64_if(old0, pt[0], early);
         const double mi = __hiloint2double((int)hi, (int)lo);
         const int pend = (int)e;
         if (ls[0] >= pend) {                                      // this lane's target moves with this group
             blu_sts_f64(pt[0], old0 + ar[0]);
             ar[0] = 0.0;
-            pt[0] = acc_s + 8u * (a0 * N + b0);
+            pt[0] = acc_s + a0 * n8 + 8u * b0;
         }
         ar[0] = fma(mi, v[0], ar[0]);
+        if (S > 1 && lrest >= pend) {                             // warp-uniform (pend comes from the record, lrest from the table)
 #pragma unroll
-        for (int s = 1; s < S; ++s) {
-            const bool p = ls[s] >= pend;
-            if (__any_sync(BLU_FULL, p)) {                        // steps > 0 hold low-l entries: they rarely move
-                if (p) {
+            for (int s = 1; s < S; ++s) {
+                if (ls[s] >= pend) {
                     const unsigned a = blu_lds_u8(idp_s + js[s]), b = blu_lds_u8(idp_s + ls[s]);
                     blu_sts_f64(pt[s], blu_lds_f64(pt[s]) + ar[s]);
                     ar[s] = 0.0;
-                    pt[s] = acc_s + 8u * (a * N + b);
+                    pt[s] = acc_s + a * n8 + 8u * b;
                 }
             }
-            ar[s] = fma(mi, v[s], ar[s]);
         }
+#pragma unroll
+        for (int s = 1; s < S; ++s) ar[s] = fma(mi, v[s], ar[s]);
         __syncwarp();                                             // tile updates of different groups stay ordered
     }
 }
@@ -253,6 +268,11 @@ __device__ __forceinline__ void blu_phi_class_run(BluPhiWalk<NS> &wk, const int 
         ar[s] = 0.0;
         pt[s] = acc_s;                                           // nothing pending: the first flush adds 0.0 to acc[0]
     }
+    int lrest = -1;
+#pragma unroll
+    for (int s = 1; s < S; ++s) lrest = max(lrest, ls[s]);
+    lrest = __reduce_max_sync(BLU_FULL, lrest);
+    const unsigned n8 = 8u * (unsigned)N;
     unsigned lastmask = 0u;
     bool havelast = false;
     do {
@@ -298,9 +318,9 @@ __device__ __forceinline__ void blu_phi_class_run(BluPhiWalk<NS> &wk, const int 
             const unsigned cp_s = ps.val_s + ps.sdb * st + (unsigned)cur.skew;
             const unsigned idp_s = ps.ids_s + ps.idsd * st + (unsigned)cur.skewb;
             if (live == (cur.g >= 32 ? BLU_FULL : (1u << cur.g) - 1u))
-                blu_phi_groups<S, true>(cur.g, live, cp_s, idp_s, ps.rec_s, T, k, N, pmin, acc_s, off, js, ls, pt, ar);
+                blu_phi_groups<S, true>(cur.g, live, cp_s, idp_s, ps.rec_s, T, k, n8, pmin, lrest, acc_s, off, js, ls, pt, ar);
             else
-                blu_phi_groups<S, false>(cur.g, live, cp_s, idp_s, ps.rec_s, T, k, N, pmin, acc_s, off, js, ls, pt, ar);
+                blu_phi_groups<S, false>(cur.g, live, cp_s, idp_s, ps.rec_s, T, k, n8, pmin, lrest, acc_s, off, js, ls, pt, ar);
 #ifdef BLU_PHI_PROFILE
             wk.tloop += clock64() - tw1;
 #endif
@@ -400,6 +420,8 @@ __device__ __forceinline__ void blu_phi_walk(const int c0, const int c1, const B
     if (lane == 0) {
         atomicAdd(&blu_prof_hdr->stamp[13], (unsigned long long)wk.tpre); atomicAdd(&blu_prof_hdr->stamp[14], (unsigned long long)wk.texp);
         atomicAdd(&blu_prof_hdr->stamp[10], (unsigned long long)wk.twait); atomicAdd(&blu_prof_hdr->stamp[15], (unsigned long long)wk.tloop);
+        const int gwp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (gwp < 8192) { blu_prof_warp[gwp][1] = wk.tloop; blu_prof_warp[gwp][2] = wk.tpre + wk.texp; blu_prof_warp[gwp][3] = wk.twait; }
     }
 #endif
 }
@@ -820,6 +842,7 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
         atomicAdd(&hdr->stamp[11], (unsigned long long)(clock64() - prof_t0));
         atomicAdd(&hdr->stamp[12], 1ull);
         atomicMax(&hdr->stamp[8], (unsigned long long)(clock64() - prof_t0));
+        if (gw < 8192) blu_prof_warp[gw][0] = clock64() - prof_t0;
     }
 #endif
     unsigned supp = __reduce_or_sync(BLU_FULL, wsupp);

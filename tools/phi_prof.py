@@ -23,3 +23,19 @@ d = b - a
 w = max(d[12], 1)
 print("per warp: prefetch issue %.0f  expand/eff %.0f  barrier wait %.0f  group loop %.0f  (slowest warp total %d)" % (d[13] / w, d[14] / w, d[10] / w, d[15] / w, b[8]))
 print("warps %d  mean cycles per warp: total %.0f, waiting on the copy barrier %.0f (%.1f %%)" % (d[12], d[11] / max(d[12], 1), d[10] / max(d[12], 1), 100.0 * d[10] / max(d[11], 1)))
+if hasattr(lib, "blu_prof_warp_read"):
+    nW = int(d[12])
+    buf = (ctypes.c_longlong * (4 * nW))()
+    lib.blu_prof_warp_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    assert lib.blu_prof_warp_read(buf, nW) == 0
+    a = np.array(list(buf), dtype=np.int64).reshape(nW, 4)
+    tot = a[:, 0]
+    print("per-warp total cycles: min %d  p10 %d  median %d  p90 %d  max %d" % (tot.min(), np.percentile(tot, 10), np.median(tot), np.percentile(tot, 90), tot.max()))
+    cta = tot.reshape(-1, 8)
+    print("per-CTA max: min %d median %d max %d;  spread inside a CTA (max-min) median %d" % (cta.max(1).min(), np.median(cta.max(1)), cta.max(1).max(), np.median(cta.max(1) - cta.min(1))))
+    order = np.argsort(tot)
+    for name, idx in (("slowest", order[-8:]), ("fastest", order[:8])):
+        print(name, [(int(i), int(tot[i]), int(a[i, 1]), int(a[i, 2]), int(a[i, 3])) for i in idx])
+    # correlation with position in the grid
+    print("mean total by warp-in-CTA", cta.mean(0).astype(int).tolist())
+    print("mean total by CTA octile", [int(x.mean()) for x in np.array_split(cta.mean(1), 8)])
