@@ -475,8 +475,11 @@ __device__ __forceinline__ int blu_block_pinv(const double *phi, int N, const in
     if (tid < ns) diag0[tid] = phi[idx[tid] * N + idx[tid]];
     __syncthreads();
     double *res = nullptr;
-    // (a single-warp in-place elimination was measured and is slower: 20.6 us against 9.2 us at 20 models -- the rows of
-    // a column are a chain of dependent shared-memory round trips)
+    // Measured alternatives, all slower or equal (tools/tail_probe.py; 9.2 us at 20 models / 256 threads, 2.7 us at 10 / 512):
+    // a single-warp in-place elimination (20.6 us: the rows of a column are a chain of dependent shared round trips),
+    // an element-per-thread mapping (4.6 vs 4.05 us at 15 models), two pivots per barrier with the 2 x 2 block inverse
+    // (3.2 vs 2.7 us at 10 models: the step is bounded by the FP64 reciprocal + dependent FMA latency, not by the barrier,
+    // and the larger straight-line code is fetched cold -- this CTA runs it once per launch).
     if (blu_block_gj(A, V, diag0, ns, 1.0e-12, &res, tid, nthr)) {
         for (int t = tid; t < ns * ns; t += nthr) {
             const int r = t / ns, c = t - r * ns;
@@ -659,7 +662,12 @@ __device__ __forceinline__ void blu_finish_body(int N, double delta, int mode, b
         if (tid == 0) { hdr->supp = 0u; hdr->maxbits = 0ull; }
         return;
     }
-    // mirror the upper triangle, add delta on the diagonal
+    // (the header cells were written by other SMs' atomics: fetch them now, the L2 round trip overlaps the mirror loop)
+    const unsigned supp_hdr = allreduced ? 0u : hdr->supp;
+    const unsigned long long maxbits_hdr = allreduced ? 0ull : hdr->maxbits;
+    if (tid == 0) *f.amask = 0u;
+    __syncthreads();
+    // mirror the upper triangle, add delta on the diagonal; rows with any non-zero entry are "active" (see below)
     for (int e = tid; e < NN; e += nthr) {
         const int r = e / N, c = e - r * N;
         const int lo = r < c ? r : c, hi = r < c ? c : r;
@@ -667,13 +675,14 @@ __device__ __forceinline__ void blu_finish_body(int N, double delta, int mode, b
         if (r == c) v += delta;
         phi[e] = v;
         Pm[e] = v;
+        if (v != 0.0) atomicOr(f.amask, 1u << r);             // order-independent: deterministic
     }
     __syncthreads();
     unsigned supp;
     double maxabs;
     if (!allreduced) {
-        supp = hdr->supp;
-        maxabs = __longlong_as_double((long long)hdr->maxbits);
+        supp = supp_hdr;
+        maxabs = __longlong_as_double((long long)maxbits_hdr);
     } else {                              // SUM-reduced encodings
         supp = 0u;
         for (int a = 0; a < 32; ++a) if (phi[NN + a] > 0.0) supp |= 1u << a;
@@ -699,16 +708,10 @@ __device__ __forceinline__ void blu_finish_body(int N, double delta, int mode, b
     // Rows/columns of Phi that are entirely zero (models in no group with m_i != 0) split off as a
     // zero block: pinv([[A,0],[0,0]]) = [[pinv(A),0],[0,0]].  The remaining "active" block is SPD
     // in every regular evaluation and is inverted by Gauss-Jordan; Jacobi only if that fails.
-    if (tid < 32) {
-        bool nz = false;
-        if (tid < N) for (int c = 0; c < N; ++c) nz = nz || (Pm[tid * N + c] != 0.0);
-        const unsigned am = __ballot_sync(BLU_FULL, nz);
-        if (tid == 0) {
-            int cnt = 0;
-            for (int a = 0; a < N; ++a) if (am >> a & 1u) f.sidx[cnt++] = a;
-            *f.ns = cnt;
-            *f.amask = am;
-        }
+    {
+        const unsigned am = *f.amask;                        // collected by the mirror loop
+        if (tid < N && (am >> tid & 1u)) f.sidx[__popc(am & ((1u << tid) - 1u))] = tid;
+        if (tid == 0) *f.ns = __popc(am);
     }
     __syncthreads();
     const int na = *f.ns;
@@ -940,12 +943,12 @@ blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const 
         const int r = e / N, cc0 = e - r * N;
         double sum = 0.0;
         if (r <= cc0) {
-            for (int g0 = 0; g0 < ngrp; g0 += 8) {              // 8 loads in flight, group order
-                double v[8];
+            for (int g0 = 0; g0 < ngrp; g0 += 20) {             // 20 loads in flight (one batch up to 320 CTAs), group order
+                double v[20];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (g0 + u < ngrp) ? __ldcg(part2 + (size_t)(g0 + u) * NN + e) : 0.0;
+                for (int u = 0; u < 20; ++u) v[u] = (g0 + u < ngrp) ? __ldcg(part2 + (size_t)(g0 + u) * NN + e) : 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) sum += v[u];
+                for (int u = 0; u < 20; ++u) sum += v[u];
             }
         }
         f.Ph[r * BLU_JLD + cc0] = sum;
