@@ -250,8 +250,15 @@ static int build_chunks(blu_ctx *c)
         c->phi_sd = (int)(((pmaxpay + 4) + 1) / 2 * 2);
         c->idsd = (int)((idmax + 15) / 16 * 16 + 48);            // G*k bytes + 16-byte skew, rounded; slack for idle lanes
         c->phi_warps = blu_phi_smem_bytes(ns, c->phi_sd, c->idsd, c->N, (int)c->cls.size(), BLU_PHI_WARPS) <= 200 * 1024 ? BLU_PHI_WARPS : 8;
+        int per_sm = BLU_PHI_WARPS / c->phi_warps;                // CTAs per SM: what registers and shared memory allow
+        {
+            int occ = 0;
+            const size_t smem = std::max(blu_phi_smem_bytes(ns, c->phi_sd, c->idsd, c->N, (int)c->cls.size(), c->phi_warps), (size_t)BLU_FIN_SCRATCH_BYTES);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blu_phi_partial_kernel, c->phi_warps * 32, smem) == cudaSuccess && occ > 0) per_sm = occ;
+            else (void)cudaGetLastError();
+        }
         c->grid_phi = (int)std::min<long long>(std::max<long long>(1, ((long long)pch.size() + c->phi_warps * 3 - 1) / (c->phi_warps * 3)),
-                                               (long long)c->nsm * (BLU_PHI_WARPS / c->phi_warps));
+                                               (long long)c->nsm * per_sm);
         c->grid_phi = std::min(c->grid_phi, BLU_PHI_GROUP * BLU_PHI_MAXGROUPS);
         const int nW = c->grid_phi * c->phi_warps;
         const int R = pch.size() >= (size_t)nW * 36 ? 12 : (pch.size() >= (size_t)nW * 12 ? 4 : 1);      // runs per warp

@@ -799,7 +799,14 @@ blu_phi_finish_kernel(int N, int nparts, const double *__restrict__ part, double
 
 // `wchunks` lists the work of this launch (whole context or the owned slice) warp by warp: warp w of the grid walks
 // wchunks[wstart[w] .. wstart[w+1]).  ns: ring stages (2 or 4).  Dynamic shared memory: blu_phi_smem_bytes.
-__global__ void __launch_bounds__(BLU_PHI_WARPS * 32)
+// lab switch: compile for BLU_PHI_LB_C CTAs of 8 warps per SM.  Measured with 3 (80 registers, 24 warps/SM with 2 KB chunks):
+// 314 us at 20 models against 142 us -- the register cap spills the group loop (profiles/r02_phi_lab.md)
+#ifdef BLU_PHI_LB_C
+#define BLU_PHI_LB 256, BLU_PHI_LB_C
+#else
+#define BLU_PHI_LB BLU_PHI_WARPS * 32
+#endif
+__global__ void __launch_bounds__(BLU_PHI_LB)
 blu_phi_partial_kernel(const BluClass *__restrict__ cls, int ncls, int N, const BluChunk *__restrict__ wchunks, const int *__restrict__ wstart,
                        int ns, int sd, int idsd, const double *__restrict__ cinv, const unsigned char *__restrict__ gidx,
                        const unsigned short *__restrict__ lut, const unsigned *__restrict__ plut,
