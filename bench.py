@@ -751,7 +751,9 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     chk = 0.0
+    d2h_hess = 0
     for i in range(e2e_steps):
+        d2h_hess += _hess_d2h_bytes(L, full_rows_pct=sap.get_option("sym_full_rows_pct"))   # the share this download uses (adaptive)
         v, g, H = sap.variance_GH(pinned_m[i % npool].numpy())
         chk += v
         del H
@@ -826,10 +828,10 @@ def run_ours(args):
                "phases_ms": {"phi_pinv": float(np.mean(phases[:, 0])), "grad_uv": float(np.mean(phases[:, 1])),
                              "hessian": hess_ms, "eval_total": float(np.mean(phases[:, 3]))},
                "e2e": {"value": world * e2e_steps / e2e_s_max, "unit": UNIT, "steps": e2e_steps,
-                       "h2d_bytes_per_step": 8 * L, "d2h_bytes_per_step": _hess_d2h_bytes(L) + 8 * L + 8,
+                       "h2d_bytes_per_step": 8 * L, "d2h_bytes_per_step": d2h_hess // e2e_steps + 8 * L + 8,
                        "host_bytes_delivered_per_step": 8 * L * L + 8 * L + 8,
                        "api": "SAP.variance_GH(m) -> (var, grad (L,), hess (L,L)) numpy, pinned host buffers; the dense Hessian "
-                              "crosses PCIe as its upper block-triangle (1024-row panels) and host threads mirror the lower one"},
+                              "crosses PCIe as its upper block-triangle (1024-row panels) plus an adaptive share of whole bottom rows, host threads mirror the rest of the lower one"},
                "e2e_operator": {"value": world * op_steps / e2e_op_s, "unit": UNIT, "steps": op_steps,
                                 "h2d_bytes_per_step": 16 * L, "d2h_bytes_per_step": 16 * L + 8,
                                 "hess_matvec_us": mv_s * 1e6,

@@ -51,6 +51,7 @@ SIGNATURES = {
     "blu_ctx_last_timing": (c_int, [p_void, ctypes.POINTER(ctypes.c_float)]),
     "blu_ctx_last_launches": (c_int, [p_void]),
     "blu_ctx_set_option": (c_int, [p_void, ctypes.c_char_p, c_int]),
+    "blu_ctx_get_option": (c_int, [p_void, ctypes.c_char_p, ctypes.POINTER(c_int)]),
     "blu_ctx_timing_log": (c_int, [p_void, c_int]),
     "blu_ctx_timing_read": (c_int, [p_void, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(c_int)]),
     "blu_ctx_last_stamps": (c_int, [p_void, ctypes.POINTER(ctypes.c_uint64)]),

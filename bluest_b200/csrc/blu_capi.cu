@@ -108,6 +108,8 @@ struct blu_ctx {
     int mirror_threads = 0;            // 0: automatic (see download_hessian_symmetric)
     bool sym_download = true;          // dense Hessian to the host: upper block-triangle over PCIe, lower mirrored by host threads
     int sym_full_rows_pct = 10;        // share (%) of the lower triangle that still travels by DMA (the bottom rows, in full)
+    bool sym_pct_auto = true;          // adapt that share to the host: more DMA when the mirroring threads lag, less when they idle
+    int sym_calm = 0;                  // consecutive downloads in which the mirror finished with the DMA
     BluXchg *d_xchg = nullptr;         // this rank's exchange buffer (CUDA IPC shared)
     BluPeers peers{};                  // peers as mapped here; world == 0: not connected
     std::vector<void *> ipc_opened;
@@ -960,7 +962,11 @@ extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
     if (!strcmp(name, "sym_download")) { c->sym_download = value != 0; return BLU_OK; }
     if (!strcmp(name, "soa")) { c->use_soa = value != 0; return BLU_OK; }
     if (!strcmp(name, "mirror_threads")) { c->mirror_threads = value; return BLU_OK; }
-    if (!strcmp(name, "sym_full_rows_pct")) { c->sym_full_rows_pct = value; return BLU_OK; }
+    if (!strcmp(name, "sym_full_rows_pct")) {          // a value >= 0 pins the share; -1 returns to the adaptive default
+        if (value < 0) { c->sym_pct_auto = true; c->sym_full_rows_pct = 10; c->sym_calm = 0; }
+        else { c->sym_pct_auto = false; c->sym_full_rows_pct = value; }
+        return BLU_OK;
+    }
     if (!strcmp(name, "hess_onebuf")) { c->hess_onebuf = value != 0; return BLU_OK; }
     if (!strcmp(name, "phi_stages")) {          // ring depth of the Phi kernel: 2 (4 KB chunks) or 4 (2 KB chunks)
         if (value != 2 && value != 4) return fail(BLU_ERR_ARG, "phi_stages must be 2 or 4");
@@ -970,6 +976,18 @@ extern "C" int blu_ctx_set_option(blu_ctx *c, const char *name, int value)
         c->phi_stages = value;
         return build_chunks(c);
     }
+    return fail(BLU_ERR_ARG, "unknown option %s", name);
+}
+
+extern "C" int blu_ctx_get_option(blu_ctx *c, const char *name, int *value)
+{
+    if (!c || !name || !value) return fail(BLU_ERR_ARG, "null argument");
+    if (!strcmp(name, "sym_download")) { *value = c->sym_download ? 1 : 0; return BLU_OK; }
+    if (!strcmp(name, "soa")) { *value = c->use_soa ? 1 : 0; return BLU_OK; }
+    if (!strcmp(name, "mirror_threads")) { *value = c->mirror_threads; return BLU_OK; }
+    if (!strcmp(name, "sym_full_rows_pct")) { *value = c->sym_full_rows_pct; return BLU_OK; }   // the CURRENT share (adaptive or pinned)
+    if (!strcmp(name, "hess_onebuf")) { *value = c->hess_onebuf ? 1 : 0; return BLU_OK; }
+    if (!strcmp(name, "phi_stages")) { *value = c->phi_stages; return BLU_OK; }
     return fail(BLU_ERR_ARG, "unknown option %s", name);
 }
 
@@ -1160,9 +1178,21 @@ static int download_hessian_symmetric(blu_ctx *c, double *hess)
         if (dbg && (p == 0 || p == npan / 2 || p == npan - 1))
             fprintf(stderr, "[blu] panel %d arrived at %.1f ms\n", p, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     }
+    const auto t_arrived = std::chrono::steady_clock::now();      // the last panel is on the host
     if (inline_mirror) worker();                                  // no helper thread could be started
     for (auto &t : pool) t.join();
-    if (dbg) fprintf(stderr, "[blu] mirror done at %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    const auto t_done = std::chrono::steady_clock::now();
+    if (dbg) fprintf(stderr, "[blu] mirror done at %.1f ms (DMA share %d %%)\n", std::chrono::duration<double, std::milli>(t_done - t_start).count(), c->sym_full_rows_pct);
+    if (c->sym_pct_auto && err == cudaSuccess && !inline_mirror && npan >= 8) {
+        // Balance the two parties for THIS host: the download ends when the slower of DMA and mirror ends.  The mirror
+        // lagging behind the last panel means the host threads are the bottleneck -> send more rows whole over PCIe;
+        // finishing together with it (twice in a row) means they have slack -> mirror more, move fewer bytes.
+        const double total = std::chrono::duration<double, std::milli>(t_done - t_start).count();
+        const double lag = std::chrono::duration<double, std::milli>(t_done - t_arrived).count();
+        if (lag > 0.04 * total) { c->sym_full_rows_pct = std::min(40, c->sym_full_rows_pct + 5); c->sym_calm = 0; }
+        else if (lag < 0.01 * total) { if (++c->sym_calm >= 2 && c->sym_full_rows_pct > 0) { c->sym_full_rows_pct -= 5; c->sym_calm = 0; } }
+        else c->sym_calm = 0;
+    }
     if (err != cudaSuccess) return fail(BLU_ERR_CUDA, "Hessian download: %s", cudaGetErrorString(err));
     // the diagonal blocks arrived whole; the strictly-lower part of each diagonal block was copied too
     return BLU_OK;

@@ -22,7 +22,7 @@ _saved = {}
 _L1 = ("assemble_psi_c", "objectiveK_c", "gradK_c", "hessKQ_c", "cleanupK_c")
 _L2_METHODS = ("__init__", "get_variance_functions", "_m", "eval_device", "upload_m", "sync", "last_result", "last_timing",
                "timing_log", "timing_read", "last_launches", "device_ptr", "device_buffer", "stream", "close", "__del__", "compute_BLUE_estimator", "integer_projection",
-               "variance_GH_begin", "variance_GH_end", "hess_matvec", "hess_operator", "hess_matvec_device", "set_option",
+               "variance_GH_begin", "variance_GH_end", "hess_matvec", "hess_operator", "hess_matvec_device", "set_option", "get_option",
                "graph_begin", "graph_end", "graph_launch", "save_result", "set_grad_output")
 
 

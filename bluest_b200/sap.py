@@ -332,6 +332,11 @@ class SAP(object):
     def set_option(self, name, value):
         check(lib().blu_ctx_set_option(self._ctx, name.encode(), int(value)))
 
+    def get_option(self, name):
+        v = ctypes.c_int(0)
+        check(lib().blu_ctx_get_option(self._ctx, name.encode(), ctypes.byref(v)))
+        return v.value
+
     def last_launches(self):
         return int(lib().blu_ctx_last_launches(self._ctx))
 

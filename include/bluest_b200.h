@@ -204,10 +204,13 @@ int blu_ctx_timing_read(blu_ctx *ctx, float *ms, int *n);
  * "sym_download" (default 1, used when L >= 4096): blu_variance_GH moves only the upper
  * block-triangle of the (exactly symmetric) dense Hessian over PCIe and mirrors it with host threads
  * (0: one plain copy of all 8 L^2 bytes).  "mirror_threads" (default 0 = automatic): host threads of
- * that mirroring.  "sym_full_rows_pct" (default 10): share of the bottom rows moved whole by that download.
+ * that mirroring.  "sym_full_rows_pct" (default -1 = adaptive, starting at 10): share (%) of the lower triangle that still
+ * travels by DMA (the bottom rows, whole); adaptive = raised when the host threads lag the DMA, lowered when they idle.
  * "hess_onebuf": single staging buffer in the dense-Hessian kernel.  "phi_stages" (2, the default, or 4): ring
  * depth of the Phi kernel (4 = 2 KB chunks; rebuilds the kernel's work list; parent contexts only). */
 int blu_ctx_set_option(blu_ctx *ctx, const char *name, int value);
+/* Current value of an option (for "sym_full_rows_pct": the share the next download will use). */
+int blu_ctx_get_option(blu_ctx *ctx, const char *name, int *value);
 /* Number of kernels the last evaluation launched. */
 int blu_ctx_last_launches(blu_ctx *ctx);
 

@@ -12,7 +12,7 @@ sap = blu.SAP(orc.wishart_cov(N, 0), N, groups, np.ones(L), verbose=False)
 m = orc.dense_m(L, 0)
 for opt in sys.argv[1:]:
     k, v = opt.split("="); sap.set_option(k, int(v))
-for it in range(4):
+for it in range(int(os.environ.get("E2E_EVALS", "4"))):
     t0 = time.perf_counter()
     v, g, H = sap.variance_GH(m)
     print("evaluation %d: %.1f ms" % (it, (time.perf_counter() - t0) * 1e3), flush=True)
