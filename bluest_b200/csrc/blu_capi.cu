@@ -1273,14 +1273,20 @@ static int ensure_hv(blu_ctx *c)
 }
 
 // t (32 doubles at d_t) = sum over the owned rows of p_i u_i
+// Second-generation kernels (blu_matvec.cuh): 8 x 16 bytes in flight per thread, two resident CTAs per SM, one wave;
+// tools/lab/hv_lab.cu measured 58.7 us per product at 20 models against 89.3 us for the first generation.
+#define BLU_HV2_UN 8
+#define BLU_HV2_MINB 2
+#define BLU_HVA2_WARPS 8
+#define BLU_HVA2_MINB 4
 static int launch_hv_reduce(blu_ctx *c, const double *d_p, double *d_t)
 {
     const long long rows = c->hi - c->lo;
     const int rpp = BLU_HV_THREADS / (c->NP / 2);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + (long long)rpp * BLU_HV_UNROLL - 1) / ((long long)rpp * BLU_HV_UNROLL), (long long)c->nsm * 8));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + (long long)rpp * BLU_HV2_UN - 1) / ((long long)rpp * BLU_HV2_UN), (long long)c->nsm * BLU_HV2_MINB));
     unsigned *ticket = reinterpret_cast<unsigned *>(c->d_hvpart + 32 * (size_t)c->nsm * 8 + 32);
     switch (c->NP) {
-#define HV_CASE(P) case P: blu_hv_reduce_kernel<P><<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_U, d_p, c->lo, c->hi, c->d_hvpart, ticket, d_t); break;
+#define HV_CASE(P) case P: blu_hv_reduce_kernel<P, BLU_HV2_UN, BLU_HV2_MINB><<<grid, BLU_HV_THREADS, 0, c->stream>>>(c->d_U, d_p, c->lo, c->hi, c->d_hvpart, ticket, d_t); break;
         HV_CASE(4) HV_CASE(8) HV_CASE(12) HV_CASE(16) HV_CASE(20) HV_CASE(24) HV_CASE(28) HV_CASE(32)
 #undef HV_CASE
     }
@@ -1291,9 +1297,10 @@ static int launch_hv_reduce(blu_ctx *c, const double *d_p, double *d_t)
 static int launch_hv_apply(blu_ctx *c, const double *d_t, double *d_out)
 {
     const long long rows = c->hi - c->lo;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + BLU_HVA_THREADS - 1) / BLU_HVA_THREADS, (long long)c->nsm * 8));
+    const long long nblk = (rows + 31) / 32;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((nblk + BLU_HVA2_WARPS - 1) / BLU_HVA2_WARPS, (long long)c->nsm * BLU_HVA2_MINB));
     switch (c->NP) {
-#define HV_CASE(P) case P: blu_hv_apply_kernel<P><<<grid, BLU_HVA_THREADS, 0, c->stream>>>(c->d_U, c->d_Sop, c->N, d_t, c->lo, c->hi, d_out, 1); break;
+#define HV_CASE(P) case P: blu_hv_apply_kernel<P, BLU_HVA2_WARPS, BLU_HVA2_MINB><<<grid, BLU_HVA2_WARPS * 32, 0, c->stream>>>(c->d_U, c->d_Sop, c->N, d_t, c->lo, c->hi, d_out, 1); break;
         HV_CASE(4) HV_CASE(8) HV_CASE(12) HV_CASE(16) HV_CASE(20) HV_CASE(24) HV_CASE(28) HV_CASE(32)
 #undef HV_CASE
     }
@@ -1529,6 +1536,7 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     const long long L = c->L, n = L + has_t;
     const int Qs = M * (M + 1) / 2, Q = Qs + nlin, QP = ((Q + 1 + 7) / 8) * 8;      // + the right-hand-side column
     if (nlin < 0 || Q > 255) return fail(BLU_ERR_ARG, "capacitance matrix of order %d exceeds 255 (N=%d, %d dense rows)", Q, N, nlin);
+    if (M > 22) return fail(BLU_ERR_ARG, "kkt_solve: N = %d is beyond the rows kernel's register tiles (N <= 21)", N);
     for (long long t = 0; t < n + nlin; ++t) if (!(d[t] > 0.0)) return fail(BLU_ERR_ARG, "scaling d[%lld] is not positive", t);
     // host: r^-1, Lam = r^-T r^-1, Wm = Lam Z Lam  (Z = the 's' part of bz, a symmetric matrix)
     std::vector<double> rinv(MM), Lam(MM), tmp(MM), Wm(MM);
@@ -1543,7 +1551,8 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     // device buffers
     struct DevBuf { void *p = nullptr; ~DevBuf() { if (p) cudaFree(p); } };
     DevBuf bBs, bsmall, bvec, bpart;
-    const size_t nsmall = (size_t)2 * MM + (size_t)Q * Q + 2 * 256 + 8;           // rinv | Wm | cap | v | y | info
+    const int LDC = ((Q + 1 + 3) / 4) * 4;                                        // leading dimension of the capacitance matrix (+ the rhs row)
+    const size_t nsmall = (size_t)2 * MM + (size_t)Q * LDC + 256 + 8;             // rinv | Wm | cap (column-major, rhs as row Q) | y | info
     const size_t nvec = (size_t)(n + nlin) + (size_t)nlin * n + 5 * (size_t)n + nlin;   // d | Gx | bx | bz0 | g1tw | rhs | ux
     CUDA_TRY(cudaMalloc(&bBs.p, sizeof(double) * (size_t)n * QP));
     CUDA_TRY(cudaMalloc(&bsmall.p, sizeof(double) * nsmall));
@@ -1551,7 +1560,7 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     CUDA_TRY(cudaMalloc(&bpart.p, sizeof(double) * 64 * 16 * (size_t)((QP / 8) * (QP / 8 + 1) / 2)));      // partial tiles: 16 row splits at most
     double *d_part = (double *)bpart.p;
     double *d_Bs = (double *)bBs.p;
-    double *d_rinv = (double *)bsmall.p, *d_Wm = d_rinv + MM, *d_cap = d_Wm + MM, *d_v = d_cap + (size_t)Q * Q, *d_y = d_v + 256;
+    double *d_rinv = (double *)bsmall.p, *d_Wm = d_rinv + MM, *d_cap = d_Wm + MM, *d_y = d_cap + (size_t)Q * LDC;
     int *d_info = (int *)(d_y + 256);
     double *d_d = (double *)bvec.p, *d_Gx = d_d + (n + nlin), *d_bx = d_Gx + (size_t)nlin * n, *d_bz0 = d_bx + n;
     double *d_g1tw = d_bz0 + (n + nlin), *d_rhs = d_g1tw + n, *d_ux = d_rhs + n;
@@ -1568,11 +1577,24 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     cudaEventRecord(e0, st);
     c->launches = 0;
     {
-        const size_t smem = sizeof(double) * ((size_t)2 * M * (M | 1) + (size_t)BLU_KKT_WARPS * M * (N | 1));
-        CUDA_TRY(cudaFuncSetAttribute(blu_kkt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = (int)std::max<long long>(1, std::min<long long>((n + BLU_KKT_WARPS - 1) / BLU_KKT_WARPS, (long long)c->nsm * 4));
-        blu_kkt_rows_kernel<<<grid, BLU_KKT_WARPS * 32, smem, st>>>(c->d_cls, (int)c->cls.size(), N, L, has_t, scales, c->d_gidx, c->d_cinv, d_rinv, d_Wm,
-                                                                    d_d, nlin, d_Gx, d_d + n, Q, QP, d_Bs, d_g1tw);
+        // rows kernel: LW lanes per group (16 while M <= 16: two groups per warp); per sub-warp scratch = expanded inverse / staging row |
+        // gathered r^-1 columns | Tt | member ids
+        int KMAX = 1;
+        for (const BluClass &ci : c->cls) KMAX = std::max(KMAX, ci.k);
+        const int LW = (M <= 16) ? 16 : 32, GPW = 32 / LW;
+        const int KSF = (LW == 16) ? 16 : 22;                                     // blu_kkt_rows_kernel: 2 * NH
+        const int SCR = ((KSF * KSF + 2 * KMAX * LW + 16) + 1) & ~1;
+        const size_t smem = sizeof(double) * ((size_t)2 * M * (M | 1) + (size_t)BLU_KKT_WARPS * GPW * SCR) + sizeof(uint16_t) * (size_t)((c->lutlen + 7) & ~7);
+        const int grid = (int)std::max<long long>(1, std::min<long long>((n + BLU_KKT_WARPS * GPW - 1) / (BLU_KKT_WARPS * GPW), (long long)c->nsm * 2));
+        if (LW == 16) {
+            CUDA_TRY(cudaFuncSetAttribute(blu_kkt_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blu_kkt_rows_kernel<16><<<grid, BLU_KKT_WARPS * 32, smem, st>>>(c->d_cls, (int)c->cls.size(), N, L, has_t, scales, c->d_gidx, c->d_cinv, c->d_lut, c->lutlen,
+                                                                            d_rinv, d_Wm, d_d, nlin, d_Gx, d_d + n, Q, QP, KMAX, SCR, d_Bs, d_g1tw);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(blu_kkt_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blu_kkt_rows_kernel<32><<<grid, BLU_KKT_WARPS * 32, smem, st>>>(c->d_cls, (int)c->cls.size(), N, L, has_t, scales, c->d_gidx, c->d_cinv, c->d_lut, c->lutlen,
+                                                                            d_rinv, d_Wm, d_d, nlin, d_Gx, d_d + n, Q, QP, KMAX, SCR, d_Bs, d_g1tw);
+        }
         KERNEL_CHECK(c);
         blu_kkt_rhs_kernel<<<(int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)c->nsm * 8)), 256, 0, st>>>(
             n, nlin, d_bx, d_bz0, d_d, d_Gx, d_d + n, d_g1tw, Q, QP, d_rhs, d_Bs);
@@ -1581,11 +1603,9 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
         const int nsplit = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, n / 2048), ((long long)c->nsm * 6 + npairs - 1) / npairs));
         blu_kkt_syrk_kernel<<<dim3((unsigned)npairs, (unsigned)nsplit), BLU_KKT_WARPS * 32, 0, st>>>(d_Bs, n, QP, d_part);
         KERNEL_CHECK(c);
-        blu_kkt_capfold_kernel<<<(npairs * 64 + 255) / 256, 256, 0, st>>>(d_part, npairs, nsplit, Q, QP, d_cap, d_v);
+        blu_kkt_capfold_kernel<<<(npairs * 64 + 255) / 256, 256, 0, st>>>(d_part, npairs, nsplit, Q, QP, LDC, d_cap);
         KERNEL_CHECK(c);
-        const size_t csm = sizeof(double) * (size_t)Q * (Q + 1);
-        CUDA_TRY(cudaFuncSetAttribute(blu_kkt_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-        blu_kkt_chol_kernel<<<1, 512, csm, st>>>(d_cap, Q, d_v, d_y, d_info);
+        blu_kkt_chol_kernel<<<1, BLU_CHOL_T, 0, st>>>(d_cap, Q, LDC, d_y, d_info);
         KERNEL_CHECK(c);
         blu_kkt_apply_kernel<<<(int)std::max<long long>(1, std::min<long long>((n + BLU_KKT_WARPS - 1) / BLU_KKT_WARPS, (long long)c->nsm * 4)), BLU_KKT_WARPS * 32, 0, st>>>(
             d_Bs, n, Q, QP, d_y, d_d, d_rhs, d_ux);

@@ -20,7 +20,8 @@
 //                         plus the column's entry of G1^T vec(Lam Z Lam) (right-hand side) -> row of Bs (n x QP)
 //   blu_kkt_syrk_kernel   cap = I + Bs^T Bs and v = Bs^T (d * rhs) in one pass (the rhs rides along as column Q):
 //                         mma.m8n8k4.f64, one CTA per 8 x 8 tile pair, warps combined in a fixed order
-//   blu_kkt_chol_kernel   Cholesky of the Q x Q capacitance matrix + two triangular solves, one CTA
+//   blu_kkt_chol_kernel   blocked Cholesky of the Q x Q capacitance matrix (in place in L2, 16-column panels in shared
+//                         memory, the right-hand side carried as an extra row) + backward substitution, one CTA
 //   blu_kkt_apply_kernel  ux_col = d_col^2 rhs_col - d_col (Bs_col . y)
 // then Phi(ux) through the ordinary Phi kernel gives G1 ux, and uz follows on the host (O(n + N^2) work).
 #pragma once
@@ -32,93 +33,181 @@
 // svec index of (a,b), a <= b, of an M x M symmetric matrix stored by rows of the upper triangle
 __host__ __device__ __forceinline__ int blu_svec(int M, int a, int b) { return a * M - a * (a - 1) / 2 + (b - a); }
 
-// One warp per column of the reduced system.
+// Rows of the reduced system, LW lanes per column (LW = 16 while M = N + 1 <= 16: a warp works on TWO groups of the same size
+// class; LW = 32 otherwise, M <= 22).
 //   col < has_t            : the t column, X = -E_NN
 //   otherwise group i      : X = -scales * pad(Psi_i)
 // Bs[col][q] = d[col] * b_col[q],  q < Qs: svec(r^-1 X r^-T) (off-diagonal entries times sqrt 2 so that the
 // Euclidean inner product of svecs equals the trace inner product), Qs <= q < Q: Gx[q-Qs][col] / dlin[q-Qs],
 // Bs[col][Q] = d[col] * rhs_col (filled by blu_kkt_rhs_kernel), zero padding up to QP.
 // g1tw[col] = <X_col, Wm>  (Wm = Lam Z Lam, (N+1) x (N+1)): the column's entry of G1^T vec(Wm).
+// A warp walks its pairs of groups with the NEXT pair's packed inverse, member ids and scaling already in flight (registers),
+// so the DRAM round trip hides behind the products of the current pair.  Per group: the packed inverse is expanded to a
+// full k x k matrix and the member columns of r^-1 are gathered into shared memory; then lane a owns row a and keeps its
+// results in registers:
+//   Tt[a][:] = Rg[a][:] C,   Y[a][:] = Tt[a][:] Rg^T,   Rg[a][j] = r^-1[a][g_j]
+// one lane-contiguous shared read per outer step and broadcast 16-byte reads of the other operand (1.6 instructions per
+// multiply-add); the finished row leaves through a staging row so that the global stores are contiguous.
+// History (15 models): first version, global loads and an (a, b) search per entry inside the loops: 152 us; shared-memory
+// staging without prefetch and with scalar product loops: 217 us (one exposed DRAM round trip per 16 packed entries).
+template <int LW>
 __global__ void __launch_bounds__(BLU_KKT_WARPS * 32)
 blu_kkt_rows_kernel(const BluClass *__restrict__ cls, int ncls, int N, long long L, int has_t, double scales,
-                    const uint8_t *__restrict__ gidx, const double *__restrict__ cinv, const double *__restrict__ rinv,
-                    const double *__restrict__ Wm, const double *__restrict__ d, int nlin, const double *__restrict__ Gx,
-                    const double *__restrict__ dlin, int Q, int QP, double *__restrict__ Bs, double *__restrict__ g1tw)
+                    const uint8_t *__restrict__ gidx, const double *__restrict__ cinv, const unsigned short *__restrict__ lut, int lutlen,
+                    const double *__restrict__ rinv, const double *__restrict__ Wm, const double *__restrict__ d, int nlin,
+                    const double *__restrict__ Gx, const double *__restrict__ dlin, int Q, int QP, int KMAX, int SCR,
+                    double *__restrict__ Bs, double *__restrict__ g1tw)
 {
+    constexpr int GPW = 32 / LW;
+    constexpr int NH = (LW == 16) ? 8 : 11;               // register pairs per lane: M <= 2 NH, k <= 2 NH
+    constexpr int KSF = 2 * NH;                           // row pitch of the expanded inverse
+    constexpr int CV = 8;                                 // packed entries per lane: T <= CV * LW
     const int M = N + 1, Qs = M * (M + 1) / 2;
-    const int MP = M | 1;                                 // odd leading dimensions: rows of r^-1 / Tt land in different banks
-    extern __shared__ double kraw[];                      // [M*MP r^-1][M*MP Wm][WARPS x M*(N|1) Tt]
+    const int MP = M | 1;                                 // odd leading dimension: rows of r^-1 land in different banks
+    extern __shared__ __align__(16) double kraw[];        // [M*MP r^-1][M*MP Wm][sub-warps x SCR scratch][(j,l) tables]
     double *sR = kraw, *sW = kraw + M * MP;
     __shared__ BluClass scls[BLU_MAX_MODELS_C];
+    __shared__ long long spair[BLU_MAX_MODELS_C + 1];     // first flat pair index of every class
+    unsigned short *slut = reinterpret_cast<unsigned short *>(kraw + 2 * M * MP + (size_t)BLU_KKT_WARPS * GPW * SCR);
     for (int t = threadIdx.x; t < M * M; t += blockDim.x) { sR[(t / M) * MP + (t % M)] = rinv[t]; sW[(t / M) * MP + (t % M)] = Wm[t]; }
     for (int t = threadIdx.x; t < ncls; t += blockDim.x) scls[t] = cls[t];
+    for (int t = threadIdx.x; t < lutlen; t += blockDim.x) slut[t] = lut[t];
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        for (int ic = 0; ic < ncls; ++ic) { spair[ic] = acc; acc += (cls[ic].Lk + GPW - 1) / GPW; }
+        spair[ncls] = acc;
+    }
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / LW, a = lane % LW;
     const long long n = L + has_t;
     const double rt2 = 1.4142135623730951;
-    for (long long col = (long long)blockIdx.x * BLU_KKT_WARPS + w; col < n; col += (long long)gridDim.x * BLU_KKT_WARPS) {
-        double *row = Bs + col * QP;
-        const double dc = d[col];
+    // scratch of this sub-warp: [sCf / srow: KSF*KSF][sRg: KMAX*LW][sT: KMAX*LW][sg: 32 ints]
+    double *scr = kraw + 2 * M * MP + (size_t)(w * GPW + sub) * SCR;
+    double *sCf = scr, *srow = scr, *sRg = scr + KSF * KSF, *sT = sRg + KMAX * LW;
+    int *sg = reinterpret_cast<int *>(sT + KMAX * LW);
+    const long long gwarp = (long long)blockIdx.x * BLU_KKT_WARPS + w, nwarps = (long long)gridDim.x * BLU_KKT_WARPS;
+    if (has_t && gwarp == 0) {
+        // the t column, X = -E_NN: r^-1 X r^-T = -(column N of r^-1)(column N of r^-1)^T
+        double *row = Bs;
+        const double dc = d[0];
+        for (int q = lane; q < Qs; q += 32) {
+            int ra = 0, rem = q;
+            while (rem >= M - ra) { rem -= M - ra; ++ra; }
+            const int rb = ra + rem;
+            const double v = -(sR[ra * MP + N] * sR[rb * MP + N]);
+            row[q] = dc * (ra == rb ? v : rt2 * v);
+        }
+        for (int q = Qs + lane; q < QP; q += 32) row[q] = (q < Q) ? dc * Gx[(long long)(q - Qs) * n] / dlin[q - Qs] : 0.0;
+        if (lane == 0) g1tw[0] = -sW[N * MP + N];
+    }
+    const long long total = spair[ncls];
+    // operands of one pair, fetched one pair ahead
+    double cv[CV], cvn[CV], dc = 0.0, dcn = 0.0;
+    int gv = 0, gvn = 0;
+    auto fetch = [&](int ic, long long fp, double (&c8)[CV], int &g1, double &d1) {
+        const BluClass &ci = scls[ic];
+        const long long il = (fp - spair[ic]) * GPW + sub;
+        const bool act = il < ci.Lk;
+        const double *C = cinv + ci.coff + il * ci.T;
+#pragma unroll
+        for (int u = 0; u < CV; ++u) c8[u] = (act && a + u * LW < ci.T) ? __ldg(C + a + u * LW) : 0.0;
+        g1 = (act && a < ci.k) ? (int)__ldg(gidx + ci.ioff + il * ci.k + a) : 0;
+        d1 = act ? __ldg(d + ci.goff + il + has_t) : 0.0;
+    };
+    long long fp = gwarp;
+    int ic = 0;
+    while (ic < ncls && fp >= spair[ic + 1]) ++ic;
+    if (fp < total) fetch(ic, fp, cv, gv, dc);
+    while (fp < total) {
+        const BluClass ci = scls[ic];
+        const int k = ci.k, T = ci.T;
+        const unsigned short *jlt = slut + ci.lutoff;
+        const long long il = (fp - spair[ic]) * GPW + sub;
+        const bool active = il < ci.Lk;
+        const long long col = ci.goff + il + has_t;
+        const long long fpn = fp + nwarps;
+        int icn = ic;
+        while (icn < ncls && fpn >= spair[icn + 1]) ++icn;
+        if (fpn < total) fetch(icn, fpn, cvn, gvn, dcn);
+        // ---- stage: member ids, expanded inverse, <X, Wm>, member columns of r^-1 ----
+        if (a < k) sg[a] = gv;
+        __syncwarp();
         double dotw = 0.0;
-        if (col < has_t) {
-            // X = -E_NN: r^-1 X r^-T = -(column N of r^-1)(column N of r^-1)^T
-            for (int q = lane; q < Qs; q += 32) {
-                int a = 0, rem = q;
-                while (rem >= M - a) { rem -= M - a; ++a; }
-                const int b = a + rem;
-                const double v = -(sR[a * MP + N] * sR[b * MP + N]);
-                row[q] = dc * (a == b ? v : rt2 * v);
+#pragma unroll
+        for (int u = 0; u < CV; ++u) {
+            const int e = a + u * LW;
+            if (e < T) {
+                const unsigned jl = jlt[e];
+                const int j = jl >> 8, l = jl & 255u;
+                const double c = cv[u];
+                sCf[j * KSF + l] = c;
+                sCf[l * KSF + j] = c;
+                const int gj = sg[j], gl = sg[l];
+                const double wv = (j == l) ? sW[gj * MP + gj] : (sW[gj * MP + gl] + sW[gl * MP + gj]);
+                dotw = fma(c, wv, dotw);
             }
-            if (lane == 0) dotw = -sW[N * MP + N];
-        } else {
-            const long long i = col - has_t;
-            int ic = 0;
-            while (ic + 1 < ncls && i >= scls[ic + 1].goff) ++ic;
-            const BluClass ci = scls[ic];
-            const long long il = i - ci.goff;
-            const int k = ci.k;
-            const uint8_t *g = gidx + ci.ioff + il * k;
-            const double *C = cinv + ci.coff + il * ci.T;
-            const int KP = k | 1;
-            double *Tt = kraw + 2 * M * MP + (size_t)w * M * (N | 1);    // Tt[a][l] = sum_j r^-1[a][g_j] C[j][l], leading dimension KP
-            // Tt[a][l] = sum_j r^-1[a][g_j] C[j][l]
-            for (int t = lane; t < M * k; t += 32) {
-                const int a = t / k, l = t - a * k;
-                double s = 0.0;
-                for (int j = 0; j < k; ++j) {
-                    const int lo = j < l ? j : l, hi = j < l ? l : j;
-                    s = fma(sR[a * MP + g[j]], C[blu_pk(k, lo, hi)], s);
+        }
+        if (a < M)
+            for (int j = 0; j < k; ++j) sRg[j * LW + a] = sR[a * MP + sg[j]];
+        __syncwarp();
+        // ---- Tt[a][l] = sum_j Rg[a][j] C[j][l] in registers (entries l >= k are junk and never used) ----
+        {
+            double tt[2 * NH];
+#pragma unroll
+            for (int l = 0; l < 2 * NH; ++l) tt[l] = 0.0;
+            for (int j = 0; j < k; ++j) {
+                const double rg = sRg[j * LW + a];
+                const double2 *cr = reinterpret_cast<const double2 *>(sCf + j * KSF);
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const double2 c2 = cr[h];
+                    tt[2 * h] = fma(rg, c2.x, tt[2 * h]);
+                    tt[2 * h + 1] = fma(rg, c2.y, tt[2 * h + 1]);
                 }
-                Tt[a * KP + l] = s;
             }
-            __syncwarp();
-            for (int q = lane; q < Qs; q += 32) {
-                int a = 0, rem = q;
-                while (rem >= M - a) { rem -= M - a; ++a; }
-                const int b = a + rem;
-                double s = 0.0;
-                for (int l = 0; l < k; ++l) s = fma(Tt[a * KP + l], sR[b * MP + g[l]], s);
-                s *= -scales;
-                row[q] = dc * (a == b ? s : rt2 * s);
-            }
-            // <X_i, Wm> = -scales sum_{j,l} C[j][l] Wm[g_j][g_l]
-            for (int e = lane; e < ci.T; e += 32) {
-                int j = 0, rem = e;
-                while (rem >= k - j) { rem -= k - j; ++j; }
-                const int l = j + rem;
-                const double wv = (j == l) ? sW[g[j] * MP + g[j]] : (sW[g[j] * MP + g[l]] + sW[g[l] * MP + g[j]]);
-                dotw = fma(C[e], wv, dotw);
-            }
-            dotw *= -scales;
-            __syncwarp();
+#pragma unroll
+            for (int l = 0; l < 2 * NH; ++l)
+                if (l < k) sT[l * LW + a] = tt[l];
         }
-        dotw = blu_warp_sum(dotw);
-        for (int q = Qs + lane; q < QP; q += 32) {
-            double v = 0.0;
-            if (q < Q) v = dc * Gx[(long long)(q - Qs) * n + col] / dlin[q - Qs];
-            row[q] = v;                                   // column Q (the right-hand side) is written by blu_kkt_rhs_kernel
+        __syncwarp();                                       // sCf is dead from here on: srow takes its place
+        // ---- Y[a][b] = sum_l Tt[a][l] Rg[b][l] for every b (uniform over the lanes: broadcast reads) ----
+        {
+            double yy[2 * NH];
+#pragma unroll
+            for (int b = 0; b < 2 * NH; ++b) yy[b] = 0.0;
+            for (int l = 0; l < k; ++l) {
+                const double t = sT[l * LW + a];
+                const double2 *rr = reinterpret_cast<const double2 *>(sRg + l * LW);
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const double2 r2 = rr[h];
+                    yy[2 * h] = fma(t, r2.x, yy[2 * h]);
+                    yy[2 * h + 1] = fma(t, r2.y, yy[2 * h + 1]);
+                }
+            }
+            if (a < M) {
+                double *rowq = srow + blu_svec(M, a, a) - a;
+                const double f = -scales * dc;
+#pragma unroll
+                for (int b = 0; b < 2 * NH; ++b)
+                    if (b >= a && b < M) rowq[b] = (a == b ? f : rt2 * f) * yy[b];
+            }
         }
-        if (lane == 0) g1tw[col] = dotw;
+        __syncwarp();
+        if (active) {
+            double *row = Bs + col * QP;
+            for (int q = a; q < Qs; q += LW) row[q] = srow[q];
+            for (int q = Qs + a; q < QP; q += LW)           // column Q (the right-hand side) is written by blu_kkt_rhs_kernel
+                row[q] = (q < Q) ? dc * Gx[(long long)(q - Qs) * n + col] / dlin[q - Qs] : 0.0;
+        }
+#pragma unroll
+        for (int o = LW / 2; o > 0; o >>= 1) dotw += __shfl_xor_sync(BLU_FULL, dotw, o);
+        if (active && a == 0) g1tw[col] = -scales * dotw;
+        __syncwarp();                                       // scratch consumed before the next pair stages into it
+        fp = fpn; ic = icn; gv = gvn; dc = dcn;
+#pragma unroll
+        for (int u = 0; u < CV; ++u) cv[u] = cvn[u];
     }
 }
 
@@ -184,9 +273,11 @@ blu_kkt_syrk_kernel(const double *__restrict__ Bs, long long n, int QP, double *
     }
 }
 
-// cap = I + sum over the row splits (split order) of the partial tiles, mirrored; v = column Q.
-__global__ void blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, int Q, int QP,
-                                       double *__restrict__ cap, double *__restrict__ v)
+// cap = I + sum over the row splits (split order) of the partial tiles; v = column Q.
+// Output in the layout blu_kkt_chol_kernel factors in place: COLUMN-major with leading dimension LD >= Q + 1, element (i, j)
+// at cap[j * LD + i]; the right-hand side rides along as the extra ROW Q of the matrix (cap[j * LD + Q] = v_j).
+__global__ void blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, int Q, int QP, int LD,
+                                       double *__restrict__ cap)
 {
     const int NTQ = QP >> 3;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npairs * 64; t += gridDim.x * blockDim.x) {
@@ -200,70 +291,188 @@ __global__ void blu_kkt_capfold_kernel(const double *__restrict__ part, int npai
         if (r < Q && c < Q) {
             if (ti != tj || r <= c) {
                 const double val = s + (r == c ? 1.0 : 0.0);
-                cap[r * Q + c] = val;
-                cap[c * Q + r] = val;
+                cap[(size_t)r * LD + c] = val;
+                cap[(size_t)c * LD + r] = val;
             }
-        } else if (c == Q && r < Q) v[r] = s;
+        } else if (c == Q && r < Q) cap[(size_t)r * LD + Q] = s;
     }
 }
 
-// Cholesky (lower, in place) of the Q x Q SPD capacitance matrix and the solve cap y = v, one CTA.
-__global__ void __launch_bounds__(512)
-blu_kkt_chol_kernel(double *__restrict__ cap, int Q, const double *__restrict__ v, double *__restrict__ y, int *__restrict__ info)
+// Cholesky of the Q x Q SPD capacitance matrix and the solve cap y = v: ONE CTA, blocked right-looking, in place in global
+// memory (the matrix, <= 0.5 MB, lives in L2; only a 16-column panel is ever in shared memory, so Q is not limited by the
+// 227 KB of one SM -- the previous whole-matrix-in-shared version stopped at Q ~ 170, i.e. 16 models).
+//   cap   column-major lower triangle, (i, j) at cap[j*LD + i], rows 0..Q: row Q is the right-hand side v.  Carrying v as
+//         an extra row makes its factor row L[Q][:] = L^-1 v -- the forward substitution costs nothing extra.
+// Per panel of 16 columns: (1) panel -> shared (column-major, conflict-free in the row index); (2) warp 0 factors the 16 x 16
+// diagonal block in registers (lane = row, shuffles broadcast the pivot column); (3) one thread per row below applies
+// L_d^-T (136 multiply-adds against broadcast shared reads); (4) panel -> global; (5) trailing update
+// A[i][j] -= sum_c P[i][c] P[j][c]: a warp task is 64 rows x 8 columns (lane: rows l, l+32; coalesced global
+// read-modify-write, panel operands from shared), tasks entirely above the diagonal are skipped.
+// Then the backward substitution L^T y = y' by 16-column blocks from the end (warp 0 solves the block, all threads
+// propagate it into the remaining right-hand side).
+#define BLU_CHOL_T 512
+#ifdef BLU_CHOL_STAMPS                  // lab only (tools/lab/chol_lab.cu): cycles per phase, accumulated by thread 0
+__device__ long long blu_chol_cycles[8];
+#define BLU_CHOL_STAMP(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); blu_chol_cycles[i] += now_ - t_last_; t_last_ = now_; } } while (0)
+#else
+#define BLU_CHOL_STAMP(i) do { } while (0)
+#endif
+#define BLU_CHOL_PITCH 272            // rows of a panel (<= 256) + the overhang of masked rows in the trailing update
+__global__ void __launch_bounds__(BLU_CHOL_T)
+blu_kkt_chol_kernel(double *cap, int Q, int LD, double *__restrict__ y, int *__restrict__ info)
 {
-    extern __shared__ double cs[];                        // Q x (Q + 1)
-    const int ld = Q + 1, tid = threadIdx.x, nthr = blockDim.x;
-    for (int t = tid; t < Q * Q; t += nthr) cs[(t / Q) * ld + (t % Q)] = cap[t];
+    __shared__ __align__(16) double sP[16 * BLU_CHOL_PITCH];      // sP[c][r] = panel column c, row j0 + r
+    __shared__ double sD[16 * 17];                                // sD[i][s] = L_d[i][s]
+    __shared__ double sinv[16];
+    __shared__ double sy[272];
+    __shared__ double sdinv[272];                                 // 1 / L[j][j]: the backward substitution multiplies
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int R = Q + 1;
+#ifdef BLU_CHOL_STAMPS
+    long long t_last_ = clock64();
+#endif
+    if (tid == 0) s_bad = 0;
     __syncthreads();
-    // left-looking: column j = (A[j:, j] - L[j:, :j] L[j, :j]^T) / l_jj, thread i owns row i -- two barriers per column,
-    // row reads are conflict free (odd leading dimension), the pivot row is a broadcast
-    __shared__ double s_piv;
-    for (int j = 0; j < Q; ++j) {
-        double sv[1];
-        const int i = j + tid;
-        sv[0] = 0.0;
-        if (i < Q) {
-            double acc0 = cs[i * ld + j], acc1 = 0.0;
-            const double *ri = cs + i * ld, *rj = cs + j * ld;
-            int c = 0;
-#pragma unroll 4
-            for (; c + 1 < j; c += 2) {                       // independent loads batched: the plain loop waited ~35 cycles per term
-                acc0 = fma(-ri[c], rj[c], acc0);
-                acc1 = fma(-ri[c + 1], rj[c + 1], acc1);
+    for (int j0 = 0; j0 < Q; j0 += 16) {
+        const int w = min(16, Q - j0);
+        const int nrow = R - j0;
+        for (int t = tid; t < 16 * nrow; t += BLU_CHOL_T) {
+            const int c = t / nrow, r = t - c * nrow;
+            sP[c * BLU_CHOL_PITCH + r] = (c < w) ? cap[(size_t)(j0 + c) * LD + j0 + r] : 0.0;
+        }
+        __syncthreads();
+        BLU_CHOL_STAMP(0);
+        if (wid == 0) {
+            double x[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) x[c] = sP[c * BLU_CHOL_PITCH + (lane & 15)];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                if (s < w) {
+                    const double dss = __shfl_sync(BLU_FULL, x[s], s);
+                    if (!(dss > 0.0) && lane == 0 && s_bad == 0) s_bad = j0 + s + 1;
+                    const double inv = rsqrt(dss), ls = dss * inv;      // one long-latency operation on the critical chain, not two
+                    x[s] = (lane == s) ? ls : x[s] * inv;
+#pragma unroll
+                    for (int c = s + 1; c < 16; ++c) {
+                        const double lcs = __shfl_sync(BLU_FULL, x[s], c);
+                        x[c] = fma(-x[s], lcs, x[c]);
+                    }
+                    if (lane == 0) { sinv[s] = inv; sdinv[j0 + s] = inv; }
+                }
             }
-            if (c < j) acc0 = fma(-ri[c], rj[c], acc0);
-            acc0 += acc1;
-            sv[0] = acc0;
-            if (i == j) s_piv = acc0;
+            if (lane < w) {
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const double vv = (s <= lane) ? x[s] : 0.0;
+                    sD[lane * 17 + s] = vv;
+                    sP[s * BLU_CHOL_PITCH + lane] = vv;
+                }
+            }
         }
         __syncthreads();
-        const double djj = s_piv;
-        if (!(djj > 0.0)) { if (tid == 0) *info = j + 1; return; }          // same value in every thread
-        const double sj = sqrt(djj);
-        if (i < Q) cs[i * ld + j] = (i == j) ? sj : sv[0] / sj;
+        if (s_bad) { if (tid == 0) *info = s_bad; return; }         // same value in every thread
+        BLU_CHOL_STAMP(1);
+        if (tid < nrow - w) {
+            const int r = w + tid;
+            double x[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) x[c] = sP[c * BLU_CHOL_PITCH + r];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                if (s < w) {
+                    x[s] *= sinv[s];
+#pragma unroll
+                    for (int c = s + 1; c < 16; ++c) x[c] = fma(-x[s], sD[c * 17 + s], x[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sP[c * BLU_CHOL_PITCH + r] = (c < w) ? x[c] : 0.0;
+        }
         __syncthreads();
-    }
-    // forward and backward substitution by one warp (Q <= 240): lane-strided dot products, shuffle reduction
-    __shared__ double ys[256];
-    if (tid < 32) {
-        for (int i = 0; i < Q; ++i) {
-            double s = 0.0;
-            for (int c = tid; c < i; c += 32) s = fma(cs[i * ld + c], ys[c], s);
-            s = blu_warp_sum(s);
-            if (tid == 0) ys[i] = (v[i] - s) / cs[i * ld + i];
-            __syncwarp();
+        BLU_CHOL_STAMP(2);
+        for (int t = tid; t < w * nrow; t += BLU_CHOL_T) {
+            const int c = t / nrow, r = t - c * nrow;
+            cap[(size_t)(j0 + c) * LD + j0 + r] = sP[c * BLU_CHOL_PITCH + r];
         }
-        for (int i = Q - 1; i >= 0; --i) {
-            double s = 0.0;
-            for (int c = i + 1 + tid; c < Q; c += 32) s = fma(cs[c * ld + i], ys[c], s);
-            s = blu_warp_sum(s);
-            if (tid == 0) ys[i] = (ys[i] - s) / cs[i * ld + i];
-            __syncwarp();
+        BLU_CHOL_STAMP(3);
+        const int j1 = j0 + 16;
+        if (j1 < Q) {
+            const int n_r = R - j1, n_c = Q - j1;
+            const int nrb = (n_r + 63) >> 6, ncg = (n_c + 7) >> 3;
+            for (int task = wid; task < nrb * ncg; task += BLU_CHOL_T / 32) {
+                const int rb = task / ncg, cg = task - rb * ncg;
+                if (rb * 64 + 63 < 8 * cg) continue;                 // the whole task lies above the diagonal
+                const int ia = rb * 64 + lane, ib = ia + 32;
+                double acc[2][8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int col = 8 * cg + cc;
+                    const size_t base = (size_t)(j1 + col) * LD + j1;
+                    acc[0][cc] = (col < n_c && ia < n_r) ? cap[base + ia] : 0.0;
+                    acc[1][cc] = (col < n_c && ib < n_r) ? cap[base + ib] : 0.0;
+                }
+#pragma unroll 4
+                for (int c = 0; c < 16; ++c) {
+                    const double *pc = sP + c * BLU_CHOL_PITCH + 16;
+                    const double a0 = pc[ia], a1 = pc[ib];
+                    const double2 *pb = reinterpret_cast<const double2 *>(pc + 8 * cg);
+                    const double2 b01 = pb[0], b23 = pb[1], b45 = pb[2], b67 = pb[3];
+                    const double b[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) { acc[0][cc] = fma(-a0, b[cc], acc[0][cc]); acc[1][cc] = fma(-a1, b[cc], acc[1][cc]); }
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int col = 8 * cg + cc;
+                    const size_t base = (size_t)(j1 + col) * LD + j1;
+                    if (col < n_c && ia < n_r) cap[base + ia] = acc[0][cc];
+                    if (col < n_c && ib < n_r) cap[base + ib] = acc[1][cc];
+                }
+            }
         }
-        if (tid == 0) *info = 0;
+        __syncthreads();
+        BLU_CHOL_STAMP(4);
     }
+    // backward substitution: L^T y = y' (y' = row Q of the factor)
+    for (int t = tid; t < Q; t += BLU_CHOL_T) sy[t] = cap[(size_t)t * LD + Q];
     __syncthreads();
-    for (int t = tid; t < Q; t += nthr) y[t] = ys[t];
+    for (int jb = ((Q - 1) >> 4) << 4; jb >= 0; jb -= 16) {
+        const int w = min(16, Q - jb);
+        if (wid == 0) {
+            double Lc[16];                                        // lane c: column c of the diagonal block, Lc[s] = L[jb+s][jb+c]
+#pragma unroll
+            for (int s = 0; s < 16; ++s) Lc[s] = (lane < w && s >= lane && s < w) ? cap[(size_t)(jb + lane) * LD + jb + s] : 0.0;
+            double rc = (lane < w) ? sy[jb + lane] : 0.0;
+            const double dinv = (lane < w) ? sdinv[jb + lane] : 0.0;
+#pragma unroll
+            for (int s = 15; s >= 0; --s) {
+                if (s < w) {
+                    const double ys = __shfl_sync(BLU_FULL, rc * dinv, s);
+                    if (lane == s) rc = ys;
+                    else if (lane < s) rc = fma(-Lc[s], ys, rc);
+                }
+            }
+            if (lane < w) sy[jb + lane] = rc;
+        }
+        __syncthreads();
+        BLU_CHOL_STAMP(5);
+        for (int i = tid; i < jb; i += BLU_CHOL_T) {
+            const double *col = cap + (size_t)i * LD + jb;
+            double lv[16];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) lv[s] = (s < w) ? col[s] : 0.0;
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < 16; ++s) acc = fma(lv[s], (s < w) ? sy[jb + s] : 0.0, acc);
+            sy[i] -= acc;
+        }
+        __syncthreads();
+        BLU_CHOL_STAMP(6);
+    }
+    for (int t = tid; t < Q; t += BLU_CHOL_T) y[t] = sy[t];
+    if (tid == 0) *info = 0;
 }
 
 // ux[col] = d[col]^2 rhs[col] - d[col] (Bs[col][0..Q) . y).  One warp per column.
