@@ -1557,7 +1557,10 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     CUDA_TRY(cudaMalloc(&bBs.p, sizeof(double) * (size_t)n * QP));
     CUDA_TRY(cudaMalloc(&bsmall.p, sizeof(double) * nsmall));
     CUDA_TRY(cudaMalloc(&bvec.p, sizeof(double) * nvec));
-    CUDA_TRY(cudaMalloc(&bpart.p, sizeof(double) * 64 * 16 * (size_t)((QP / 8) * (QP / 8 + 1) / 2)));      // partial tiles: 16 row splits at most
+    // Gram kernel: ny CTAs share the 4 x 4 tile blocks of one row range (one block per warp), nsplit row ranges = partial tile sets; one wave
+    const int ny = (blu_kkt_syrk_blocks(QP) + BLU_SYRK_WARPS - 1) / BLU_SYRK_WARPS;
+    const int nsplit = (int)std::max<long long>(1, std::min<long long>(c->nsm / ny, (n + 63) / 64));
+    CUDA_TRY(cudaMalloc(&bpart.p, sizeof(double) * 64 * (size_t)nsplit * (size_t)((QP / 8) * (QP / 8 + 1) / 2)));
     double *d_part = (double *)bpart.p;
     double *d_Bs = (double *)bBs.p;
     double *d_rinv = (double *)bsmall.p, *d_Wm = d_rinv + MM, *d_cap = d_Wm + MM, *d_y = d_cap + (size_t)Q * LDC;
@@ -1600,10 +1603,11 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
             n, nlin, d_bx, d_bz0, d_d, d_Gx, d_d + n, d_g1tw, Q, QP, d_rhs, d_Bs);
         KERNEL_CHECK(c);
         const int NTQ = QP / 8, npairs = NTQ * (NTQ + 1) / 2;
-        const int nsplit = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, n / 2048), ((long long)c->nsm * 6 + npairs - 1) / npairs));
-        blu_kkt_syrk_kernel<<<dim3((unsigned)npairs, (unsigned)nsplit), BLU_KKT_WARPS * 32, 0, st>>>(d_Bs, n, QP, d_part);
+        const size_t ssm = blu_kkt_syrk_smem(QP);
+        CUDA_TRY(cudaFuncSetAttribute(blu_kkt_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+        blu_kkt_syrk_kernel<<<dim3((unsigned)nsplit, (unsigned)ny), BLU_SYRK_WARPS * 32, ssm, st>>>(d_Bs, n, QP, d_part);
         KERNEL_CHECK(c);
-        blu_kkt_capfold_kernel<<<(npairs * 64 + 255) / 256, 256, 0, st>>>(d_part, npairs, nsplit, Q, QP, LDC, d_cap);
+        blu_kkt_capfold_kernel<<<npairs, 256, 0, st>>>(d_part, npairs, nsplit, Q, QP, LDC, d_cap);
         KERNEL_CHECK(c);
         blu_kkt_chol_kernel<<<1, BLU_CHOL_T, 0, st>>>(d_cap, Q, LDC, d_y, d_info);
         KERNEL_CHECK(c);

@@ -19,7 +19,8 @@
 //                         the member columns of r^-1, the nlin constraint entries, everything times d_col (= D^-1/2),
 //                         plus the column's entry of G1^T vec(Lam Z Lam) (right-hand side) -> row of Bs (n x QP)
 //   blu_kkt_syrk_kernel   cap = I + Bs^T Bs and v = Bs^T (d * rhs) in one pass (the rhs rides along as column Q):
-//                         mma.m8n8k4.f64, one CTA per 8 x 8 tile pair, warps combined in a fixed order
+//                         mma.m8n8k4.f64, a CTA per row range with the rows staged once in shared memory, all tile pairs
+//                         dealt to its warps; CTA partials folded in a fixed order
 //   blu_kkt_chol_kernel   blocked Cholesky of the Q x Q capacitance matrix (in place in L2, 16-column panels in shared
 //                         memory, the right-hand side carried as an extra row) + backward substitution, one CTA
 //   blu_kkt_apply_kernel  ux_col = d_col^2 rhs_col - d_col (Bs_col . y)
@@ -27,6 +28,7 @@
 #pragma once
 #include "blu_common.cuh"
 #include "blu_hess.cuh"
+#include "blu_stream.cuh"
 
 #define BLU_KKT_WARPS 8
 
@@ -225,77 +227,160 @@ __global__ void blu_kkt_rhs_kernel(long long n, int nlin, const double *__restri
     }
 }
 
-// cap = I + Bs^T Bs and v = Bs^T (d * rhs) (column Q of Bs): ONE CTA PER TILE PAIR (ti <= tj) of the QP = 8 NTQ
-// columns.  The 8 warps split the rows; a lane's fragment of tile t (row 4 s + (lane & 3), column 8 t + (lane >> 2)) is
-// the A operand for t = ti and the B operand for t = tj of mma.m8n8k4.f64; four independent accumulator pairs per
-// warp hide the DMMA latency.  Bs (n x QP doubles, tens of MB) is L2 resident, so re-reading two tile columns per
-// pair costs L2 bandwidth only.  Warps are combined in warp order: no partial tiles in HBM, no atomics, bit-reproducible.
-__global__ void __launch_bounds__(BLU_KKT_WARPS * 32)
+// cap = I + Bs^T Bs and v = Bs^T (d * rhs) (column Q of Bs) on the FP64 tensor cores.  A CTA owns a contiguous range of
+// rows: 32-row chunks are staged in shared memory by bulk asynchronous copies (one 8 QP-byte row per copy, 3 stages, row
+// pitch QP + 4 doubles so that the four sample rows of a fragment fall into different banks), so an element of Bs crosses
+// L2 -> SM once per CTA that needs it.  The NTQ x NTQ grid of 8 x 8 tiles is cut into 4 x 4 BLOCKS; every block that touches
+// the upper triangle belongs to one warp (16 warps per CTA; gridDim.y CTAs share a row range when there are more than 16
+// blocks).  Per 4 rows a warp loads 4 + 4 fragments (a lane's fragment of tile t: row 4 s + (lane & 3), column
+// 8 t + (lane >> 2) -- the A operand for t = ti, the B operand for t = tj of mma.m8n8k4.f64) with immediate offsets and
+// issues 16 DMMAs: no address arithmetic, no predicates in the loop.  Partial tiles per row range, folded in a fixed order
+// by blu_kkt_capfold_kernel: no atomics, bit-reproducible.
+// History (15 models, 32768 x 144): one CTA per tile pair and row split, fragments straight from L2: 108 us (every tile
+// column re-read NTQ + 1 times, 717 MB through L2 for a 37.7 MB matrix); rows staged once but the pairs dealt to the warps
+// through a run table: 85 us, 30 instructions per DMMA (per-pair address arithmetic and predicated reloads).
+#define BLU_SYRK_WARPS 16
+#define BLU_SYRK_RC 32
+#define BLU_SYRK_NS 3
+__host__ __device__ __forceinline__ size_t blu_kkt_syrk_smem(int QP) { return sizeof(double) * ((size_t)BLU_SYRK_NS * BLU_SYRK_RC * (QP + 4) + 64); }
+__host__ __device__ __forceinline__ int blu_kkt_syrk_blocks(int QP) { const int nb = ((QP >> 3) + 3) >> 2; return nb * (nb + 1) / 2; }
+
+// explicit shared-space load (32-bit address, immediate offsets fold into the instruction)
+__device__ __forceinline__ double blu_kkt_lds(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+__global__ void __launch_bounds__(BLU_SYRK_WARPS * 32, 1)
 blu_kkt_syrk_kernel(const double *__restrict__ Bs, long long n, int QP, double *__restrict__ part)
 {
-    // grid (tile pairs, row splits): more CTAs per SM = more strided L2 reads in flight (one split was latency bound:
-    // long_scoreboard 59 warps per issue, tensor pipe 4 %); partial 8 x 8 tiles, folded in split order by the next kernel
-    __shared__ double red[BLU_KKT_WARPS][64];
-    const int NTQ = QP >> 3;
-    int ti = 0, rem = blockIdx.x;
-    while (rem >= NTQ - ti) { rem -= NTQ - ti; ++ti; }
-    const int tj = ti + rem;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) double ssm[];         // [NS][RC][PITCH] + slack for the fragments of padding tiles
+    __shared__ __align__(8) unsigned long long bars[BLU_SYRK_NS];
+    const int PITCH = QP + 4;
+    const int NTQ = QP >> 3, npairs = NTQ * (NTQ + 1) / 2;
+    const int nb = (NTQ + 3) >> 2;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int ks = lane & 3, cq = lane >> 2;
-    const long long rows_per = (((n + gridDim.y - 1) / gridDim.y) + 15) / 16 * 16;
-    const long long r0 = (long long)blockIdx.y * rows_per;
+    if (tid == 0) {
+        for (int s = 0; s < BLU_SYRK_NS; ++s) blu_mbar_init(&bars[s], 1);
+        blu_mbar_fence_init();
+    }
+    __syncthreads();
+    // this warp's block (bi <= bj) of the nb x nb block grid, or none
+    int bi = 0, rem = blockIdx.y * BLU_SYRK_WARPS + w;
+    while (bi < nb && rem >= nb - bi) { rem -= nb - bi; ++bi; }
+    const bool have = bi < nb;
+    const int bj = bi + rem;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    const long long rows_per = ((n + gridDim.x - 1) / gridDim.x + BLU_SYRK_RC - 1) / BLU_SYRK_RC * BLU_SYRK_RC;
+    const long long r0 = (long long)blockIdx.x * rows_per;
     long long r1 = r0 + rows_per;
     if (r1 > n) r1 = n;
-    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-    const double *pi = Bs + 8 * ti + cq, *pj = Bs + 8 * tj + cq;
-    for (long long base = r0 + (long long)w * 32; base < r1; base += (long long)BLU_KKT_WARPS * 32) {
-        double fi[8], fj[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const long long row = base + 4 * u + ks;
-            const bool ok = row < r1;
-            fi[u] = ok ? __ldg(pi + row * QP) : 0.0;
-            fj[u] = ok ? __ldg(pj + row * QP) : 0.0;
+    const int nchunk = r1 > r0 ? (int)((r1 - r0 + BLU_SYRK_RC - 1) / BLU_SYRK_RC) : 0;
+    auto issue = [&](int ch) {                            // warp 0, all lanes: one row per lane
+        const int st = ch % BLU_SYRK_NS;
+        const long long rb = r0 + (long long)ch * BLU_SYRK_RC;
+        const int cr = (int)((r1 - rb) < BLU_SYRK_RC ? (r1 - rb) : BLU_SYRK_RC);
+        if (lane == 0) blu_mbar_expect_tx(&bars[st], (unsigned)(cr * QP * 8));
+        __syncwarp();
+        if (lane < cr) blu_bulk_g2s(ssm + ((size_t)st * BLU_SYRK_RC + lane) * PITCH, Bs + (rb + lane) * QP, (unsigned)(QP * 8), &bars[st]);
+    };
+    if (w == 0)
+        for (int ch = 0; ch < BLU_SYRK_NS - 1 && ch < nchunk; ++ch) issue(ch);
+    const unsigned s_base = blu_smem_u32(ssm);
+    // byte offset of this lane's fragment of tile 4 bi (A side) / 4 bj (B side) inside a stage, row ks
+    const unsigned offA = (unsigned)((ks * PITCH + cq + 32 * bi) * 8), offB = (unsigned)((ks * PITCH + cq + 32 * bj) * 8);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int st = ch % BLU_SYRK_NS;
+        if (w == 0 && ch + BLU_SYRK_NS - 1 < nchunk) issue(ch + BLU_SYRK_NS - 1);      // the stage consumed one iteration ago (barrier below)
+        blu_mbar_wait(&bars[st], (unsigned)((ch / BLU_SYRK_NS) & 1));
+        const long long rb = r0 + (long long)ch * BLU_SYRK_RC;
+        const int cr = (int)((r1 - rb) < BLU_SYRK_RC ? (r1 - rb) : BLU_SYRK_RC);
+        if (cr < BLU_SYRK_RC) {                           // last chunk of the range: the missing rows count as zeros
+            double *sb = ssm + (size_t)st * BLU_SYRK_RC * PITCH;
+            for (int t = tid; t < (BLU_SYRK_RC - cr) * PITCH; t += blockDim.x) sb[cr * PITCH + t] = 0.0;
+            __syncthreads();
         }
+        if (have) {
+            const unsigned sa = s_base + (unsigned)(st * BLU_SYRK_RC * PITCH * 8);
+#pragma unroll 2
+            for (int r4 = 0; r4 < BLU_SYRK_RC / 4; ++r4) {
+                const unsigned ra = sa + (unsigned)(r4 * 4 * PITCH * 8);
+                double fa[4], fb[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) blu_dmma(acc[u & 3][0], acc[u & 3][1], fi[u], fj[u]);
+                for (int i = 0; i < 4; ++i) { fa[i] = blu_kkt_lds(ra + offA + 64u * i); fb[i] = blu_kkt_lds(ra + offB + 64u * i); }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) blu_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            }
+        }
+        __syncthreads();                                  // stage consumed before it is refilled
     }
-    const double c0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-    const double c1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
-    red[w][cq * 8 + 2 * ks] = c0;                        // C fragment: row cq, cols 2 ks + {0,1}
-    red[w][cq * 8 + 2 * ks + 1] = c1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        double s = 0.0;
+    // C fragment: row cq, cols 2 ks + {0,1} of the 8 x 8 tile; tiles below the diagonal or in the padding are dropped
+    if (have) {
 #pragma unroll
-        for (int ww = 0; ww < BLU_KKT_WARPS; ++ww) s += red[ww][threadIdx.x];
-        part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + threadIdx.x] = s;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ti = 4 * bi + i, tj = 4 * bj + j;
+                if (ti <= tj && tj < NTQ) {
+                    const int p = ti * NTQ - ti * (ti - 1) / 2 + (tj - ti);
+                    double *dst = part + ((size_t)blockIdx.x * npairs + p) * 64 + cq * 8 + 2 * ks;
+                    dst[0] = acc[i][j][0];
+                    dst[1] = acc[i][j][1];
+                }
+            }
     }
 }
 
-// cap = I + sum over the row splits (split order) of the partial tiles; v = column Q.
+// cap = I + sum over the row ranges (fixed order) of the partial tiles; v = column Q.
 // Output in the layout blu_kkt_chol_kernel factors in place: COLUMN-major with leading dimension LD >= Q + 1, element (i, j)
 // at cap[j * LD + i]; the right-hand side rides along as the extra ROW Q of the matrix (cap[j * LD + Q] = v_j).
-__global__ void blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, int Q, int QP, int LD,
-                                       double *__restrict__ cap)
+// Four threads per element, each sums a contiguous quarter of the row ranges with 8 loads in flight; the quarters are
+// combined by a fixed shuffle tree.
+__global__ void __launch_bounds__(256)
+blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, int Q, int QP, int LD, double *__restrict__ cap)
 {
     const int NTQ = QP >> 3;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npairs * 64; t += gridDim.x * blockDim.x) {
-        const int p = t >> 6, e = t & 63;
-        int ti = 0, rem = p;
-        while (rem >= NTQ - ti) { rem -= NTQ - ti; ++ti; }
-        const int tj = ti + rem;
-        double s = 0.0;
-        for (int sp = 0; sp < nsplit; ++sp) s += part[((size_t)sp * npairs + p) * 64 + e];
-        const int r = 8 * ti + (e >> 3), c = 8 * tj + (e & 7);
-        if (r < Q && c < Q) {
-            if (ti != tj || r <= c) {
-                const double val = s + (r == c ? 1.0 : 0.0);
-                cap[(size_t)r * LD + c] = val;
-                cap[(size_t)c * LD + r] = val;
-            }
-        } else if (c == Q && r < Q) cap[(size_t)r * LD + Q] = s;
+    const int t = blockIdx.x * 64 + (threadIdx.x >> 2), sub = threadIdx.x & 3;       // 64 elements (one tile) per CTA
+    const int p = t >> 6, e = t & 63;
+    double s = 0.0;
+    if (p < npairs) {
+        const int nq = (nsplit + 3) >> 2;
+        const int s0 = sub * nq, s1 = min(nsplit, s0 + nq);
+        const double *src = part + (size_t)p * 64 + e;
+        const size_t stride = (size_t)npairs * 64;
+        int sp = s0;
+        for (; sp + 8 <= s1; sp += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(sp + u) * stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; sp < s1; ++sp) s += __ldg(src + (size_t)sp * stride);
     }
+    s += __shfl_xor_sync(BLU_FULL, s, 1);
+    s += __shfl_xor_sync(BLU_FULL, s, 2);
+    if (p >= npairs || sub != 0) return;
+    int ti = 0, rem = p;
+    while (rem >= NTQ - ti) { rem -= NTQ - ti; ++ti; }
+    const int tj = ti + rem;
+    const int r = 8 * ti + (e >> 3), c = 8 * tj + (e & 7);
+    if (r < Q && c < Q) {
+        if (ti != tj || r <= c) {
+            const double val = s + (r == c ? 1.0 : 0.0);
+            cap[(size_t)r * LD + c] = val;
+            cap[(size_t)c * LD + r] = val;
+        }
+    } else if (c == Q && r < Q) cap[(size_t)r * LD + Q] = s;
 }
 
 // Cholesky of the Q x Q SPD capacitance matrix and the solve cap y = v: ONE CTA, blocked right-looking, in place in global
