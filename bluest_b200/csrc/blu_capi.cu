@@ -115,6 +115,8 @@ struct blu_ctx {
     std::vector<void *> ipc_opened;
     double *d_Sop = nullptr;           // S = 2 pinv(Phi) of the evaluation the resident U factor belongs to (the operator's own copy)
     double *d_hvpart = nullptr, *d_hvp = nullptr, *d_hvout = nullptr;   // Hessian mat-vec: CTA partials of t, staged p and H p
+    void *kkt_ws[4] = {nullptr, nullptr, nullptr, nullptr};            // blu_kkt_solve workspace (Bs | small | vectors | partial tiles), kept between solves
+    size_t kkt_cap[4] = {0, 0, 0, 0};
     int hv_grid = 1;
     bool uv_ready = false, v_ready = false;   // U (and V) hold the factors of the last want_hess evaluation
     std::vector<cudaEvent_t> evlog;    // optional per-evaluation event log (4 events per evaluation)
@@ -183,6 +185,7 @@ extern "C" int blu_ctx_destroy(blu_ctx *c)
     for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
     cudaFree(c->d_xchg);
     cudaFree(c->d_hvpart); cudaFree(c->d_hvp); cudaFree(c->d_hvout); cudaFree(c->d_Sop);
+    for (int q = 0; q < 4; ++q) { if (c->kkt_ws[q]) cudaFree(c->kkt_ws[q]); c->kkt_ws[q] = nullptr; c->kkt_cap[q] = 0; }
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     if (c->h_m) cudaFreeHost(c->h_m);
     if (c->h_grad) cudaFreeHost(c->h_grad);
@@ -485,6 +488,7 @@ extern "C" int blu_ctx_clone(blu_ctx *p, blu_ctx **out)
     c->d_m = c->d_part = c->d_phi = c->d_pinv = c->d_x = c->d_S = c->d_grad = c->d_U = c->d_V = c->d_H = nullptr;
     c->d_hdr = nullptr; c->h_hdr = nullptr; c->h_m = c->h_grad = nullptr; c->pend_hess = nullptr; c->pending = false;
     c->d_xchg = nullptr; c->peers = BluPeers{}; c->d_Sop = c->d_hvpart = c->d_hvp = c->d_hvout = nullptr;
+    for (int q = 0; q < 4; ++q) { c->kkt_ws[q] = nullptr; c->kkt_cap[q] = 0; }
     c->H_rows = 0; c->uv_ready = c->v_ready = false; c->capturing = false; c->d_grad_out = nullptr; c->timed = false;
 #define CL_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int code_ = fail(e_ == cudaErrorMemoryAllocation ? BLU_ERR_NOMEM : BLU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); blu_ctx_destroy(c); return code_; } } while (0)
     const size_t NN = (size_t)c->N * c->N;
@@ -1549,18 +1553,30 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
     };
     sandwich(Z, Wm.data());
     // device buffers
-    struct DevBuf { void *p = nullptr; ~DevBuf() { if (p) cudaFree(p); } };
+    // workspace: an interior-point solve calls this once per iteration with the same sizes, so the buffers (37.7 MB of Bs at 15
+    // models) stay with the context instead of being allocated and freed per call (that alone was > 1 ms of a 2.4 ms call)
+    struct DevBuf { void *p = nullptr; };
     DevBuf bBs, bsmall, bvec, bpart;
+    auto reserve = [&](int slot, size_t bytes, DevBuf &out) -> cudaError_t {
+        if (c->kkt_cap[slot] < bytes) {
+            if (c->kkt_ws[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->kkt_ws[slot]); c->kkt_ws[slot] = nullptr; c->kkt_cap[slot] = 0; }
+            cudaError_t e_ = cudaMalloc(&c->kkt_ws[slot], bytes);
+            if (e_ != cudaSuccess) return e_;
+            c->kkt_cap[slot] = bytes;
+        }
+        out.p = c->kkt_ws[slot];
+        return cudaSuccess;
+    };
     const int LDC = ((Q + 1 + 3) / 4) * 4;                                        // leading dimension of the capacitance matrix (+ the rhs row)
     const size_t nsmall = (size_t)2 * MM + (size_t)Q * LDC + 256 + 8;             // rinv | Wm | cap (column-major, rhs as row Q) | y | info
     const size_t nvec = (size_t)(n + nlin) + (size_t)nlin * n + 5 * (size_t)n + nlin;   // d | Gx | bx | bz0 | g1tw | rhs | ux
-    CUDA_TRY(cudaMalloc(&bBs.p, sizeof(double) * (size_t)n * QP));
-    CUDA_TRY(cudaMalloc(&bsmall.p, sizeof(double) * nsmall));
-    CUDA_TRY(cudaMalloc(&bvec.p, sizeof(double) * nvec));
+    CUDA_TRY(reserve(0, sizeof(double) * (size_t)n * QP, bBs));
+    CUDA_TRY(reserve(1, sizeof(double) * nsmall, bsmall));
+    CUDA_TRY(reserve(2, sizeof(double) * nvec, bvec));
     // Gram kernel: ny CTAs share the 4 x 4 tile blocks of one row range (one block per warp), nsplit row ranges = partial tile sets; one wave
     const int ny = (blu_kkt_syrk_blocks(QP) + BLU_SYRK_WARPS - 1) / BLU_SYRK_WARPS;
     const int nsplit = (int)std::max<long long>(1, std::min<long long>(c->nsm / ny, (n + 63) / 64));
-    CUDA_TRY(cudaMalloc(&bpart.p, sizeof(double) * 64 * (size_t)nsplit * (size_t)((QP / 8) * (QP / 8 + 1) / 2)));
+    CUDA_TRY(reserve(3, sizeof(double) * 64 * (size_t)nsplit * (size_t)((QP / 8) * (QP / 8 + 1) / 2), bpart));
     double *d_part = (double *)bpart.p;
     double *d_Bs = (double *)bBs.p;
     double *d_rinv = (double *)bsmall.p, *d_Wm = d_rinv + MM, *d_cap = d_Wm + MM, *d_y = d_cap + (size_t)Q * LDC;
@@ -1776,10 +1792,11 @@ static int batch_reserve(blu_batch *b, int B)
     CUDA_TRY(cudaMalloc(&b->d_var, sizeof(double) * PB));
     CUDA_TRY(cudaMalloc(&b->d_flags, sizeof(unsigned) * PB));
     CUDA_TRY(cudaMalloc(&b->d_grad, sizeof(double) * (size_t)B * b->gtot));
-    CUDA_TRY(cudaHostAlloc(&b->h_m, sizeof(double) * (size_t)B * b->Lm, cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc(&b->h_var, sizeof(double) * PB, cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc(&b->h_flags, sizeof(unsigned) * PB, cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc(&b->h_grad, sizeof(double) * (size_t)B * b->gtot, cudaHostAllocDefault));
+    // pinned AND mapped: small batches are evaluated straight on these buffers (see blu_batch_eval)
+    CUDA_TRY(cudaHostAlloc(&b->h_m, sizeof(double) * (size_t)B * b->Lm, cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc(&b->h_var, sizeof(double) * PB, cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc(&b->h_flags, sizeof(unsigned) * PB, cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc(&b->h_grad, sizeof(double) * (size_t)B * b->gtot, cudaHostAllocMapped));
     b->capB = B;
     return BLU_OK;
 }
@@ -1795,19 +1812,33 @@ extern "C" int blu_batch_eval(blu_batch *b, const double *m, int B, double delta
     if (rc) return rc;
     const size_t PB = (size_t)b->P * B;
     memcpy(b->h_m, m, sizeof(double) * (size_t)B * b->Lm);
-    CUDA_TRY(cudaMemcpyAsync(b->d_m, b->h_m, sizeof(double) * (size_t)B * b->Lm, cudaMemcpyHostToDevice, b->stream));
+    // Small batches (<= 128 KB each way): the kernel reads the sample vectors from and writes variance / flags / gradient to the
+    // MAPPED pinned host buffers directly -- one launch and one synchronisation instead of one H2D and three D2H copy operations
+    // in front of and behind a 30 us kernel (each ~6 us of DMA set-up on the stream).  Larger batches keep the explicit copies.
+    const bool zc = (size_t)B * b->Lm <= 16384 && (size_t)B * b->gtot <= 16384 && !getenv("BLU_BATCH_NO_ZEROCOPY");
+    double *k_m = b->d_m, *k_var = b->d_var, *k_grad = b->d_grad;
+    unsigned *k_flags = b->d_flags;
+    if (zc) {
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&k_m, b->h_m, 0));
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&k_var, b->h_var, 0));
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&k_flags, b->h_flags, 0));
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&k_grad, b->h_grad, 0));
+    } else
+        CUDA_TRY(cudaMemcpyAsync(b->d_m, b->h_m, sizeof(double) * (size_t)B * b->Lm, cudaMemcpyHostToDevice, b->stream));
     const bool dbg = getenv("BLU_DEBUG_TIMING") != nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, b->stream); }
     dim3 grid((unsigned)b->P, (unsigned)B);
-    blu_batch_eval_kernel<<<grid, BLU_BATCH_WARPS * 32, b->smem, b->stream>>>(b->d_probs, b->d_m, b->Lm, delta, grad ? 1 : 0, b->Lmax, b->capC, b->capG, b->resident ? 1 : 0, b->d_hdrs, b->d_scratch,
-                                                                             b->d_var, b->d_flags, b->d_grad);
+    blu_batch_eval_kernel<<<grid, BLU_BATCH_WARPS * 32, b->smem, b->stream>>>(b->d_probs, k_m, b->Lm, delta, grad ? 1 : 0, b->Lmax, b->capC, b->capG, b->resident ? 1 : 0, b->d_hdrs, b->d_scratch,
+                                                                             k_var, k_flags, k_grad);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BLU_ERR_CUDA, "batch kernel launch failed: %s", cudaGetErrorString(e));
     if (dbg) cudaEventRecord(e1, b->stream);
-    CUDA_TRY(cudaMemcpyAsync(b->h_var, b->d_var, sizeof(double) * PB, cudaMemcpyDeviceToHost, b->stream));
-    CUDA_TRY(cudaMemcpyAsync(b->h_flags, b->d_flags, sizeof(unsigned) * PB, cudaMemcpyDeviceToHost, b->stream));
-    if (grad) CUDA_TRY(cudaMemcpyAsync(b->h_grad, b->d_grad, sizeof(double) * (size_t)B * b->gtot, cudaMemcpyDeviceToHost, b->stream));
+    if (!zc) {
+        CUDA_TRY(cudaMemcpyAsync(b->h_var, b->d_var, sizeof(double) * PB, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->h_flags, b->d_flags, sizeof(unsigned) * PB, cudaMemcpyDeviceToHost, b->stream));
+        if (grad) CUDA_TRY(cudaMemcpyAsync(b->h_grad, b->d_grad, sizeof(double) * (size_t)B * b->gtot, cudaMemcpyDeviceToHost, b->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     if (dbg) {
         float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);

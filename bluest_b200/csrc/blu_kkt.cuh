@@ -395,6 +395,11 @@ blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, 
 // read-modify-write, panel operands from shared), tasks entirely above the diagonal are skipped.
 // Then the backward substitution L^T y = y' by 16-column blocks from the end (warp 0 solves the block, all threads
 // propagate it into the remaining right-hand side).
+// Measured (tools/lab/chol_lab.cu, Q = 138): 80 us = 155 k cycles -- diagonal blocks 51 k (a 350-cycle dependent chain per
+// column: shuffle, rsqrt, 15 shuffles, multiply-add), trailing updates 45 k (bound by ONE SM's FP64 and shared-memory issue,
+// 64 x 8 tasks include the waste above the diagonal), rows below 14 k, panel load + store 19 k, backward substitution 26 k.
+// Copying the whole matrix into shared memory first (it fits up to 16 models) changed the total by 3 %: L2 latency is not
+// what limits it; the next step would be DMMA tile blocks for the trailing update.
 #define BLU_CHOL_T 512
 #ifdef BLU_CHOL_STAMPS                  // lab only (tools/lab/chol_lab.cu): cycles per phase, accumulated by thread 0
 __device__ long long blu_chol_cycles[8];

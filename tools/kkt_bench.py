@@ -1,6 +1,6 @@
 """KKT solve (scope-table row f1) at N models, all groups: device time of repeated solves (the first call pays the lazy
 module load of its kernels).  Under `ncu --metrics gpu__time_duration.sum -k regex:blu_kkt` it gives the per-kernel split."""
-import os, sys
+import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
@@ -20,9 +20,12 @@ for N in [int(a) for a in sys.argv[1:]] or [15]:
     bx = rng.randn(n)
     Z = rng.randn(M, M); Z = Z + Z.T
     bz = np.concatenate([rng.randn(n + nlin), Z.ravel()])
-    ms = []
+    ms, wall = [], []
     for it in range(6):
+        t0 = time.perf_counter()
         ux, uz, t = sap.kkt_solve(has_t, scales, Gx, d, r, bx, bz, return_ms=True)
+        wall.append((time.perf_counter() - t0) * 1e3)
         ms.append(t)
-    print("N=%d L=%d Q=%d: device ms per solve %s" % (N, L, M * (M + 1) // 2 + nlin, " ".join("%.3f" % t for t in ms)), flush=True)
+    print("N=%d L=%d Q=%d: device ms per solve %s | through the host API %s" % (N, L, M * (M + 1) // 2 + nlin, " ".join("%.3f" % t for t in ms),
+                                                                              " ".join("%.2f" % t for t in wall)), flush=True)
     sap.close()

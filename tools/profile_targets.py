@@ -25,6 +25,8 @@ def main():
         section_n20()
     if what in ("all", "batch"):
         section_batch()
+    if what in ("kkt_hv",):
+        section_kkt_hv()
     print("profile_targets: done")
 
 
@@ -46,6 +48,33 @@ def section_n15():
     Z = rng.randn(M, M); Z = Z + Z.T
     sap.kkt_solve(has_t, scales, Gx, 0.5 + rng.rand(n + nlin), np.eye(M) + 0.1 * rng.randn(M, M), rng.randn(n),
                   np.concatenate([rng.randn(n + nlin), Z.ravel()]))
+    sap.close()
+
+
+def section_kkt_hv():
+    # KKT solve at 15 models (three solves: the third is the one captured) and the Hessian-operator product at 20 models
+    N = 15
+    ga = blu.enumerate_group_arrays(N)
+    L = sum(len(g) for g in ga)
+    costs = blu.group_costs(ga, 2.0 ** (N - np.arange(N))); costs = costs / costs.max()
+    sap = blu.SAP(orc.wishart_cov(N, 0), N, ga, costs, verbose=False)
+    Gx, scales, has_t = sap.sdp_linear_rows(budget_mode=True)
+    rng = np.random.RandomState(0)
+    n, nlin, M = L + 1, Gx.shape[0], N + 1
+    Z = rng.randn(M, M); Z = Z + Z.T
+    for _ in range(3):
+        sap.kkt_solve(has_t, scales, Gx, 0.5 + rng.rand(n + nlin), np.eye(M) + 0.1 * rng.randn(M, M), rng.randn(n),
+                      np.concatenate([rng.randn(n + nlin), Z.ravel()]))
+    sap.close()
+    N = 20
+    ga = blu.enumerate_group_arrays(N)
+    L = sum(len(g) for g in ga)
+    sap = blu.SAP(orc.wishart_cov(N, 0), N, ga, np.ones(L), verbose=False)
+    v, g, op = sap.variance_GH_operator(orc.dense_m(L, 0))
+    p = torch.randn(L, dtype=torch.float64, device="cuda"); out = torch.empty_like(p)
+    for _ in range(4):
+        sap.hess_matvec_device(p, out)
+    sap.sync()
     sap.close()
 
 
