@@ -38,11 +38,11 @@ struct BluBatchProb {              // one problem of the batch: pointers into it
 //            thread has independent loads in flight: a warp walking its groups one dependent L2 access at a time would
 //            be pure latency), two barriers per chunk.
 template <typename Body>
-__device__ __forceinline__ void blu_batch_walk(const BluBatchProb &pr, bool resident, double *sC, uint8_t *sG, unsigned short *sjl, Body body)
+__device__ __forceinline__ void blu_batch_walk(const BluBatchProb &pr, const BluClass *scls, bool resident, double *sC, uint8_t *sG, unsigned short *sjl, Body body)
 {
     const int tid = threadIdx.x, nthr = blockDim.x, w = tid >> 5, lane = tid & 31;
     for (int ic = 0; ic < pr.ncls; ++ic) {
-        const BluClass ci = pr.cls[ic];
+        const BluClass ci = scls[ic];                     // the shared-memory copy: pr.cls is an L2 round trip per class
         const int k = ci.k, T = ci.T;
         const unsigned short *jl = sjl + ci.lutoff;
         if (resident) {
@@ -142,7 +142,11 @@ blu_batch_eval_kernel(const BluBatchProb *__restrict__ probs, const double *__re
     if (resident) blu_mbar_wait(&s_bar, 0u);
     BLU_STAMP(hdr, 1);                                   // [1] operands staged
     // ---- Phi: warp per group, lane per packed entry, warp-private tile (targets inside a group are distinct) ----
-    blu_batch_walk(pr, resident != 0, sC, sG, sjl, [&](const BluClass &ci, long long il, const uint8_t *g, const double *C, const unsigned short *jlt, int ln) {
+    // Measured alternatives of this phase at 10 models (12.2 us of the 26 us kernel; tools/batch_stamps.py): operands of the next step
+    // fetched before the current read-modify-write: 15.3 us; gather form (a warp per target entry scanning the group masks, sums in
+    // registers): 14.6 us -- divergence makes every scan step pay the full path.  The phase is bound by instruction issue on ONE SM
+    // (36 k packed entries, half-empty steps for k <= 7); the next step would be a cluster of CTAs per evaluation.
+    blu_batch_walk(pr, scls, resident != 0, sC, sG, sjl, [&](const BluClass &ci, long long il, const uint8_t *g, const double *C, const unsigned short *jlt, int ln) {
         const double mi = sm[ci.goff + il];
         if (mi != 0.0) {
             for (int e = ln; e < ci.T; e += 32) {
@@ -179,29 +183,30 @@ blu_batch_eval_kernel(const BluBatchProb *__restrict__ probs, const double *__re
     // ---- gradient: grad_i = - x_g^T Cinv_i x_g ----
     double *gout = grad_out + pr.goff * B + (long long)b * pr.L;
     if (resident) {
-        // one group per THREAD, class by class (no shuffles, independent chains): the data sits in shared memory
-        for (int ic = 0; ic < pr.ncls; ++ic) {
+        // one group per THREAD over the FLAT group index (no shuffles, independent chains): the data sits in shared memory.
+        // (Class by class, thread 0 owned a group of EVERY class -- 220 dependent entry steps at 10 models, 10.6 us -- while
+        // three quarters of the threads had none; flat, the longest chain is one group of the largest class: 1.2 us.)
+        for (long long i = tid; i < pr.L; i += nthr) {
+            const int ic = blu_batch_class_of(scls, pr.ncls, i);
             const int k = scls[ic].k, T = scls[ic].T;
-            const long long Lk = scls[ic].Lk, goffc = scls[ic].goff, ioff = scls[ic].ioff, coff = scls[ic].coff;
-            for (long long il = tid; il < Lk; il += nthr) {
-                const uint8_t *g = sG + ioff + il * k;
-                const double *C = sC + coff + il * T;
-                double s = 0.0;
-                int e = 0;
-                for (int j = 0; j < k; ++j) {
-                    const double xj = sx[g[j]];
-                    double row = 0.5 * C[e] * xj;                 // diagonal entry counts once
-                    ++e;
-                    for (int l = j + 1; l < k; ++l, ++e) row = fma(C[e], sx[g[l]], row);
-                    s = fma(2.0 * xj, row, s);
-                }
-                gout[goffc + il] = -s;
+            const long long il = i - scls[ic].goff;
+            const uint8_t *g = sG + scls[ic].ioff + il * k;
+            const double *C = sC + scls[ic].coff + il * T;
+            double s = 0.0;
+            int e = 0;
+            for (int j = 0; j < k; ++j) {
+                const double xj = sx[g[j]];
+                double row = 0.5 * C[e] * xj;                 // diagonal entry counts once
+                ++e;
+                for (int l = j + 1; l < k; ++l, ++e) row = fma(C[e], sx[g[l]], row);
+                s = fma(2.0 * xj, row, s);
             }
+            gout[i] = -s;
         }
         BLU_STAMP(hdr, 9);                               // [9] gradient written (this thread's share)
         return;
     }
-    blu_batch_walk(pr, false, sC, sG, sjl, [&](const BluClass &ci, long long il, const uint8_t *g, const double *C, const unsigned short *jlt, int ln) {
+    blu_batch_walk(pr, scls, false, sC, sG, sjl, [&](const BluClass &ci, long long il, const uint8_t *g, const double *C, const unsigned short *jlt, int ln) {
         double s = 0.0;
         for (int e = ln; e < ci.T; e += 32) {
             const unsigned jl = jlt[e];
