@@ -36,6 +36,14 @@
 #define BLU_GRAM_GROUP 16                    // CTAs per group of the in-kernel reduction
 #define BLU_GRAM_MAXGROUPS 40
 
+// explicit shared-space load of one double (32-bit address)
+__device__ __forceinline__ double blu_gram_lds(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 template <int NT, bool TELE>
 __global__ void __launch_bounds__(BLU_GRAM_WARPS * 32)
 blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n, int N, long long slab, int spc,
@@ -73,7 +81,7 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
 #pragma unroll
         for (int p = 0; p < NPAIR; ++p) { acc[h][p][0] = 0.0; acc[h][p][1] = 0.0; }
 
-    auto issue = [&](long long sb, int st) -> int {       // copy samples [sb, sb+cnt) into stage st; returns the skew
+    auto issue = [&](long long sb, int st) {              // copy samples [sb, sb+cnt) into stage st
         const long long cnt = (s1 - sb) < spc ? (s1 - sb) : spc;
         const unsigned long long addr = (unsigned long long)(Y + sb * N);
         const int skew = (int)((addr & 15ull) >> 3);
@@ -82,46 +90,76 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
             blu_mbar_expect_tx(&bars[st], bytes);
             blu_bulk_g2s(stages + (size_t)st * BLU_GRAM_STAGE_DOUBLES, (const void *)(addr & ~15ull), bytes, &bars[st]);
         }
-        return skew;
     };
-    int skew[BLU_GRAM_NS];
+    // A lane's fragment of tile t is (sample ks, column 8 t + cq) of every block of 4 samples: a FIXED byte offset inside the block
+    // plus a per-row stride -- or, for the column of ones and the padding columns, a constant slot with stride 0.  Addresses are
+    // 32-bit shared-space values advanced by additions only: no predicates, no index arithmetic, no selects in the block loop
+    // (the first version spent 4.5 instructions per DMMA on them and kept the ring's skew in local memory).
+    __shared__ double s_const[2];
+    if (threadIdx.x == 0) { s_const[0] = 0.0; s_const[1] = 1.0; }
+    __syncthreads();
+    const unsigned zero_a = blu_smem_u32(&s_const[0]), one_a = blu_smem_u32(&s_const[1]);
+    const unsigned stage_a = blu_smem_u32(stages);
+    unsigned off1[NT], str1[NT], off2[NT], str2[NT];      // off: relative to the chunk's first sample (str != 0) or absolute (str == 0)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const int col = 8 * t + cq;
+        if (col < N) { off1[t] = (unsigned)((ks * N + col) * 8); str1[t] = (unsigned)(N * 8); }
+        else { off1[t] = (col == N) ? one_a : zero_a; str1[t] = 0u; }
+        if (TELE && col >= 1 && col < N) { off2[t] = off1[t] - 8u; str2[t] = str1[t]; }     // Z_j = Y_j - Y_{j-1}
+        else { off2[t] = zero_a; str2[t] = 0u; }
+    }
     long long sissue = s0;                                // next chunk to issue
     int nissued = 0;
-    for (; nissued < BLU_GRAM_NS - 1 && sissue < s1; ++nissued, sissue += spc) skew[nissued] = issue(sissue, nissued);
+    for (; nissued < BLU_GRAM_NS - 1 && sissue < s1; ++nissued, sissue += spc) issue(sissue, nissued);
     int it = 0;
     for (long long sb = s0; sb < s1; sb += spc, ++it) {
         const int st = it % BLU_GRAM_NS;
         if (sissue < s1) {                                // refill the stage consumed one step ago
-            const int sn = (it + BLU_GRAM_NS - 1) % BLU_GRAM_NS;
-            skew[sn] = issue(sissue, sn);
+            issue(sissue, (it + BLU_GRAM_NS - 1) % BLU_GRAM_NS);
             sissue += spc;
         }
         blu_mbar_wait(&bars[st], (unsigned)((it / BLU_GRAM_NS) & 1));
-        const double *base = stages + (size_t)st * BLU_GRAM_STAGE_DOUBLES + skew[st];
         const int cnt = (int)((s1 - sb) < spc ? (s1 - sb) : spc);
-        for (int r0 = 0; r0 < cnt; r0 += 8) {
+        const int skew = (int)((((unsigned long long)(Y + sb * N)) & 15ull) >> 3);
+        if (cnt & 7) {                                    // last chunk of the slab: the missing samples of its last block of 8 count as zeros
+            double *sp = stages + (size_t)st * BLU_GRAM_STAGE_DOUBLES + skew + (size_t)cnt * N;
+            const int nz = (((cnt + 7) & ~7) - cnt) * N;
+            for (int z = lane; z < nz; z += 32) sp[z] = 0.0;
+            __syncwarp();
+        }
+        const unsigned base = stage_a + (unsigned)((st * BLU_GRAM_STAGE_DOUBLES + skew) * 8);
+        unsigned pa[NT], pb[NT], qa[NT], qb[NT];          // block h = 0 / h = 1 (4 samples further down)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int row = r0 + 4 * h + ks;
-                const bool rok = row < cnt;
-                double f[NT];
+        for (int t = 0; t < NT; ++t) {
+            pa[t] = str1[t] ? base + off1[t] : off1[t];
+            pb[t] = pa[t] + 4u * str1[t];
+            qa[t] = str2[t] ? base + off2[t] : off2[t];
+            qb[t] = qa[t] + 4u * str2[t];
+        }
+        const int nb8 = (cnt + 7) >> 3;
+        for (int b8 = 0; b8 < nb8; ++b8) {
+            double f0[NT], f1[NT];
 #pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    const int col = 8 * t + cq;
-                    double v = 0.0;
-                    if (rok) {
-                        if (col < N) {
-                            v = base[row * N + col];
-                            if (TELE && col > 0) v -= base[row * N + col - 1];        // Z_j = Y_j - Y_{j-1}
-                        } else if (col == N) v = 1.0;
-                    }
-                    f[t] = v;
-                }
-                int p = 0;
+            for (int t = 0; t < NT; ++t) { f0[t] = blu_gram_lds(pa[t]); f1[t] = blu_gram_lds(pb[t]); }
+            if (TELE) {
 #pragma unroll
-                for (int ti = 0; ti < NT; ++ti)
+                for (int t = 0; t < NT; ++t) { f0[t] -= blu_gram_lds(qa[t]); f1[t] -= blu_gram_lds(qb[t]); }
+            }
+            int p = 0;
 #pragma unroll
-                    for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[h][p][0], acc[h][p][1], f[ti], f[tj]); ++p; }
+            for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+                for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[0][p][0], acc[0][p][1], f0[ti], f0[tj]); ++p; }
+            p = 0;
+#pragma unroll
+            for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+                for (int tj = ti; tj < NT; ++tj) { blu_dmma(acc[1][p][0], acc[1][p][1], f1[ti], f1[tj]); ++p; }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                pa[t] += 8u * str1[t]; pb[t] += 8u * str1[t];
+                if (TELE) { qa[t] += 8u * str2[t]; qb[t] += 8u * str2[t]; }
             }
         }
         __syncwarp();                                   // stage consumed before it is refilled
@@ -193,12 +231,12 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
         const int r = e / NPG, c = e - r * NPG;
         double sum = 0.0;
         if ((r >> 3) <= (c >> 3)) {
-            for (int g0 = 0; g0 < ngrp; g0 += 8) {
-                double v[8];
+            for (int g0 = 0; g0 < ngrp; g0 += 20) {          // 296 CTAs = 19 groups: one batch of loads in flight
+                double v[20];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (g0 + u < ngrp) ? __ldcg(part2 + (size_t)(g0 + u) * E + e) : 0.0;
+                for (int u = 0; u < 20; ++u) v[u] = (g0 + u < ngrp) ? __ldcg(part2 + (size_t)(g0 + u) * E + e) : 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) sum += v[u];
+                for (int u = 0; u < 20; ++u) sum += v[u];
             }
         }
         G[e] = sum;
@@ -223,7 +261,7 @@ template <int NT>
 static cudaError_t blu_gram_launch(bool tele, const double *dY, long long ystride, long long n, int N, int n_out, int grid, long long slab,
                                    double *d_part, double *d_G, unsigned *d_tickets, cudaStream_t st)
 {
-    const int spc = (512 / N) & ~3;                      // samples per stage: multiple of 4, <= 512 doubles
+    const int spc = (512 / N) & ~7;                      // samples per stage: multiple of 8 (the block loop consumes 8 at a time), <= 512 doubles
     const size_t smem = sizeof(double) * ((size_t)BLU_GRAM_NS * BLU_GRAM_WARPS * BLU_GRAM_STAGE_DOUBLES + (size_t)BLU_GRAM_WARPS * (8 * NT) * (8 * NT))
                         + sizeof(unsigned long long) * BLU_GRAM_NS * BLU_GRAM_WARPS;
     cudaError_t e;

@@ -234,7 +234,7 @@ __global__ void blu_kkt_rhs_kernel(long long n, int nlin, const double *__restri
 // the upper triangle belongs to one warp (16 warps per CTA; gridDim.y CTAs share a row range when there are more than 16
 // blocks).  Per 4 rows a warp loads 4 + 4 fragments (a lane's fragment of tile t: row 4 s + (lane & 3), column
 // 8 t + (lane >> 2) -- the A operand for t = ti, the B operand for t = tj of mma.m8n8k4.f64) with immediate offsets and
-// issues 16 DMMAs: no address arithmetic, no predicates in the loop.  Partial tiles per row range, folded in a fixed order
+// issues 16 DMMAs (10 in a block on the diagonal): no address arithmetic, no predicates in the loop.  Partial tiles per row range, folded in a fixed order
 // by blu_kkt_capfold_kernel: no atomics, bit-reproducible.
 // History (15 models, 32768 x 144): one CTA per tile pair and row split, fragments straight from L2: 108 us (every tile
 // column re-read NTQ + 1 times, 717 MB through L2 for a 37.7 MB matrix); rows staged once but the pairs dealt to the warps
@@ -315,10 +315,17 @@ blu_kkt_syrk_kernel(const double *__restrict__ Bs, long long n, int QP, double *
                 double fa[4], fb[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { fa[i] = blu_kkt_lds(ra + offA + 64u * i); fb[i] = blu_kkt_lds(ra + offB + 64u * i); }
+                if (bi != bj) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) blu_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+                        for (int j = 0; j < 4; ++j) blu_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+                } else {                                  // a block on the diagonal: its tiles below the diagonal are never stored
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = i; j < 4; ++j) blu_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+                }
             }
         }
         __syncthreads();                                  // stage consumed before it is refilled
