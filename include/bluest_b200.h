@@ -159,7 +159,9 @@ int blu_candidate_variances(blu_ctx *ctx, const double *basephi, int LL, const i
  *   ctxs   P contexts on one device, inverses set.  maps == NULL: one input vector is the concatenation of the
  *          problems' own sample vectors.  maps[p] (L_p indices into a shared vector of length Lm): mosap's mappings.
  *   blu_batch_eval: m (B, Lm) host row-major -> var, flags (P, B); grad (optional): for problem p a (B, L_p) block at
- *          offset B * (L_0 + ... + L_{p-1}), filled with inf where BLU_FLAG_TINY (misc.py:484).  No Hessian. */
+ *          offset B * (L_0 + ... + L_{p-1}), filled with inf where BLU_FLAG_TINY (misc.py:484).  No Hessian.
+ *          Batches of up to 128 KB each way are evaluated directly on mapped pinned host buffers (no copy operations
+ *          around the kernel); environment variable BLU_BATCH_NO_ZEROCOPY forces the explicit copies. */
 typedef struct blu_batch blu_batch;
 int blu_batch_create(blu_ctx **ctxs, int P, const int64_t *const *maps, int64_t Lm, blu_batch **out);
 int blu_batch_eval(blu_batch *batch, const double *m, int B, double delta, double *var, unsigned *flags, double *grad);
@@ -176,7 +178,8 @@ int blu_batch_destroy(blu_batch *batch);
  *        [0 G^T; G -W^T W] [ux; uz] = [bx; bz]     (uz UNSCALED: a cvxopt kktsolver returns W uz)
  * Diagonal + rank (N+1)(N+2)/2 + nlin: one weighted Gram contraction over the packed inverses (FP64 tensor cores)
  * and a Cholesky of that order, instead of the dense (L+1)^3/3.  device_ms (optional): CUDA-event time of the
- * device part. */
+ * device part.  Limits: N <= 21 and (N+1)(N+2)/2 + nlin <= 255.  The device workspace (n x (Q+1) doubles and the
+ * partial Gram tiles) stays with the context between calls and is released by blu_ctx_destroy. */
 int blu_kkt_solve(blu_ctx *ctx, int has_t, double scales, int nlin, const double *Gx, const double *d, const double *r,
                   const double *bx, const double *bz, double *ux, double *uz, float *device_ms);
 

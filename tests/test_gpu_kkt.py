@@ -23,7 +23,10 @@ def _problem(N, K, seed):
     return sap, o, costs
 
 
-@pytest.mark.parametrize("N,K,budget_mode,seed", [(5, 5, True, 0), (6, 6, True, 1), (6, 6, False, 2), (8, 3, True, 3), (10, 10, True, 4), (10, 10, False, 5)])
+# N >= 16 takes the 32-lanes-per-group form of the rows kernel, several CTAs per row range in the Gram kernel (more than 16
+# tile blocks) and a capacitance matrix beyond what one SM's shared memory holds (the blocked Cholesky works in L2)
+@pytest.mark.parametrize("N,K,budget_mode,seed", [(5, 5, True, 0), (6, 6, True, 1), (6, 6, False, 2), (8, 3, True, 3), (10, 10, True, 4), (10, 10, False, 5),
+                                                  (17, 3, True, 6), (20, 2, False, 7), (16, 4, True, 8)])
 def test_kkt_solve_matches_dense_kkt(N, K, budget_mode, seed):
     sap, o, costs = _problem(N, K, seed)
     L, M = o.L, N + 1

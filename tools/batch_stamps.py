@@ -1,5 +1,8 @@
+"""MOSAP 4 outputs x 10 models: a few `variances` / `variance_GH(nohess)` calls.  Run with BLU_DEBUG_TIMING=1 to print the
+milestones of CTA 0 of the batched kernel (staging, Phi, inverse, gradient) that DESIGN.md quotes."""
 import os, sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/oracle")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import bluest_b200 as blu, oracle as orc
 N, No = 10, 4
