@@ -178,19 +178,30 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
             }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < E; t += blockDim.x) {
-        const int r = t / NPG, c = t - r * NPG;
-        double sum = 0.0;
-        if ((r >> 3) <= (c >> 3)) {                           // lower tiles are never produced
+    // Only the upper tile pairs exist.  All three reduction levels walk them as 16-byte pairs: NPAIR * 32 double2 per tile set, one
+    // per thread at 20 models (192 <= 256 threads), so the last CTA of a group has its 16 loads -- and the last group its <= 20 --
+    // in flight ONCE instead of once per 256 elements of the padded square (three dependent L2 round trips per level before).
+    constexpr int NE2 = NPAIR * 32;
+    auto elem = [&](int t) -> int {                       // double2 index -> element offset (row-major NPG x NPG, even column)
+        const int p = t >> 5, q = t & 31;
+        int ti = 0, rem = p;
+        while (rem >= NT - ti) { rem -= NT - ti; ++ti; }
+        return (8 * ti + (q >> 2)) * NPG + 8 * (ti + rem) + 2 * (q & 3);
+    };
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int t = tid; t < NE2; t += nthr) {
+        const int e = elem(t);
+        double2 sum = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int ww = 0; ww < BLU_GRAM_WARPS; ++ww) sum += sall[(size_t)ww * E + t];
+        for (int ww = 0; ww < BLU_GRAM_WARPS; ++ww) {
+            const double2 v = *reinterpret_cast<const double2 *>(sall + (size_t)ww * E + e);
+            sum.x += v.x; sum.y += v.y;
         }
-        part[(size_t)blockIdx.x * E + t] = sum;
+        *reinterpret_cast<double2 *>(part + (size_t)blockIdx.x * E + e) = sum;
     }
 
     // ---- fused reduction over CTAs: last CTA of a group folds the group (CTA order), last group folds the groups ----
     __shared__ int s_last;
-    const int tid = threadIdx.x, nthr = blockDim.x;
     const int grp = blockIdx.x / BLU_GRAM_GROUP;
     const int ngrp = (gridDim.x + BLU_GRAM_GROUP - 1) / BLU_GRAM_GROUP;
     const int members = min(BLU_GRAM_GROUP, (int)gridDim.x - grp * BLU_GRAM_GROUP);
@@ -205,17 +216,17 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
     if (!s_last) return;
     __threadfence();
     double *part2 = part + (size_t)gridDim.x * E;
-    for (int e = tid; e < E; e += nthr) {
-        const int r = e / NPG, c = e - r * NPG;
-        double v[BLU_GRAM_GROUP];
-        const bool up = (r >> 3) <= (c >> 3);
+    for (int t = tid; t < NE2; t += nthr) {
+        const int e = elem(t);
+        double2 v[BLU_GRAM_GROUP];
         const double *pp = part + (size_t)grp * BLU_GRAM_GROUP * E + e;
 #pragma unroll
-        for (int cc = 0; cc < BLU_GRAM_GROUP; ++cc) v[cc] = (up && cc < members) ? __ldcg(pp + (size_t)cc * E) : 0.0;
-        double sum = 0.0;
+        for (int cc = 0; cc < BLU_GRAM_GROUP; ++cc)
+            v[cc] = (cc < members) ? __ldcg(reinterpret_cast<const double2 *>(pp + (size_t)cc * E)) : make_double2(0.0, 0.0);
+        double2 sum = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int cc = 0; cc < BLU_GRAM_GROUP; ++cc) sum += v[cc];
-        part2[(size_t)grp * E + e] = sum;
+        for (int cc = 0; cc < BLU_GRAM_GROUP; ++cc) { sum.x += v[cc].x; sum.y += v[cc].y; }
+        *reinterpret_cast<double2 *>(part2 + (size_t)grp * E + e) = sum;
     }
     __threadfence();
     __syncthreads();
@@ -227,19 +238,18 @@ blu_gram_kernel(const double *__restrict__ Yall, long long ystride, long long n,
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int e = tid; e < E; e += nthr) {
-        const int r = e / NPG, c = e - r * NPG;
-        double sum = 0.0;
-        if ((r >> 3) <= (c >> 3)) {
-            for (int g0 = 0; g0 < ngrp; g0 += 20) {          // 296 CTAs = 19 groups: one batch of loads in flight
-                double v[20];
+    for (int t = tid; t < NE2; t += nthr) {
+        const int e = elem(t);
+        double2 sum = make_double2(0.0, 0.0);
+        for (int g0 = 0; g0 < ngrp; g0 += 20) {          // 296 CTAs = 19 groups: one batch of loads in flight
+            double2 v[20];
 #pragma unroll
-                for (int u = 0; u < 20; ++u) v[u] = (g0 + u < ngrp) ? __ldcg(part2 + (size_t)(g0 + u) * E + e) : 0.0;
+            for (int u = 0; u < 20; ++u)
+                v[u] = (g0 + u < ngrp) ? __ldcg(reinterpret_cast<const double2 *>(part2 + (size_t)(g0 + u) * E + e)) : make_double2(0.0, 0.0);
 #pragma unroll
-                for (int u = 0; u < 20; ++u) sum += v[u];
-            }
+            for (int u = 0; u < 20; ++u) { sum.x += v[u].x; sum.y += v[u].y; }
         }
-        G[e] = sum;
+        *reinterpret_cast<double2 *>(G + e) = sum;
     }
 }
 
