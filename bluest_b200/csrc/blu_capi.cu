@@ -1623,7 +1623,7 @@ extern "C" int blu_kkt_solve(blu_ctx *c, int has_t, double scales, int nlin, con
         CUDA_TRY(cudaFuncSetAttribute(blu_kkt_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
         blu_kkt_syrk_kernel<<<dim3((unsigned)nsplit, (unsigned)ny), BLU_SYRK_WARPS * 32, ssm, st>>>(d_Bs, n, QP, d_part);
         KERNEL_CHECK(c);
-        blu_kkt_capfold_kernel<<<npairs, 256, 0, st>>>(d_part, npairs, nsplit, Q, QP, LDC, d_cap);
+        blu_kkt_capfold_kernel<<<npairs * 2, 256, 0, st>>>(d_part, npairs, nsplit, Q, QP, LDC, d_cap);
         KERNEL_CHECK(c);
         blu_kkt_chol_kernel<<<1, BLU_CHOL_T, 0, st>>>(d_cap, Q, LDC, d_y, d_info);
         KERNEL_CHECK(c);

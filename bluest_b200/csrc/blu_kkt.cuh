@@ -350,17 +350,17 @@ blu_kkt_syrk_kernel(const double *__restrict__ Bs, long long n, int QP, double *
 // cap = I + sum over the row ranges (fixed order) of the partial tiles; v = column Q.
 // Output in the layout blu_kkt_chol_kernel factors in place: COLUMN-major with leading dimension LD >= Q + 1, element (i, j)
 // at cap[j * LD + i]; the right-hand side rides along as the extra ROW Q of the matrix (cap[j * LD + Q] = v_j).
-// Four threads per element, each sums a contiguous quarter of the row ranges with 8 loads in flight; the quarters are
-// combined by a fixed shuffle tree.
+// Eight threads per element, each sums a contiguous eighth of the row ranges with its loads in flight together; the
+// eighths are combined by a fixed shuffle tree.
 __global__ void __launch_bounds__(256)
 blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, int Q, int QP, int LD, double *__restrict__ cap)
 {
     const int NTQ = QP >> 3;
-    const int t = blockIdx.x * 64 + (threadIdx.x >> 2), sub = threadIdx.x & 3;       // 64 elements (one tile) per CTA
+    const int t = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;       // 32 elements (half a tile) per CTA
     const int p = t >> 6, e = t & 63;
     double s = 0.0;
     if (p < npairs) {
-        const int nq = (nsplit + 3) >> 2;
+        const int nq = (nsplit + 7) >> 3;
         const int s0 = sub * nq, s1 = min(nsplit, s0 + nq);
         const double *src = part + (size_t)p * 64 + e;
         const size_t stride = (size_t)npairs * 64;
@@ -372,10 +372,17 @@ blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, 
 #pragma unroll
             for (int u = 0; u < 8; ++u) s += v[u];
         }
-        for (; sp < s1; ++sp) s += __ldg(src + (size_t)sp * stride);
+        if (sp < s1) {                                        // the remainder as one predicated batch
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (sp + u < s1) ? __ldg(src + (size_t)(sp + u) * stride) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
     }
     s += __shfl_xor_sync(BLU_FULL, s, 1);
     s += __shfl_xor_sync(BLU_FULL, s, 2);
+    s += __shfl_xor_sync(BLU_FULL, s, 4);
     if (p >= npairs || sub != 0) return;
     int ti = 0, rem = p;
     while (rem >= NTQ - ti) { rem -= NTQ - ti; ++ti; }
@@ -583,8 +590,12 @@ blu_kkt_apply_kernel(const double *__restrict__ Bs, long long n, int Q, int QP, 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long long col = (long long)blockIdx.x * BLU_KKT_WARPS + w; col < n; col += (long long)gridDim.x * BLU_KKT_WARPS) {
         const double *row = Bs + col * QP;
+        double v[8];                                      // Q <= 255: the whole row in flight at once (one L2 round trip per row, not one per 32 entries)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (lane + 32 * u < Q) ? __ldg(row + lane + 32 * u) : 0.0;
         double s = 0.0;
-        for (int q = lane; q < Q; q += 32) s = fma(row[q], sy[q], s);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = fma(v[u], (lane + 32 * u < Q) ? sy[lane + 32 * u] : 0.0, s);
         s = blu_warp_sum(s);
         if (lane == 0) ux[col] = d[col] * (d[col] * rhs[col] - s);
     }
