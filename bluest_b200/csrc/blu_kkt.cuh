@@ -413,7 +413,9 @@ blu_kkt_capfold_kernel(const double *__restrict__ part, int npairs, int nsplit, 
 // column: shuffle, rsqrt, 15 shuffles, multiply-add), trailing updates 45 k (bound by ONE SM's FP64 and shared-memory issue,
 // 64 x 8 tasks include the waste above the diagonal), rows below 14 k, panel load + store 19 k, backward substitution 26 k.
 // Copying the whole matrix into shared memory first (it fits up to 16 models) changed the total by 3 %: L2 latency is not
-// what limits it; the next step would be DMMA tile blocks for the trailing update.
+// what limits it; the next step would be DMMA tile blocks for the trailing update.  Also measured: factoring the next diagonal
+// block one panel ahead (warp 0) while the other warps finish the trailing update -- correct, but the KKT solve stayed at
+// 0.204-0.209 ms (0.206-0.208 before): the update that can hide behind the chain is too short at these orders.  Not kept.
 #define BLU_CHOL_T 512
 #ifdef BLU_CHOL_STAMPS                  // lab only (tools/lab/chol_lab.cu): cycles per phase, accumulated by thread 0
 __device__ long long blu_chol_cycles[8];
